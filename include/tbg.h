@@ -1,0 +1,104 @@
+/*
+ * tbg.h — C ABI of the B200-native TextBoxGAN training-step hot path.
+ *
+ * Every entry point takes raw device pointers + explicit shapes + a cudaStream_t (as void*),
+ * allocates nothing, returns 0 on success and a negative code on failure (message through
+ * tbg_last_error(), thread-local), and never throws across the boundary.  These are the
+ * conventions of the reference's one native plugin, the TF op `UpFirDn2D`
+ * (models/custom_stylegan2/layers/upfirdn/upfirdn_2d.cu:232-324: shape checks -> Status,
+ * output owned by the framework, launch on the framework's stream), extended to the library
+ * calls TensorFlow made on the reference's behalf (cuDNN convs, cuBLAS GEMMs, Eigen
+ * element-wise kernels, ResourceApplyAdam) — see SURVEY.md §2.1 and INTEGRATION.md.
+ *
+ * Layout conventions: activations are NHWC bf16 ([B, H, W, C], C contiguous); weights handed to
+ * the GEMM kernels are bf16 "K-major" matrices [N, K] with K = (tap_h, tap_w, Cin) flattened;
+ * parameters, gradients of parameters, modulation vectors and optimiser state are fp32.
+ */
+#ifndef TBG_H_
+#define TBG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBG_OK 0
+#define TBG_ERR_INVALID_ARG (-1)
+#define TBG_ERR_CUDA (-2)
+#define TBG_ERR_UNSUPPORTED (-3)
+
+/* Last error message of the calling thread ("" if none). */
+const char* tbg_last_error(void);
+/* Library/ABI version (bumped when a signature changes). */
+int tbg_version(void);
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+ * gpu_launches counter). tbg_reset_launch_count() zeroes it. */
+long long tbg_launch_count(void);
+void tbg_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *
+ * Replaces: tf.nn.conv2d / conv2d_transpose as called from
+ *   modulated_conv2d.py:99-112 (ModulatedConv2D.call, non-fused algebra :95-96,119-121),
+ *   upfirdn_2d_v2.py:65-103 (upsample_conv_2d), :106-113 (conv_downsample_2d),
+ *   conv.py:51-73 (Conv2D.call), and their cuDNN backward passes (dgrad is the same kernel
+ *   on re-laid-out weights).
+ *
+ * GEMM view: rows = output pixels (128-pixel boxes of one or several images), columns = n_total
+ * output channels, K = taps_h*taps_w*Cin.  up=1 treats columns as (phase_y, phase_x, cout) and
+ * scatters phase (py,px) of GEMM row (b,i,j) to output pixel (2i+py, 2j+px): the fused
+ * transposed-conv + FIR of upsample_conv_2d (DESIGN.md §"up path").
+ *
+ * Epilogue, in reference order (modulated_conv2d.py:119-121, noise.py:21, bias_act.py:25-34,
+ * discriminator.py:82): v = acc*col_scale[b,c]; v += noise[b,y,x]*noise_strength[0];
+ * v += bias[c]; v = act(v)*act_gain; v = (v + residual)*res_scale (if residual).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tbg_conv_args {
+  const void* x;   /* bf16 [B, H, W, Cin] */
+  const void* w;   /* bf16 [n_total, taps_h*taps_w*Cin] */
+  void* out;       /* bf16 (or fp32 if out_fp32) [B, out_H, out_W, cout] */
+  int B, H, W, Cin;
+  int Ho, Wo;      /* GEMM row grid (output pixels; for up=1 the input grid) */
+  int n_total;     /* GEMM columns: cout, or 4*cout when up=1 */
+  int cout;        /* channels of the output tensor */
+  int taps_h, taps_w;
+  int pad_h, pad_w;       /* input coord = o*stride - pad + tap */
+  int stride_h, stride_w; /* 1 or 2 */
+  int up;                 /* 0 | 1 */
+  const float* col_scale;      /* [B, cout] or NULL */
+  const float* bias;           /* [cout] or NULL */
+  const float* noise;          /* [B, out_H, out_W] or NULL */
+  const float* noise_strength; /* device scalar, required if noise */
+  const void* residual;        /* bf16, same shape as out, or NULL */
+  float res_scale;
+  int act;         /* 0 linear, 1 leaky-relu(0.2) */
+  float act_gain;  /* multiplies after act (sqrt(2) for lrelu) */
+  int out_fp32;    /* 0: bf16 output, 1: fp32 output */
+} tbg_conv_args;
+
+int tbg_conv2d_igemm(const tbg_conv_args* args, void* stream);
+
+/* Weight gradient of the same convolution (split over pixel blocks, fp32 atomics):
+ *   gw[n, (th,tw), c] += sum_{b,ho,wo} gy[b, ho, wo, n] * x[b, ho*s-pad+th, wo*s-pad+tw, c]
+ * Replaces cuDNN's backward-filter pass behind tape.gradient (training_step.py:224-235).
+ * gw is fp32 [n_total, taps_h*taps_w*Cin] and must be zeroed (or hold a running sum) by the
+ * caller.  For up=1, gy is the 2x-resolution tensor and n indexes (py,px,cout). */
+typedef struct tbg_wgrad_args {
+  const void* x;   /* bf16 [B, H, W, Cin] */
+  const void* gy;  /* bf16 [B, gy_H, gy_W, cout] */
+  float* gw;       /* fp32 [n_total, taps_h*taps_w*Cin] */
+  int B, H, W, Cin;
+  int Ho, Wo;
+  int n_total, cout;
+  int taps_h, taps_w, pad_h, pad_w, stride_h, stride_w;
+  int up;
+} tbg_wgrad_args;
+
+int tbg_conv2d_wgrad(const tbg_wgrad_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBG_H_ */

@@ -1,0 +1,390 @@
+// Implicit-GEMM convolution for sm_100a: TMA (tiled mode, shifted boxes, zero OOB fill) feeds
+// 128-pixel x 64-channel activation tiles and N x 64 weight tiles into 128B-swizzled shared
+// memory; one elected thread issues tcgen05.mma (M=128, N<=256, K=16) into double-buffered TMEM
+// accumulators; four epilogue warps drain TMEM with tcgen05.ld and apply the StyleGAN2 epilogue
+// (demod scale, noise, bias, leaky-ReLU, residual) before writing NHWC bf16/fp32.
+//
+// Reference behaviour covered: ModulatedConv2D.call (modulated_conv2d.py:66-122, non-fused
+// algebra), upsample_conv_2d (upfirdn_2d_v2.py:65-103, as a 4-phase GEMM), Conv2D.call
+// (conv.py:51-73), Noise.call (noise.py:12-22), BiasAct.call (bias_act.py:25-34), the residual
+// merge of DiscriminatorBlock.call (discriminator.py:82).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tbg {
+
+struct ConvKernelParams {
+  int B;
+  int bw_log2, bh_log2, bn_log2;  // M-tile box (output pixels): bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_b, tiles_n;
+  int block_n;  // columns per N tile (multiple of 32, <= 256)
+  int n_total;
+  int cin_chunks;  // Cin / 64
+  int cin;
+  int taps_h, taps_w;
+  int in_off_h, in_off_w;  // = -pad
+  int stride_h, stride_w;
+  int up;
+  int cout;
+  int out_H, out_W;
+  int stages;
+  // epilogue
+  const float* col_scale;
+  const float* bias;
+  const float* noise;
+  const float* noise_strength;
+  const __nv_bfloat16* residual;
+  float res_scale;
+  int act;
+  float act_gain;
+  int out_fp32;
+  void* out;
+};
+
+static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
+static constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+
+  const int stages = p.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + stages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + stages * b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int k_blocks = p.taps_h * p.taps_w * p.cin_chunks;
+  const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2, bn = 1 << p.bn_log2;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.tiles_n;
+        const int m_tile = tile / p.tiles_n;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tb = m_tile / (p.tiles_w * p.tiles_h);
+        const int w_base = tw * bw * p.stride_w + p.in_off_w;
+        const int h_base = th * bh * p.stride_h + p.in_off_h;
+        const int n_base = tb * bn;
+        int kcol = 0;
+        for (int ty = 0; ty < p.taps_h; ++ty) {
+          for (int tx = 0; tx < p.taps_w; ++tx) {
+            for (int ch = 0; ch < p.cin_chunks; ++ch, kcol += 64) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
+              tma_load_4d(smA + stage * kABytes, &tmA, &full[stage], ch * 64, w_base + tx, h_base + ty, n_base);
+              tma_load_2d(smB + stage * b_bytes, &tmB, &full[stage], kcol, n_tile * p.block_n);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.block_n), 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc_stage = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc_stage], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smB + stage * b_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tfull[acc_stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int e = warp - 4;
+    const int r = e * 32 + lane;
+    const int w_in = r & (bw - 1);
+    const int h_in = (r >> p.bw_log2) & (bh - 1);
+    const int n_in = r >> (p.bw_log2 + p.bh_log2);
+    const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.tiles_n;
+      const int m_tile = tile / p.tiles_n;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tb = m_tile / (p.tiles_w * p.tiles_h);
+      const int b = tb * bn + n_in;
+      const int ho = th * bh + h_in;
+      const int wo = tw * bw + w_in;
+      const bool valid = b < p.B;
+      const int acc_stage = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc_stage], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
+                             static_cast<uint32_t>(acc_stage * p.block_n);
+      for (int j = 0; j < p.block_n / 32; ++j) {
+        const int col0 = n_tile * p.block_n + j * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + j * 32, v);
+        tmem_ld_wait();
+        if (valid && col0 < p.n_total) {
+          int c0 = col0, oy = ho, ox = wo;
+          if (p.up) {
+            const int ph = col0 / p.cout;
+            c0 = col0 - ph * p.cout;
+            oy = 2 * ho + (ph >> 1);
+            ox = 2 * wo + (ph & 1);
+          }
+          const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
+          const size_t off = pix * p.cout + c0;
+          const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
+          const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
+          const float* bs = p.bias ? p.bias + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+            if (cs) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(cs + g * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(cs + g * 8 + 4));
+              f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+              f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+            }
+            if (p.noise) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += nz;
+            }
+            if (bs) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
+            if (p.residual) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + off + g * 8));
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 rf = __bfloat1622float2(rh[i]);
+                f[2 * i] = (f[2 * i] + rf.x) * p.res_scale;
+                f[2 * i + 1] = (f[2 * i + 1] + rf.y) * p.res_scale;
+              }
+            }
+            if (p.out_fp32) {
+              float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
+              uint4 pk;
+              pk.x = pack_bf16x2(f[0], f[1]);
+              pk.y = pack_bf16x2(f[2], f[3]);
+              pk.z = pack_bf16x2(f[4], f[5]);
+              pk.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(o) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc_stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace tbg
+
+using namespace tbg;
+
+extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
+  if (!a) return set_error(TBG_ERR_INVALID_ARG, "tbg_conv2d_igemm: null args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  TBG_CHECK_ARG(a->x && a->w && a->out, "tbg_conv2d_igemm: null tensor pointer");
+  TBG_CHECK_ARG(a->B >= 1 && a->H >= 1 && a->W >= 1, "tbg_conv2d_igemm: bad input shape B=%d H=%d W=%d", a->B, a->H, a->W);
+  TBG_CHECK_ARG(a->Cin >= 64 && a->Cin % 64 == 0, "tbg_conv2d_igemm: Cin=%d must be a multiple of 64", a->Cin);
+  TBG_CHECK_ARG(is_pow2(a->Ho) && is_pow2(a->Wo), "tbg_conv2d_igemm: Ho=%d Wo=%d must be powers of two", a->Ho, a->Wo);
+  TBG_CHECK_ARG(a->cout >= 32 && a->cout % 32 == 0, "tbg_conv2d_igemm: cout=%d must be a multiple of 32", a->cout);
+  TBG_CHECK_ARG(a->up == 0 || a->up == 1, "tbg_conv2d_igemm: up must be 0 or 1");
+  TBG_CHECK_ARG(a->n_total == (a->up ? 4 * a->cout : a->cout), "tbg_conv2d_igemm: n_total=%d inconsistent with cout=%d up=%d",
+                a->n_total, a->cout, a->up);
+  TBG_CHECK_ARG(a->taps_h >= 1 && a->taps_w >= 1 && a->taps_h <= 8 && a->taps_w <= 8, "tbg_conv2d_igemm: bad taps");
+  TBG_CHECK_ARG((a->stride_h == 1 || a->stride_h == 2) && (a->stride_w == 1 || a->stride_w == 2),
+                "tbg_conv2d_igemm: strides must be 1 or 2");
+  TBG_CHECK_ARG(!a->noise || a->noise_strength, "tbg_conv2d_igemm: noise without noise_strength");
+  TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                "tbg_conv2d_igemm: tensors must be 16-byte aligned");
+
+  ConvKernelParams p{};
+  p.B = a->B;
+  const int bw = a->Wo < 128 ? a->Wo : 128;
+  int bh = 128 / bw;
+  if (bh > a->Ho) bh = a->Ho;
+  const int bn = 128 / (bw * bh);
+  // with a stride-2 load the TMA box spans 2*b elements and must stay <= 256
+  TBG_CHECK_ARG(bw * a->stride_w <= 256 && bh * a->stride_h <= 256, "tbg_conv2d_igemm: tile box too large");
+  p.bw_log2 = ilog2(bw);
+  p.bh_log2 = ilog2(bh);
+  p.bn_log2 = ilog2(bn);
+  p.tiles_w = a->Wo / bw;
+  p.tiles_h = a->Ho / bh;
+  p.tiles_b = (a->B + bn - 1) / bn;
+  // N tile: largest of 256/128/64/32 that divides n_total (keeps every tile full)
+  int block_n = 256;
+  while (block_n > 32 && (a->n_total % block_n) != 0) block_n >>= 1;
+  if (a->n_total % block_n != 0) block_n = 32;
+  // prefer >= 2 N tiles' worth of parallelism only when M tiles are scarce
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+  while (block_n > 64 && tiles_m * (a->n_total / block_n) < num_sms() && (a->n_total % (block_n / 2)) == 0) block_n >>= 1;
+  p.block_n = block_n;
+  p.tiles_n = (a->n_total + block_n - 1) / block_n;
+  p.n_total = a->n_total;
+  p.cin = a->Cin;
+  p.cin_chunks = a->Cin / 64;
+  p.taps_h = a->taps_h;
+  p.taps_w = a->taps_w;
+  p.in_off_h = -a->pad_h;
+  p.in_off_w = -a->pad_w;
+  p.stride_h = a->stride_h;
+  p.stride_w = a->stride_w;
+  p.up = a->up;
+  p.cout = a->cout;
+  p.out_H = a->up ? 2 * a->Ho : a->Ho;
+  p.out_W = a->up ? 2 * a->Wo : a->Wo;
+  p.col_scale = a->col_scale;
+  p.bias = a->bias;
+  p.noise = a->noise;
+  p.noise_strength = a->noise_strength;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.res_scale = a->res_scale;
+  p.act = a->act;
+  p.act_gain = a->act_gain;
+  p.out_fp32 = a->out_fp32;
+  p.out = a->out;
+
+  const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/;
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
+    const uint64_t strides[4] = {0, (uint64_t)a->Cin * 2, (uint64_t)a->W * a->Cin * 2, (uint64_t)a->H * a->W * a->Cin * 2};
+    // with element stride s the box spans b*s source elements and delivers b of them
+    const uint32_t box[4] = {64, (uint32_t)(bw * a->stride_w), (uint32_t)(bh * a->stride_h), (uint32_t)bn};
+    const uint32_t estr[4] = {1, (uint32_t)a->stride_w, (uint32_t)a->stride_h, 1};
+    int rc = encode_tmap_bf16(&tmA, a->x, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)a->taps_h * a->taps_w * a->Cin;
+    const uint64_t dims[2] = {K, (uint64_t)a->n_total};
+    const uint64_t strides[2] = {0, K * 2};
+    const uint32_t box[2] = {64, (uint32_t)block_n};
+    int rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}

@@ -1,0 +1,45 @@
+// Host-side helpers of the C ABI: thread-local error string, launch counter, TMA descriptor
+// encoding through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/tbg.h"
+
+namespace tbg {
+
+char* last_error_buf();  // thread-local, 512 bytes
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define TBG_CHECK_ARG(cond, ...)                                  \
+  do {                                                            \
+    if (!(cond)) return tbg::set_error(TBG_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define TBG_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return tbg::set_error(TBG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                               \
+  } while (0)
+
+// Encode a tiled bf16 tensor map. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
+// Returns 0 or sets the error string.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swizzle);
+
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace tbg

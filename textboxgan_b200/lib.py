@@ -1,0 +1,91 @@
+"""ctypes binding of ``libtbg.so`` — the C-ABI boundary declared in ``include/tbg.h``.
+
+The product path has no fallback: if the shared library is missing the import of the first op
+raises.  (The reference loads its plugin with ``tf.load_op_library`` and likewise fails hard,
+models/custom_stylegan2/layers/upfirdn/custom_ops.py:182-207.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libtbg.so"
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_float = C.c_float
+
+
+class TbgError(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero status (mirrors a TF ``Status`` error)."""
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("w", c_void_p), ("out", c_void_p),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int),
+        ("Ho", c_int), ("Wo", c_int),
+        ("n_total", c_int), ("cout", c_int),
+        ("taps_h", c_int), ("taps_w", c_int),
+        ("pad_h", c_int), ("pad_w", c_int),
+        ("stride_h", c_int), ("stride_w", c_int),
+        ("up", c_int),
+        ("col_scale", c_void_p), ("bias", c_void_p), ("noise", c_void_p), ("noise_strength", c_void_p),
+        ("residual", c_void_p), ("res_scale", c_float),
+        ("act", c_int), ("act_gain", c_float), ("out_fp32", c_int),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("gy", c_void_p), ("gw", c_void_p),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int),
+        ("Ho", c_int), ("Wo", c_int),
+        ("n_total", c_int), ("cout", c_int),
+        ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int),
+        ("stride_h", c_int), ("stride_w", c_int),
+        ("up", c_int),
+    ]
+
+
+_lib = None
+
+# every symbol include/tbg.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("tbg_last_error", C.c_char_p, []),
+    ("tbg_version", c_int, []),
+    ("tbg_launch_count", C.c_longlong, []),
+    ("tbg_reset_launch_count", None, []),
+    ("tbg_conv2d_igemm", c_int, [C.POINTER(ConvArgs), c_void_p]),
+    ("tbg_conv2d_wgrad", c_int, [C.POINTER(WgradArgs), c_void_p]),
+]
+
+
+def exported_symbols() -> list[str]:
+    return [s[0] for s in _SIGNATURES]
+
+
+def load() -> C.CDLL:
+    """Load ``libtbg.so`` (built in-tree by ``textboxgan_b200.build``); raise if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TbgError(
+            f"{LIB_PATH} not found: run `python -m textboxgan_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU or PyTorch fallback for the hot path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, restype, argtypes in _SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().tbg_last_error().decode("utf-8", "replace")
+        raise TbgError(f"{what} failed with status {status}: {msg}")
