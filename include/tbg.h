@@ -47,33 +47,36 @@ void tbg_reset_launch_count(void);
  *   on re-laid-out weights).
  *
  * GEMM view: rows = output pixels (128-pixel boxes of one or several images), columns = n_total
- * output channels, K = taps_h*taps_w*Cin.  up=1 treats columns as (phase_y, phase_x, cout) and
- * scatters phase (py,px) of GEMM row (b,i,j) to output pixel (2i+py, 2j+px): the fused
- * transposed-conv + FIR of upsample_conv_2d (DESIGN.md §"up path").
+ * output channels, K = taps_h*taps_w*Cin.  up_h/up_w treat columns as (phase_y, phase_x, cout) and
+ * scatter phase (py,px) of GEMM row (b,i,j) to output pixel (2i+py, 2j+px): the fused
+ * transposed-conv + FIR of upsample_conv_2d, and the input-gradient of every stride-2
+ * convolution (DESIGN.md §"geometry algebra").
  *
  * Epilogue, in reference order (modulated_conv2d.py:119-121, noise.py:21, bias_act.py:25-34,
  * discriminator.py:82): v = acc*col_scale[b,c]; v += noise[b,y,x]*noise_strength[0];
- * v += bias[c]; v = act(v)*act_gain; v = (v + residual)*res_scale (if residual).
+ * v += bias[c]; v = act(v)*act_gain; v = (v + residual)*res_scale (if residual; res_first
+ * moves the residual merge in front of the activation, the ResNet-unit order of the OCR head).
  * ------------------------------------------------------------------------------------------ */
 typedef struct tbg_conv_args {
   const void* x;   /* bf16 [B, H, W, Cin] */
   const void* w;   /* bf16 [n_total, taps_h*taps_w*Cin] */
   void* out;       /* bf16 (or fp32 if out_fp32) [B, out_H, out_W, cout] */
   int B, H, W, Cin;
-  int Ho, Wo;      /* GEMM row grid (output pixels; for up=1 the input grid) */
-  int n_total;     /* GEMM columns: cout, or 4*cout when up=1 */
+  int Ho, Wo;      /* GEMM row grid (output pixels; along an up axis: the input grid) */
+  int n_total;     /* GEMM columns: cout * (1+up_h) * (1+up_w) */
   int cout;        /* channels of the output tensor */
   int taps_h, taps_w;
   int pad_h, pad_w;       /* input coord = o*stride - pad + tap */
   int stride_h, stride_w; /* 1 or 2 */
-  int up;                 /* 0 | 1 */
+  int up_h, up_w;         /* 0 | 1 per axis: 2-phase transposed conv along that axis */
   const float* col_scale;      /* [B, cout] or NULL */
   const float* bias;           /* [cout] or NULL */
   const float* noise;          /* [B, out_H, out_W] or NULL */
   const float* noise_strength; /* device scalar, required if noise */
   const void* residual;        /* bf16, same shape as out, or NULL */
   float res_scale;
-  int act;         /* 0 linear, 1 leaky-relu(0.2) */
+  int res_first;   /* 0: v = (act(v)*gain + residual)*res_scale; 1: v = act((v + residual)*res_scale)*gain */
+  int act;         /* 0 linear, 1 leaky-relu(0.2), 2 relu */
   float act_gain;  /* multiplies after act (sqrt(2) for lrelu) */
   int out_fp32;    /* 0: bf16 output, 1: fp32 output */
 } tbg_conv_args;
@@ -84,7 +87,7 @@ int tbg_conv2d_igemm(const tbg_conv_args* args, void* stream);
  *   gw[n, (th,tw), c] += sum_{b,ho,wo} gy[b, ho, wo, n] * x[b, ho*s-pad+th, wo*s-pad+tw, c]
  * Replaces cuDNN's backward-filter pass behind tape.gradient (training_step.py:224-235).
  * gw is fp32 [n_total, taps_h*taps_w*Cin] and must be zeroed (or hold a running sum) by the
- * caller.  For up=1, gy is the 2x-resolution tensor and n indexes (py,px,cout). */
+ * caller.  Along an up axis gy is the 2x-resolution tensor and n indexes (py,px,cout). */
 typedef struct tbg_wgrad_args {
   const void* x;   /* bf16 [B, H, W, Cin] */
   const void* gy;  /* bf16 [B, gy_H, gy_W, cout] */
@@ -93,10 +96,34 @@ typedef struct tbg_wgrad_args {
   int Ho, Wo;
   int n_total, cout;
   int taps_h, taps_w, pad_h, pad_w, stride_h, stride_w;
-  int up;
+  int up_h, up_w;
 } tbg_wgrad_args;
 
 int tbg_conv2d_wgrad(const tbg_wgrad_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * upfirdn2d — drop-in for the reference's TF custom op
+ *   UpFirDn2D(x: T[major,inH,inW,minor], k: T[kH,kW]; upx,upy,downx,downy,padx0,padx1,pady0,pady1)
+ *   -> y: T[major,outH,outW,minor]          (upfirdn_2d.cu:310-324, Compute :232-307)
+ * pad (crop if negative) -> zero-insert upsample -> correlate with the flipped FIR -> decimate,
+ * fp32 accumulation.  dtype_bf16 = 0: T = float, 1: T = bf16; k is always fp32.
+ * outW = (inW*upx + padx0 + padx1 - kW + downx) / downx (same for H).  Errors mirror the op's
+ * OP_REQUIRES checks and are returned as TBG_ERR_INVALID_ARG.
+ * ------------------------------------------------------------------------------------------ */
+int tbg_upfirdn2d(const void* x, const float* k, void* y, int dtype_bf16, int major, int inH, int inW, int minor,
+                  int kH, int kW, int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                  void* stream);
+
+/* tf.keras.optimizers.Adam (optimizer_v2) update of a flat fp32 buffer — replaces the per-variable
+ * ResourceApplyAdam ops behind optimizer.apply_gradients (training_step.py:235):
+ *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= lr_t*m/(sqrt(v)+eps),
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host. */
+int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                  float eps, void* stream);
+
+/* dst = src + (dst - src)*beta over a flat fp32 buffer — Generator.set_as_moving_average_of
+ * (generator.py:48-59). */
+int tbg_ema_step(float* dst, const float* src, long long n, float beta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,114 @@
+"""CPU emulation of the two tensor-core entry points (TEST INFRASTRUCTURE).
+
+Lets the host-side logic (geometry algebra, weight re-layouts, autograd wiring, model code) be
+checked against the oracle on a machine without a GPU.  It implements the *documented semantics*
+of ``tbg_conv2d_igemm`` / ``tbg_conv2d_wgrad`` (include/tbg.h) with dense torch ops; the product
+never imports it."""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+
+def _gather_tap(xp, PH, PW, ty, tx, pad, stride, Ho, Wo):
+    h0 = PH + ty - pad[0]
+    w0 = PW + tx - pad[1]
+    return xp[:, h0: h0 + (Ho - 1) * stride[0] + 1: stride[0], w0: w0 + (Wo - 1) * stride[1] + 1: stride[1], :]
+
+
+def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_scale=None, bias=None, noise=None,
+                     noise_strength=None, residual=None, res_scale=1.0, res_first=False, act=0, act_gain=1.0, out_fp32=False, out=None):
+    if isinstance(up, bool):
+        up = (int(up), int(up))
+    B, H, W_, Cin = x.shape
+    ph, pw = 1 + up[0], 1 + up[1]
+    n_total = w.shape[0]
+    cout = n_total // (ph * pw)
+    w6 = w.reshape(ph, pw, cout, taps[0], taps[1], Cin).to(torch.float64)
+    PH = taps[0] + pad[0] + stride[0] * Ho + 2
+    PW = taps[1] + pad[1] + stride[1] * Wo + 2
+    xp = F.pad(x.to(torch.float64), (0, 0, PW, PW, PH, PH))
+    acc = torch.zeros(B, Ho, Wo, ph, pw, cout, dtype=torch.float64)
+    for ty in range(taps[0]):
+        for tx in range(taps[1]):
+            xs = _gather_tap(xp, PH, PW, ty, tx, pad, stride, Ho, Wo)
+            acc += torch.einsum("bhwc,pqoc->bhwpqo", xs, w6[:, :, :, ty, tx, :])
+    y = acc.permute(0, 1, 3, 2, 4, 5).reshape(B, Ho * ph, Wo * pw, cout)
+    if col_scale is not None:
+        y = y * col_scale[:, None, None, :].double()
+    if noise is not None:
+        y = y + noise[..., None].double() * noise_strength.double().reshape(())
+    if bias is not None:
+        y = y + bias.double()
+    if residual is not None and res_first:
+        y = (y + residual.double()) * res_scale
+    if act == 1:
+        y = F.leaky_relu(y, 0.2)
+    elif act == 2:
+        y = torch.relu(y)
+    y = y * act_gain
+    if residual is not None and not res_first:
+        y = (y + residual.double()) * res_scale
+    return y.to(torch.float32 if out_fp32 else x.dtype)
+
+
+def emu_conv2d_wgrad(x, gy, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), gw=None):
+    if isinstance(up, bool):
+        up = (int(up), int(up))
+    B, H, W_, Cin = x.shape
+    ph, pw = 1 + up[0], 1 + up[1]
+    cout = gy.shape[3]
+    PH = taps[0] + pad[0] + stride[0] * Ho + 2
+    PW = taps[1] + pad[1] + stride[1] * Wo + 2
+    xp = F.pad(x.to(torch.float64), (0, 0, PW, PW, PH, PH))
+    g6 = gy.to(torch.float64).reshape(B, Ho, ph, Wo, pw, cout)
+    out = torch.zeros(ph, pw, cout, taps[0], taps[1], Cin, dtype=torch.float64)
+    for ty in range(taps[0]):
+        for tx in range(taps[1]):
+            xs = _gather_tap(xp, PH, PW, ty, tx, pad, stride, Ho, Wo)
+            out[:, :, :, ty, tx, :] = torch.einsum("bhwc,bhpwqo->pqoc", xs, g6)
+    res = out.reshape(ph * pw * cout, taps[0] * taps[1] * Cin).to(torch.float32 if x.dtype != torch.float64 else torch.float64)
+    if gw is not None:
+        gw += res
+        return gw
+    return res
+
+
+def emu_upfirdn2d(x, k, *, upx=1, upy=1, downx=1, downy=1, padx0=0, padx1=0, pady0=0, pady1=0):
+    """Documented semantics of tbg_upfirdn2d == upfirdn_2d_ref (upfirdn_2d_v2.py:249-305)."""
+    from oracle.stylegan import upfirdn_2d_ref
+
+    return upfirdn_2d_ref(x, k.cpu().numpy(), upx, upy, downx, downy, padx0, padx1, pady0, pady1).contiguous()
+
+
+def emu_adam_step(p, g, m, v, lr_t, beta1, beta2, eps):
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    p.sub_(lr_t * m / (v.sqrt() + eps))
+
+
+def emu_ema_step(dst, src, beta):
+    dst.copy_(src + (dst - src) * beta)
+
+
+@contextlib.contextmanager
+def emulated_kernels(act_dtype=torch.float32):
+    """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import layers as L
+
+    saved = (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step)
+    K.conv2d_igemm = emu_conv2d_igemm
+    K.conv2d_wgrad = emu_conv2d_wgrad
+    K.upfirdn2d = emu_upfirdn2d
+    K.adam_step = emu_adam_step
+    K.ema_step = emu_ema_step
+    C._as_bf16 = lambda t: t.contiguous()
+    L.ACT_DTYPE = act_dtype
+    try:
+        yield
+    finally:
+        (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step) = saved

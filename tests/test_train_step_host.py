@@ -1,0 +1,107 @@
+"""Host-side logic of the product against the oracle, with the tensor-core entry points replaced
+by their CPU emulation (tests/emu.py): geometry algebra, weight re-layouts, autograd wiring of all
+orders (R1 / path-length double backward), the three optimiser updates and the EMA."""
+import copy
+
+import pytest
+import torch
+
+from common import perturbed_params, rel_err, small_cfg
+from emu import emulated_kernels
+from oracle import aster as OA
+from oracle import stylegan as OS
+from oracle import train_step as OT
+from textboxgan_b200.aster_inferer import AsterInferer
+from textboxgan_b200.discriminator import Discriminator
+from textboxgan_b200.generator import Generator
+from textboxgan_b200.optimizers import Adam, update_optimizer_params
+from textboxgan_b200.training_step import TrainingStep
+
+
+def _build(cfg, GP, DP, with_ocr):
+    G = Generator(cfg, device="cpu", seed=0)
+    G.load_state_dict(GP)
+    D = Discriminator(cfg, device="cpu", seed=0)
+    D.load_state_dict(DP)
+    aster = AsterInferer(cfg, device="cpu") if with_ocr else None
+    g_opt = update_optimizer_params(cfg.g_opt)
+    d_opt = update_optimizer_params(cfg.d_opt)
+    mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
+    pl_mean = torch.zeros(())
+    ts = TrainingStep(G, D, aster, mk(g_opt), mk(g_opt), mk(d_opt), cfg.g_opt["reg_interval"],
+                      cfg.d_opt["reg_interval"], pl_mean, cfg)
+    return G, D, ts, pl_mean
+
+
+@pytest.mark.parametrize("do_r1,do_pl,with_ocr", [(False, False, True), (True, True, False)])
+def test_train_step_matches_oracle(do_r1, do_pl, with_ocr):
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    real, words, labels = OT.synthetic_batch(cfg, 4, g)
+    draws = OT.make_draws(cfg, 4, g, with_pl=do_pl)
+    st = OT.StepState(copy.deepcopy(GP), copy.deepcopy(DP), OA.init_aster_params(), OT.make_adam(cfg.g_opt),
+                      OT.make_adam(cfg.g_opt), OT.make_adam(cfg.d_opt), torch.zeros(()))
+    ref_out, ref_grads, _ = OT.train_step(st, cfg, real, torch.zeros(()), words, labels, do_r1, do_pl, 1e-4, draws,
+                                          fused=False, with_ocr=with_ocr, ret_grads=True)
+    with emulated_kernels():
+        G, D, ts, pl_mean = _build(cfg, GP, DP, with_ocr)
+        d2 = dict(draws)
+        d2["keep_grads"] = True
+        out = ts.dist_train_step(real, torch.zeros(()), words, labels, do_r1, do_pl, 1e-4, draws=d2)
+        # losses
+        flat = lambda o: [float(v) for v in (*o[0], *o[1], o[2])]
+        for a, b in zip(flat(out), flat(ref_out)):
+            assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (flat(out), flat(ref_out))
+        # gradients of the three groups (fp32 both sides; lrelu sign flips at |pre|~1e-7 make a
+        # few elements differ, hence the 5e-3 bound relative to each tensor's max)
+        g_grads, o_grads, d_grads = ts.last_grads
+        for names, got, ref in ((ts._g_names, g_grads, ref_grads[0]), (ts._ocr_names, o_grads, ref_grads[1]),
+                                (ts._d_names, d_grads, ref_grads[2])):
+            if got is None:
+                continue
+            for n, a in zip(names, got):
+                if n not in ref:
+                    assert a is None or float(a.abs().max()) == 0.0
+                    continue
+                assert rel_err(a, ref[n]) < 5e-3, (n, rel_err(a, ref[n]))
+        # updated weights (three Adam updates at pre-update gradients) and state
+        for n, p in G.params.items():
+            assert rel_err(p, st.G[n]) < 2e-3, n
+        for n, p in D.params.items():
+            assert rel_err(p, st.D[n]) < 2e-3, n
+        if do_pl:
+            assert abs(float(pl_mean) - float(st.pl_mean)) < 1e-4 * max(1.0, abs(float(st.pl_mean)))
+        assert ts.g_optimizer.iterations.numpy() == 1 and ts.d_optimizer.iterations.numpy() == 1
+
+
+def test_ema_matches_oracle():
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    GP2 = {k: v + 0.01 * torch.randn(v.shape, generator=g) for k, v in GP.items()}
+    with emulated_kernels():
+        G = Generator(cfg, device="cpu", seed=0)
+        G.load_state_dict(GP2)
+        Gc = Generator(cfg, device="cpu", seed=0)
+        Gc.load_state_dict(GP)
+        Gc.set_as_moving_average_of(G)
+    clone = copy.deepcopy(GP)
+    OT.set_as_moving_average_of(clone, GP2)
+    for n, p in Gc.params.items():
+        assert rel_err(p, clone[n]) < 1e-6, n
+
+
+def test_adam_is_tf_keras_adam():
+    """epsilon sits outside the bias-corrected sqrt (unlike torch.optim.Adam)."""
+    with emulated_kernels():
+        p = torch.tensor([1.0, -2.0, 3.0, 0.5, 1.5])
+        g = torch.tensor([0.1, -0.2, 0.3, 1e-9, 0.0])
+        opt = Adam(0.002, beta_1=0.0, beta_2=0.99, epsilon=1e-8)
+        v = p.clone().requires_grad_(True)
+        opt.apply_gradients([(g, v)])
+        t = 1
+        m = g
+        vv = (1 - 0.99) * g * g
+        lr_t = 0.002 * (1 - 0.99 ** t) ** 0.5 / (1 - 0.0 ** t)
+        ref = p - lr_t * m / (vv.sqrt() + 1e-8)
+        assert torch.allclose(v.detach(), ref, rtol=1e-6, atol=1e-9)
+        assert opt.iterations.numpy() == 1

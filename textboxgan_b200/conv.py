@@ -1,0 +1,289 @@
+"""Convolution geometry algebra + autograd bindings of the tcgen05 implicit-GEMM kernels.
+
+Every convolution on the TextBoxGAN path is one *geometry*: per spatial axis either
+
+* ``s1``  out[p]      = sum_u in[p + u - pad]      * W[u]        (stride 1),
+* ``s2``  out[p]      = sum_u in[2p + u - pad]     * W[u]        (stride 2),
+* ``up``  out[2q+phi] = sum_t in[q + t - pad]      * W[phi, t]   (2-phase transposed conv).
+
+The family is closed under transposition (s1 <-> s1 with flipped taps, s2 <-> up), so forward,
+input-gradient and their second-order terms all run on the same ``tbg_conv2d_igemm`` kernel, and
+weight gradients on ``tbg_conv2d_wgrad``.  Reference sites: ModulatedConv2D.call
+(modulated_conv2d.py:66-122), upsample_conv_2d (upfirdn_2d_v2.py:65-103: transposed 3x3 conv +
+4x4 FIR folded into a 4-phase 3x3 GEMM), conv_downsample_2d (upfirdn_2d_v2.py:106-113: 4x4 FIR +
+strided conv folded into a 6x6 / 4x4 stride-2 conv), Conv2D.call (conv.py:51-73).
+
+The three autograd Functions (conv, conv-of-cotangent, weight-gradient) call each other in their
+backward passes, so gradients of any order are available — required by the path-length and R1
+regularisers (training_step.py:323-333, 363-368).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from functools import lru_cache
+from typing import Optional, Tuple
+
+import torch
+
+from . import kernels as K
+
+
+@dataclass(frozen=True)
+class Axis:
+    kind: str   # 's1' | 's2' | 'up'
+    k: int      # taps (per phase for 'up')
+    pad: int
+
+    @property
+    def phases(self) -> int:
+        return 2 if self.kind == "up" else 1
+
+    def out_size(self, n_in: int) -> int:
+        if self.kind == "up":
+            return 2 * n_in
+        if self.kind == "s2":
+            assert n_in % 2 == 0
+            return n_in // 2
+        return n_in
+
+    def adjoint(self) -> "Axis":
+        if self.kind == "s1":
+            return Axis("s1", self.k, self.k - 1 - self.pad)
+        if self.kind == "s2":
+            # gx[2q+phi] = sum_t gy[q + t - 1] * W[u], u = phi + pad + 2 - 2t  (zero if u outside [0,k))
+            assert self.k <= 6 and 2 * self.pad + 2 >= self.k - 1, "s2 adjoint needs 3 taps/phase"
+            return Axis("up", 3, 1)
+        # up(T,P) -> s2(2T, 2(T-1-P)),  W'[u] = W[phi=u%2, t=T-1-u//2]
+        return Axis("s2", 2 * self.k, 2 * (self.k - 1 - self.pad))
+
+
+@dataclass(frozen=True)
+class ConvGeom:
+    """One convolution: input grid (H, W), channel counts and the two axis specs."""
+    H: int
+    W: int
+    cin: int
+    cout: int
+    ah: Axis
+    aw: Axis
+
+    @property
+    def out_hw(self) -> Tuple[int, int]:
+        return self.ah.out_size(self.H), self.aw.out_size(self.W)
+
+    @property
+    def n_total(self) -> int:
+        return self.cout * self.ah.phases * self.aw.phases
+
+    @property
+    def k_total(self) -> int:
+        return self.ah.k * self.aw.k * self.cin
+
+    @property
+    def grid(self) -> Tuple[int, int]:
+        """GEMM row grid: output pixels, or input pixels along an 'up' axis."""
+        oh, ow = self.out_hw
+        return (self.H if self.ah.kind == "up" else oh, self.W if self.aw.kind == "up" else ow)
+
+    def adjoint(self) -> "ConvGeom":
+        oh, ow = self.out_hw
+        return ConvGeom(oh, ow, self.cout, self.cin, self.ah.adjoint(), self.aw.adjoint())
+
+    def kernel_kwargs(self) -> dict:
+        gh, gw = self.grid
+        return dict(
+            Ho=gh, Wo=gw, taps=(self.ah.k, self.aw.k), pad=(self.ah.pad, self.aw.pad),
+            stride=(2 if self.ah.kind == "s2" else 1, 2 if self.aw.kind == "s2" else 1),
+            up=(int(self.ah.kind == "up"), int(self.aw.kind == "up")),
+        )
+
+    def flops(self, batch: int) -> float:
+        gh, gw = self.grid
+        return 2.0 * batch * gh * gw * self.n_total * self.k_total
+
+
+# ----------------------------------------------------------------------------------------------
+# weight re-layout for the adjoint geometry (differentiable torch indexing on parameter-sized
+# tensors; activations never pass through here)
+# ----------------------------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def _axis_adjoint_map(kind: str, k: int, pad: int):
+    """Index/mask tables mapping the flattened (phase, tap) axis of W to that of the adjoint."""
+    src = Axis(kind, k, pad)
+    dst = src.adjoint()
+    idx = torch.zeros(dst.phases, dst.k, dtype=torch.long)
+    mask = torch.zeros(dst.phases, dst.k)
+    if kind == "s1":
+        for u in range(k):
+            idx[0, u] = k - 1 - u
+            mask[0, u] = 1.0
+    elif kind == "s2":
+        for phi in range(2):
+            for t in range(3):
+                u = phi + pad + 2 - 2 * t
+                if 0 <= u < k:
+                    idx[phi, t] = u
+                    mask[phi, t] = 1.0
+    else:  # up(T=k, P=pad): W'[u] = W[phi=u%2, t=T-1-u//2]; source flat index = phi*T + t
+        for u in range(2 * k):
+            idx[0, u] = (u % 2) * k + (k - 1 - u // 2)
+            mask[0, u] = 1.0
+    return idx.flatten(), mask.flatten()
+
+
+def _tables_on(device, kind, k, pad):
+    idx, mask = _axis_adjoint_map(kind, k, pad)
+    return idx.to(device), mask.to(device)
+
+
+def relayout_for_adjoint(wmat: torch.Tensor, g: ConvGeom) -> torch.Tensor:
+    """[n_total, K] weights of ``g`` -> [n_total', K'] weights of ``g.adjoint()``."""
+    ph, pw = g.ah.phases, g.aw.phases
+    w6 = wmat.reshape(ph, pw, g.cout, g.ah.k, g.aw.k, g.cin)
+    # bring (phase_h, tap_h) and (phase_w, tap_w) together: [O, I, ph*kh, pw*kw]
+    w4 = w6.permute(2, 5, 0, 3, 1, 4).reshape(g.cout, g.cin, ph * g.ah.k, pw * g.aw.k)
+    ih, mh = _tables_on(wmat.device, g.ah.kind, g.ah.k, g.ah.pad)
+    iw, mw = _tables_on(wmat.device, g.aw.kind, g.aw.k, g.aw.pad)
+    w4 = w4.index_select(2, ih) * mh.to(w4.dtype)[None, None, :, None]
+    w4 = w4.index_select(3, iw) * mw.to(w4.dtype)[None, None, None, :]
+    a = g.adjoint()
+    # -> [ph', pw', I(as out), kh', kw', O(as in)]
+    w6a = w4.reshape(g.cout, g.cin, a.ah.phases, a.ah.k, a.aw.phases, a.aw.k).permute(2, 4, 1, 3, 5, 0)
+    return w6a.reshape(a.n_total, a.k_total)
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd Functions
+# ----------------------------------------------------------------------------------------------
+def _as_bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous()
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = conv_g(x, W).  x bf16 NHWC, W fp32 [n_total, K] (rounded to bf16 for the tensor cores)."""
+
+    @staticmethod
+    def forward(ctx, x, wmat, geom: ConvGeom, epi: Optional[dict]):
+        ctx.geom = geom
+        ctx.save_for_backward(x, wmat)
+        return K.conv2d_igemm(_as_bf16(x), _as_bf16(wmat), **geom.kernel_kwargs(), **(epi or {}))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wmat = ctx.saved_tensors
+        g = ctx.geom
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = conv(gy, relayout_for_adjoint(wmat, g), g.adjoint())
+        if ctx.needs_input_grad[1]:
+            gw = conv_wgrad(x, gy, g)
+        return gx, gw, None, None
+
+
+class _WgradFn(torch.autograd.Function):
+    """gW = wgrad_g(x, gy): fp32 [n_total, K]."""
+
+    @staticmethod
+    def forward(ctx, x, gy, geom: ConvGeom):
+        ctx.geom = geom
+        ctx.save_for_backward(x, gy)
+        return K.conv2d_wgrad(_as_bf16(x), _as_bf16(gy), **geom.kernel_kwargs())
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        g = ctx.geom
+        gx = ggy = None
+        if ctx.needs_input_grad[0]:
+            gx = conv(gy, relayout_for_adjoint(ggw, g), g.adjoint())
+        if ctx.needs_input_grad[1]:
+            ggy = conv(x, ggw, g)
+        return gx, ggy, None
+
+
+def conv(x: torch.Tensor, wmat: torch.Tensor, geom: ConvGeom, epi: Optional[dict] = None) -> torch.Tensor:
+    """Differentiable (any order) convolution; ``epi`` (fused epilogue kwargs of
+    kernels.conv2d_igemm) may only be used where no gradient flows through the epilogue terms."""
+    assert x.shape[1] == geom.H and x.shape[2] == geom.W and x.shape[3] == geom.cin, (tuple(x.shape), geom)
+    assert wmat.shape == (geom.n_total, geom.k_total), (tuple(wmat.shape), geom)
+    return _ConvFn.apply(x, wmat, geom, epi)
+
+
+def conv_wgrad(x: torch.Tensor, gy: torch.Tensor, geom: ConvGeom) -> torch.Tensor:
+    return _WgradFn.apply(x, gy, geom)
+
+
+# ----------------------------------------------------------------------------------------------
+# weight preparation: reference HWIO weights -> GEMM matrices of each geometry
+# ----------------------------------------------------------------------------------------------
+FIR_1D = (1.0, 3.0, 3.0, 1.0)   # resample_kernel [1,3,3,1] (synthesis_block.py:36, discriminator.py:44)
+
+
+def plain_geom(H: int, W: int, cin: int, cout: int, k: int) -> ConvGeom:
+    """SAME stride-1 k x k convolution (modulated_conv2d.py:110-112, conv.py:69-71)."""
+    return ConvGeom(H, W, cin, cout, Axis("s1", k, k // 2), Axis("s1", k, k // 2))
+
+
+def plain_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
+    kh, kw, I, O = w_hwio.shape
+    return w_hwio.permute(3, 0, 1, 2).reshape(O, kh * kw * I)
+
+
+def up_geom(h: int, w: int, cin: int, cout: int) -> ConvGeom:
+    """upsample_conv_2d (upfirdn_2d_v2.py:65-103) as a 4-phase 3x3 GEMM over the input grid."""
+    return ConvGeom(h, w, cin, cout, Axis("up", 3, 1), Axis("up", 3, 1))
+
+
+@lru_cache(maxsize=None)
+def _up_coef() -> torch.Tensor:
+    """C[phi, t, kh] = k1[1 - kh - phi + 2t] with k1 = [1,3,3,1]/4 (FIR gain 4 = 2 per axis,
+    pad0 = pad1 = 1: compute_paddings(up, is_conv), upfirdn_2d_v2.py:36-39)."""
+    k1 = [v / 4.0 for v in FIR_1D]
+    c = torch.zeros(2, 3, 3)
+    for phi in range(2):
+        for t in range(3):
+            for kh in range(3):
+                j = 1 - kh - phi + 2 * t
+                if 0 <= j < 4:
+                    c[phi, t, kh] = k1[j]
+    return c
+
+
+def up_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
+    """Weff[(py,px,o), (ty,tx,i)] = sum_{kh,kw} C[py,ty,kh] C[px,tx,kw] w[kh,kw,i,o]."""
+    c = _up_coef().to(w_hwio.device, w_hwio.dtype)
+    weff = torch.einsum("pak,qbl,klio->pqoabi", c, c, w_hwio)
+    O, I = w_hwio.shape[3], w_hwio.shape[2]
+    return weff.reshape(4 * O, 9 * I)
+
+
+def down_geom(H: int, W: int, cin: int, cout: int, k: int, reduce_height: bool) -> ConvGeom:
+    """conv_downsample_2d (upfirdn_2d_v2.py:106-113): 4x4 FIR (pad0 = (k+1)//2 + ..., A.4) followed
+    by a VALID k x k conv of stride (2|1, 2), folded into one (k+3) x (k+3) convolution."""
+    kk = k + 3
+    pad0 = (2 + (k - 1) + 1) // 2            # compute_paddings(down, is_conv): p=(4-2)+(k-1); pad0=(p+1)//2
+    aw = Axis("s2", kk, pad0)
+    ah = Axis("s2", kk, pad0) if reduce_height else Axis("s1", kk, pad0)
+    return ConvGeom(H, W, cin, cout, ah, aw)
+
+
+@lru_cache(maxsize=None)
+def _fold_table(k: int) -> torch.Tensor:
+    """S[u, t] = kf[u - t] with kf = [1,3,3,1]/8 (FIR gain 1)."""
+    kf = [v / 8.0 for v in FIR_1D]
+    s = torch.zeros(k + 3, k)
+    for u in range(k + 3):
+        for t in range(k):
+            if 0 <= u - t < 4:
+                s[u, t] = kf[u - t]
+    return s
+
+
+def down_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
+    """G[uy,ux] = sum_{ty,tx} kf[uy-ty] kf[ux-tx] w[ty,tx]  ->  [O, (k+3)^2 * I]."""
+    k = w_hwio.shape[0]
+    s = _fold_table(k).to(w_hwio.device, w_hwio.dtype)
+    g = torch.einsum("ut,vs,tsio->ouvi", s, s, w_hwio)
+    O, I = w_hwio.shape[3], w_hwio.shape[2]
+    return g.reshape(O, (k + 3) * (k + 3) * I)

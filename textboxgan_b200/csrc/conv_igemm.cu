@@ -24,7 +24,8 @@ struct ConvKernelParams {
   int taps_h, taps_w;
   int in_off_h, in_off_w;  // = -pad
   int stride_h, stride_w;
-  int up;
+  int up_h, up_w;
+  int Ho, Wo;  // valid GEMM-row grid (tiles may overhang; rows outside are masked)
   int cout;
   int out_H, out_W;
   int stages;
@@ -35,6 +36,7 @@ struct ConvKernelParams {
   const float* noise_strength;
   const __nv_bfloat16* residual;
   float res_scale;
+  int res_first;  // 1: residual is added before the activation (ResNet unit), 0: after (D block)
   int act;
   float act_gain;
   int out_fp32;
@@ -176,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int b = tb * bn + n_in;
       const int ho = th * bh + h_in;
       const int wo = tw * bw + w_in;
-      const bool valid = b < p.B;
+      const bool valid = (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc_stage], acc_phase);
@@ -190,11 +192,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_wait();
         if (valid && col0 < p.n_total) {
           int c0 = col0, oy = ho, ox = wo;
-          if (p.up) {
+          if (p.up_h | p.up_w) {
             const int ph = col0 / p.cout;
             c0 = col0 - ph * p.cout;
-            oy = 2 * ho + (ph >> 1);
-            ox = 2 * wo + (ph & 1);
+            const int py = p.up_w ? (ph >> 1) : ph;
+            const int px = p.up_w ? (ph & 1) : 0;
+            oy = p.up_h ? 2 * ho + py : ho;
+            ox = p.up_w ? 2 * wo + px : wo;
           }
           const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
           const size_t off = pix * p.cout + c0;
@@ -222,21 +226,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
-            if (p.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
+            float rres[8];
             if (p.residual) {
               const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + off + g * 8));
               const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 rf = __bfloat1622float2(rh[i]);
-                f[2 * i] = (f[2 * i] + rf.x) * p.res_scale;
-                f[2 * i + 1] = (f[2 * i + 1] + rf.y) * p.res_scale;
+                rres[2 * i] = rf.x;
+                rres[2 * i + 1] = rf.y;
               }
+              if (p.res_first) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
+            if (p.residual && !p.res_first) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
             }
             if (p.out_fp32) {
               float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
@@ -288,11 +304,13 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   TBG_CHECK_ARG(a->x && a->w && a->out, "tbg_conv2d_igemm: null tensor pointer");
   TBG_CHECK_ARG(a->B >= 1 && a->H >= 1 && a->W >= 1, "tbg_conv2d_igemm: bad input shape B=%d H=%d W=%d", a->B, a->H, a->W);
   TBG_CHECK_ARG(a->Cin >= 64 && a->Cin % 64 == 0, "tbg_conv2d_igemm: Cin=%d must be a multiple of 64", a->Cin);
-  TBG_CHECK_ARG(is_pow2(a->Ho) && is_pow2(a->Wo), "tbg_conv2d_igemm: Ho=%d Wo=%d must be powers of two", a->Ho, a->Wo);
+  TBG_CHECK_ARG(a->Ho >= 1 && a->Wo >= 1, "tbg_conv2d_igemm: bad output grid Ho=%d Wo=%d", a->Ho, a->Wo);
   TBG_CHECK_ARG(a->cout >= 32 && a->cout % 32 == 0, "tbg_conv2d_igemm: cout=%d must be a multiple of 32", a->cout);
-  TBG_CHECK_ARG(a->up == 0 || a->up == 1, "tbg_conv2d_igemm: up must be 0 or 1");
-  TBG_CHECK_ARG(a->n_total == (a->up ? 4 * a->cout : a->cout), "tbg_conv2d_igemm: n_total=%d inconsistent with cout=%d up=%d",
-                a->n_total, a->cout, a->up);
+  TBG_CHECK_ARG((a->up_h == 0 || a->up_h == 1) && (a->up_w == 0 || a->up_w == 1), "tbg_conv2d_igemm: up_h/up_w must be 0 or 1");
+  TBG_CHECK_ARG(a->n_total == a->cout * (1 + a->up_h) * (1 + a->up_w),
+                "tbg_conv2d_igemm: n_total=%d inconsistent with cout=%d up=(%d,%d)", a->n_total, a->cout, a->up_h, a->up_w);
+  TBG_CHECK_ARG(!(a->up_h && a->stride_h != 1) && !(a->up_w && a->stride_w != 1), "tbg_conv2d_igemm: up with stride on one axis");
+  TBG_CHECK_ARG(a->act >= 0 && a->act <= 2, "tbg_conv2d_igemm: act must be 0 (linear), 1 (lrelu) or 2 (relu)");
   TBG_CHECK_ARG(a->taps_h >= 1 && a->taps_w >= 1 && a->taps_h <= 8 && a->taps_w <= 8, "tbg_conv2d_igemm: bad taps");
   TBG_CHECK_ARG((a->stride_h == 1 || a->stride_h == 2) && (a->stride_w == 1 || a->stride_w == 2),
                 "tbg_conv2d_igemm: strides must be 1 or 2");
@@ -303,17 +321,20 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 
   ConvKernelParams p{};
   p.B = a->B;
-  const int bw = a->Wo < 128 ? a->Wo : 128;
+  const int wo_p2 = 1 << ilog2(a->Wo), ho_p2 = 1 << ilog2(a->Ho);  // next powers of two
+  const int bw = wo_p2 < 128 ? wo_p2 : 128;
   int bh = 128 / bw;
-  if (bh > a->Ho) bh = a->Ho;
+  if (bh > ho_p2) bh = ho_p2;
   const int bn = 128 / (bw * bh);
   // with a stride-2 load the TMA box spans 2*b elements and must stay <= 256
   TBG_CHECK_ARG(bw * a->stride_w <= 256 && bh * a->stride_h <= 256, "tbg_conv2d_igemm: tile box too large");
   p.bw_log2 = ilog2(bw);
   p.bh_log2 = ilog2(bh);
   p.bn_log2 = ilog2(bn);
-  p.tiles_w = a->Wo / bw;
-  p.tiles_h = a->Ho / bh;
+  p.tiles_w = (a->Wo + bw - 1) / bw;
+  p.tiles_h = (a->Ho + bh - 1) / bh;
+  p.Ho = a->Ho;
+  p.Wo = a->Wo;
   p.tiles_b = (a->B + bn - 1) / bn;
   // N tile: largest of 256/128/64/32 that divides n_total (keeps every tile full)
   int block_n = 256;
@@ -333,16 +354,18 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.in_off_w = -a->pad_w;
   p.stride_h = a->stride_h;
   p.stride_w = a->stride_w;
-  p.up = a->up;
+  p.up_h = a->up_h;
+  p.up_w = a->up_w;
   p.cout = a->cout;
-  p.out_H = a->up ? 2 * a->Ho : a->Ho;
-  p.out_W = a->up ? 2 * a->Wo : a->Wo;
+  p.out_H = a->up_h ? 2 * a->Ho : a->Ho;
+  p.out_W = a->up_w ? 2 * a->Wo : a->Wo;
   p.col_scale = a->col_scale;
   p.bias = a->bias;
   p.noise = a->noise;
   p.noise_strength = a->noise_strength;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.res_scale = a->res_scale;
+  p.res_first = a->res_first;
   p.act = a->act;
   p.act_gain = a->act_gain;
   p.out_fp32 = a->out_fp32;

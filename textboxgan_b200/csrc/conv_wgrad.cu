@@ -23,7 +23,7 @@ struct WgradParams {
   int p_log2;                     // log2(P), P in {32, 64}
   int tiles_w, tiles_h, tiles_b;  // pixel tiles
   int m_tiles;                    // ceil(n_total / 128)
-  int n_total, cout, up;
+  int n_total, cout, up_h, up_w;
   int cin, block_c, c_tiles;      // N tiling of input channels
   int taps_h, taps_w;
   int subtiles;                   // taps * c_tiles
@@ -123,12 +123,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
           for (int j = 0; j < 2; ++j) {
             const int n0 = m_tile * 128 + j * 64;
             int c0 = n0, wy = th * bh, wx = tw * bw;
-            if (p.up) {
+            if (p.up_h | p.up_w) {
               const int ph = n0 / p.cout;
               c0 = n0 - ph * p.cout;
-              wy = 2 * wy + (ph >> 1);
-              wx = 2 * wx + (ph & 1);
-              if (ph >= 4) c0 = p.cout;  // past the last phase: force OOB -> zero fill
+              const int py = p.up_w ? (ph >> 1) : ph;
+              const int px = p.up_w ? (ph & 1) : 0;
+              if (p.up_h) wy = 2 * wy + py;
+              if (p.up_w) wx = 2 * wx + px;
+              if (n0 >= p.n_total) c0 = p.cout;  // past the last phase: force OOB -> zero fill
             }
             tma_load_4d(sa + j * chunk_bytes, &tmGY, &full[stage], c0, wx, wy, tb * bn);
           }
@@ -245,19 +247,20 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   TBG_CHECK_ARG(a->x && a->gy && a->gw, "tbg_conv2d_wgrad: null tensor pointer");
   TBG_CHECK_ARG(a->Cin >= 64 && a->Cin % 64 == 0, "tbg_conv2d_wgrad: Cin=%d must be a multiple of 64", a->Cin);
   TBG_CHECK_ARG(a->cout >= 32 && a->cout % 32 == 0, "tbg_conv2d_wgrad: cout=%d must be a multiple of 32", a->cout);
-  TBG_CHECK_ARG(is_pow2(a->Ho) && is_pow2(a->Wo), "tbg_conv2d_wgrad: Ho=%d Wo=%d must be powers of two", a->Ho, a->Wo);
-  TBG_CHECK_ARG(a->up == 0 || a->up == 1, "tbg_conv2d_wgrad: up must be 0 or 1");
-  TBG_CHECK_ARG(a->n_total == (a->up ? 4 * a->cout : a->cout), "tbg_conv2d_wgrad: n_total inconsistent");
-  TBG_CHECK_ARG(!(a->up && (a->stride_h != 1 || a->stride_w != 1)), "tbg_conv2d_wgrad: up with stride unsupported");
+  TBG_CHECK_ARG(a->Ho >= 1 && a->Wo >= 1, "tbg_conv2d_wgrad: bad grid Ho=%d Wo=%d", a->Ho, a->Wo);
+  TBG_CHECK_ARG((a->up_h == 0 || a->up_h == 1) && (a->up_w == 0 || a->up_w == 1), "tbg_conv2d_wgrad: up_h/up_w must be 0 or 1");
+  TBG_CHECK_ARG(a->n_total == a->cout * (1 + a->up_h) * (1 + a->up_w), "tbg_conv2d_wgrad: n_total inconsistent");
+  TBG_CHECK_ARG(!(a->up_h && a->stride_h != 1) && !(a->up_w && a->stride_w != 1), "tbg_conv2d_wgrad: up with stride on one axis");
   TBG_CHECK_ARG((a->stride_h == 1 || a->stride_h == 2) && (a->stride_w == 1 || a->stride_w == 2),
                 "tbg_conv2d_wgrad: strides must be 1 or 2");
-  TBG_CHECK_ARG(a->up == 0 || a->cout % 64 == 0, "tbg_conv2d_wgrad: up needs cout %% 64 == 0");
+  TBG_CHECK_ARG((a->up_h | a->up_w) == 0 || a->cout % 64 == 0, "tbg_conv2d_wgrad: up needs cout %% 64 == 0");
 
   WgradParams p{};
   p.B = a->B;
   p.n_total = a->n_total;
   p.cout = a->cout;
-  p.up = a->up;
+  p.up_h = a->up_h;
+  p.up_w = a->up_w;
   p.cin = a->Cin;
   p.block_c = a->Cin < 256 ? a->Cin : 256;
   if (a->Cin % p.block_c != 0) p.block_c = 64;
@@ -287,15 +290,16 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   while (P > 1 && (int64_t)P > (int64_t)npix * a->B) P >>= 1;  // tiny problems
   if (P < 16) P = 16;
   p.p_log2 = ilog2(P);
-  const int bw = a->Wo < P ? a->Wo : P;
+  const int wo_p2 = 1 << ilog2(a->Wo), ho_p2 = 1 << ilog2(a->Ho);
+  const int bw = wo_p2 < P ? wo_p2 : P;
   int bh = P / bw;
-  if (bh > a->Ho) bh = a->Ho;
+  if (bh > ho_p2) bh = ho_p2;
   const int bn = P / (bw * bh);
   p.bw_log2 = ilog2(bw);
   p.bh_log2 = ilog2(bh);
   p.bn_log2 = ilog2(bn);
-  p.tiles_w = a->Wo / bw;
-  p.tiles_h = a->Ho / bh;
+  p.tiles_w = (a->Wo + bw - 1) / bw;
+  p.tiles_h = (a->Ho + bh - 1) / bh;
   p.tiles_b = (a->B + bn - 1) / bn;
   const int k_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
 
@@ -324,12 +328,12 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
 
   CUtensorMap tmGY, tmX;
   {
-    const int gH = a->up ? 2 * a->Ho : a->Ho, gW = a->up ? 2 * a->Wo : a->Wo;
-    const int es = a->up ? 2 : 1;
+    const int gH = a->up_h ? 2 * a->Ho : a->Ho, gW = a->up_w ? 2 * a->Wo : a->Wo;
+    const int esh = a->up_h ? 2 : 1, esw = a->up_w ? 2 : 1;
     const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)gW, (uint64_t)gH, (uint64_t)a->B};
     const uint64_t strides[4] = {0, (uint64_t)a->cout * 2, (uint64_t)gW * a->cout * 2, (uint64_t)gH * gW * a->cout * 2};
-    const uint32_t box[4] = {64, (uint32_t)(bw * es), (uint32_t)(bh * es), (uint32_t)bn};
-    const uint32_t estr[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+    const uint32_t box[4] = {64, (uint32_t)(bw * esw), (uint32_t)(bh * esh), (uint32_t)bn};
+    const uint32_t estr[4] = {1, (uint32_t)esw, (uint32_t)esh, 1};
     int rc = encode_tmap_bf16(&tmGY, a->gy, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }

@@ -1,0 +1,236 @@
+// HBM-bound kernels of the training step: optimiser / EMA updates over flat fp32 buffers, the
+// generic upfirdn2d resampler (the reference's one native op) and small fused element-wise passes.
+// All are grid-stride, 128-bit vectorised where alignment allows, and sized to a multiple of the
+// SM count.
+#include <initializer_list>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tbg {
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = static_cast<long long>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ----------------------------------------------------------------------------------------------
+// tf.keras.optimizers.Adam (optimizer_v2, non-amsgrad) on a flat buffer:
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr_t * m / (sqrt(v) + eps)
+// with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host (train.py:58-75).
+// ----------------------------------------------------------------------------------------------
+// Pointers may start at any 4-byte boundary as long as they share the same 16-byte phase: the
+// first `head` and the last few elements are handled with scalar accesses, the body with float4.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, int head, float lr_t, float b1, float b2, float eps) {
+  const long long n4 = (n - head) >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float4* p4 = reinterpret_cast<float4*>(p + head);
+  const float4* g4 = reinterpret_cast<const float4*>(g + head);
+  float4* m4 = reinterpret_cast<float4*>(m + head);
+  float4* v4 = reinterpret_cast<float4*>(v + head);
+  for (long long i = tid; i < n4; i += stride) {
+    float4 pp = p4[i];
+    const float4 gg = g4[i];
+    float4 mm = m4[i];
+    float4 vv = v4[i];
+#define TBG_ADAM1(c)                               \
+  mm.c = b1 * mm.c + (1.f - b1) * gg.c;            \
+  vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;     \
+  pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);
+    TBG_ADAM1(x) TBG_ADAM1(y) TBG_ADAM1(z) TBG_ADAM1(w)
+#undef TBG_ADAM1
+    p4[i] = pp;
+    m4[i] = mm;
+    v4[i] = vv;
+  }
+  // scalar head [0, head) and tail [head + 4*n4, n)
+  const long long tail0 = head + (n4 << 2);
+  const long long n_scalar = head + (n - tail0);
+  for (long long s = tid; s < n_scalar; s += stride) {
+    const long long i = s < head ? s : tail0 + (s - head);
+    const float gg = g[i];
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    p[i] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+// dst = src + (dst - src) * beta     (generator.py:48-59, lerp(sw, cw, beta))
+__global__ void ema_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, int head, float beta) {
+  const long long n4 = (n - head) >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float4* d4 = reinterpret_cast<float4*>(dst + head);
+  const float4* s4 = reinterpret_cast<const float4*>(src + head);
+  for (long long i = tid; i < n4; i += stride) {
+    float4 d = d4[i];
+    const float4 s = s4[i];
+    d.x = s.x + (d.x - s.x) * beta;
+    d.y = s.y + (d.y - s.y) * beta;
+    d.z = s.z + (d.z - s.z) * beta;
+    d.w = s.w + (d.w - s.w) * beta;
+    d4[i] = d;
+  }
+  const long long tail0 = head + (n4 << 2);
+  const long long n_scalar = head + (n - tail0);
+  for (long long s = tid; s < n_scalar; s += stride) {
+    const long long i = s < head ? s : tail0 + (s - head);
+    dst[i] = src[i] + (dst[i] - src[i]) * beta;
+  }
+}
+
+// Common scalar head so that (ptr + head) is 16-byte aligned for every pointer, or n (all scalar)
+// when the pointers do not share a 16-byte phase.
+static long long common_head(long long n, std::initializer_list<const void*> ptrs) {
+  uintptr_t phase = reinterpret_cast<uintptr_t>(*ptrs.begin()) & 15;
+  for (const void* q : ptrs)
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != phase) return n;
+  long long head = ((16 - static_cast<long long>(phase)) & 15) >> 2;
+  return head < n ? head : n;
+}
+
+// ----------------------------------------------------------------------------------------------
+// upfirdn2d: pad -> zero-insert upsample -> FIR (correlation with the flipped kernel) -> decimate,
+// on [major, inH, inW, minor] tensors; same contract as the reference's TF op
+// (upfirdn_2d.cu:64-117 generic kernel, 232-307 host op).  fp32 accumulate; T in {float, bf16}.
+// One thread per output element, minor fastest (coalesced for NHWC, minor = channels).
+// ----------------------------------------------------------------------------------------------
+struct UpfirdnParams {
+  int upx, upy, downx, downy, padx0, pady0;
+  int major, inH, inW, minor, kH, kW, outH, outW;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int c = a / b;
+  if (c * b > a) c--;
+  return c;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void upfirdn2d_kernel(const T* __restrict__ x, const float* __restrict__ k, T* __restrict__ y,
+                                 const UpfirdnParams p) {
+  __shared__ float sk[64];
+  for (int i = threadIdx.x; i < p.kH * p.kW; i += blockDim.x) sk[i] = k[i];
+  __syncthreads();
+  const long long total = static_cast<long long>(p.major) * p.outH * p.outW * p.minor;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int mi = static_cast<int>(idx % p.minor);
+    long long r = idx / p.minor;
+    const int ox = static_cast<int>(r % p.outW);
+    r /= p.outW;
+    const int oy = static_cast<int>(r % p.outH);
+    const int mj = static_cast<int>(r / p.outH);
+    // receptive field in input coordinates (same arithmetic as upfirdn_2d.cu:76-93)
+    const int midY = oy * p.downy + p.upy - 1 - p.pady0;
+    const int inY0 = min(max(floor_div(midY, p.upy), 0), p.inH);
+    const int hh = min(max(floor_div(midY + p.kH, p.upy), 0), p.inH) - inY0;
+    const int kY0 = midY + p.kH - (inY0 + 1) * p.upy;
+    const int midX = ox * p.downx + p.upx - 1 - p.padx0;
+    const int inX0 = min(max(floor_div(midX, p.upx), 0), p.inW);
+    const int ww = min(max(floor_div(midX + p.kW, p.upx), 0), p.inW) - inX0;
+    const int kX0 = midX + p.kW - (inX0 + 1) * p.upx;
+    float acc = 0.f;
+    for (int yy = 0; yy < hh; ++yy) {
+      const int ky = kY0 - yy * p.upy;
+      const T* xrow = x + ((static_cast<long long>(mj) * p.inH + inY0 + yy) * p.inW + inX0) * p.minor + mi;
+      for (int xx = 0; xx < ww; ++xx) {
+        const int kx = kX0 - xx * p.upx;
+        acc += to_f<T>(xrow[static_cast<long long>(xx) * p.minor]) * sk[ky * p.kW + kx];
+      }
+    }
+    y[idx] = from_f<T>(acc);
+  }
+}
+
+}  // namespace tbg
+
+using namespace tbg;
+
+extern "C" int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1,
+                             float beta2, float eps, void* stream_v) {
+  TBG_CHECK_ARG(p && g && m && v && n >= 0, "tbg_adam_step: bad arguments");
+  TBG_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 3) == 0,
+                "tbg_adam_step: buffers must be 4-byte aligned");
+  if (n == 0) return TBG_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int head = static_cast<int>(common_head(n, {p, g, m, v}));
+  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(p, g, m, v, n, head, lr_t, beta1, beta2, eps);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_ema_step(float* dst, const float* src, long long n, float beta, void* stream_v) {
+  TBG_CHECK_ARG(dst && src && n >= 0, "tbg_ema_step: bad arguments");
+  TBG_CHECK_ARG(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0,
+                "tbg_ema_step: buffers must be 4-byte aligned");
+  if (n == 0) return TBG_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int head = static_cast<int>(common_head(n, {dst, src}));
+  ema_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(dst, src, n, head, beta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_upfirdn2d(const void* x, const float* k, void* y, int dtype_bf16, int major, int inH, int inW,
+                             int minor, int kH, int kW, int upx, int upy, int downx, int downy, int padx0, int padx1,
+                             int pady0, int pady1, void* stream_v) {
+  // same argument checks as UpFirDn2DOp::Compute (upfirdn_2d.cu:241-266)
+  TBG_CHECK_ARG(x && k && y, "tbg_upfirdn2d: null pointer");
+  TBG_CHECK_ARG(upx >= 1 && upy >= 1, "upx and upy must be at least 1x1");
+  TBG_CHECK_ARG(downx >= 1 && downy >= 1, "downx and downy must be at least 1x1");
+  TBG_CHECK_ARG(kW >= 1 && kH >= 1 && kW * kH <= 64, "kernel must be between 1x1 and 64 taps");
+  TBG_CHECK_ARG(major >= 1 && inH >= 1 && inW >= 1 && minor >= 1, "input must have rank 4 with positive dims");
+  UpfirdnParams p;
+  p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0;
+  p.major = major; p.inH = inH; p.inW = inW; p.minor = minor; p.kH = kH; p.kW = kW;
+  p.outW = (inW * upx + padx0 + padx1 - kW + downx) / downx;
+  p.outH = (inH * upy + pady0 + pady1 - kH + downy) / downy;
+  TBG_CHECK_ARG(p.outW >= 1 && p.outH >= 1, "output must be at least 1x1");
+  const long long total = static_cast<long long>(major) * p.outH * p.outW * minor;
+  TBG_CHECK_ARG(total <= 0x7fffffffLL * 8, "output too large");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (dtype_bf16)
+    upfirdn2d_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), k, reinterpret_cast<__nv_bfloat16*>(y), p);
+  else
+    upfirdn2d_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(x), k,
+                                                                       reinterpret_cast<float*>(y), p);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}

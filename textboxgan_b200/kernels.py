@@ -38,13 +38,14 @@ def conv2d_igemm(
     taps: tuple[int, int],
     pad: tuple[int, int],
     stride: tuple[int, int] = (1, 1),
-    up: bool = False,
+    up: tuple[int, int] | bool = (0, 0),
     col_scale: Optional[torch.Tensor] = None,   # fp32 [B, cout]
     bias: Optional[torch.Tensor] = None,        # fp32 [cout]
     noise: Optional[torch.Tensor] = None,       # fp32 [B, out_H, out_W]
     noise_strength: Optional[torch.Tensor] = None,  # fp32 scalar tensor
     residual: Optional[torch.Tensor] = None,    # bf16, shape of out
     res_scale: float = 1.0,
+    res_first: bool = False,
     act: int = 0,
     act_gain: float = 1.0,
     out_fp32: bool = False,
@@ -52,10 +53,12 @@ def conv2d_igemm(
 ) -> torch.Tensor:
     _require(x, torch.bfloat16, "x")
     _require(w, torch.bfloat16, "w")
+    if isinstance(up, bool):
+        up = (int(up), int(up))
     B, H, W_, Cin = x.shape
     n_total = w.shape[0]
-    cout = n_total // 4 if up else n_total
-    oH, oW = (2 * Ho, 2 * Wo) if up else (Ho, Wo)
+    cout = n_total // ((1 + up[0]) * (1 + up[1]))
+    oH, oW = Ho * (1 + up[0]), Wo * (1 + up[1])
     if w.shape[1] != taps[0] * taps[1] * Cin:
         raise _lib.TbgError(f"w: expected K={taps[0] * taps[1] * Cin}, got {w.shape[1]}")
     if out is None:
@@ -69,9 +72,9 @@ def conv2d_igemm(
         x=_ptr(x), w=_ptr(w), out=_ptr(out),
         B=B, H=H, W=W_, Cin=Cin, Ho=Ho, Wo=Wo, n_total=n_total, cout=cout,
         taps_h=taps[0], taps_w=taps[1], pad_h=pad[0], pad_w=pad[1],
-        stride_h=stride[0], stride_w=stride[1], up=int(up),
+        stride_h=stride[0], stride_w=stride[1], up_h=up[0], up_w=up[1],
         col_scale=_ptr(col_scale), bias=_ptr(bias), noise=_ptr(noise), noise_strength=_ptr(noise_strength),
-        residual=_ptr(residual), res_scale=res_scale, act=act, act_gain=act_gain, out_fp32=int(out_fp32),
+        residual=_ptr(residual), res_scale=res_scale, res_first=int(res_first), act=act, act_gain=act_gain, out_fp32=int(out_fp32),
     )
     _lib.check(_lib.load().tbg_conv2d_igemm(C.byref(a), _stream()), "tbg_conv2d_igemm")
     return out
@@ -86,14 +89,16 @@ def conv2d_wgrad(
     taps: tuple[int, int],
     pad: tuple[int, int],
     stride: tuple[int, int] = (1, 1),
-    up: bool = False,
+    up: tuple[int, int] | bool = (0, 0),
     gw: Optional[torch.Tensor] = None,          # fp32 [n_total, taps*Cin], accumulated into
 ) -> torch.Tensor:
     _require(x, torch.bfloat16, "x")
     _require(gy, torch.bfloat16, "gy")
+    if isinstance(up, bool):
+        up = (int(up), int(up))
     B, H, W_, Cin = x.shape
     cout = gy.shape[3]
-    n_total = 4 * cout if up else cout
+    n_total = cout * (1 + up[0]) * (1 + up[1])
     if gw is None:
         gw = torch.zeros((n_total, taps[0] * taps[1] * Cin), device=x.device, dtype=torch.float32)
     _require(gw, torch.float32, "gw")
@@ -101,7 +106,40 @@ def conv2d_wgrad(
         x=_ptr(x), gy=_ptr(gy), gw=_ptr(gw),
         B=B, H=H, W=W_, Cin=Cin, Ho=Ho, Wo=Wo, n_total=n_total, cout=cout,
         taps_h=taps[0], taps_w=taps[1], pad_h=pad[0], pad_w=pad[1],
-        stride_h=stride[0], stride_w=stride[1], up=int(up),
+        stride_h=stride[0], stride_w=stride[1], up_h=up[0], up_w=up[1],
     )
     _lib.check(_lib.load().tbg_conv2d_wgrad(C.byref(a), _stream()), "tbg_conv2d_wgrad")
     return gw
+
+
+def upfirdn2d(x: torch.Tensor, k: torch.Tensor, *, upx=1, upy=1, downx=1, downy=1, padx0=0, padx1=0, pady0=0,
+              pady1=0) -> torch.Tensor:
+    """x: [major, inH, inW, minor] fp32 or bf16 (contiguous); k: fp32 [kH, kW]."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.TbgError(f"upfirdn2d: unsupported dtype {x.dtype}")
+    _require(x, x.dtype, "x")
+    _require(k, torch.float32, "k")
+    major, inH, inW, minor = x.shape
+    kH, kW = k.shape
+    outW = (inW * upx + padx0 + padx1 - kW + downx) // downx
+    outH = (inH * upy + pady0 + pady1 - kH + downy) // downy
+    y = torch.empty((major, max(outH, 0), max(outW, 0), minor), device=x.device, dtype=x.dtype)
+    st = _lib.load().tbg_upfirdn2d(_ptr(x), _ptr(k), _ptr(y), int(x.dtype == torch.bfloat16), major, inH, inW, minor,
+                                   kH, kW, upx, upy, downx, downy, padx0, padx1, pady0, pady1, _stream())
+    _lib.check(st, "tbg_upfirdn2d")
+    return y
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float, beta1: float,
+              beta2: float, eps: float) -> None:
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _require(t, torch.float32, n)
+    st = _lib.load().tbg_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr_t, beta1, beta2, eps, _stream())
+    _lib.check(st, "tbg_adam_step")
+
+
+def ema_step(dst: torch.Tensor, src: torch.Tensor, beta: float) -> None:
+    _require(dst, torch.float32, "dst")
+    _require(src, torch.float32, "src")
+    st = _lib.load().tbg_ema_step(_ptr(dst), _ptr(src), dst.numel(), beta, _stream())
+    _lib.check(st, "tbg_ema_step")

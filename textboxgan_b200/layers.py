@@ -1,0 +1,121 @@
+"""Device-side StyleGAN2 layers of TextBoxGAN (NHWC, bf16 activations, fp32 parameters).
+
+Host code only orchestrates: the contractions run on the tcgen05 kernels through
+:mod:`textboxgan_b200.conv`; parameter-sized algebra (modulation vectors, demodulation
+coefficients, weight re-layouts) is fp32 torch on tensors of at most a few MB.
+
+Layer-by-layer correspondence with the reference (models/custom_stylegan2/layers/):
+``dense`` dense.py:13-29 · ``bias_act`` bias_act.py:25-34 · ``modulated_conv2d``
+modulated_conv2d.py:66-122 (non-fused algebra :95-96,119-121: scale activations by the style,
+convolve with the shared weight, scale by the demodulation coefficient) · ``to_rgb``
+to_rgb.py:28-33 · ``upsample_rgb`` upfirdn_2d_v2.py:58-62 · ``minibatch_std``
+mini_batch_std.py:10-35.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import conv as C
+from . import upfirdn as U
+
+Params = Dict[str, torch.Tensor]
+SQRT2 = math.sqrt(2.0)
+ACT_DTYPE = torch.bfloat16
+
+
+def runtime_coef(weight_shape, gain: float = 1.0, lrmul: float = 1.0) -> float:
+    """commons.py:4-12"""
+    fan_in = 1
+    for d in weight_shape[:-1]:
+        fan_in *= int(d)
+    return gain / math.sqrt(fan_in) * lrmul
+
+
+def dense(x: torch.Tensor, w: torch.Tensor, gain: float = 1.0, lrmul: float = 1.0) -> torch.Tensor:
+    return x.reshape(x.shape[0], -1).float() @ (runtime_coef(w.shape, gain, lrmul) * w)
+
+
+def lrelu(x: torch.Tensor) -> torch.Tensor:
+    return F.leaky_relu(x, 0.2) * SQRT2
+
+
+def style_scale(style: torch.Tensor, P: Params, prefix: str) -> torch.Tensor:
+    """s = mod_bias(mod_dense(y)) + 1   (modulated_conv2d.py:75-76)."""
+    return dense(style, P[prefix + "/mod_dense/w"]) + P[prefix + "/mod_bias/b"] + 1.0
+
+
+def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str, *, up: bool,
+                     demodulate: bool = True, noise: Optional[torch.Tensor] = None,
+                     noise_strength: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                     act: bool = False, fused_epilogue: bool = False) -> torch.Tensor:
+    """x: [B,H,W,I] bf16 -> [B,H',W',O] bf16, including (optionally) noise, bias and activation.
+
+    ``fused_epilogue`` applies demod/noise/bias/lrelu inside the GEMM epilogue; it is only legal
+    when no gradient is needed through those terms (inference), otherwise the terms are applied
+    with differentiable element-wise ops."""
+    w_raw = P[prefix + "/w"]
+    kh, kw, I, O = w_raw.shape
+    w = runtime_coef(w_raw.shape) * w_raw                                   # :71
+    s = style_scale(style, P, prefix)                                       # [B,I]
+    B, H, W_, _ = x.shape
+    if up:
+        geom = C.up_geom(H, W_, I, O)
+        wmat = C.up_wmat(w)
+    else:
+        geom = C.plain_geom(H, W_, I, O, kh)
+        wmat = C.plain_wmat(w)
+    xs = (x.float() * s[:, None, None, :]).to(ACT_DTYPE)                    # :96
+    d = None
+    if demodulate:
+        q = (w * w).sum(dim=(0, 1))                                         # [I,O]
+        d = torch.rsqrt((s * s) @ q + 1e-8)                                 # :80-82  [B,O]
+    if fused_epilogue:
+        epi = dict(col_scale=d.contiguous() if d is not None else None,
+                   noise=noise.contiguous() if noise is not None else None,
+                   noise_strength=noise_strength.reshape(1).contiguous() if noise is not None else None,
+                   bias=bias.contiguous() if bias is not None else None,
+                   act=1 if act else 0, act_gain=SQRT2 if act else 1.0)
+        with torch.no_grad():
+            return C.conv(xs, wmat, geom, epi)
+    y = C.conv(xs, wmat, geom).float()
+    if d is not None:
+        y = y * d[:, None, None, :]                                         # :121
+    if noise is not None:
+        y = y + noise[..., None] * noise_strength                           # noise.py:21
+    if bias is not None:
+        y = y + bias                                                        # bias_act.py:25-31
+    if act:
+        y = lrelu(y)
+    return y.to(ACT_DTYPE)
+
+
+def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str) -> torch.Tensor:
+    """1x1 modulated conv without demodulation + bias, fp32 [B,H,W,3] (to_rgb.py:28-33)."""
+    w_raw = P[prefix + "/conv/w"]                                           # [1,1,C,3]
+    w = runtime_coef(w_raw.shape) * w_raw[0, 0]
+    s = style_scale(style, P, prefix + "/conv")
+    ws = s[:, :, None] * w[None]                                            # [B,C,3]
+    B, H, W_, Cc = x.shape
+    y = torch.bmm(x.reshape(B, H * W_, Cc).float(), ws).reshape(B, H, W_, 3)
+    return y + P[prefix + "/bias/b"]
+
+
+def upsample_rgb(y: torch.Tensor) -> torch.Tensor:
+    """upsample_2d(y) with k = outer([1,3,3,1])/64*4, pad (2,1) (synthesis_block.py:97-99,152) on
+    the native upfirdn2d op; y is fp32 [B,H,W,3]."""
+    return U.upsample_2d_nhwc(y.contiguous())
+
+
+def minibatch_std(x: torch.Tensor, group_size: int = 4) -> torch.Tensor:
+    """mini_batch_std.py:10-35 on NHWC: returns the [B,1] per-sample statistic (fp32)."""
+    B = x.shape[0]
+    g = min(group_size, B)
+    y = x.float().reshape(g, B // g, -1)
+    y = y - y.mean(dim=0, keepdim=True)
+    y = torch.sqrt((y * y).mean(dim=0) + 1e-8)
+    y = y.mean(dim=1, keepdim=True)                                         # [B/g, 1]
+    return y.repeat(g, 1)

@@ -30,9 +30,9 @@ class ConvArgs(C.Structure):
         ("taps_h", c_int), ("taps_w", c_int),
         ("pad_h", c_int), ("pad_w", c_int),
         ("stride_h", c_int), ("stride_w", c_int),
-        ("up", c_int),
+        ("up_h", c_int), ("up_w", c_int),
         ("col_scale", c_void_p), ("bias", c_void_p), ("noise", c_void_p), ("noise_strength", c_void_p),
-        ("residual", c_void_p), ("res_scale", c_float),
+        ("residual", c_void_p), ("res_scale", c_float), ("res_first", c_int),
         ("act", c_int), ("act_gain", c_float), ("out_fp32", c_int),
     ]
 
@@ -45,7 +45,7 @@ class WgradArgs(C.Structure):
         ("n_total", c_int), ("cout", c_int),
         ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int),
         ("stride_h", c_int), ("stride_w", c_int),
-        ("up", c_int),
+        ("up_h", c_int), ("up_w", c_int),
     ]
 
 
@@ -59,6 +59,10 @@ _SIGNATURES = [
     ("tbg_reset_launch_count", None, []),
     ("tbg_conv2d_igemm", c_int, [C.POINTER(ConvArgs), c_void_p]),
     ("tbg_conv2d_wgrad", c_int, [C.POINTER(WgradArgs), c_void_p]),
+    ("tbg_upfirdn2d", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),
+    ("tbg_adam_step", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, c_float, c_float, c_float,
+                              c_float, c_void_p]),
+    ("tbg_ema_step", c_int, [c_void_p, c_void_p, C.c_longlong, c_float, c_void_p]),
 ]
 
 

@@ -1,0 +1,125 @@
+"""``tf.keras.optimizers.Adam`` (optimizer_v2, non-amsgrad) as used by train.py:58-75, over the
+flat parameter buffers of :class:`textboxgan_b200.model_base.Model`.
+
+``apply_gradients`` mirrors what the reference gets implicitly in replica context
+(training_step.py:233-235): cross-replica SUM of the gradients (one all-reduce over the flat
+gradient buffer instead of one per variable), then the Adam update (one ``tbg_adam_step`` launch
+instead of one ResourceApplyAdam per variable).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+class _Iterations:
+    """``optimizer.iterations`` with the ``.numpy()`` accessor train.py:179,211 uses."""
+
+    def __init__(self):
+        self.value = 0
+
+    def numpy(self) -> int:
+        return self.value
+
+    def __int__(self) -> int:
+        return self.value
+
+
+class Adam:
+    def __init__(self, learning_rate: float = 0.001, beta_1: float = 0.9, beta_2: float = 0.999,
+                 epsilon: float = 1e-7):
+        self.learning_rate = float(learning_rate)
+        self.beta_1 = float(beta_1)
+        self.beta_2 = float(beta_2)
+        self.epsilon = float(epsilon)
+        self.iterations = _Iterations()
+        self._slots: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+    # -- helpers -------------------------------------------------------------------------------
+    @staticmethod
+    def _aligned_like(n: int, phase: int, device) -> torch.Tensor:
+        """fp32 buffer of ``n`` elements whose address has the same 16-byte phase as the
+        parameter range it shadows, so that the vectorised kernel path applies to all four."""
+        buf = torch.zeros(n + 4, dtype=torch.float32, device=device)
+        return buf[phase: phase + n]
+
+    def _lr_t(self) -> float:
+        t = self.iterations.value + 1
+        return self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+
+    # -- Keras surface -------------------------------------------------------------------------
+    def apply_gradients(self, grads_and_vars: Iterable[Tuple[torch.Tensor, torch.Tensor]], model=None,
+                        names: Optional[Sequence[str]] = None) -> None:
+        """Flat-buffer fast path when ``model``/``names`` identify a contiguous variable range
+        (the three groups of training_step.py:194-213 all do); per-variable path otherwise."""
+        grads_and_vars = [(g, v) for g, v in grads_and_vars]
+        if model is not None and names is not None:
+            self._apply_flat(model, list(names), [g for g, _ in grads_and_vars])
+        else:
+            for g, v in grads_and_vars:
+                if g is None:
+                    continue
+                self._apply_flat_range(v.detach().reshape(-1), g.detach().reshape(-1).float().contiguous(), id(v))
+        self.iterations.value += 1
+
+    def _apply_flat(self, model, names: List[str], grads: List[Optional[torch.Tensor]]) -> None:
+        start, end = model.flat_range(names)
+        p = model.flat[start:end]
+        key = (id(model), start, end)
+        if key not in self._slots:
+            phase = start % 4
+            self._slots[key] = tuple(self._aligned_like(end - start, phase, p.device) for _ in range(3))
+        g, m, v = self._slots[key]
+        parts = []
+        for n, gr in zip(names, grads):
+            parts.append(gr.reshape(-1).float() if gr is not None else p.new_zeros(model.segments[n][1]))
+        torch.cat(parts, out=g)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)      # SUM: every loss already carries 1/global_batch
+        K.adam_step(p, g, m, v, self._lr_t(), self.beta_1, self.beta_2, self.epsilon)
+
+    def _apply_flat_range(self, p: torch.Tensor, g: torch.Tensor, key_id: int) -> None:
+        key = (key_id, 0, p.numel())
+        if key not in self._slots:
+            self._slots[key] = (None, torch.zeros_like(p), torch.zeros_like(p))
+        _, m, v = self._slots[key]
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        K.adam_step(p, g, m, v, self._lr_t(), self.beta_1, self.beta_2, self.epsilon)
+
+    # -- checkpointing ---------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        return {
+            "iterations": self.iterations.value,
+            "hyper": (self.learning_rate, self.beta_1, self.beta_2, self.epsilon),
+            "slots": {f"{k[1]}:{k[2]}": (m.detach().cpu().clone(), v.detach().cpu().clone())
+                      for k, (_, m, v) in self._slots.items()},
+        }
+
+    def load_state_dict(self, state: dict, model=None) -> None:
+        self.iterations.value = int(state["iterations"])
+        self._pending_slots = state.get("slots", {})
+        if model is not None:
+            for rng, (m, v) in self._pending_slots.items():
+                start, end = (int(s) for s in rng.split(":"))
+                key = (id(model), start, end)
+                p = model.flat[start:end]
+                g, mm, vv = (self._aligned_like(end - start, start % 4, p.device) for _ in range(3))
+                mm.copy_(m)
+                vv.copy_(v)
+                self._slots[key] = (g, mm, vv)
+
+
+def update_optimizer_params(params: dict) -> dict:
+    """train.py:110-129 (lazy-regularisation correction of lr and betas)."""
+    p = dict(params)
+    mb_ratio = p["reg_interval"] / (p["reg_interval"] + 1)
+    p["learning_rate"] = p["learning_rate"] * mb_ratio
+    p["beta1"] = p["beta1"] ** mb_ratio
+    p["beta2"] = p["beta2"] ** mb_ratio
+    return p

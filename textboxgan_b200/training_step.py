@@ -1,0 +1,197 @@
+"""TrainingStep — one G + D + OCR training iteration (mirror of training_step.py:14-402).
+
+Same constructor arguments, same ``dist_train_step`` signature and return structure as the
+reference, so ``train.py`` drives it unchanged apart from its imports.  Differences that are
+consequences of the B200 design, not of behaviour:
+
+* one process per GPU: ``cfg.strategy.run`` is a local call and the seven ``strategy.reduce``
+  calls (training_step.py:106-134) are one packed all-reduce;
+* the three ``tape.gradient`` + ``apply_gradients`` pairs (:194-213) are three
+  ``torch.autograd.grad`` calls on the shared graph followed by three flat-buffer Adam updates
+  (gradient all-reduce SUM + one ``tbg_adam_step`` each); all gradients are taken at the
+  pre-update weights, exactly as with the reference's single persistent tape;
+* ``draws`` optionally injects the random tensors for parity tests.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+
+from .aster_inferer import AsterInferer
+from .config import Config
+from .discriminator import Discriminator
+from .generator import Generator
+from .losses import discriminator_loss, generator_loss, mean_squared_loss, softmax_cross_entropy_loss
+from .optimizers import Adam
+from .utils import mask_text_box
+
+
+class TrainingStep:
+    """Infer the model, computes the associated losses and backpropagates them."""
+
+    def __init__(
+        self,
+        generator: Generator,
+        discriminator: Discriminator,
+        aster_ocr: Optional[AsterInferer],
+        g_optimizer: Adam,
+        ocr_optimizer: Adam,
+        d_optimizer: Adam,
+        g_reg_interval: int,
+        d_reg_interval: int,
+        pl_mean: torch.Tensor,
+        cfg: Optional[Config] = None,
+    ):
+        if cfg is None:
+            cfg = generator.cfg
+        self.cfg = cfg
+        self.generator = generator
+        self.discriminator = discriminator
+        self.aster_ocr = aster_ocr
+        self.g_optimizer = g_optimizer
+        self.ocr_optimizer = ocr_optimizer
+        self.d_optimizer = d_optimizer
+        self.g_reg_interval = g_reg_interval
+        self.d_reg_interval = d_reg_interval
+        self.batch_size = cfg.batch_size
+        self.batch_size_per_gpu = cfg.batch_size_per_gpu
+        self.pl_mean = pl_mean
+
+        pl_minibatch_shrink = 2                                               # training_step.py:41-46
+        self.pl_minibatch_shrink = pl_minibatch_shrink if self.batch_size_per_gpu // pl_minibatch_shrink >= 1 \
+            else self.batch_size_per_gpu
+        self.pl_weight = float(self.pl_minibatch_shrink)
+        self.pl_decay = 0.01
+        self.r1_gamma = 10.0
+        self.ocr_loss_type = cfg.ocr_loss_type
+        self.z_dim = cfg.z_dim
+        self.char_width = cfg.char_width
+        self.pl_noise_scaler = 1.0 / math.sqrt(float(cfg.image_width) * float(cfg.char_height))   # :53-55
+
+        # variable groups of :196, :203, :210 — contiguous ranges of the flat buffers
+        self._g_names = generator.trainable_names(("synthesis/", "latent_encoder/"))
+        self._ocr_names = generator.trainable_names(("word_encoder/", "synthesis/"))
+        self._d_names = discriminator.trainable_names()
+
+    # ------------------------------------------------------------------------------------------
+    def dist_train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
+                        ocr_loss_weight: float, draws: Optional[dict] = None):
+        """training_step.py:57-136.  Returns ``((reg_g, g, pl), (reg_d, d, r1), ocr)`` summed over
+        replicas (every loss already carries 1/global_batch)."""
+        strategy = self.cfg.strategy
+        if strategy is None:
+            gen_losses, disc_losses, ocr_loss = self._train_step(real_images, ocr_images, input_words, ocr_labels,
+                                                                 do_r1_reg, do_pl_reg, ocr_loss_weight, draws)
+            return gen_losses, disc_losses, ocr_loss
+        gen_losses, disc_losses, ocr_loss = strategy.run(
+            self._train_step,
+            args=(real_images, ocr_images, input_words, ocr_labels, do_r1_reg, do_pl_reg, ocr_loss_weight, draws))
+        red = strategy.reduce_many(list(gen_losses) + list(disc_losses) + [ocr_loss])
+        mean_pl = red[2] if do_pl_reg else torch.zeros((), device=red[0].device)
+        return (red[0], red[1], mean_pl), (red[3], red[4], red[5]), red[6]
+
+    # ------------------------------------------------------------------------------------------
+    def _train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
+                    ocr_loss_weight: float, draws: Optional[dict] = None):
+        """training_step.py:138-222"""
+        draws = draws or {}
+        G, D = self.generator, self.discriminator
+        dev = G.device
+        z = draws["z"].to(dev) if "z" in draws else torch.randn(self.batch_size_per_gpu, self.z_dim, device=dev)
+        fake_images = G((input_words, z), training=True, draws=draws)                        # :178
+        fake_images = mask_text_box(fake_images, input_words, self.char_width)              # :180
+
+        fake_scores, reg_g_loss, g_loss, pl_penalty = self._get_generator_losses(fake_images, do_pl_reg,
+                                                                                 input_words, draws)
+        reg_d_loss, d_loss, r1_penalty = self._get_discriminator_losses(fake_scores, real_images, do_r1_reg)
+        if self.aster_ocr is not None:
+            ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
+            ocr_loss = ocr_loss_weight * ocr_loss                                            # :191-192
+        else:
+            ocr_loss = None
+
+        g_vars = [G.params[n] for n in self._g_names]
+        o_vars = [G.params[n] for n in self._ocr_names]
+        d_vars = [D.params[n] for n in self._d_names]
+        # three tape.gradient calls on one persistent tape (:194-213): all at pre-update weights
+        g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
+        o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
+            if ocr_loss is not None else None
+        d_grads = torch.autograd.grad(reg_d_loss, d_vars, allow_unused=True)
+        self.last_grads = (g_grads, o_grads, d_grads) if draws.get("keep_grads") else None
+
+        if not draws.get("skip_updates"):
+            self.g_optimizer.apply_gradients(zip(g_grads, g_vars), model=G, names=self._g_names)
+            if o_grads is not None:
+                self.ocr_optimizer.apply_gradients(zip(o_grads, o_vars), model=G, names=self._ocr_names)
+            self.d_optimizer.apply_gradients(zip(d_grads, d_vars), model=D, names=self._d_names)
+
+        gen_losses = (reg_g_loss.detach(), g_loss.detach(), pl_penalty.detach())
+        disc_losses = (reg_d_loss.detach(), d_loss.detach(), r1_penalty.detach())
+        ocr_out = (ocr_loss / ocr_loss_weight).detach() if ocr_loss is not None else torch.zeros((), device=dev)
+        return gen_losses, disc_losses, ocr_out
+
+    # ------------------------------------------------------------------------------------------
+    def _get_discriminator_losses(self, fake_scores, real_images, do_r1_reg: bool):
+        """training_step.py:237-266"""
+        if do_r1_reg:
+            real_scores, r1_penalty = self._r1_reg(real_images)
+        else:
+            real_scores = self.discriminator(real_images)
+            r1_penalty = torch.zeros((), device=real_scores.device)
+        d_loss = discriminator_loss(fake_scores, real_scores, self.batch_size)
+        reg_d_loss = d_loss + r1_penalty
+        return reg_d_loss, d_loss, r1_penalty
+
+    def _get_generator_losses(self, fake_images, do_pl_reg: bool, input_words, draws: dict):
+        """training_step.py:268-298"""
+        fake_scores = self.discriminator(fake_images)
+        g_loss = generator_loss(fake_scores, self.batch_size)
+        pl_penalty = self._path_length_reg(input_words, draws) if do_pl_reg \
+            else torch.zeros((), device=fake_scores.device)
+        reg_g_loss = g_loss + pl_penalty
+        return fake_scores, reg_g_loss, g_loss, pl_penalty
+
+    def _path_length_reg(self, input_words, draws: dict):
+        """training_step.py:300-347"""
+        G = self.generator
+        dev = G.device
+        pl_minibatch = max(1, self.batch_size_per_gpu // self.pl_minibatch_shrink)
+        pl_z = draws["pl_z"].to(dev) if "pl_z" in draws else torch.randn(pl_minibatch, self.z_dim, device=dev)
+        pl_draws = {"noises": draws["pl_noises"]} if "pl_noises" in draws else {}
+        # generator(...) with the default training=False (:325-329)
+        pl_fake_images, pl_style = G((input_words[:pl_minibatch], pl_z), batch_size=pl_minibatch, ret_style=True,
+                                     draws=pl_draws)
+        noise = draws["pl_image_noise"].to(dev) if "pl_image_noise" in draws else torch.randn_like(pl_fake_images)
+        pl_noise = noise * self.pl_noise_scaler
+        pl_noise_applied = (pl_fake_images * pl_noise).sum()
+        (pl_grads,) = torch.autograd.grad(pl_noise_applied, pl_style, create_graph=True)    # :333
+        pl_lengths = torch.sqrt((pl_grads ** 2).sum(dim=2).mean(dim=1))                      # :334-336
+        with torch.no_grad():                                                                # :338-341
+            self.pl_mean.copy_(self.pl_mean + self.pl_decay * (pl_lengths.mean() - self.pl_mean))
+        pl_penalty = (pl_lengths - self.pl_mean) ** 2                                        # :344
+        pl_penalty = pl_penalty * self.pl_minibatch_shrink * self.g_reg_interval             # :346
+        return pl_penalty.sum() / self.batch_size                                            # :347
+
+    def _r1_reg(self, real_images):
+        """training_step.py:349-373"""
+        real_images = real_images.detach().requires_grad_(True)
+        real_scores = self.discriminator(real_images)
+        real_loss = real_scores.sum()
+        (real_grads,) = torch.autograd.grad(real_loss, real_images, create_graph=True)
+        r1_penalty = (real_grads ** 2).sum(dim=(1, 2, 3))[:, None]
+        r1_penalty = r1_penalty * (0.5 * self.r1_gamma) * self.d_reg_interval
+        r1_penalty = r1_penalty.sum() / self.batch_size
+        return real_scores, r1_penalty
+
+    def _get_ocr_loss(self, fake_images, ocr_labels, ocr_images):
+        """training_step.py:375-402"""
+        fake_images_ocr_format = self.aster_ocr.convert_inputs(fake_images, ocr_labels, blank_label=1, cfg=self.cfg)
+        logits = self.aster_ocr(fake_images_ocr_format)
+        if self.ocr_loss_type == "mse":
+            real_logits = self.aster_ocr(ocr_images)
+            return mean_squared_loss(real_logits, logits, self.batch_size)
+        elif self.ocr_loss_type == "softmax_crossentropy":
+            return softmax_cross_entropy_loss(logits, ocr_labels, self.batch_size)
