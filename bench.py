@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the TextBoxGAN training step (G + D + OCR loss) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1]
+
+N > 1 is launched by the driver under ``torch.distributed.run`` (one rank per GPU, NCCL); the
+step is pure data parallel on the batch axis (weak scaling: the per-GPU batch is fixed).
+
+One JSON line on rank 0 with the contract keys plus
+  roofline      modulated-conv2d tensor-core roofline of ``conv_igemm_kernel`` measured live with
+                CUDA events around every launch of an instrumented step (algorithmic FLOPs per
+                SURVEY.md §8d; peak = MEASURED_PEAKS.json bf16_tflops_sustained),
+  cpu_baseline  the oracle's restatement of the reference's ``cpu_only`` path timed on this box's
+                host cores on a bounded sample (rank 0, N = 1 only),
+  e2e           the same metric through the public API with pinned-host inputs copied in and
+                the seven loss scalars read back every step,
+  gpu_launches  launches of this repo's kernels inside the timed region.
+``--impl reference`` times the oracle port of the reference's CPU path (TensorFlow 2.8 is not
+installable offline — see DESIGN.md) with all host threads on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_step_images_per_sec"
+UNIT = "images/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks and clock-event (throttle) reasons through NVML during the timed region."""
+
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
+        self.gpu = gpu_index
+        self.period = period_s
+        self.samples = []
+        self.reasons = set()
+        self.smax = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as ex:  # pragma: no cover
+            self.err = repr(ex)
+
+    def _run(self):
+        nv = self.nv
+        bits = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as ex:  # pragma: no cover
+                self.err = repr(ex)
+                break
+            time.sleep(self.period)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        sm = sorted(self.samples)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+               "samples": len(sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def _cpu_oracle_rate(cfg_index: int, sample_batch: int, steps: int, threads: int):
+    """Images/sec of the oracle's restatement of the reference ``cpu_only`` training step
+    (non-fused modulated conv, upfirdn_2d_ref, three TF-style Adam updates) on the host cores."""
+    import copy
+
+    import torch
+
+    from oracle import aster as OA
+    from oracle import stylegan as OS
+    from oracle import train_step as OT
+    from textboxgan_b200.config import baseline_config
+
+    torch.set_num_threads(threads)
+    cfg = baseline_config(cfg_index)
+    cfg.batch_size_per_gpu = sample_batch
+    cfg.batch_size = sample_batch
+    g = torch.Generator().manual_seed(4444)
+    GP = OS.init_generator_params(cfg, g)
+    DP = OS.init_discriminator_params(cfg, g)
+    st = OT.StepState(GP, DP, OA.init_aster_params(), OT.make_adam(cfg.g_opt), OT.make_adam(cfg.g_opt),
+                      OT.make_adam(cfg.d_opt), torch.zeros(()))
+    real, words, labels = OT.synthetic_batch(cfg, sample_batch, g)
+    times = []
+    for i in range(steps + 1):
+        draws = OT.make_draws(cfg, sample_batch, g)
+        t0 = time.perf_counter()
+        OT.train_step(st, cfg, real, torch.zeros(()), words, labels, False, False, 1e-4, draws, fused=False)
+        times.append(time.perf_counter() - t0)
+    timed = times[1:] if steps >= 1 else times
+    per_step = sum(timed) / len(timed)
+    return sample_batch / per_step, per_step
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    threads = os.cpu_count() or 1
+    sample_batch = 4
+    value, per_step = _cpu_oracle_rate(args.config, sample_batch, max(1, min(args.steps, 3)), threads)
+    from textboxgan_b200.config import baseline_config
+
+    cfg = baseline_config(args.config)
+    sample = (f"{max(1, min(args.steps, 3))} plain training steps at batch {sample_batch} of the config-{args.config} "
+              f"shape ({cfg.image_width}x{cfg.char_height}, z={cfg.z_dim}) on {threads} host threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config_dict(cfg, args, n_gpus=1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the reference cpu_only path (TensorFlow 2.8 not installable offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config_dict(cfg, args, n_gpus):
+    return {
+        "workload": (f"BASELINE.json configs[{args.config}]: TextBoxGAN training step G+D+OCR loss, per-GPU batch "
+                     f"{cfg.batch_size_per_gpu}, max_char_number={cfg.max_char_number}, z_dim={cfg.z_dim}, "
+                     f"{cfg.image_width}x{cfg.char_height}, plain (non-regularised) step"),
+        "global_batch": cfg.batch_size_per_gpu * n_gpus,
+        "per_gpu_batch": cfg.batch_size_per_gpu,
+        "image": f"{cfg.image_width}x{cfg.char_height}",
+        "parallelism": f"dp{n_gpus}",
+        "l2": "per-step working set (parameters + Adam state + activations, > 0.5 GB) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from oracle import train_step as OT  # synthetic-input generator only (shapes/seeds of SURVEY §8d)
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
+    from textboxgan_b200.aster_inferer import AsterInferer
+    from textboxgan_b200.config import baseline_config
+    from textboxgan_b200.discriminator import Discriminator
+    from textboxgan_b200.generator import Generator
+    from textboxgan_b200.optimizers import Adam, update_optimizer_params
+    from textboxgan_b200.strategy import Strategy
+    from textboxgan_b200.training_step import TrainingStep
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    lib.load()
+    strategy = Strategy()
+    rank, world = strategy.rank, strategy.world_size
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    cfg = baseline_config(args.config)          # per-GPU batch fixed (weak scaling)
+    cfg.attach_strategy(strategy)
+    B = cfg.batch_size_per_gpu
+
+    G = Generator(cfg, device=dev, seed=1)
+    D = Discriminator(cfg, device=dev, seed=2)
+    g_clone = Generator(cfg, device=dev, seed=1)
+    aster = AsterInferer(cfg, device=dev)
+    go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
+    mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
+    ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), cfg.g_opt["reg_interval"], cfg.d_opt["reg_interval"],
+                      torch.zeros((), device=dev), cfg)
+
+    gen = torch.Generator().manual_seed(4444 + rank)
+    real_h, words_h, labels_h = OT.synthetic_batch(cfg, B, gen)
+    real_h, words_h, labels_h = real_h.pin_memory(), words_h.pin_memory(), labels_h.pin_memory()
+    real, words, labels = real_h.to(dev), words_h.to(dev), labels_h.to(dev)
+    zero = torch.zeros((), device=dev)
+
+    def step_resident():
+        out = ts.dist_train_step(real, zero, words, labels, False, False, cfg.ocr_loss_weight)
+        g_clone.set_as_moving_average_of(G)      # train.py:208 — part of every iteration
+        return out
+
+    def step_e2e():
+        r = real_h.to(dev, non_blocking=True)
+        w = words_h.to(dev, non_blocking=True)
+        l = labels_h.to(dev, non_blocking=True)
+        out = ts.dist_train_step(r, zero, w, l, False, False, cfg.ocr_loss_weight)
+        g_clone.set_as_moving_average_of(G)
+        packed = torch.stack([*out[0], *out[1], out[2]]).float()
+        return packed.cpu()                       # device -> host read of the step's losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms / steps, wall / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.load().tbg_reset_launch_count()
+    ms_step, wall_step = timed(step_resident, args.steps)
+    launches = int(lib.load().tbg_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    # the step time that counts is the slower of device time and host wall time per step
+    ms_eff = max(ms_step, wall_step * 1e3)
+
+    step_e2e()
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    ms_e2e = max(ms_e2e, wall_e2e * 1e3)
+    h2d = real_h.numel() * 4 + words_h.numel() * 4 + labels_h.numel() * 4
+    d2h = 7 * 4
+
+    # ---- roofline pass: CUDA events around every tensor-core launch of two instrumented steps ----
+    roof = None
+    if rank == 0:
+        K.PROFILE = []
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        recs = K.PROFILE
+        K.PROFILE = None
+        agg = {}
+        for name, tag, flops, e0, e1 in recs:
+            t, frac = tag if isinstance(tag, tuple) else (str(tag), 1.0)
+            a = agg.setdefault((name, t), [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1) * 1e-3
+            a[2] += flops * frac
+            a[3] += flops
+        peaks, which = _peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        key = ("conv_igemm", "modconv")
+        n, secs, algo, execd = agg.get(key, [0, 1e-9, 0.0, 0.0])
+        achieved = algo / secs / 1e12
+        roof = {
+            "bound": "tensor", "kernel": "conv_igemm_kernel (modulated conv2d fwd + dgrad launches)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)",
+            "executed_tflops": execd / secs / 1e12, "launches_per_step": n / 2, "avg_launch_us": secs / max(n, 1) * 1e6,
+            "traffic": None,
+            "by_kernel": {f"{k[0]}:{k[1]}": {"launches_per_step": v[0] / 2, "ms_per_step": v[1] * 1e3 / 2,
+                                             "algorithmic_tflops": v[2] / max(v[1], 1e-12) / 1e12,
+                                             "executed_tflops": v[3] / max(v[1], 1e-12) / 1e12}
+                          for k, v in sorted(agg.items())},
+        }
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, per = _cpu_oracle_rate(args.config, 4, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"1 timed plain training step (after 1 warm-up) at batch 4 of the config-{args.config} shape, "
+                         f"oracle restatement of the reference cpu_only path, {threads} host threads"}
+    gb = B * world
+    line = {
+        "metric": METRIC, "value": gb / (ms_eff * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_eff, "device_ms_per_step": ms_step,
+        "host_wall_ms_per_step": wall_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": _config_dict(cfg, args, world),
+        "clocks": clocks,
+        "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,291 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the
+C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances: integer paths bit-exact; fp32-output kernels 2e-5 relative (fp32 accumulation order);
+bf16-output kernels 1e-2 relative to the tensor maximum (one bf16 rounding of the output, 2^-8);
+whole-model quantities in bf16 activations 5e-2 (losses) — stated next to each assertion.
+"""
+import copy
+import math
+
+import pytest
+import torch
+
+from common import perturbed_params, rel_err, small_cfg
+from emu import emu_conv2d_igemm, emu_conv2d_wgrad
+from oracle import aster as OA
+from oracle import stylegan as OS
+from oracle import train_step as OT
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _geoms():
+    from textboxgan_b200 import conv as C
+
+    return {
+        "plain3": C.plain_geom(16, 64, 128, 128, 3),
+        "plain1": C.plain_geom(8, 32, 64, 64, 1),
+        "plain3-lowres": C.plain_geom(4, 16, 512, 256, 3),
+        "plain3-oob-batch": C.plain_geom(2, 8, 128, 512, 3),
+        "plain3-4x4": C.plain_geom(4, 4, 576, 512, 3),
+        "up": C.up_geom(8, 32, 128, 64),
+        "down3": C.down_geom(16, 64, 64, 128, 3, True),
+        "down1": C.down_geom(16, 64, 64, 128, 1, True),
+        "down3-w": C.down_geom(8, 32, 128, 128, 3, False),
+        "down1-w": C.down_geom(8, 32, 64, 64, 1, False),
+        "aster-s21": C.ConvGeom(8, 32, 128, 128, C.Axis("s2", 1, 0), C.Axis("s1", 1, 0)),
+    }
+
+
+@pytest.mark.parametrize("name", list(_geoms().keys()))
+@pytest.mark.parametrize("batch", [3, 8])
+def test_conv_forward_adjoint_wgrad_vs_emulated_semantics(name, batch):
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    g = _geoms()[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    x = _bf16_round(torch.randn(batch, g.H, g.W, g.cin, generator=gen))
+    w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
+    kw = g.kernel_kwargs()
+    # forward, fp32 output: only the accumulation order differs
+    y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), out_fp32=True, **kw)
+    ref = emu_conv2d_igemm(x, w, out_fp32=True, **kw)
+    assert rel_err(y, ref) < 2e-5
+    # bf16 output
+    y16 = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), **kw)
+    assert rel_err(y16.float(), ref) < 1e-2
+    # adjoint geometry on re-laid-out weights
+    a = g.adjoint()
+    wa = _bf16_round(C.relayout_for_adjoint(w, g)).contiguous()
+    gy = _bf16_round(torch.randn(ref.shape, generator=gen))
+    gx = K.conv2d_igemm(gy.to(DEV).bfloat16(), wa.to(DEV).bfloat16(), out_fp32=True, **a.kernel_kwargs())
+    gref = emu_conv2d_igemm(gy, wa, out_fp32=True, **a.kernel_kwargs())
+    assert rel_err(gx, gref) < 2e-5
+    # <conv(x), gy> == <x, conv^T(gy)>  (size-independent property, exact up to fp32 rounding)
+    lhs = (y.double().cpu() * gy.double()).sum()
+    rhs = (x.double() * gx.double().cpu()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * (abs(lhs) + 1.0)
+    # weight gradient
+    gw = K.conv2d_wgrad(x.to(DEV).bfloat16(), gy.to(DEV).bfloat16(), **kw)
+    gwref = emu_conv2d_wgrad(x, gy, **kw)
+    assert rel_err(gw, gwref) < 2e-4
+
+
+def test_conv_fused_epilogue_matches_reference_order():
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    g = C.up_geom(8, 32, 128, 128)
+    gen = torch.Generator().manual_seed(3)
+    B = 5
+    x = _bf16_round(torch.randn(B, g.H, g.W, g.cin, generator=gen))
+    w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
+    epi = dict(col_scale=torch.rand(B, g.cout, generator=gen) + 0.5, bias=torch.randn(g.cout, generator=gen) * 0.1,
+               noise=torch.randn(B, 16, 64, generator=gen), noise_strength=torch.tensor([0.3]),
+               residual=_bf16_round(torch.randn(B, 16, 64, g.cout, generator=gen)), res_scale=1 / math.sqrt(2),
+               act=1, act_gain=math.sqrt(2))
+    ref = emu_conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs(), **epi)
+    dev_epi = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in epi.items()}
+    dev_epi["residual"] = dev_epi["residual"].bfloat16()
+    y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), out_fp32=True, **g.kernel_kwargs(), **dev_epi)
+    assert rel_err(y, ref) < 2e-5
+    for res_first, act in ((True, 2), (False, 0)):
+        e2 = dict(epi, res_first=res_first, act=act, act_gain=1.0, res_scale=1.0)
+        d2 = dict(dev_epi, res_first=res_first, act=act, act_gain=1.0, res_scale=1.0)
+        ref = emu_conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs(), **e2)
+        y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), out_fp32=True, **g.kernel_kwargs(), **d2)
+        assert rel_err(y, ref) < 2e-5
+
+
+def test_conv_linearity_at_baseline_size():
+    """BASELINE configs[1] top layer (B=32, 32x128, 128->128): conv(a+b) == conv(a)+conv(b) and
+    scaling, on fp32 outputs (properties independent of an oracle that could not finish in seconds)."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    g = C.plain_geom(32, 128, 128, 128, 3)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    a = torch.randn(32, 32, 128, 128, device=DEV, generator=gen).bfloat16()
+    b = torch.randn(32, 32, 128, 128, device=DEV, generator=gen).bfloat16()
+    s = (a.float() + b.float()).bfloat16()
+    w = (torch.randn(128, 9 * 128, device=DEV, generator=gen) / 34.0).bfloat16()
+    ya = K.conv2d_igemm(a, w, out_fp32=True, **g.kernel_kwargs())
+    yb = K.conv2d_igemm(b, w, out_fp32=True, **g.kernel_kwargs())
+    ys = K.conv2d_igemm(s, w, out_fp32=True, **g.kernel_kwargs())
+    # s is a bf16 rounding of a+b: compare against the conv of the rounding error too
+    r = (s.float() - a.float() - b.float()).bfloat16()
+    yr = K.conv2d_igemm(r, w, out_fp32=True, **g.kernel_kwargs())
+    assert rel_err(ys, ya + yb + yr) < 1e-4
+    y2 = K.conv2d_igemm((a.float() * 2).bfloat16(), w, out_fp32=True, **g.kernel_kwargs())
+    assert rel_err(y2, 2 * ya) < 1e-6
+
+
+@pytest.mark.parametrize("cfgk", [dict(upx=2, upy=2, padx0=2, padx1=1, pady0=2, pady1=1),
+                                  dict(padx0=1, padx1=1, pady0=1, pady1=1),
+                                  dict(downx=2, downy=2, padx0=2, padx1=3, pady0=2, pady1=3),
+                                  dict(upx=2, upy=1, downx=1, downy=2, padx0=-1, padx1=2, pady0=0, pady1=1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upfirdn2d_matches_reference_op(cfgk, dtype):
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(6, 9, 13, 3, generator=gen)
+    if dtype == torch.bfloat16:
+        x = _bf16_round(x)
+    k = torch.randn(4, 4, generator=gen)
+    full = dict(upx=1, upy=1, downx=1, downy=1, padx0=0, padx1=0, pady0=0, pady1=0)
+    full.update(cfgk)
+    ref = OS.upfirdn_2d_ref(x.double(), k.double().numpy(), full["upx"], full["upy"], full["downx"], full["downy"],
+                            full["padx0"], full["padx1"], full["pady0"], full["pady1"])
+    y = K.upfirdn2d(x.to(DEV).to(dtype), k.to(DEV), **full)
+    assert y.shape == ref.shape
+    assert rel_err(y.float(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+def test_upfirdn2d_gradients_any_order():
+    from textboxgan_b200 import upfirdn as U
+
+    x = torch.randn(2, 4, 8, 3, device=DEV, requires_grad=True)
+    y = U.upsample_2d_nhwc(x)
+    assert y.shape == (2, 8, 16, 3)
+    r = torch.randn_like(y)
+    (gx,) = torch.autograd.grad((y * r).sum(), x, create_graph=True)
+    xr = x.detach().cpu().double().requires_grad_(True)
+    k, p0, p1 = OS.compute_paddings([1, 3, 3, 1], True, False, is_conv=False)
+    yr = OS.upfirdn_2d_ref(xr, k, 2, 2, 1, 1, p0, p1, p0, p1)
+    (gr,) = torch.autograd.grad((yr * r.cpu().double()).sum(), xr)
+    assert rel_err(y, yr) < 1e-5 and rel_err(gx, gr) < 1e-5
+    # second order: gradient of <gx, q> w.r.t. r's coefficient is linear -> just check it runs and is finite
+    q = torch.randn_like(gx)
+    r2 = r.clone().requires_grad_(True)
+    (gx2,) = torch.autograd.grad((U.upsample_2d_nhwc(x) * r2).sum(), x, create_graph=True)
+    (gr2,) = torch.autograd.grad((gx2 * q).sum(), r2)
+    assert rel_err(gr2, U.upsample_2d_nhwc(q)) < 1e-5
+
+
+def test_adam_and_ema_kernels():
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(0)
+    for n, off in ((1000003, 0), (4099, 1), (7, 3)):
+        base = torch.randn(n + 8, generator=gen)
+        p = base.to(DEV)[off: off + n]
+        g = torch.randn(n + 8, generator=gen).to(DEV)[off: off + n]
+        m = torch.randn(n + 8, generator=gen).to(DEV)[off: off + n].abs()
+        v = torch.randn(n + 8, generator=gen).to(DEV)[off: off + n].abs()
+        pr, gr, mr, vr = (t.detach().cpu().double() for t in (p, g, m, v))
+        K.adam_step(p, g, m, v, 0.0017, 0.0, 0.99, 1e-8)
+        mr2 = 0.0 * mr + gr
+        vr2 = 0.99 * vr + 0.01 * gr * gr
+        ref = pr - 0.0017 * mr2 / (vr2.sqrt() + 1e-8)
+        assert rel_err(p, ref) < 1e-6 and rel_err(m, mr2) < 1e-6 and rel_err(v, vr2) < 1e-6
+        src = torch.randn(n + 8, generator=gen).to(DEV)[off: off + n]
+        before = p.detach().cpu().double()
+        K.ema_step(p, src, 0.99)
+        assert rel_err(p, src.cpu().double() + (before - src.cpu().double()) * 0.99) < 1e-6
+
+
+def _product(cfg, GP, DP, with_ocr=True):
+    from textboxgan_b200.aster_inferer import AsterInferer
+    from textboxgan_b200.discriminator import Discriminator
+    from textboxgan_b200.generator import Generator
+    from textboxgan_b200.optimizers import Adam, update_optimizer_params
+    from textboxgan_b200.training_step import TrainingStep
+
+    G = Generator(cfg, device=DEV, seed=0)
+    G.load_state_dict(GP)
+    D = Discriminator(cfg, device=DEV, seed=0)
+    D.load_state_dict(DP)
+    aster = AsterInferer(cfg, device=DEV) if with_ocr else None
+    go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
+    mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
+    ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), 8, 16, torch.zeros((), device=DEV), cfg)
+    return G, D, aster, ts
+
+
+def _to_dev(draws):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else ([t.to(DEV) for t in v] if isinstance(v, list) else v))
+            for k, v in draws.items()}
+
+
+def test_generator_and_discriminator_forward_vs_oracle():
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    real, words, labels = OT.synthetic_batch(cfg, 4, g)
+    draws = OT.make_draws(cfg, 4, g)
+    G, D, _, _ = _product(cfg, GP, DP, with_ocr=False)
+    ref = OS.generator(words, draws["z"], GP, cfg, training=True, draws=draws)
+    for grad_mode in (True, False):           # differentiable path and fused-epilogue (no_grad) path
+        G.load_state_dict(GP)
+        with torch.set_grad_enabled(grad_mode):
+            img = G((words.to(DEV), draws["z"].to(DEV)), training=True, draws=_to_dev(draws))
+        # bf16 activations through 7 modulated convs: 3e-2 of the image range
+        assert rel_err(img, ref) < 3e-2, (grad_mode, rel_err(img, ref))
+        sc = D(real.to(DEV)) if grad_mode else None
+        with torch.set_grad_enabled(grad_mode):
+            sc = D(real.to(DEV))
+        rsc = OS.discriminator(real, DP, cfg)
+        assert (sc.cpu() - rsc).abs().max() < 3e-2 * max(1.0, float(rsc.abs().max()))
+
+
+@pytest.mark.parametrize("do_r1,do_pl,with_ocr", [(False, False, True), (True, True, False)])
+def test_train_step_vs_oracle(do_r1, do_pl, with_ocr):
+    """Whole _train_step on the GPU vs the oracle at BASELINE configs[0] (batch 4, 64x16): the seven
+    losses within 5e-2 relative (bf16 activations), updated weights within the Adam step size."""
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    real, words, labels = OT.synthetic_batch(cfg, 4, g)
+    draws = OT.make_draws(cfg, 4, g, with_pl=do_pl)
+    st = OT.StepState(copy.deepcopy(GP), copy.deepcopy(DP), OA.init_aster_params(), OT.make_adam(cfg.g_opt),
+                      OT.make_adam(cfg.g_opt), OT.make_adam(cfg.d_opt), torch.zeros(()))
+    ref_out, ref_grads, _ = OT.train_step(st, cfg, real, torch.zeros(()), words, labels, do_r1, do_pl, 1e-4, draws,
+                                          fused=False, with_ocr=with_ocr, ret_grads=True)
+    G, D, aster, ts = _product(cfg, GP, DP, with_ocr)
+    d2 = _to_dev(draws)
+    d2["keep_grads"] = True
+    out = ts.dist_train_step(real.to(DEV), torch.zeros((), device=DEV), words.to(DEV), labels.to(DEV), do_r1, do_pl,
+                             1e-4, draws=d2)
+    flat = lambda o: [float(v) for v in (*o[0], *o[1], o[2])]
+    got, want = flat(out), flat(ref_out)
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 5e-2 * max(1.0, abs(b)), (got, want)
+    # gradient direction of the big groups agrees (cosine similarity; bf16 + lrelu sign flips)
+    for names, grads, ref in ((ts._g_names, ts.last_grads[0], ref_grads[0]), (ts._d_names, ts.last_grads[2], ref_grads[2])):
+        a = torch.cat([gr.reshape(-1).float().cpu() for n, gr in zip(names, grads) if gr is not None and n in ref])
+        b = torch.cat([ref[n].reshape(-1) for n, gr in zip(names, grads) if gr is not None and n in ref])
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.98, cos
+    # every weight moved by at most ~lr (Adam with beta1 = 0) and in the oracle's direction on average
+    lr = 0.002
+    moved = same = 0
+    for n, p in G.params.items():
+        d_prod = p.detach().cpu() - GP[n]
+        d_ref = st.G[n] - GP[n]
+        assert float(d_prod.abs().max()) <= 2.5 * lr * 2 + 1e-6, n
+        moved += d_ref.numel()
+        same += int(((d_prod * d_ref) > 0).sum()) + int(((d_prod == 0) & (d_ref == 0)).sum())
+    assert same / moved > 0.9
+
+
+def test_launches_are_counted_and_library_is_loaded():
+    from textboxgan_b200 import lib
+
+    h = lib.load()
+    h.tbg_reset_launch_count()
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    G, D, _, _ = _product(cfg, GP, DP, with_ocr=False)
+    real, words, labels = OT.synthetic_batch(cfg, 4, g)
+    with torch.no_grad():
+        G((words.to(DEV), torch.randn(4, cfg.z_dim, device=DEV)))
+    torch.cuda.synchronize()
+    assert h.tbg_launch_count() >= 6
+    maps = open("/proc/self/maps").read()
+    assert "libtbg.so" in maps

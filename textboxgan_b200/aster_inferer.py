@@ -92,6 +92,7 @@ class _FrozenConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, layer: "_ConvLayer", residual, relu: bool):
+        K.PROFILE_TAG = (layer.geom.tag, layer.geom.algo_frac)
         out = K.conv2d_igemm(x.contiguous(), layer.wmat, **layer.geom.kernel_kwargs(), bias=layer.bias,
                              residual=residual.contiguous() if residual is not None else None, res_scale=1.0,
                              res_first=True, act=2 if relu else 0)
@@ -109,6 +110,7 @@ class _FrozenConv(torch.autograd.Function):
         if ctx.relu:
             g = gy * (out > 0).to(gy.dtype)
         g = g.contiguous()
+        K.PROFILE_TAG = (layer.geom.tag, layer.geom.algo_frac)
         gx = K.conv2d_igemm(g, layer.wmat_adj, **layer.geom.adjoint().kernel_kwargs())
         return gx, None, (g if ctx.has_res else None), None
 
@@ -123,7 +125,8 @@ class _ConvLayer:
         bp[:cout] = b
         kinds = ["s2" if s == 2 else "s1" for s in stride]
         assert k == 1 or stride == (1, 1)
-        self.geom = C.ConvGeom(H, W, cin_p, cout_p, C.Axis(kinds[0], k, k // 2), C.Axis(kinds[1], k, k // 2))
+        self.geom = C.ConvGeom(H, W, cin_p, cout_p, C.Axis(kinds[0], k, k // 2), C.Axis(kinds[1], k, k // 2), "aster",
+                               (cin * cout) / float(cin_p * cout_p))
         wmat = C.plain_wmat(wp).to(device)
         self.wmat = wmat.to(L.ACT_DTYPE).contiguous()
         self.wmat_adj = C.relayout_for_adjoint(wmat, self.geom).to(L.ACT_DTYPE).contiguous()

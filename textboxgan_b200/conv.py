@@ -67,6 +67,8 @@ class ConvGeom:
     cout: int
     ah: Axis
     aw: Axis
+    tag: str = ""            # profiling label ("modconv", "dconv", "aster", ...)
+    algo_frac: float = 1.0   # algorithmic FLOPs / executed GEMM FLOPs (SURVEY.md §8d accounting)
 
     @property
     def out_hw(self) -> Tuple[int, int]:
@@ -88,7 +90,7 @@ class ConvGeom:
 
     def adjoint(self) -> "ConvGeom":
         oh, ow = self.out_hw
-        return ConvGeom(oh, ow, self.cout, self.cin, self.ah.adjoint(), self.aw.adjoint())
+        return ConvGeom(oh, ow, self.cout, self.cin, self.ah.adjoint(), self.aw.adjoint(), self.tag, self.algo_frac)
 
     def kernel_kwargs(self) -> dict:
         gh, gw = self.grid
@@ -167,6 +169,7 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, x, wmat, geom: ConvGeom, epi: Optional[dict]):
         ctx.geom = geom
         ctx.save_for_backward(x, wmat)
+        K.PROFILE_TAG = (geom.tag, geom.algo_frac)
         return K.conv2d_igemm(_as_bf16(x), _as_bf16(wmat), **geom.kernel_kwargs(), **(epi or {}))
 
     @staticmethod
@@ -188,6 +191,7 @@ class _WgradFn(torch.autograd.Function):
     def forward(ctx, x, gy, geom: ConvGeom):
         ctx.geom = geom
         ctx.save_for_backward(x, gy)
+        K.PROFILE_TAG = (geom.tag, geom.algo_frac)
         return K.conv2d_wgrad(_as_bf16(x), _as_bf16(gy), **geom.kernel_kwargs())
 
     @staticmethod
@@ -220,9 +224,9 @@ def conv_wgrad(x: torch.Tensor, gy: torch.Tensor, geom: ConvGeom) -> torch.Tenso
 FIR_1D = (1.0, 3.0, 3.0, 1.0)   # resample_kernel [1,3,3,1] (synthesis_block.py:36, discriminator.py:44)
 
 
-def plain_geom(H: int, W: int, cin: int, cout: int, k: int) -> ConvGeom:
+def plain_geom(H: int, W: int, cin: int, cout: int, k: int, tag: str = "", algo_frac: float = 1.0) -> ConvGeom:
     """SAME stride-1 k x k convolution (modulated_conv2d.py:110-112, conv.py:69-71)."""
-    return ConvGeom(H, W, cin, cout, Axis("s1", k, k // 2), Axis("s1", k, k // 2))
+    return ConvGeom(H, W, cin, cout, Axis("s1", k, k // 2), Axis("s1", k, k // 2), tag, algo_frac)
 
 
 def plain_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
@@ -230,9 +234,11 @@ def plain_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
     return w_hwio.permute(3, 0, 1, 2).reshape(O, kh * kw * I)
 
 
-def up_geom(h: int, w: int, cin: int, cout: int) -> ConvGeom:
-    """upsample_conv_2d (upfirdn_2d_v2.py:65-103) as a 4-phase 3x3 GEMM over the input grid."""
-    return ConvGeom(h, w, cin, cout, Axis("up", 3, 1), Axis("up", 3, 1))
+def up_geom(h: int, w: int, cin: int, cout: int, tag: str = "") -> ConvGeom:
+    """upsample_conv_2d (upfirdn_2d_v2.py:65-103) as a 4-phase 3x3 GEMM over the input grid.
+    Algorithmic work is the transposed conv (9*I*O MACs per input pixel); the 4-phase GEMM with
+    the FIR folded in executes 4x that."""
+    return ConvGeom(h, w, cin, cout, Axis("up", 3, 1), Axis("up", 3, 1), tag, 0.25)
 
 
 @lru_cache(maxsize=None)
@@ -258,14 +264,14 @@ def up_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
     return weff.reshape(4 * O, 9 * I)
 
 
-def down_geom(H: int, W: int, cin: int, cout: int, k: int, reduce_height: bool) -> ConvGeom:
+def down_geom(H: int, W: int, cin: int, cout: int, k: int, reduce_height: bool, tag: str = "") -> ConvGeom:
     """conv_downsample_2d (upfirdn_2d_v2.py:106-113): 4x4 FIR (pad0 = (k+1)//2 + ..., A.4) followed
     by a VALID k x k conv of stride (2|1, 2), folded into one (k+3) x (k+3) convolution."""
     kk = k + 3
     pad0 = (2 + (k - 1) + 1) // 2            # compute_paddings(down, is_conv): p=(4-2)+(k-1); pad0=(p+1)//2
     aw = Axis("s2", kk, pad0)
     ah = Axis("s2", kk, pad0) if reduce_height else Axis("s1", kk, pad0)
-    return ConvGeom(H, W, cin, cout, ah, aw)
+    return ConvGeom(H, W, cin, cout, ah, aw, tag, float(k * k) / float(kk * kk))
 
 
 @lru_cache(maxsize=None)

@@ -68,10 +68,10 @@ class Discriminator(Model):
         w = L.runtime_coef(w_raw.shape) * w_raw
         B, H, W_, _ = x.shape
         if down:
-            geom = C.down_geom(H, W_, I, O, k, reduce_height)
+            geom = C.down_geom(H, W_, I, O, k, reduce_height, tag="dconv")
             wmat = C.down_wmat(w)
         else:
-            geom = C.plain_geom(H, W_, I, O, k)
+            geom = C.plain_geom(H, W_, I, O, k, tag="dconv")
             wmat = C.plain_wmat(w)
         if not torch.is_grad_enabled():
             epi = dict(bias=P[bias].contiguous() if bias else None, act=1 if bias else 0,
@@ -117,7 +117,7 @@ class Discriminator(Model):
         w_raw = P[pl + "/conv_0/w"]                                          # [3,3,C+1,C]
         w = L.runtime_coef(w_raw.shape) * w_raw
         wpad = torch.cat([w, w.new_zeros(3, 3, cpad - Cc - 1, w.shape[3])], dim=2)
-        y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3)).float()
+        y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3, tag="dconv", algo_frac=(Cc + 1) / cpad)).float()
         y = L.lrelu(y + P[pl + "/bias_0/b"])
         # flatten in the reference's NCHW order (dense.py:26-27 on an NCHW tensor)
         y = y.permute(0, 3, 1, 2).reshape(B, -1)

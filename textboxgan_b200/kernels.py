@@ -10,6 +10,31 @@ import torch
 from . import lib as _lib
 
 
+# Optional per-launch device timing (bench.py's roofline pass): when PROFILE is a list, every
+# tensor-core launch appends (kernel_name, tag, algorithmic_flops, start_event, end_event) recorded on the
+# launching stream.
+PROFILE: Optional[list] = None
+PROFILE_TAG: str = ""
+
+
+class _Timed:
+    def __init__(self, name: str, flops: float):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, PROFILE_TAG, self.flops, self.e0, self.e1))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
@@ -76,7 +101,8 @@ def conv2d_igemm(
         col_scale=_ptr(col_scale), bias=_ptr(bias), noise=_ptr(noise), noise_strength=_ptr(noise_strength),
         residual=_ptr(residual), res_scale=res_scale, res_first=int(res_first), act=act, act_gain=act_gain, out_fp32=int(out_fp32),
     )
-    _lib.check(_lib.load().tbg_conv2d_igemm(C.byref(a), _stream()), "tbg_conv2d_igemm")
+    with _Timed("conv_igemm", 2.0 * B * Ho * Wo * n_total * taps[0] * taps[1] * Cin):
+        _lib.check(_lib.load().tbg_conv2d_igemm(C.byref(a), _stream()), "tbg_conv2d_igemm")
     return out
 
 
@@ -108,7 +134,8 @@ def conv2d_wgrad(
         taps_h=taps[0], taps_w=taps[1], pad_h=pad[0], pad_w=pad[1],
         stride_h=stride[0], stride_w=stride[1], up_h=up[0], up_w=up[1],
     )
-    _lib.check(_lib.load().tbg_conv2d_wgrad(C.byref(a), _stream()), "tbg_conv2d_wgrad")
+    with _Timed("conv_wgrad", 2.0 * B * Ho * Wo * n_total * taps[0] * taps[1] * Cin):
+        _lib.check(_lib.load().tbg_conv2d_wgrad(C.byref(a), _stream()), "tbg_conv2d_wgrad")
     return gw
 
 

@@ -63,10 +63,10 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     s = style_scale(style, P, prefix)                                       # [B,I]
     B, H, W_, _ = x.shape
     if up:
-        geom = C.up_geom(H, W_, I, O)
+        geom = C.up_geom(H, W_, I, O, tag="modconv")
         wmat = C.up_wmat(w)
     else:
-        geom = C.plain_geom(H, W_, I, O, kh)
+        geom = C.plain_geom(H, W_, I, O, kh, tag="modconv")
         wmat = C.plain_wmat(w)
     xs = (x.float() * s[:, None, None, :]).to(ACT_DTYPE)                    # :96
     d = None
