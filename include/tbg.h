@@ -117,13 +117,29 @@ int tbg_upfirdn2d(const void* x, const float* k, void* y, int dtype_bf16, int ma
 /* tf.keras.optimizers.Adam (optimizer_v2) update of a flat fp32 buffer — replaces the per-variable
  * ResourceApplyAdam ops behind optimizer.apply_gradients (training_step.py:235):
  *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  p -= lr_t*m/(sqrt(v)+eps),
- * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host. */
-int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-                  float eps, void* stream);
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host, either by value or — when lr_t_dev is
+ * non-NULL — through a device scalar (so that a captured CUDA graph can be replayed with the
+ * step-dependent bias correction updated outside the graph). */
+int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, const float* lr_t_dev,
+                  float beta1, float beta2, float eps, void* stream);
 
 /* dst = src + (dst - src)*beta over a flat fp32 buffer — Generator.set_as_moving_average_of
  * (generator.py:48-59). */
 int tbg_ema_step(float* dst, const float* src, long long n, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-sequence LSTM recurrence of the frozen OCR head (BiLSTM encoder of ASTER, reached through
+ * AsterInferer.call, aster_inferer.py:28-37).  xp = x @ W_ih + b for all steps is computed by the
+ * caller; gate order i, f, g, o; H must be 256.
+ *   fwd:  xp f32 [D,B,T,4H], w_packed bf16 [D,H(k),H(j),4] -> h f32 [D,B,T,H],
+ *         gates f32 [D,B,T,4H] (post-activation), c f32 [D,B,T,H]
+ *   bwd:  g_h f32 [D,B,T,H] (+ saved gates, c), wT_packed bf16 [D,H(j),H(k),4] -> g_xp f32 [D,B,T,4H]
+ * (input gradient only: the head is frozen, training_step.py:201-206).
+ * ------------------------------------------------------------------------------------------ */
+int tbg_lstm_seq_fwd(const float* xp, const void* w_packed, float* h_out, float* gates_out, float* c_out, int D, int B,
+                     int T, int H, void* stream);
+int tbg_lstm_seq_bwd(const float* g_h, const float* gates, const float* c_saved, const void* wT_packed, float* g_xp,
+                     int D, int B, int T, int H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,8 @@ def emu_upfirdn2d(x, k, *, upx=1, upy=1, downx=1, downy=1, padx0=0, padx1=0, pad
 
 
 def emu_adam_step(p, g, m, v, lr_t, beta1, beta2, eps):
+    if torch.is_tensor(lr_t):
+        lr_t = float(lr_t)
     m.mul_(beta1).add_(g, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
     p.sub_(lr_t * m / (v.sqrt() + eps))
@@ -93,6 +95,50 @@ def emu_ema_step(dst, src, beta):
     dst.copy_(src + (dst - src) * beta)
 
 
+def emu_lstm_seq_fwd(xp, w_packed):
+    """Documented semantics of tbg_lstm_seq_fwd (gate order i,f,g,o; w_packed[d,k,j,g])."""
+    D, B, T, H4 = xp.shape
+    H = H4 // 4
+    w_hh = w_packed.double().permute(0, 1, 3, 2).reshape(D, H, 4 * H)            # [d,k,(g,j)]
+    h = torch.zeros(D, B, H, dtype=torch.float64)
+    c = torch.zeros(D, B, H, dtype=torch.float64)
+    hs, gs, cs = [], [], []
+    for t in range(T):
+        gates = xp[:, :, t].double() + torch.bmm(h, w_hh)
+        i, f, g, o = gates.chunk(4, dim=-1)
+        i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+        c = f * c + i * g
+        h = o * torch.tanh(c)
+        hs.append(h)
+        cs.append(c)
+        gs.append(torch.cat([i, f, g, o], dim=-1))
+    return (torch.stack(hs, 2).to(xp.dtype), torch.stack(gs, 2).to(xp.dtype), torch.stack(cs, 2).to(xp.dtype))
+
+
+def emu_lstm_seq_bwd(g_h, gates, c, wT_packed):
+    D, B, T, H = g_h.shape
+    w_hh = wT_packed.double().permute(0, 2, 3, 1).reshape(D, H, 4 * H)            # [d,k,(g,j)]
+    dh_rec = torch.zeros(D, B, H, dtype=torch.float64)
+    dc_next = torch.zeros(D, B, H, dtype=torch.float64)
+    out = torch.zeros(D, B, T, 4 * H, dtype=torch.float64)
+    for t in range(T - 1, -1, -1):
+        i, f, g, o = gates[:, :, t].double().chunk(4, dim=-1)
+        cc = c[:, :, t].double()
+        cp = c[:, :, t - 1].double() if t > 0 else torch.zeros_like(cc)
+        dh = g_h[:, :, t].double() + dh_rec
+        tc = torch.tanh(cc)
+        do = dh * tc * o * (1 - o)
+        dc = dh * o * (1 - tc * tc) + dc_next
+        di = dc * g * i * (1 - i)
+        df = dc * cp * f * (1 - f)
+        dg = dc * i * (1 - g * g)
+        dc_next = dc * f
+        dgates = torch.cat([di, df, dg, do], dim=-1)
+        out[:, :, t] = dgates
+        dh_rec = torch.bmm(dgates, w_hh.transpose(1, 2))
+    return out.to(g_h.dtype)
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -100,15 +146,19 @@ def emulated_kernels(act_dtype=torch.float32):
     from textboxgan_b200 import kernels as K
     from textboxgan_b200 import layers as L
 
-    saved = (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step)
+    saved = (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
+             K.lstm_seq_fwd, K.lstm_seq_bwd)
     K.conv2d_igemm = emu_conv2d_igemm
     K.conv2d_wgrad = emu_conv2d_wgrad
     K.upfirdn2d = emu_upfirdn2d
     K.adam_step = emu_adam_step
     K.ema_step = emu_ema_step
+    K.lstm_seq_fwd = emu_lstm_seq_fwd
+    K.lstm_seq_bwd = emu_lstm_seq_bwd
     C._as_bf16 = lambda t: t.contiguous()
     L.ACT_DTYPE = act_dtype
     try:
         yield
     finally:
-        (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step) = saved
+        (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
+         K.lstm_seq_fwd, K.lstm_seq_bwd) = saved

@@ -136,6 +136,33 @@ class _ConvLayer:
         return _FrozenConv.apply(x, self, residual, relu)
 
 
+class _LstmLayer:
+    """Frozen BiLSTM layer: stacked input projections + recurrent weights packed for the kernels."""
+
+    def __init__(self, P, name: str, device):
+        self.w_ih = torch.stack([P[f"{name}/fw/w_ih"], P[f"{name}/bw/w_ih"]]).to(device).float()
+        self.b = torch.stack([P[f"{name}/fw/b"], P[f"{name}/bw/b"]])[:, None, None, :].to(device).float()
+        w_hh = torch.stack([P[f"{name}/fw/w_hh"], P[f"{name}/bw/w_hh"]]).to(device).float()    # [2,H,4H]
+        D, H, _ = w_hh.shape
+        w4 = w_hh.reshape(D, H, 4, H)                                              # [d, k, gate, j]
+        self.w_packed = w4.permute(0, 1, 3, 2).contiguous().to(L.ACT_DTYPE)        # [d, k, j, gate]
+        self.wT_packed = w4.permute(0, 3, 1, 2).contiguous().to(L.ACT_DTYPE)       # [d, j, k, gate]
+
+
+class _LstmSeq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, layer: _LstmLayer):
+        h, gates, c = K.lstm_seq_fwd(xp.contiguous(), layer.w_packed)
+        ctx.layer = layer
+        ctx.save_for_backward(gates, c)
+        return h
+
+    @staticmethod
+    def backward(ctx, g_h):
+        gates, c = ctx.saved_tensors
+        return K.lstm_seq_bwd(g_h.contiguous(), gates, c, ctx.layer.wT_packed), None
+
+
 class AsterInferer:
     """Reads the word written in a text box (aster_inferer.py:7-37)."""
 
@@ -151,6 +178,7 @@ class AsterInferer:
         P = weights if weights is not None else init_aster_params(seed)
         self.P = {k: v.to(self.device).float() for k, v in P.items()}
         self._build_encoder(P)
+        self.lstm = {n: _LstmLayer(P, n, self.device) for n in ("rnn/l0", "rnn/l1")}
 
     # ------------------------------------------------------------------------------------------
     def _build_encoder(self, P) -> None:
@@ -191,21 +219,12 @@ class AsterInferer:
         return h, c
 
     def _bilstm(self, x: torch.Tensor, name: str) -> torch.Tensor:
-        P = self.P
-        B, T, _ = x.shape
-        # both directions advance together: index 0 walks t = 0..T-1, index 1 walks t = T-1..0
-        w_ih = torch.stack([P[f"{name}/fw/w_ih"], P[f"{name}/bw/w_ih"]])            # [2,512,1024]
-        w_hh = torch.stack([P[f"{name}/fw/w_hh"], P[f"{name}/bw/w_hh"]])            # [2,256,1024]
-        b = torch.stack([P[f"{name}/fw/b"], P[f"{name}/bw/b"]])[:, None, None, :]
-        xp = torch.einsum("btk,dkn->dbtn", x, w_ih) + b                             # [2,B,T,1024]
-        xp = torch.stack([xp[0], xp[1].flip(1)])                                    # time-reverse the bw stream
-        h = x.new_zeros(2, B, LSTM_HIDDEN)
-        c = x.new_zeros(2, B, LSTM_HIDDEN)
-        hs = []
-        for t in range(T):
-            h, c = self._lstm_cell(xp[:, :, t], h, c, w_hh)
-            hs.append(h)
-        hs = torch.stack(hs, dim=2)                                                 # [2,B,T,256]
+        """Both directions in one whole-sequence launch (``tbg_lstm_seq_fwd``): the input projections
+        for all steps are one batched GEMM, the backward stream is time-reversed around the kernel."""
+        lay = self.lstm[name]
+        xp = torch.einsum("btk,dkn->dbtn", x, lay.w_ih) + lay.b                     # [2,B,T,1024]
+        xp = torch.stack([xp[0], xp[1].flip(1)]).contiguous()
+        hs = _LstmSeq.apply(xp, lay)                                                # [2,B,T,256]
         return torch.cat([hs[0], hs[1].flip(1)], dim=2)
 
     def _decoder(self, mem: torch.Tensor, steps: int) -> torch.Tensor:

@@ -134,9 +134,22 @@ def _axis_adjoint_map(kind: str, k: int, pad: int):
     return idx.flatten(), mask.flatten()
 
 
+_DEVICE_CACHE: dict = {}
+
+
+def _on_device(key, device, make):
+    """Constant tables are uploaded once per device (never during a CUDA-graph capture)."""
+    k = (key, str(device))
+    t = _DEVICE_CACHE.get(k)
+    if t is None:
+        t = make()
+        t = tuple(x.to(device) for x in t) if isinstance(t, tuple) else t.to(device)
+        _DEVICE_CACHE[k] = t
+    return t
+
+
 def _tables_on(device, kind, k, pad):
-    idx, mask = _axis_adjoint_map(kind, k, pad)
-    return idx.to(device), mask.to(device)
+    return _on_device(("adj", kind, k, pad), device, lambda: _axis_adjoint_map(kind, k, pad))
 
 
 def relayout_for_adjoint(wmat: torch.Tensor, g: ConvGeom) -> torch.Tensor:
@@ -258,7 +271,7 @@ def _up_coef() -> torch.Tensor:
 
 def up_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
     """Weff[(py,px,o), (ty,tx,i)] = sum_{kh,kw} C[py,ty,kh] C[px,tx,kw] w[kh,kw,i,o]."""
-    c = _up_coef().to(w_hwio.device, w_hwio.dtype)
+    c = _on_device(("upcoef",), w_hwio.device, _up_coef).to(w_hwio.dtype)
     weff = torch.einsum("pak,qbl,klio->pqoabi", c, c, w_hwio)
     O, I = w_hwio.shape[3], w_hwio.shape[2]
     return weff.reshape(4 * O, 9 * I)
@@ -289,7 +302,7 @@ def _fold_table(k: int) -> torch.Tensor:
 def down_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
     """G[uy,ux] = sum_{ty,tx} kf[uy-ty] kf[ux-tx] w[ty,tx]  ->  [O, (k+3)^2 * I]."""
     k = w_hwio.shape[0]
-    s = _fold_table(k).to(w_hwio.device, w_hwio.dtype)
+    s = _on_device(("fold", k), w_hwio.device, lambda: _fold_table(k)).to(w_hwio.dtype)
     g = torch.einsum("ut,vs,tsio->ouvi", s, s, w_hwio)
     O, I = w_hwio.shape[3], w_hwio.shape[2]
     return g.reshape(O, (k + 3) * (k + 3) * I)

@@ -318,6 +318,9 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                 "tbg_conv2d_igemm: tensors must be 16-byte aligned");
+  TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->col_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
+                "tbg_conv2d_igemm: col_scale / bias / residual must be 16-byte aligned (vector loads in the epilogue)");
 
   ConvKernelParams p{};
   p.B = a->B;

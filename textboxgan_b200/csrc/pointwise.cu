@@ -36,7 +36,9 @@ static int grid_for(long long work_items, int threads, int per_sm = 8) {
 // Pointers may start at any 4-byte boundary as long as they share the same 16-byte phase: the
 // first `head` and the last few elements are handled with scalar accesses, the body with float4.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, int head, float lr_t, float b1, float b2, float eps) {
+                            float* __restrict__ v, long long n, int head, float lr_t, const float* __restrict__ lr_t_dev,
+                            float b1, float b2, float eps) {
+  if (lr_t_dev != nullptr) lr_t = __ldg(lr_t_dev);
   const long long n4 = (n - head) >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -178,8 +180,8 @@ __global__ void upfirdn2d_kernel(const T* __restrict__ x, const float* __restric
 
 using namespace tbg;
 
-extern "C" int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1,
-                             float beta2, float eps, void* stream_v) {
+extern "C" int tbg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
+                             const float* lr_t_dev, float beta1, float beta2, float eps, void* stream_v) {
   TBG_CHECK_ARG(p && g && m && v && n >= 0, "tbg_adam_step: bad arguments");
   TBG_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 3) == 0,
@@ -187,7 +189,7 @@ extern "C" int tbg_adam_step(float* p, const float* g, float* m, float* v, long 
   if (n == 0) return TBG_OK;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int head = static_cast<int>(common_head(n, {p, g, m, v}));
-  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(p, g, m, v, n, head, lr_t, beta1, beta2, eps);
+  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(p, g, m, v, n, head, lr_t, lr_t_dev, beta1, beta2, eps);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -122,13 +122,15 @@ class Generator(Model):
                 batch_avg = wb[:, 0].mean(dim=0)
                 w_avg = P["latent_encoder/w_avg"]
                 w_avg.copy_(batch_avg + (w_avg - batch_avg) * self.w_ema_decay)
-            z2 = draws["z2"] if "z2" in draws else torch.randn_like(z)      # :49
+            z2 = draws["z2"].to(z.device) if "z2" in draws else torch.randn_like(z)   # :49
             wb2 = self._mapping(z2)[:, None, :].expand(-1, n, -1)
-            coin = draws["mix_coin"] if "mix_coin" in draws else float(torch.rand(()))
-            if coin < self.style_mixing_prob:                                # :55-60
-                cutoff = draws["mix_cutoff"] if "mix_cutoff" in draws else int(torch.randint(1, n, ()))
-            else:
-                cutoff = n
+            # :55-60 — one scalar coin / cutoff per batch, drawn on the device (no host sync, so the
+            # whole step can be replayed from a CUDA graph)
+            coin = torch.as_tensor(draws["mix_coin"], device=z.device, dtype=torch.float32) if "mix_coin" in draws \
+                else torch.rand((), device=z.device)
+            cut = torch.as_tensor(draws["mix_cutoff"], device=z.device) if "mix_cutoff" in draws \
+                else torch.randint(1, n, (), device=z.device)
+            cutoff = torch.where(coin < self.style_mixing_prob, cut, torch.full_like(cut, n))
             idx = torch.arange(n, device=z.device)[None, :, None]
             wb = torch.where(idx < cutoff, wb, wb2)
         if not training:

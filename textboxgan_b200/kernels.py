@@ -41,6 +41,14 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+def _aligned(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Epilogue vectors are read with 128-bit loads; parameters living at odd offsets of a flat
+    buffer are copied to an aligned scratch tensor first (a few hundred bytes)."""
+    if t is None or t.data_ptr() % 16 == 0:
+        return t
+    return t.clone()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -93,6 +101,7 @@ def conv2d_igemm(
             _require(t, torch.float32, n)
     if residual is not None:
         _require(residual, torch.bfloat16, "residual")
+    col_scale, bias = _aligned(col_scale), _aligned(bias)
     a = _lib.ConvArgs(
         x=_ptr(x), w=_ptr(w), out=_ptr(out),
         B=B, H=H, W=W_, Cin=Cin, Ho=Ho, Wo=Wo, n_total=n_total, cout=cout,
@@ -157,11 +166,17 @@ def upfirdn2d(x: torch.Tensor, k: torch.Tensor, *, upx=1, upy=1, downx=1, downy=
     return y
 
 
-def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float, beta1: float,
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t, beta1: float,
               beta2: float, eps: float) -> None:
+    """``lr_t`` is a Python float or a 1-element fp32 device tensor (CUDA-graph friendly)."""
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _require(t, torch.float32, n)
-    st = _lib.load().tbg_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr_t, beta1, beta2, eps, _stream())
+    lr_dev = None
+    if torch.is_tensor(lr_t):
+        _require(lr_t, torch.float32, "lr_t")
+        lr_dev, lr_t = lr_t, 0.0
+    st = _lib.load().tbg_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr_t, _ptr(lr_dev), beta1, beta2,
+                                   eps, _stream())
     _lib.check(st, "tbg_adam_step")
 
 
@@ -170,3 +185,27 @@ def ema_step(dst: torch.Tensor, src: torch.Tensor, beta: float) -> None:
     _require(src, torch.float32, "src")
     st = _lib.load().tbg_ema_step(_ptr(dst), _ptr(src), dst.numel(), beta, _stream())
     _lib.check(st, "tbg_ema_step")
+
+
+def lstm_seq_fwd(xp: torch.Tensor, w_packed: torch.Tensor):
+    """xp f32 [D,B,T,4H]; w_packed bf16 [D,H,H,4] -> (h [D,B,T,H], gates [D,B,T,4H], c [D,B,T,H])."""
+    _require(xp, torch.float32, "xp")
+    _require(w_packed, torch.bfloat16, "w_packed")
+    D, B, T, H4 = xp.shape
+    H = H4 // 4
+    h = torch.empty((D, B, T, H), device=xp.device, dtype=torch.float32)
+    gates = torch.empty((D, B, T, H4), device=xp.device, dtype=torch.float32)
+    c = torch.empty((D, B, T, H), device=xp.device, dtype=torch.float32)
+    st = _lib.load().tbg_lstm_seq_fwd(_ptr(xp), _ptr(w_packed), _ptr(h), _ptr(gates), _ptr(c), D, B, T, H, _stream())
+    _lib.check(st, "tbg_lstm_seq_fwd")
+    return h, gates, c
+
+
+def lstm_seq_bwd(g_h: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, wT_packed: torch.Tensor) -> torch.Tensor:
+    _require(g_h, torch.float32, "g_h")
+    _require(wT_packed, torch.bfloat16, "wT_packed")
+    D, B, T, H = g_h.shape
+    g_xp = torch.empty((D, B, T, 4 * H), device=g_h.device, dtype=torch.float32)
+    st = _lib.load().tbg_lstm_seq_bwd(_ptr(g_h), _ptr(gates), _ptr(c), _ptr(wT_packed), _ptr(g_xp), D, B, T, H, _stream())
+    _lib.check(st, "tbg_lstm_seq_bwd")
+    return g_xp

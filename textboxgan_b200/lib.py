@@ -60,9 +60,11 @@ _SIGNATURES = [
     ("tbg_conv2d_igemm", c_int, [C.POINTER(ConvArgs), c_void_p]),
     ("tbg_conv2d_wgrad", c_int, [C.POINTER(WgradArgs), c_void_p]),
     ("tbg_upfirdn2d", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),
-    ("tbg_adam_step", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, c_float, c_float, c_float,
-                              c_float, c_void_p]),
+    ("tbg_adam_step", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, c_float, c_void_p, c_float,
+                              c_float, c_float, c_void_p]),
     ("tbg_ema_step", c_int, [c_void_p, c_void_p, C.c_longlong, c_float, c_void_p]),
+    ("tbg_lstm_seq_fwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    ("tbg_lstm_seq_bwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
 ]
 
 

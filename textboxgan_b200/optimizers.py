@@ -38,6 +38,8 @@ class Adam:
         self.beta_2 = float(beta_2)
         self.epsilon = float(epsilon)
         self.iterations = _Iterations()
+        self._lr_dev: Optional[torch.Tensor] = None   # device copy of lr_t (CUDA-graph replay)
+        self.defer_iteration = False                   # True while a captured graph owns the update
         self._slots: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
 
     # -- helpers -------------------------------------------------------------------------------
@@ -52,6 +54,19 @@ class Adam:
         t = self.iterations.value + 1
         return self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
 
+    def use_device_lr(self, device) -> None:
+        """Route lr_t through a device scalar; call :meth:`refresh_device_lr` before each replay."""
+        if self._lr_dev is None:
+            self._lr_dev = torch.zeros(1, dtype=torch.float32, device=device)
+        self.refresh_device_lr()
+
+    def refresh_device_lr(self) -> None:
+        if self._lr_dev is not None:
+            self._lr_dev.fill_(self._lr_t())
+
+    def _lr_arg(self):
+        return self._lr_dev if self._lr_dev is not None else self._lr_t()
+
     # -- Keras surface -------------------------------------------------------------------------
     def apply_gradients(self, grads_and_vars: Iterable[Tuple[torch.Tensor, torch.Tensor]], model=None,
                         names: Optional[Sequence[str]] = None) -> None:
@@ -65,7 +80,8 @@ class Adam:
                 if g is None:
                     continue
                 self._apply_flat_range(v.detach().reshape(-1), g.detach().reshape(-1).float().contiguous(), id(v))
-        self.iterations.value += 1
+        if not self.defer_iteration:
+            self.iterations.value += 1
 
     def _apply_flat(self, model, names: List[str], grads: List[Optional[torch.Tensor]]) -> None:
         start, end = model.flat_range(names)
@@ -81,7 +97,7 @@ class Adam:
         torch.cat(parts, out=g)
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)      # SUM: every loss already carries 1/global_batch
-        K.adam_step(p, g, m, v, self._lr_t(), self.beta_1, self.beta_2, self.epsilon)
+        K.adam_step(p, g, m, v, self._lr_arg(), self.beta_1, self.beta_2, self.epsilon)
 
     def _apply_flat_range(self, p: torch.Tensor, g: torch.Tensor, key_id: int) -> None:
         key = (key_id, 0, p.numel())
@@ -90,7 +106,7 @@ class Adam:
         _, m, v = self._slots[key]
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        K.adam_step(p, g, m, v, self._lr_t(), self.beta_1, self.beta_2, self.epsilon)
+        K.adam_step(p, g, m, v, self._lr_arg(), self.beta_1, self.beta_2, self.epsilon)
 
     # -- checkpointing ---------------------------------------------------------------------------
     def state_dict(self) -> dict:

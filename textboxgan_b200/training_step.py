@@ -74,12 +74,20 @@ class TrainingStep:
         self._g_names = generator.trainable_names(("synthesis/", "latent_encoder/"))
         self._ocr_names = generator.trainable_names(("word_encoder/", "synthesis/"))
         self._d_names = discriminator.trainable_names()
+        # CUDA-graph replay of the step (one graph per (do_r1_reg, do_pl_reg) variant — the
+        # reference's tf.function likewise retraces per Python bool, train.py:182-183)
+        self.use_cuda_graph = False
+        self._graphs = {}
+        self._static = None
 
     # ------------------------------------------------------------------------------------------
     def dist_train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
                         ocr_loss_weight: float, draws: Optional[dict] = None):
         """training_step.py:57-136.  Returns ``((reg_g, g, pl), (reg_d, d, r1), ocr)`` summed over
         replicas (every loss already carries 1/global_batch)."""
+        if self.use_cuda_graph and not draws:
+            return self._graphed_step(real_images, ocr_images, input_words, ocr_labels, do_r1_reg, do_pl_reg,
+                                      ocr_loss_weight)
         strategy = self.cfg.strategy
         if strategy is None:
             gen_losses, disc_losses, ocr_loss = self._train_step(real_images, ocr_images, input_words, ocr_labels,
@@ -91,6 +99,80 @@ class TrainingStep:
         red = strategy.reduce_many(list(gen_losses) + list(disc_losses) + [ocr_loss])
         mean_pl = red[2] if do_pl_reg else torch.zeros((), device=red[0].device)
         return (red[0], red[1], mean_pl), (red[3], red[4], red[5]), red[6]
+
+    # ------------------------------------------------------------------------------------------
+    def _eager_reduced_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg, do_pl_reg,
+                            ocr_loss_weight):
+        gen_losses, disc_losses, ocr_loss = self._train_step(real_images, ocr_images, input_words, ocr_labels,
+                                                             do_r1_reg, do_pl_reg, ocr_loss_weight, None)
+        vals = list(gen_losses) + list(disc_losses) + [ocr_loss]
+        strategy = self.cfg.strategy
+        if strategy is not None:
+            vals = strategy.reduce_many(vals)
+        return torch.stack([v.float().reshape(()) for v in vals])
+
+    def _graphed_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg, do_pl_reg,
+                      ocr_loss_weight):
+        """Replay the whole iteration (forward, three backward passes, gradient all-reduces, three
+        Adam updates) from a CUDA graph: inputs are copied into static buffers, the step-dependent
+        scalars (Adam bias correction, OCR loss weight) live in device memory."""
+        dev = self.generator.device
+        opts = (self.g_optimizer, self.ocr_optimizer, self.d_optimizer)
+        if self._static is None:
+            self._static = {
+                "real": torch.empty_like(real_images, device=dev),
+                "words": torch.empty_like(input_words, device=dev),
+                "labels": torch.empty_like(ocr_labels, device=dev),
+                "ocr_images": ocr_images.to(dev).clone() if torch.is_tensor(ocr_images)
+                else torch.zeros((), device=dev),
+                "ocr_w": torch.zeros((), device=dev),
+            }
+            for o in opts:
+                o.use_device_lr(dev)
+        st = self._static
+        st["real"].copy_(real_images, non_blocking=True)
+        st["words"].copy_(input_words, non_blocking=True)
+        st["labels"].copy_(ocr_labels, non_blocking=True)
+        if torch.is_tensor(ocr_images) and ocr_images.dim() > 0:
+            st["ocr_images"].copy_(ocr_images, non_blocking=True)
+        st["ocr_w"].fill_(float(ocr_loss_weight))
+        for o in opts:
+            o.refresh_device_lr()
+        key = (bool(do_r1_reg), bool(do_pl_reg))
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first use of this variant: run it eagerly once (lazy allocations, cuFuncSetAttribute,
+            # optimiser slots), then capture
+            out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0], key[1],
+                                           st["ocr_w"])
+            self._graphs[key] = {"graph": None, "out": out, "warm": 1}
+            res = out
+        elif entry["graph"] is None:
+            for o in opts:
+                o.defer_iteration = True
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0],
+                                               key[1], st["ocr_w"])
+            for o in opts:
+                o.defer_iteration = False
+            entry["graph"], entry["out"] = graph, out
+            graph.replay()
+            self._bump_iterations()
+            res = out
+        else:
+            entry["graph"].replay()
+            self._bump_iterations()
+            res = entry["out"]
+        r = res.unbind(0)
+        return (r[0], r[1], r[2]), (r[3], r[4], r[5]), r[6]
+
+    def _bump_iterations(self):
+        self.g_optimizer.iterations.value += 1
+        self.d_optimizer.iterations.value += 1
+        if self.aster_ocr is not None:
+            self.ocr_optimizer.iterations.value += 1
 
     # ------------------------------------------------------------------------------------------
     def _train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
