@@ -209,6 +209,7 @@ def run_ours(args) -> None:
     mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
     ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), cfg.g_opt["reg_interval"], cfg.d_opt["reg_interval"],
                       torch.zeros((), device=dev), cfg)
+    ts.use_cuda_graph = not args.eager      # whole iteration replayed from a CUDA graph
 
     gen = torch.Generator().manual_seed(4444 + rank)
     real_h, words_h, labels_h = OT.synthetic_batch(cfg, B, gen)
@@ -260,7 +261,8 @@ def run_ours(args) -> None:
         sampler.start()
     lib.load().tbg_reset_launch_count()
     ms_step, wall_step = timed(step_resident, args.steps)
-    launches = int(lib.load().tbg_launch_count())
+    # host-issued launches (EMA, eager mode) + launches replayed from the captured graph
+    launches = int(lib.load().tbg_launch_count()) + args.steps * ts.graph_launches(False, False)
     clocks = sampler.stop() if rank == 0 else None
     # the step time that counts is the slower of device time and host wall time per step
     ms_eff = max(ms_step, wall_step * 1e3)
@@ -275,6 +277,7 @@ def run_ours(args) -> None:
     roof = None
     if rank == 0:
         K.PROFILE = []
+        ts.use_cuda_graph = False                 # instrumented eager steps: events around every launch
         for _ in range(2):
             step_resident()
         torch.cuda.synchronize()
@@ -337,6 +340,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

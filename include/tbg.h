@@ -141,6 +141,30 @@ int tbg_lstm_seq_fwd(const float* xp, const void* w_packed, float* h_out, float*
 int tbg_lstm_seq_bwd(const float* g_h, const float* gates, const float* c_saved, const void* wT_packed, float* g_xp,
                      int D, int B, int T, int H, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused HBM-bound passes of the plain (first-order) step.  x/xs/g* activations are bf16
+ * [B, HW, C] (NHWC flattened), C % 8 == 0; per-sample vectors are fp32 [B, C].
+ *   tbg_modulate       xs = x * s[b,c]                                   (modulated_conv2d.py:96)
+ *   tbg_modulate_bwd   gx = gxs * s ;  gs[b,c] += sum_hw gxs*x           (gs must be zeroed)
+ *   tbg_bias_act_bwd   backward of out = act(y0*d + noise*ns + bias)*gain (+ residual)
+ *                      (modulated_conv2d.py:121, noise.py:21, bias_act.py:25-34, discriminator.py:82):
+ *                      gy0 = g_pre*d (bf16) and, when S1 != NULL, the zero-initialised sums
+ *                      S1 = sum_hw g_pre, Spre = sum_hw g_pre*pre, Snz = sum_hw g_pre*noise, from
+ *                      which d(bias), d(noise strength) and d(d) follow on [B, C] tensors.
+ *                      act: 0 linear, 1 leaky-relu(0.2), 2 relu.
+ *   tbg_torgb_fwd/bwd  y[p,j] = sum_c x[p,c]*ws[b,c,j] (+ bias[j]), j < 3   (to_rgb.py:28-33);
+ *                      bwd: gx = gy . ws^T (bf16), gws[b,c,j] += sum_p x*gy (gws must be zeroed)
+ * ------------------------------------------------------------------------------------------ */
+int tbg_modulate(const void* x, const float* s, void* xs, int B, int HW, int C, void* stream);
+int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, void* gx, float* gs, int B, int HW, int C,
+                     void* stream);
+int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise, const float* d,
+                     void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C, int act, float gain,
+                     void* stream);
+int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C, void* stream);
+int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

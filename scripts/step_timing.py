@@ -49,4 +49,7 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=35, max_name_column_width=60))
+os.makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/profile_table.txt", "w").write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=80, max_name_column_width=90))
+# attribute GPU time to the python call sites issuing the kernels (by module of the stack top)
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=70))

@@ -139,6 +139,53 @@ def emu_lstm_seq_bwd(g_h, gates, c, wT_packed):
     return out.to(g_h.dtype)
 
 
+def emu_modulate(x, s):
+    return (x.double() * s.double().reshape(s.shape[0], *([1] * (x.dim() - 2)), s.shape[1])).to(x.dtype)
+
+
+def emu_modulate_bwd(gxs, x, s):
+    sb = s.double().reshape(s.shape[0], *([1] * (x.dim() - 2)), s.shape[1])
+    gx = (gxs.double() * sb).to(x.dtype)
+    gs = (gxs.double() * x.double()).reshape(x.shape[0], -1, x.shape[-1]).sum(1).to(s.dtype)
+    return gx, gs
+
+
+def emu_bias_act_bwd(g_out, out, *, residual=None, noise=None, d=None, act=True, gain=1.0, want_sums=True):
+    B, C = out.shape[0], out.shape[-1]
+    o = out.double()
+    if residual is not None:
+        o = o - residual.double()
+    neg = 0.0 if int(act) == 2 else 0.2
+    slope = torch.where(o > 0, torch.ones_like(o), torch.full_like(o, neg)) if act else torch.ones_like(o)
+    gp = g_out.double() * gain * slope
+    pre = torch.where(slope > 0, o / (gain * slope.clamp_min(1e-30)), torch.zeros_like(o))
+    dd = d.double().reshape(B, *([1] * (out.dim() - 2)), C) if d is not None else 1.0
+    gy0 = (gp * dd).to(out.dtype)
+    if not want_sums:
+        return gy0, None, None, None
+    S1 = gp.reshape(B, -1, C).sum(1).float()
+    Spre = (gp * pre).reshape(B, -1, C).sum(1).float()
+    Snz = (gp * noise.double()[..., None]).reshape(B, -1, C).sum(1).float() if noise is not None \
+        else torch.zeros(B, C)
+    return gy0, S1, Spre, Snz
+
+
+def emu_torgb_fwd(x, ws, bias):
+    B = x.shape[0]
+    y = torch.bmm(x.double().reshape(B, -1, x.shape[-1]), ws.double()).reshape(*x.shape[:-1], 3)
+    if bias is not None:
+        y = y + bias.double()
+    return y.float()
+
+
+def emu_torgb_bwd(x, ws, gy):
+    B = x.shape[0]
+    g = gy.double().reshape(B, -1, 3)
+    gx = torch.bmm(g, ws.double().transpose(1, 2)).reshape(x.shape).to(x.dtype)
+    gws = torch.bmm(x.double().reshape(B, -1, x.shape[-1]).transpose(1, 2), g).float()
+    return gx, gws
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -147,7 +194,9 @@ def emulated_kernels(act_dtype=torch.float32):
     from textboxgan_b200 import layers as L
 
     saved = (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
-             K.lstm_seq_fwd, K.lstm_seq_bwd)
+             K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd, K.torgb_bwd)
+    K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
+    K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
     K.conv2d_igemm = emu_conv2d_igemm
     K.conv2d_wgrad = emu_conv2d_wgrad
     K.upfirdn2d = emu_upfirdn2d
@@ -161,4 +210,5 @@ def emulated_kernels(act_dtype=torch.float32):
         yield
     finally:
         (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
-         K.lstm_seq_fwd, K.lstm_seq_bwd) = saved
+         K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd,
+         K.torgb_bwd) = saved

@@ -192,6 +192,45 @@ def test_adam_and_ema_kernels():
         assert rel_err(p, src.cpu().double() + (before - src.cpu().double()) * 0.99) < 1e-6
 
 
+@pytest.mark.parametrize("B,H,W,C", [(4, 4, 16, 512), (3, 32, 128, 128), (5, 2, 8, 64)])
+def test_fused_pointwise_kernels_vs_emulated_semantics(B, H, W, C):
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(B * 1000 + C)
+    x = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    g = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    s = torch.randn(B, C, generator=gen) + 1.0
+    d = torch.rand(B, C, generator=gen) + 0.5
+    nz = torch.randn(B, H, W, generator=gen)
+    res = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    xd, gd, rd = (t.to(DEV).bfloat16() for t in (x, g, res))
+    xs = K.modulate(xd, s.to(DEV))
+    assert rel_err(xs.float(), emu.emu_modulate(x, s)) < 1e-2
+    gx, gs = K.modulate_bwd(gd, xd, s.to(DEV))
+    rgx, rgs = emu.emu_modulate_bwd(g, x, s)
+    assert rel_err(gx.float(), rgx) < 1e-2 and rel_err(gs, rgs) < 1e-4
+    for kw in (dict(noise=nz, d=d, act=True, gain=math.sqrt(2)), dict(residual=res, act=True, gain=1.0),
+               dict(act=False, gain=1.0)):
+        dkw = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()}
+        if "residual" in dkw:
+            dkw["residual"] = dkw["residual"].bfloat16()
+        out = K.bias_act_bwd(gd, xd, **dkw)
+        ref = emu.emu_bias_act_bwd(g, x, **kw)
+        assert rel_err(out[0].float(), ref[0]) < 1e-2
+        assert rel_err(out[1], ref[1]) < 1e-4 and rel_err(out[2], ref[2]) < 1e-4
+        if "noise" in kw:
+            assert rel_err(out[3], ref[3]) < 1e-4
+    ws = torch.randn(B, C, 3, generator=gen) / math.sqrt(C)
+    bias = torch.randn(3, generator=gen)
+    y = K.torgb_fwd(xd, ws.to(DEV), bias.to(DEV))
+    assert rel_err(y, emu.emu_torgb_fwd(x, ws, bias)) < 1e-5
+    gy = torch.randn(B, H, W, 3, generator=gen)
+    tgx, tgws = K.torgb_bwd(xd, ws.to(DEV), gy.to(DEV))
+    rtx, rtw = emu.emu_torgb_bwd(x, ws, gy)
+    assert rel_err(tgx.float(), rtx) < 1e-2 and rel_err(tgws, rtw) < 1e-4
+
+
 def _product(cfg, GP, DP, with_ocr=True):
     from textboxgan_b200.aster_inferer import AsterInferer
     from textboxgan_b200.discriminator import Discriminator

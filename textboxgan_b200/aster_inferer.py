@@ -106,10 +106,9 @@ class _FrozenConv(torch.autograd.Function):
     def backward(ctx, gy):
         layer = ctx.layer
         (out,) = ctx.saved_tensors
-        g = gy
+        g = gy.contiguous()
         if ctx.relu:
-            g = gy * (out > 0).to(gy.dtype)
-        g = g.contiguous()
+            g = K.bias_act_bwd(g, out, act=2, gain=1.0, want_sums=False)[0]
         K.PROFILE_TAG = (layer.geom.tag, layer.geom.algo_frac)
         gx = K.conv2d_igemm(g, layer.wmat_adj, **layer.geom.adjoint().kernel_kwargs())
         return gx, None, (g if ctx.has_res else None), None

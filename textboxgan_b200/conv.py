@@ -152,16 +152,36 @@ def _tables_on(device, kind, k, pad):
     return _on_device(("adj", kind, k, pad), device, lambda: _axis_adjoint_map(kind, k, pad))
 
 
+def _axis_relayout(w: torch.Tensor, dim: int, ax: Axis) -> torch.Tensor:
+    """Re-index the combined (phase, tap) axis ``dim`` of ``w`` for the adjoint of ``ax`` using only
+    pad / reshape / flip / transpose (cheap, differentiable; equals the index tables of
+    ``_axis_adjoint_map``)."""
+    shp = list(w.shape)
+    if ax.kind == "s1":                                   # W'[u] = W[k-1-u]
+        return w.flip(dim)
+    if ax.kind == "up":                                   # [phi, t] -> u = 2(T-1-t) + phi
+        T = ax.k
+        v = w.reshape(shp[:dim] + [2, T] + shp[dim + 1:]).flip(dim + 1).transpose(dim, dim + 1)
+        return v.reshape(shp[:dim] + [2 * T] + shp[dim + 1:])
+    # s2(k, pad) -> up(3, 1): u' = u + (2 - pad) = phi + 4 - 2t on a zero-padded 6-tap kernel
+    front = 2 - ax.pad
+    back = 6 - ax.k - front
+    assert front >= 0 and back >= 0, "s2 adjoint needs k <= 6 and pad <= 2"
+    if front or back:
+        pads = [0, 0] * (w.dim() - 1 - dim) + [front, back]
+        w = torch.nn.functional.pad(w, pads)
+    v = w.reshape(shp[:dim] + [3, 2] + shp[dim + 1:]).flip(dim).transpose(dim, dim + 1)   # [phi, t]
+    return v.reshape(shp[:dim] + [6] + shp[dim + 1:])
+
+
 def relayout_for_adjoint(wmat: torch.Tensor, g: ConvGeom) -> torch.Tensor:
     """[n_total, K] weights of ``g`` -> [n_total', K'] weights of ``g.adjoint()``."""
     ph, pw = g.ah.phases, g.aw.phases
     w6 = wmat.reshape(ph, pw, g.cout, g.ah.k, g.aw.k, g.cin)
     # bring (phase_h, tap_h) and (phase_w, tap_w) together: [O, I, ph*kh, pw*kw]
     w4 = w6.permute(2, 5, 0, 3, 1, 4).reshape(g.cout, g.cin, ph * g.ah.k, pw * g.aw.k)
-    ih, mh = _tables_on(wmat.device, g.ah.kind, g.ah.k, g.ah.pad)
-    iw, mw = _tables_on(wmat.device, g.aw.kind, g.aw.k, g.aw.pad)
-    w4 = w4.index_select(2, ih) * mh.to(w4.dtype)[None, None, :, None]
-    w4 = w4.index_select(3, iw) * mw.to(w4.dtype)[None, None, None, :]
+    w4 = _axis_relayout(w4, 2, g.ah)
+    w4 = _axis_relayout(w4, 3, g.aw)
     a = g.adjoint()
     # -> [ph', pw', I(as out), kh', kw', O(as in)]
     w6a = w4.reshape(g.cout, g.cin, a.ah.phases, a.ah.k, a.aw.phases, a.aw.k).permute(2, 4, 1, 3, 5, 0)

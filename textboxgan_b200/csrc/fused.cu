@@ -1,0 +1,419 @@
+// Fused HBM-bound passes around the tensor-core convolutions of the plain (first-order) training
+// step.  Each replaces a chain of element-wise / reduction ops of the reference graph:
+//
+//   modulate          xs = x * s[b,c]                              (modulated_conv2d.py:96)
+//   modulate_bwd      gx = gxs * s ; gs[b,c] = sum_hw gxs * x       (its gradient)
+//   bias_act_bwd      gradient of  out = act(y0*d + noise*ns + bias)*gain (+ residual)
+//                     (modulated_conv2d.py:121, noise.py:21, bias_act.py:25-34, discriminator.py:82):
+//                     gy0 = g_pre*d and the three per-(b,c) sums from which the gradients of
+//                     d, bias and the noise strength follow
+//   torgb_fwd / bwd   y[p,j] = sum_c x[p,c]*ws[b,c,j] (+ bias)      (to_rgb.py:28-33, N = 3 — HBM-bound)
+//
+// Layout: NHWC bf16 activations, 8 channels (16 bytes) per thread, fp32 math.  Reductions over
+// pixels are done per CTA in registers and combined with fp32 atomics into [B, C] buffers.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tbg {
+
+static int sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct bf16x8 {
+  uint4 v;
+};
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// xs = x * s[b, c]
+// ---------------------------------------------------------------------------------------------
+__global__ void modulate_kernel(const uint4* __restrict__ x, const float* __restrict__ s, uint4* __restrict__ xs,
+                                long long n_vec, int hw, int c8) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const int cv = static_cast<int>(i % c8);
+    const long long pix = i / c8;
+    const int b = static_cast<int>(pix / hw);
+    float f[8];
+    unpack8(__ldg(x + i), f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8 + 4));
+    f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+    f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+    xs[i] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gx = gxs * s ; gs[b,c] += sum_{pixels of the CTA's chunk} gxs * x
+// grid = (chunks, B); block = c8 * rows threads: thread (r, cv) walks pixels r, r+rows, ...
+// ---------------------------------------------------------------------------------------------
+__global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* __restrict__ x,
+                                    const float* __restrict__ s, uint4* __restrict__ gx, float* __restrict__ gs,
+                                    int hw, int c8, int pix_per_cta) {
+  extern __shared__ float red[];  // [rows][c8*8]
+  const int b = blockIdx.y;
+  const int rows = blockDim.x / c8;
+  const int cv = threadIdx.x % c8;
+  const int r = threadIdx.x / c8;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  float sv[8], acc[8];
+  {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8 + 4));
+    sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (r < rows) {
+    for (int p = p0 + r; p < p1; p += rows) {
+      const long long idx = (static_cast<long long>(b) * hw + p) * c8 + cv;
+      float g[8], xv[8];
+      unpack8(__ldg(gxs + idx), g);
+      unpack8(__ldg(x + idx), xv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] = fmaf(g[i], xv[i], acc[i]);
+        g[i] *= sv[i];
+      }
+      gx[idx] = pack8(g);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[(r * c8 + cv) * 8 + i] = acc[i];
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[(rr * c8 + cv) * 8 + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(gs + (static_cast<long long>(b) * c8 + cv) * 8 + i, acc[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of  out = act(y0*d + nz*ns + bias)*gain (+ res):
+//   slope = act ? (out - res > 0 ? 1 : 0.2) : 1 ;  g_pre = g_out*gain*slope ;  gy0 = g_pre*d
+//   S1[b,c] += g_pre ; Spre[b,c] += g_pre*pre ; Snz[b,c] += g_pre*nz      (pre = (out-res)/(gain*slope))
+// ---------------------------------------------------------------------------------------------
+__global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ out,
+                                    const uint4* __restrict__ res, const float* __restrict__ noise,
+                                    const float* __restrict__ d, uint4* __restrict__ gy0, float* __restrict__ S1,
+                                    float* __restrict__ Spre, float* __restrict__ Snz, int hw, int c8,
+                                    int pix_per_cta, int act, float gain, int want_sums) {
+  extern __shared__ float red[];  // [rows][c8*8][3]
+  const int b = blockIdx.y;
+  const int rows = blockDim.x / c8;
+  const int cv = threadIdx.x % c8;
+  const int r = threadIdx.x / c8;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  float dv[8], a1[8], a2[8], a3[8];
+  if (d != nullptr) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(d + (static_cast<long long>(b) * c8 + cv) * 8));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(d + (static_cast<long long>(b) * c8 + cv) * 8 + 4));
+    dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dv[i] = 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a1[i] = a2[i] = a3[i] = 0.f;
+  const float inv_gain = 1.f / gain;
+  if (r < rows) {
+    for (int p = p0 + r; p < p1; p += rows) {
+      const long long pix = static_cast<long long>(b) * hw + p;
+      const long long idx = pix * c8 + cv;
+      float g[8], o[8];
+      unpack8(__ldg(g_out + idx), g);
+      unpack8(__ldg(out + idx), o);
+      if (res != nullptr) {
+        float rv[8];
+        unpack8(__ldg(res + idx), rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] -= rv[i];
+      }
+      const float nz = (noise != nullptr) ? __ldg(noise + pix) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float neg_slope = (act == 2) ? 0.f : 0.2f;       // 1: leaky-relu(0.2), 2: relu
+        const float slope = (act && !(o[i] > 0.f)) ? neg_slope : 1.f;
+        const float gp = g[i] * gain * slope;
+        const float pre = (slope > 0.f) ? o[i] * inv_gain / slope : 0.f;
+        a1[i] += gp;
+        a2[i] = fmaf(gp, pre, a2[i]);
+        a3[i] = fmaf(gp, nz, a3[i]);
+        g[i] = gp * dv[i];
+      }
+      gy0[idx] = pack8(g);
+    }
+  }
+  if (!want_sums) return;
+  const int cw = c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[(r * cw + cv * 8 + i) * 3 + 0] = a1[i];
+    red[(r * cw + cv * 8 + i) * 3 + 1] = a2[i];
+    red[(r * cw + cv * 8 + i) * 3 + 2] = a3[i];
+  }
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a1[i] += red[(rr * cw + cv * 8 + i) * 3 + 0];
+        a2[i] += red[(rr * cw + cv * 8 + i) * 3 + 1];
+        a3[i] += red[(rr * cw + cv * 8 + i) * 3 + 2];
+      }
+    const long long o0 = (static_cast<long long>(b) * c8 + cv) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(S1 + o0 + i, a1[i]);
+      atomicAdd(Spre + o0 + i, a2[i]);
+      if (noise != nullptr) atomicAdd(Snz + o0 + i, a3[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ToRGB: y[p, j] = sum_c x[p,c] * ws[b,c,j] (+ bias[j]); one warp per pixel, lanes over channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void torgb_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws, const float* __restrict__ bias,
+                                 float* __restrict__ y, int B, int hw, int c8) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n_pix = static_cast<long long>(B) * hw;
+  for (long long pix = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pix < n_pix;
+       pix += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const int b = static_cast<int>(pix / hw);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int cv = lane; cv < c8; cv += 32) {
+      float f[8];
+      unpack8(__ldg(x + pix * c8 + cv), f);
+      const float* w = ws + (static_cast<long long>(b) * c8 + cv) * 24;  // [c][3]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a0 = fmaf(f[i], __ldg(w + i * 3 + 0), a0);
+        a1 = fmaf(f[i], __ldg(w + i * 3 + 1), a1);
+        a2 = fmaf(f[i], __ldg(w + i * 3 + 2), a2);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      float* yo = y + pix * 3;
+      yo[0] = a0 + (bias ? __ldg(bias + 0) : 0.f);
+      yo[1] = a1 + (bias ? __ldg(bias + 1) : 0.f);
+      yo[2] = a2 + (bias ? __ldg(bias + 2) : 0.f);
+    }
+  }
+}
+
+// gx[p,c] = sum_j gy[p,j]*ws[b,c,j] ; gws[b,c,j] += sum_p x[p,c]*gy[p,j]
+__global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws, const float* __restrict__ gy,
+                                 uint4* __restrict__ gx, float* __restrict__ gws, int hw, int c8, int pix_per_cta) {
+  extern __shared__ float red[];  // [rows][c8*8][3]
+  const int b = blockIdx.y;
+  const int rows = blockDim.x / c8;
+  const int cv = threadIdx.x % c8;
+  const int r = threadIdx.x / c8;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  float w[8][3], acc[8][3];
+  {
+    const float* wp = ws + (static_cast<long long>(b) * c8 + cv) * 24;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        w[i][j] = __ldg(wp + i * 3 + j);
+        acc[i][j] = 0.f;
+      }
+  }
+  if (r < rows) {
+    for (int p = p0 + r; p < p1; p += rows) {
+      const long long pix = static_cast<long long>(b) * hw + p;
+      const float g0 = __ldg(gy + pix * 3 + 0), g1 = __ldg(gy + pix * 3 + 1), g2 = __ldg(gy + pix * 3 + 2);
+      float xv[8], o[8];
+      unpack8(__ldg(x + pix * c8 + cv), xv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = g0 * w[i][0] + g1 * w[i][1] + g2 * w[i][2];
+        acc[i][0] = fmaf(xv[i], g0, acc[i][0]);
+        acc[i][1] = fmaf(xv[i], g1, acc[i][1]);
+        acc[i][2] = fmaf(xv[i], g2, acc[i][2]);
+      }
+      gx[pix * c8 + cv] = pack8(o);
+    }
+  }
+  const int cw = c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) red[(r * cw + cv * 8 + i) * 3 + j] = acc[i][j];
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] += red[(rr * cw + cv * 8 + i) * 3 + j];
+    float* o = gws + (static_cast<long long>(b) * c8 + cv) * 24;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) atomicAdd(o + i * 3 + j, acc[i][j]);
+  }
+}
+
+// launch geometry for the (chunks, B) reduction kernels
+struct RedGeom {
+  int threads, rows, pix_per_cta, chunks;
+  size_t smem;
+};
+static RedGeom red_geom(int B, int hw, int c8, int per_elem_floats) {
+  RedGeom g;
+  int rows = 256 / c8;
+  if (rows < 1) rows = 1;
+  if (rows > hw) rows = hw;
+  g.rows = rows;
+  g.threads = rows * c8;
+  // aim at ~4 CTAs per SM overall
+  int chunks = (4 * sms() + B - 1) / B;
+  int max_chunks = (hw + rows - 1) / rows;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  g.pix_per_cta = (hw + chunks - 1) / chunks;
+  g.chunks = (hw + g.pix_per_cta - 1) / g.pix_per_cta;
+  g.smem = static_cast<size_t>(rows) * c8 * 8 * per_elem_floats * sizeof(float);
+  return g;
+}
+
+}  // namespace tbg
+
+using namespace tbg;
+
+#define TBG_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int tbg_modulate(const void* x, const float* s, void* xs, int B, int HW, int C, void* stream_v) {
+  TBG_CHECK_ARG(x && s && xs, "tbg_modulate: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && HW >= 1, "tbg_modulate: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(x) && TBG_ALIGNED16(s) && TBG_ALIGNED16(xs), "tbg_modulate: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n_vec = static_cast<long long>(B) * HW * (C / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = static_cast<long long>(sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  modulate_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), s,
+                                                                reinterpret_cast<uint4*>(xs), n_vec, HW, C / 8);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, void* gx, float* gs, int B, int HW, int C,
+                                void* stream_v) {
+  TBG_CHECK_ARG(gxs && x && s && gx && gs, "tbg_modulate_bwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_modulate_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(gxs) && TBG_ALIGNED16(x) && TBG_ALIGNED16(s) && TBG_ALIGNED16(gx),
+                "tbg_modulate_bwd: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, C / 8, 1);
+  modulate_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
+      reinterpret_cast<const uint4*>(gxs), reinterpret_cast<const uint4*>(x), s, reinterpret_cast<uint4*>(gx), gs, HW,
+      C / 8, g.pix_per_cta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise,
+                                const float* d, void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C,
+                                int act, float gain, void* stream_v) {
+  TBG_CHECK_ARG(g_out && out && gy0, "tbg_bias_act_bwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_bias_act_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(!noise || Snz, "tbg_bias_act_bwd: noise without Snz");
+  TBG_CHECK_ARG((S1 == nullptr) == (Spre == nullptr), "tbg_bias_act_bwd: S1 and Spre go together");
+  TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out) && TBG_ALIGNED16(residual) && TBG_ALIGNED16(d) && TBG_ALIGNED16(gy0),
+                "tbg_bias_act_bwd: 16-byte alignment required");
+  TBG_CHECK_ARG(gain > 0.f, "tbg_bias_act_bwd: gain must be positive");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, C / 8, 3);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bias_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  bias_act_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
+      reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), reinterpret_cast<const uint4*>(residual),
+      noise, d, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, HW, C / 8, g.pix_per_cta, act, gain, S1 != nullptr);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C,
+                             void* stream_v) {
+  TBG_CHECK_ARG(x && ws && y, "tbg_torgb_fwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && HW >= 1, "tbg_torgb_fwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(x), "tbg_torgb_fwd: x must be 16-byte aligned");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n_pix = static_cast<long long>(B) * HW;
+  long long blocks = (n_pix + 7) / 8;
+  const long long cap = static_cast<long long>(sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  torgb_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), ws, bias, y, B, HW, C / 8);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
+                             void* stream_v) {
+  TBG_CHECK_ARG(x && ws && gy && gx && gws, "tbg_torgb_bwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_torgb_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(x) && TBG_ALIGNED16(gx), "tbg_torgb_bwd: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, C / 8, 3);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  torgb_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(reinterpret_cast<const uint4*>(x), ws, gy,
+                                                                      reinterpret_cast<uint4*>(gx), gws, HW, C / 8,
+                                                                      g.pix_per_cta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}

@@ -16,21 +16,30 @@ static constexpr int kH = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
+static constexpr int kQ = 4;            // the 256-long dot products are split over 4 thread groups
+static constexpr int kThreads = kH * kQ;
+
 // w_packed: [D][H (k)][H (j)][4 gates] bf16  (gate order i, f, g, o)
+// 1024 threads: thread (q, j) accumulates k in [64q, 64q+64) for hidden unit j — four times the
+// loads in flight per SM of a 256-thread version, which is what bounds this latency-bound stream.
 template <int BS>
-__global__ void __launch_bounds__(kH) lstm_fwd_kernel(const float* __restrict__ xp, const __nv_bfloat16* __restrict__ w_packed,
-                                                      float* __restrict__ h_out, float* __restrict__ gates_out,
-                                                      float* __restrict__ c_out, int B, int T, int groups) {
+__global__ void __launch_bounds__(kThreads) lstm_fwd_kernel(const float* __restrict__ xp,
+                                                            const __nv_bfloat16* __restrict__ w_packed,
+                                                            float* __restrict__ h_out, float* __restrict__ gates_out,
+                                                            float* __restrict__ c_out, int B, int T, int groups) {
   __shared__ float h_s[BS][kH];
-  const int j = threadIdx.x;
+  __shared__ float part[kQ - 1][BS][4][kH];
+  const int j = threadIdx.x & (kH - 1);
+  const int q = threadIdx.x >> 8;
   const int d = blockIdx.x / groups;
   const int b0 = (blockIdx.x % groups) * BS;
   const uint2* w = reinterpret_cast<const uint2*>(w_packed) + static_cast<size_t>(d) * kH * kH;
   float c[BS];
 #pragma unroll
-  for (int s = 0; s < BS; ++s) {
-    c[s] = 0.f;
-    h_s[s][j] = 0.f;
+  for (int s = 0; s < BS; ++s) c[s] = 0.f;
+  if (q == 0) {
+#pragma unroll
+    for (int s = 0; s < BS; ++s) h_s[s][j] = 0.f;
   }
   __syncthreads();
   for (int t = 0; t < T; ++t) {
@@ -38,28 +47,28 @@ __global__ void __launch_bounds__(kH) lstm_fwd_kernel(const float* __restrict__ 
 #pragma unroll
     for (int s = 0; s < BS; ++s) {
       const int b = b0 + s;
-      if (b < B) {
+      if (q == 0 && b < B) {
         const float* xr = xp + ((static_cast<size_t>(d) * B + b) * T + t) * (4 * kH);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) acc[s][g] = xr[g * kH + j];
+        for (int g = 0; g < 4; ++g) acc[s][g] = __ldg(xr + g * kH + j);
       } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[s][g] = 0.f;
       }
     }
-    // 16 independent 8-byte loads in flight per thread (x2 by unrolling) keep the L2 stream busy
-#pragma unroll 2
-    for (int k0 = 0; k0 < kH; k0 += 16) {
+    const int kbeg = q * (kH / kQ);
+#pragma unroll
+    for (int k0 = 0; k0 < kH / kQ; k0 += 16) {
       uint2 wv[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + static_cast<size_t>(k0 + u) * kH + j);
+      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + static_cast<size_t>(kbeg + k0 + u) * kH + j);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u].x));
         const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u].y));
 #pragma unroll
         for (int s = 0; s < BS; ++s) {
-          const float hk = h_s[s][k0 + u];
+          const float hk = h_s[s][kbeg + k0 + u];
           acc[s][0] = fmaf(hk, w01.x, acc[s][0]);
           acc[s][1] = fmaf(hk, w01.y, acc[s][1]);
           acc[s][2] = fmaf(hk, w23.x, acc[s][2]);
@@ -67,26 +76,38 @@ __global__ void __launch_bounds__(kH) lstm_fwd_kernel(const float* __restrict__ 
         }
       }
     }
-    __syncthreads();  // every thread has finished reading h_s of step t-1
+    if (q > 0) {
 #pragma unroll
-    for (int s = 0; s < BS; ++s) {
-      const int b = b0 + s;
-      const float ig = sigmoidf_(acc[s][0]);
-      const float fg = sigmoidf_(acc[s][1]);
-      const float gg = tanhf(acc[s][2]);
-      const float og = sigmoidf_(acc[s][3]);
-      c[s] = fg * c[s] + ig * gg;
-      const float h = og * tanhf(c[s]);
-      h_s[s][j] = h;
-      if (b < B) {
-        const size_t row = (static_cast<size_t>(d) * B + b) * T + t;
-        float* gr = gates_out + row * (4 * kH);
-        gr[j] = ig;
-        gr[kH + j] = fg;
-        gr[2 * kH + j] = gg;
-        gr[3 * kH + j] = og;
-        c_out[row * kH + j] = c[s];
-        h_out[row * kH + j] = h;
+      for (int s = 0; s < BS; ++s)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) part[q - 1][s][g][j] = acc[s][g];
+    }
+    __syncthreads();  // partial sums visible; every thread has finished reading h_s of step t-1
+    if (q == 0) {
+#pragma unroll
+      for (int s = 0; s < BS; ++s) {
+        const int b = b0 + s;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int qq = 0; qq < kQ - 1; ++qq) acc[s][g] += part[qq][s][g][j];
+        const float ig = sigmoidf_(acc[s][0]);
+        const float fg = sigmoidf_(acc[s][1]);
+        const float gg = tanhf(acc[s][2]);
+        const float og = sigmoidf_(acc[s][3]);
+        c[s] = fg * c[s] + ig * gg;
+        const float h = og * tanhf(c[s]);
+        h_s[s][j] = h;
+        if (b < B) {
+          const size_t row = (static_cast<size_t>(d) * B + b) * T + t;
+          float* gr = gates_out + row * (4 * kH);
+          gr[j] = ig;
+          gr[kH + j] = fg;
+          gr[2 * kH + j] = gg;
+          gr[3 * kH + j] = og;
+          c_out[row * kH + j] = c[s];
+          h_out[row * kH + j] = h;
+        }
       }
     }
     __syncthreads();
@@ -95,12 +116,14 @@ __global__ void __launch_bounds__(kH) lstm_fwd_kernel(const float* __restrict__ 
 
 // wT_packed: [D][H (j)][H (k)][4 gates] bf16 — the same weights indexed for dh_prev[k] = sum_j,g
 template <int BS>
-__global__ void __launch_bounds__(kH) lstm_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ gates,
-                                                      const float* __restrict__ c_saved,
-                                                      const __nv_bfloat16* __restrict__ wT_packed,
-                                                      float* __restrict__ g_xp, int B, int T, int groups) {
+__global__ void __launch_bounds__(kThreads) lstm_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ gates,
+                                                            const float* __restrict__ c_saved,
+                                                            const __nv_bfloat16* __restrict__ wT_packed,
+                                                            float* __restrict__ g_xp, int B, int T, int groups) {
   __shared__ float dg_s[BS][4][kH];
-  const int j = threadIdx.x;
+  __shared__ float part[kQ - 1][BS][kH];
+  const int j = threadIdx.x & (kH - 1);
+  const int q = threadIdx.x >> 8;
   const int d = blockIdx.x / groups;
   const int b0 = (blockIdx.x % groups) * BS;
   const uint2* w = reinterpret_cast<const uint2*>(wT_packed) + static_cast<size_t>(d) * kH * kH;
@@ -108,60 +131,75 @@ __global__ void __launch_bounds__(kH) lstm_bwd_kernel(const float* __restrict__ 
 #pragma unroll
   for (int s = 0; s < BS; ++s) dh_rec[s] = dc_next[s] = 0.f;
   for (int t = T - 1; t >= 0; --t) {
+    if (q == 0) {
 #pragma unroll
-    for (int s = 0; s < BS; ++s) {
-      const int b = b0 + s;
-      float di = 0.f, df = 0.f, dgg = 0.f, dog = 0.f;
-      if (b < B) {
-        const size_t row = (static_cast<size_t>(d) * B + b) * T + t;
-        const float* gr = gates + row * (4 * kH);
-        const float ig = gr[j], fg = gr[kH + j], gg = gr[2 * kH + j], og = gr[3 * kH + j];
-        const float cc = c_saved[row * kH + j];
-        const float cp = (t > 0) ? c_saved[(row - 1) * kH + j] : 0.f;
-        const float dh = g_h[row * kH + j] + dh_rec[s];
-        const float tc = tanhf(cc);
-        dog = dh * tc * og * (1.f - og);
-        const float dc = dh * og * (1.f - tc * tc) + dc_next[s];
-        di = dc * gg * ig * (1.f - ig);
-        df = dc * cp * fg * (1.f - fg);
-        dgg = dc * ig * (1.f - gg * gg);
-        dc_next[s] = dc * fg;
-        float* go = g_xp + row * (4 * kH);
-        go[j] = di;
-        go[kH + j] = df;
-        go[2 * kH + j] = dgg;
-        go[3 * kH + j] = dog;
+      for (int s = 0; s < BS; ++s) {
+        const int b = b0 + s;
+        float di = 0.f, df = 0.f, dgg = 0.f, dog = 0.f;
+        if (b < B) {
+          const size_t row = (static_cast<size_t>(d) * B + b) * T + t;
+          const float* gr = gates + row * (4 * kH);
+          const float ig = __ldg(gr + j), fg = __ldg(gr + kH + j), gg = __ldg(gr + 2 * kH + j), og = __ldg(gr + 3 * kH + j);
+          const float cc = __ldg(c_saved + row * kH + j);
+          const float cp = (t > 0) ? __ldg(c_saved + (row - 1) * kH + j) : 0.f;
+          const float dh = __ldg(g_h + row * kH + j) + dh_rec[s];
+          const float tc = tanhf(cc);
+          dog = dh * tc * og * (1.f - og);
+          const float dc = dh * og * (1.f - tc * tc) + dc_next[s];
+          di = dc * gg * ig * (1.f - ig);
+          df = dc * cp * fg * (1.f - fg);
+          dgg = dc * ig * (1.f - gg * gg);
+          dc_next[s] = dc * fg;
+          float* go = g_xp + row * (4 * kH);
+          go[j] = di;
+          go[kH + j] = df;
+          go[2 * kH + j] = dgg;
+          go[3 * kH + j] = dog;
+        }
+        dg_s[s][0][j] = di;
+        dg_s[s][1][j] = df;
+        dg_s[s][2][j] = dgg;
+        dg_s[s][3][j] = dog;
       }
-      dg_s[s][0][j] = di;
-      dg_s[s][1][j] = df;
-      dg_s[s][2][j] = dgg;
-      dg_s[s][3][j] = dog;
     }
     __syncthreads();
     float acc[BS];
 #pragma unroll
     for (int s = 0; s < BS; ++s) acc[s] = 0.f;
-#pragma unroll 2
-    for (int j0 = 0; j0 < kH; j0 += 16) {
+    const int jbeg = q * (kH / kQ);
+#pragma unroll
+    for (int j0 = 0; j0 < kH / kQ; j0 += 16) {
       uint2 wv[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + static_cast<size_t>(j0 + u) * kH + j);  // thread index plays k
+      for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + static_cast<size_t>(jbeg + j0 + u) * kH + j);  // thread index plays k
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u].x));
         const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[u].y));
 #pragma unroll
         for (int s = 0; s < BS; ++s) {
-          acc[s] = fmaf(dg_s[s][0][j0 + u], w01.x, acc[s]);
-          acc[s] = fmaf(dg_s[s][1][j0 + u], w01.y, acc[s]);
-          acc[s] = fmaf(dg_s[s][2][j0 + u], w23.x, acc[s]);
-          acc[s] = fmaf(dg_s[s][3][j0 + u], w23.y, acc[s]);
+          acc[s] = fmaf(dg_s[s][0][jbeg + j0 + u], w01.x, acc[s]);
+          acc[s] = fmaf(dg_s[s][1][jbeg + j0 + u], w01.y, acc[s]);
+          acc[s] = fmaf(dg_s[s][2][jbeg + j0 + u], w23.x, acc[s]);
+          acc[s] = fmaf(dg_s[s][3][jbeg + j0 + u], w23.y, acc[s]);
         }
       }
     }
+    if (q > 0) {
 #pragma unroll
-    for (int s = 0; s < BS; ++s) dh_rec[s] = acc[s];
+      for (int s = 0; s < BS; ++s) part[q - 1][s][j] = acc[s];
+    }
     __syncthreads();
+    if (q == 0) {
+#pragma unroll
+      for (int s = 0; s < BS; ++s) {
+        float v = acc[s];
+#pragma unroll
+        for (int qq = 0; qq < kQ - 1; ++qq) v += part[qq][s][j];
+        dh_rec[s] = v;
+      }
+    }
+    // (the next iteration's first __syncthreads orders the reads of `part` / `dg_s` before their reuse)
   }
 }
 
@@ -177,10 +215,10 @@ extern "C" int tbg_lstm_seq_fwd(const float* xp, const void* w_packed, float* h_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (B >= 16) {
     const int groups = (B + 1) / 2;
-    lstm_fwd_kernel<2><<<D * groups, kH, 0, stream>>>(xp, reinterpret_cast<const __nv_bfloat16*>(w_packed), h_out,
+    lstm_fwd_kernel<2><<<D * groups, kThreads, 0, stream>>>(xp, reinterpret_cast<const __nv_bfloat16*>(w_packed), h_out,
                                                       gates_out, c_out, B, T, groups);
   } else {
-    lstm_fwd_kernel<1><<<D * B, kH, 0, stream>>>(xp, reinterpret_cast<const __nv_bfloat16*>(w_packed), h_out,
+    lstm_fwd_kernel<1><<<D * B, kThreads, 0, stream>>>(xp, reinterpret_cast<const __nv_bfloat16*>(w_packed), h_out,
                                                  gates_out, c_out, B, T, B);
   }
   count_launch();
@@ -196,10 +234,10 @@ extern "C" int tbg_lstm_seq_bwd(const float* g_h, const float* gates, const floa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (B >= 16) {
     const int groups = (B + 1) / 2;
-    lstm_bwd_kernel<2><<<D * groups, kH, 0, stream>>>(g_h, gates, c_saved, reinterpret_cast<const __nv_bfloat16*>(wT_packed),
+    lstm_bwd_kernel<2><<<D * groups, kThreads, 0, stream>>>(g_h, gates, c_saved, reinterpret_cast<const __nv_bfloat16*>(wT_packed),
                                                       g_xp, B, T, groups);
   } else {
-    lstm_bwd_kernel<1><<<D * B, kH, 0, stream>>>(g_h, gates, c_saved, reinterpret_cast<const __nv_bfloat16*>(wT_packed),
+    lstm_bwd_kernel<1><<<D * B, kThreads, 0, stream>>>(g_h, gates, c_saved, reinterpret_cast<const __nv_bfloat16*>(wT_packed),
                                                  g_xp, B, T, B);
   }
   count_launch();

@@ -60,12 +60,12 @@ class Discriminator(Model):
 
     # ------------------------------------------------------------------------------------------
     def _conv(self, x, name: str, *, bias: Optional[str], down: bool, reduce_height: bool = False,
-              residual: Optional[torch.Tensor] = None):
+              residual: Optional[torch.Tensor] = None, scale: float = 1.0):
         """Conv2D.call (conv.py:51-73) + BiasAct (bias_act.py:25-34) [+ residual merge :82]."""
         P = self.params
         w_raw = P[name]
         k, _, I, O = w_raw.shape
-        w = L.runtime_coef(w_raw.shape) * w_raw
+        w = (L.runtime_coef(w_raw.shape) * scale) * w_raw
         B, H, W_, _ = x.shape
         if down:
             geom = C.down_geom(H, W_, I, O, k, reduce_height, tag="dconv")
@@ -79,6 +79,14 @@ class Discriminator(Model):
                        residual=residual.contiguous() if residual is not None else None,
                        res_scale=INV_SQRT2 if residual is not None else 1.0)
             return C.conv(x, wmat, geom, epi)
+        if L.use_fused():
+            from .fused import ConvAct
+
+            if residual is not None:
+                # (lrelu(v)*sqrt2 + skip)/sqrt2 == lrelu(v) + skip/sqrt2: the caller pre-scales the
+                # (linear) skip branch, so the merge is a plain residual add in the epilogue
+                return ConvAct.apply(x, wmat, P[bias], residual, geom, 1.0)
+            return ConvAct.apply(x, wmat, P[bias] if bias else None, None, geom, L.SQRT2)
         y = C.conv(x, wmat, geom)
         if bias is None and residual is None:
             return y
@@ -102,7 +110,8 @@ class Discriminator(Model):
         for (h, w), (nh, nw) in zip(res[:-1], res[1:]):
             pb = f"{h}x{w}"
             rh = h != nh
-            skip = self._conv(x, pb + "/skip/w", bias=None, down=True, reduce_height=rh)
+            skip = self._conv(x, pb + "/skip/w", bias=None, down=True, reduce_height=rh,
+                              scale=INV_SQRT2 if L.use_fused() else 1.0)
             x = self._conv(x, pb + "/conv_0/w", bias=pb + "/bias_0/b", down=False)
             x = self._conv(x, pb + "/conv_1/w", bias=pb + "/bias_1/b", down=True, reduce_height=rh, residual=skip)
         rf = res[-1]

@@ -1,0 +1,115 @@
+"""First-order fused layer Functions of the plain training step.
+
+Each Function is one reference layer group executed as a handful of kernels, with a hand-written
+backward (no autograd tape through the element-wise terms):
+
+* :class:`ModConvAct` — ModulatedConv2D + Noise + BiasAct (modulated_conv2d.py:66-122, noise.py:12-22,
+  bias_act.py:25-34): ``modulate`` -> tcgen05 conv with the demod/noise/bias/lrelu epilogue; backward
+  = ``bias_act_bwd`` -> input-gradient conv + weight-gradient conv -> ``modulate_bwd``.
+* :class:`ConvAct` — Conv2D + BiasAct (+ residual merge) of the discriminator (conv.py:51-73,
+  discriminator.py:68-84).
+* :class:`ToRGB` — the N = 3 modulated 1x1 convolution (to_rgb.py:28-33).
+
+They are only differentiable once.  The path-length and R1 regularisers (double backward,
+training_step.py:323-333, 363-368) run the same layers through the composable primitives of
+:mod:`textboxgan_b200.conv` inside ``layers.double_backward()``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+from .conv import ConvGeom, relayout_for_adjoint
+
+
+def _act_dtype():
+    from . import layers as L
+
+    return L.ACT_DTYPE
+
+
+class ModConvAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, d, wmat, noise, ns, bias, geom: ConvGeom, gain: float):
+        act = _act_dtype()
+        x = x.contiguous()
+        s = s.contiguous()
+        d = d.contiguous()
+        xs = K.modulate(x, s)
+        K.PROFILE_TAG = (geom.tag, geom.algo_frac)
+        out = K.conv2d_igemm(xs, wmat.to(act).contiguous(), **geom.kernel_kwargs(), col_scale=d,
+                             noise=noise.contiguous(), noise_strength=ns.reshape(1), bias=bias, act=1, act_gain=gain)
+        # adjoint weights once per step (the synthesis layers are back-propagated twice, :194-206)
+        wadj = relayout_for_adjoint(wmat, geom).to(act).contiguous()
+        ctx.save_for_backward(x, xs, out, s, d, wadj, noise, ns, bias)
+        ctx.geom, ctx.gain = geom, gain
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, xs, out, s, d, wadj, noise, ns, bias = ctx.saved_tensors
+        g = ctx.geom
+        gy0, S1, Spre, Snz = K.bias_act_bwd(g_out.contiguous(), out, noise=noise.contiguous(), d=d, act=True,
+                                            gain=ctx.gain)
+        gd = (Spre - ns * Snz - bias[None, :] * S1) / d
+        gbias = S1.sum(dim=0)
+        gns = Snz.sum().reshape(ns.shape)
+        K.PROFILE_TAG = (g.tag, g.algo_frac)
+        gxs = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
+        gw = K.conv2d_wgrad(xs, gy0, **g.kernel_kwargs())
+        gx, gs = K.modulate_bwd(gxs, x, s)
+        return gx, gs, gd, gw, None, gns, gbias, None, None
+
+
+class ConvAct(torch.autograd.Function):
+    """out = lrelu(conv(x, W) + bias)*gain (+ residual)   |   out = conv(x, W) when bias is None."""
+
+    @staticmethod
+    def forward(ctx, x, wmat, bias, residual, geom: ConvGeom, gain: float):
+        act = _act_dtype()
+        x = x.contiguous()
+        has_act = bias is not None
+        K.PROFILE_TAG = (geom.tag, geom.algo_frac)
+        out = K.conv2d_igemm(x, wmat.to(act).contiguous(), **geom.kernel_kwargs(), bias=bias, act=1 if has_act else 0,
+                             act_gain=gain if has_act else 1.0,
+                             residual=residual.contiguous() if residual is not None else None, res_scale=1.0)
+        wadj = relayout_for_adjoint(wmat, geom).to(act).contiguous() if ctx.needs_input_grad[0] else None
+        ctx.save_for_backward(x, wadj, out if has_act else None, residual if has_act else None)
+        ctx.geom, ctx.gain, ctx.has_act, ctx.has_res = geom, gain, has_act, residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, wadj, out, residual = ctx.saved_tensors
+        g = ctx.geom
+        g_out = g_out.contiguous()
+        gbias = None
+        if ctx.has_act:
+            gy0, S1, _, _ = K.bias_act_bwd(g_out, out, residual=residual, act=True, gain=ctx.gain)
+            gbias = S1.sum(dim=0)
+        else:
+            gy0 = g_out
+        K.PROFILE_TAG = (g.tag, g.algo_frac)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
+        gw = K.conv2d_wgrad(x, gy0, **g.kernel_kwargs()) if ctx.needs_input_grad[1] else None
+        return gx, gw, gbias, (g_out if ctx.has_res else None), None, None
+
+
+class ToRGB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ws, bias):
+        x = x.contiguous()
+        ws = ws.contiguous()
+        ctx.save_for_backward(x, ws)
+        return K.torgb_fwd(x, ws, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, ws = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx, gws = K.torgb_bwd(x, ws, gy)
+        return gx, gws, gy.sum(dim=(0, 1, 2))

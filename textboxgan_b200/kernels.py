@@ -209,3 +209,71 @@ def lstm_seq_bwd(g_h: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, wT_pac
     st = _lib.load().tbg_lstm_seq_bwd(_ptr(g_h), _ptr(gates), _ptr(c), _ptr(wT_packed), _ptr(g_xp), D, B, T, H, _stream())
     _lib.check(st, "tbg_lstm_seq_bwd")
     return g_xp
+
+
+def _bhwc(t: torch.Tensor):
+    B, C = t.shape[0], t.shape[-1]
+    return B, t.numel() // (B * C), C
+
+
+def modulate(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """xs = x * s[b, c];  x bf16 [B,...,C], s fp32 [B,C]."""
+    _require(x, torch.bfloat16, "x")
+    _require(s, torch.float32, "s")
+    B, HW, C = _bhwc(x)
+    xs = torch.empty_like(x)
+    _lib.check(_lib.load().tbg_modulate(_ptr(x), _ptr(s), _ptr(xs), B, HW, C, _stream()), "tbg_modulate")
+    return xs
+
+
+def modulate_bwd(gxs: torch.Tensor, x: torch.Tensor, s: torch.Tensor):
+    _require(gxs, torch.bfloat16, "gxs")
+    _require(x, torch.bfloat16, "x")
+    _require(s, torch.float32, "s")
+    B, HW, C = _bhwc(x)
+    gx = torch.empty_like(x)
+    gs = torch.zeros_like(s)
+    st = _lib.load().tbg_modulate_bwd(_ptr(gxs), _ptr(x), _ptr(s), _ptr(gx), _ptr(gs), B, HW, C, _stream())
+    _lib.check(st, "tbg_modulate_bwd")
+    return gx, gs
+
+
+def bias_act_bwd(g_out: torch.Tensor, out: torch.Tensor, *, residual=None, noise=None, d=None, act=True,
+                 gain: float = 1.0, want_sums: bool = True):
+    """Returns (gy0 bf16, S1, Spre, Snz) — see include/tbg.h."""
+    _require(g_out, torch.bfloat16, "g_out")
+    _require(out, torch.bfloat16, "out")
+    B, HW, C = _bhwc(out)
+    gy0 = torch.empty_like(out)
+    S1 = Spre = Snz = None
+    if want_sums:
+        sums = torch.zeros((3, B, C), device=out.device, dtype=torch.float32)
+        S1, Spre, Snz = sums[0], sums[1], sums[2]
+    st = _lib.load().tbg_bias_act_bwd(_ptr(g_out), _ptr(out), _ptr(residual), _ptr(noise), _ptr(d), _ptr(gy0),
+                                      _ptr(S1), _ptr(Spre), _ptr(Snz) if noise is not None or want_sums else None,
+                                      B, HW, C, int(act), float(gain), _stream())
+    _lib.check(st, "tbg_bias_act_bwd")
+    return gy0, S1, Spre, Snz
+
+
+def torgb_fwd(x: torch.Tensor, ws: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x bf16 [B,H,W,C], ws fp32 [B,C,3], bias fp32 [3] -> y fp32 [B,H,W,3]."""
+    _require(x, torch.bfloat16, "x")
+    _require(ws, torch.float32, "ws")
+    B, HW, C = _bhwc(x)
+    y = torch.empty(x.shape[:-1] + (3,), device=x.device, dtype=torch.float32)
+    st = _lib.load().tbg_torgb_fwd(_ptr(x), _ptr(ws), _ptr(bias), _ptr(y), B, HW, C, _stream())
+    _lib.check(st, "tbg_torgb_fwd")
+    return y
+
+
+def torgb_bwd(x: torch.Tensor, ws: torch.Tensor, gy: torch.Tensor):
+    _require(x, torch.bfloat16, "x")
+    _require(ws, torch.float32, "ws")
+    _require(gy, torch.float32, "gy")
+    B, HW, C = _bhwc(x)
+    gx = torch.empty_like(x)
+    gws = torch.zeros_like(ws)
+    st = _lib.load().tbg_torgb_bwd(_ptr(x), _ptr(ws), _ptr(gy), _ptr(gx), _ptr(gws), B, HW, C, _stream())
+    _lib.check(st, "tbg_torgb_bwd")
+    return gx, gws

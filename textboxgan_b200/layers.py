@@ -26,6 +26,29 @@ Params = Dict[str, torch.Tensor]
 SQRT2 = math.sqrt(2.0)
 ACT_DTYPE = torch.bfloat16
 
+# Plain steps run every layer group as a fused first-order Function (textboxgan_b200.fused); code
+# that needs gradients of gradients (path-length / R1 regularisers) wraps its forward pass in
+# ``double_backward()`` to get the composable, arbitrarily differentiable primitives instead.
+FUSED = True
+_DOUBLE_BACKWARD = False
+
+
+class double_backward:
+    def __enter__(self):
+        global _DOUBLE_BACKWARD
+        self.prev = _DOUBLE_BACKWARD
+        _DOUBLE_BACKWARD = True
+        return self
+
+    def __exit__(self, *exc):
+        global _DOUBLE_BACKWARD
+        _DOUBLE_BACKWARD = self.prev
+        return False
+
+
+def use_fused() -> bool:
+    return FUSED and torch.is_grad_enabled() and not _DOUBLE_BACKWARD
+
 
 def runtime_coef(weight_shape, gain: float = 1.0, lrmul: float = 1.0) -> float:
     """commons.py:4-12"""
@@ -68,12 +91,18 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     else:
         geom = C.plain_geom(H, W_, I, O, kh, tag="modconv")
         wmat = C.plain_wmat(w)
-    xs = (x.float() * s[:, None, None, :]).to(ACT_DTYPE)                    # :96
     d = None
     if demodulate:
         q = (w * w).sum(dim=(0, 1))                                         # [I,O]
         d = torch.rsqrt((s * s) @ q + 1e-8)                                 # :80-82  [B,O]
+    if use_fused() and act and noise is not None and bias is not None and d is not None and not fused_epilogue:
+        from .fused import ModConvAct
+
+        return ModConvAct.apply(x, s, d, wmat, noise, noise_strength, bias, geom, SQRT2)
     if fused_epilogue:
+        from . import kernels as K
+
+        xs = K.modulate(x.contiguous(), s.contiguous())                     # :96
         epi = dict(col_scale=d.contiguous() if d is not None else None,
                    noise=noise.contiguous() if noise is not None else None,
                    noise_strength=noise_strength.reshape(1).contiguous() if noise is not None else None,
@@ -81,6 +110,7 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
                    act=1 if act else 0, act_gain=SQRT2 if act else 1.0)
         with torch.no_grad():
             return C.conv(xs, wmat, geom, epi)
+    xs = (x.float() * s[:, None, None, :]).to(ACT_DTYPE)                    # :96
     y = C.conv(xs, wmat, geom).float()
     if d is not None:
         y = y * d[:, None, None, :]                                         # :121
@@ -99,6 +129,10 @@ def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str) -> torc
     w = runtime_coef(w_raw.shape) * w_raw[0, 0]
     s = style_scale(style, P, prefix + "/conv")
     ws = s[:, :, None] * w[None]                                            # [B,C,3]
+    if use_fused():
+        from .fused import ToRGB
+
+        return ToRGB.apply(x, ws, P[prefix + "/bias/b"])
     B, H, W_, Cc = x.shape
     y = torch.bmm(x.reshape(B, H * W_, Cc).float(), ws).reshape(B, H, W_, 3)
     return y + P[prefix + "/bias/b"]

@@ -65,6 +65,11 @@ _SIGNATURES = [
     ("tbg_ema_step", c_int, [c_void_p, c_void_p, C.c_longlong, c_float, c_void_p]),
     ("tbg_lstm_seq_fwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     ("tbg_lstm_seq_bwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    ("tbg_modulate", c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    ("tbg_modulate_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    ("tbg_bias_act_bwd", c_int, [c_void_p] * 9 + [c_int] * 4 + [c_float, c_void_p]),
+    ("tbg_torgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
 ]
 
 

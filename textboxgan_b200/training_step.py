@@ -23,6 +23,7 @@ from .aster_inferer import AsterInferer
 from .config import Config
 from .discriminator import Discriminator
 from .generator import Generator
+from . import layers as L
 from .losses import discriminator_loss, generator_loss, mean_squared_loss, softmax_cross_entropy_loss
 from .optimizers import Adam
 from .utils import mask_text_box
@@ -150,11 +151,16 @@ class TrainingStep:
         elif entry["graph"] is None:
             for o in opts:
                 o.defer_iteration = True
+            from . import lib as _lib
+
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            n0 = _lib.load().tbg_launch_count()
             with torch.cuda.graph(graph):
                 out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0],
                                                key[1], st["ocr_w"])
+            # launches of this repo's kernels recorded in the graph (replayed on every step)
+            entry["tbg_launches"] = int(_lib.load().tbg_launch_count() - n0)
             for o in opts:
                 o.defer_iteration = False
             entry["graph"], entry["out"] = graph, out
@@ -167,6 +173,11 @@ class TrainingStep:
             res = entry["out"]
         r = res.unbind(0)
         return (r[0], r[1], r[2]), (r[3], r[4], r[5]), r[6]
+
+    def graph_launches(self, do_r1_reg: bool = False, do_pl_reg: bool = False) -> int:
+        """Number of this repo's kernel launches inside the captured graph of a step variant."""
+        e = self._graphs.get((bool(do_r1_reg), bool(do_pl_reg)))
+        return int(e.get("tbg_launches", 0)) if e else 0
 
     def _bump_iterations(self):
         self.g_optimizer.iterations.value += 1
@@ -244,8 +255,9 @@ class TrainingStep:
         pl_z = draws["pl_z"].to(dev) if "pl_z" in draws else torch.randn(pl_minibatch, self.z_dim, device=dev)
         pl_draws = {"noises": draws["pl_noises"]} if "pl_noises" in draws else {}
         # generator(...) with the default training=False (:325-329)
-        pl_fake_images, pl_style = G((input_words[:pl_minibatch], pl_z), batch_size=pl_minibatch, ret_style=True,
-                                     draws=pl_draws)
+        with L.double_backward():
+            pl_fake_images, pl_style = G((input_words[:pl_minibatch], pl_z), batch_size=pl_minibatch, ret_style=True,
+                                         draws=pl_draws)
         noise = draws["pl_image_noise"].to(dev) if "pl_image_noise" in draws else torch.randn_like(pl_fake_images)
         pl_noise = noise * self.pl_noise_scaler
         pl_noise_applied = (pl_fake_images * pl_noise).sum()
@@ -260,7 +272,8 @@ class TrainingStep:
     def _r1_reg(self, real_images):
         """training_step.py:349-373"""
         real_images = real_images.detach().requires_grad_(True)
-        real_scores = self.discriminator(real_images)
+        with L.double_backward():
+            real_scores = self.discriminator(real_images)
         real_loss = real_scores.sum()
         (real_grads,) = torch.autograd.grad(real_loss, real_images, create_graph=True)
         r1_penalty = (real_grads ** 2).sum(dim=(1, 2, 3))[:, None]
