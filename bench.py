@@ -275,14 +275,15 @@ def run_ours(args) -> None:
 
     # ---- roofline pass: CUDA events around every tensor-core launch of two instrumented steps ----
     roof = None
+    # every rank runs the two instrumented eager steps (they contain collectives); rank 0 records
+    K.PROFILE = [] if rank == 0 else None
+    ts.use_cuda_graph = False                     # events around every launch need eager launches
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    recs = K.PROFILE
+    K.PROFILE = None
     if rank == 0:
-        K.PROFILE = []
-        ts.use_cuda_graph = False                 # instrumented eager steps: events around every launch
-        for _ in range(2):
-            step_resident()
-        torch.cuda.synchronize()
-        recs = K.PROFILE
-        K.PROFILE = None
         agg = {}
         for name, tag, flops, e0, e1 in recs:
             t, frac = tag if isinstance(tag, tuple) else (str(tag), 1.0)
