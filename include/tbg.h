@@ -165,6 +165,22 @@ int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, i
 int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Weight preparation / gradient fold.  From the fp32 HWIO master weight w[KH,KW,I,O] (KH,KW <= 3)
+ * build, in one launch, the bf16 GEMM matrix of a convolution geometry, the matrix of its adjoint
+ * geometry and (optionally) q[i,o] = coef^2 * sum_taps w^2 (demodulation, modulated_conv2d.py:80-82):
+ *   fwd[(p,q,o),(t,u,i)] = coef * sum_{kh,kw} Ty[p,t,kh] Tx[q,u,kw] w[kh,kw,i,o]     (rows Opad, cols Ipad)
+ *   adj[(p,q,i),(t,u,o)] = coef * sum_{kh,kw} Ty'[p,t,kh] Tx'[q,u,kw] w[kh,kw,i,o]
+ * `tables` is a HOST array of 4 blocks {P, T, K, 36 floats [P][T][K]} for Ty, Tx, Ty', Tx' (identity
+ * for plain convs; FIR-folded tables for upsample_conv_2d / conv_downsample_2d,
+ * upfirdn_2d_v2.py:65-113).  coef is the equalised-LR runtime coefficient (commons.py:4-12).
+ * tbg_wfold is the transpose: gw += coef * fold(gfwd) (+ 2 coef^2 w gq), gfwd fp32 in fwd layout.
+ * ------------------------------------------------------------------------------------------ */
+int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad, int Opad,
+              void* fwd, void* adj, float* q, void* stream);
+int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
+              int I, int O, int Ipad, int Opad, float* gw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,42 @@ class Tensor(torch.Tensor):
     def __len__(self):
         return super().shape[0]
 
+    # tf.Tensor is immutable: augmented assignment rebinds to a new tensor (and may broadcast)
+    def __imul__(self, other):
+        return self * other
+
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __itruediv__(self, other):
+        return self / other
+
+    def __getitem__(self, idx):
+        """TF/NumPy-style indexing incl. reversed slices ``[::-1]`` (torch rejects negative steps)."""
+        items = idx if isinstance(idx, tuple) else (idx,)
+        flips, new_items, dim = [], [], 0
+        for it in items:
+            if it is None:
+                new_items.append(it)
+                continue
+            if it is Ellipsis:
+                new_items.append(it)
+                dim = None
+                continue
+            if isinstance(it, slice) and it.step is not None and it.step < 0:
+                assert it.step == -1 and it.start is None and it.stop is None and dim is not None
+                flips.append(dim)
+                new_items.append(slice(None))
+            else:
+                new_items.append(it)
+            if dim is not None and not (isinstance(it, torch.Tensor) and it.dtype == torch.bool and it.dim() > 1):
+                dim += 1
+        base = torch.flip(self, dims=flips) if flips else self
+        return torch.Tensor.__getitem__(base, tuple(new_items) if isinstance(idx, tuple) else new_items[0])
+
     def __bool__(self):
         return builtins_bool(self.detach().as_subclass(torch.Tensor).item())
 
@@ -63,7 +99,7 @@ def _t(x, dtype=None) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         y = x if isinstance(x, Tensor) else x.as_subclass(Tensor)
     else:
-        y = torch.as_tensor(np.asarray(x)).as_subclass(Tensor)
+        y = torch.as_tensor(np.ascontiguousarray(np.asarray(x))).as_subclass(Tensor)
         if y.dtype == torch.float64 and dtype is None:
             y = y.to(DEFAULT_FLOAT)
     if dtype is not None and y.dtype != dtype:
@@ -491,7 +527,10 @@ class _Distribute(types.ModuleType):
         SUM = "SUM"
         MEAN = "MEAN"
 
-    class MirroredStrategy:
+    class Strategy:
+        pass
+
+    class MirroredStrategy(Strategy):
         num_replicas_in_sync = 1
 
         def run(self, fn, args=(), kwargs=None):

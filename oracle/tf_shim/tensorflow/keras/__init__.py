@@ -218,3 +218,23 @@ from . import preprocessing  # noqa: E402,F401
 sys.modules["tensorflow.keras.layers"] = layers
 sys.modules["tensorflow.keras.optimizers"] = optimizers
 sys.modules["tensorflow.keras.losses"] = losses
+
+
+class _Metrics(types.ModuleType):
+    class Mean:  # utils/loss_tracker.py imports it; not on the hot path
+        def __init__(self, name=None):
+            self.total, self.count = 0.0, 0
+
+        def __call__(self, v):
+            self.total += float(v)
+            self.count += 1
+
+        def result(self):
+            return self.total / max(self.count, 1)
+
+        def reset_states(self):
+            self.total, self.count = 0.0, 0
+
+
+metrics = _Metrics("tensorflow.keras.metrics")
+sys.modules["tensorflow.keras.metrics"] = metrics

@@ -47,6 +47,10 @@ def to64(draws):
 
 
 def rel_err(a, b):
+    import numpy as np
+
+    a = torch.as_tensor(np.asarray(a)) if not torch.is_tensor(a) else a
+    b = torch.as_tensor(np.asarray(b)) if not torch.is_tensor(b) else b
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()

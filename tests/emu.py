@@ -186,6 +186,34 @@ def emu_torgb_bwd(x, ws, gy):
     return gx, gws
 
 
+def emu_wprep(w_raw, spec, *, want_adj=True, want_q=False, act_dtype=None):
+    """Documented semantics of tbg_wprep (include/tbg.h) with the spec's per-axis tables."""
+    from textboxgan_b200 import layers as L
+
+    fy, fx, ay, ax = [t.double() for t in spec.tables]
+    w = w_raw.double() * spec.coef
+    wp = torch.zeros(spec.KH, spec.KW, spec.Ipad, spec.Opad, dtype=torch.float64)
+    wp[:, :, : spec.I, : spec.O] = w
+    fwd = torch.einsum("ptk,qul,klio->pqotui", fy, fx, wp).reshape(spec.fwd_rows, spec.fwd_cols).to(L.ACT_DTYPE)
+    adj = torch.einsum("ptk,qul,klio->pqituo", ay, ax, wp).reshape(spec.adj_rows, spec.adj_cols).to(L.ACT_DTYPE) \
+        if want_adj else None
+    q = (w * w).sum(dim=(0, 1)).float() if want_q else None
+    return fwd, adj, q
+
+
+def emu_wfold(gfwd, spec, *, gq=None, w_raw=None, out=None):
+    fy, fx, _, _ = [t.double() for t in spec.tables]
+    g6 = gfwd.double().reshape(fy.shape[0], fx.shape[0], spec.Opad, fy.shape[1], fx.shape[1], spec.Ipad)
+    gw = torch.einsum("ptk,qul,pqotui->klio", fy, fx, g6)[:, :, : spec.I, : spec.O] * spec.coef
+    if gq is not None:
+        gw = gw + 2.0 * spec.coef * spec.coef * w_raw.double() * gq.double()[None, None]
+    gw = gw.float()
+    if out is not None:
+        out += gw
+        return out
+    return gw
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -197,6 +225,8 @@ def emulated_kernels(act_dtype=torch.float32):
              K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd, K.torgb_bwd)
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
+    saved_w = (K.wprep, K.wfold)
+    K.wprep, K.wfold = emu_wprep, emu_wfold
     K.conv2d_igemm = emu_conv2d_igemm
     K.conv2d_wgrad = emu_conv2d_wgrad
     K.upfirdn2d = emu_upfirdn2d
@@ -212,3 +242,4 @@ def emulated_kernels(act_dtype=torch.float32):
         (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
          K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd,
          K.torgb_bwd) = saved
+        K.wprep, K.wfold = saved_w

@@ -231,6 +231,39 @@ def test_fused_pointwise_kernels_vs_emulated_semantics(B, H, W, C):
     assert rel_err(tgx.float(), rtx) < 1e-2 and rel_err(tgws, rtw) < 1e-4
 
 
+@pytest.mark.parametrize("kind,k,rh,I,O", [("plain", 3, True, 128, 256), ("plain", 1, True, 64, 128), ("up", 3, True, 128, 64),
+                                          ("down", 3, True, 64, 128), ("down", 1, True, 128, 128),
+                                          ("down", 3, False, 256, 256), ("plain", 3, True, 513, 512)])
+def test_weight_prep_and_fold_vs_emulated_semantics(kind, k, rh, I, O):
+    import emu
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import layers as L
+
+    spec = C.weight_spec(kind, 8, 16, I, O, k, rh)
+    gen = torch.Generator().manual_seed(I + O + k)
+    w = torch.randn(k, k, I, O, generator=gen)
+    fwd, adj, q = K.wprep(w.to(DEV), spec, want_adj=True, want_q=True)
+    rf, ra, rq = emu.emu_wprep(w, spec, want_adj=True, want_q=True)
+    # outputs are bf16 roundings of identical fp32 sums (<= 9 terms): bit-exact up to 1 ulp
+    assert rel_err(fwd.float(), rf.float()) < 4e-3 and rel_err(adj.float(), ra.float()) < 4e-3
+    assert rel_err(q, rq) < 1e-5
+    g = torch.randn(spec.fwd_rows, spec.fwd_cols, generator=gen)
+    gq = torch.randn(I, O, generator=gen)
+    out = K.wfold(g.to(DEV), spec, gq=gq.to(DEV), w_raw=w.to(DEV))
+    ref = emu.emu_wfold(g, spec, gq=gq, w_raw=w)
+    assert rel_err(out, ref) < 1e-5
+    # fold is the exact transpose of prep: <prep(w), g> == <w, fold(g)>
+    lhs = (emu.emu_wprep(w.double(), spec, want_adj=False)[0].double() * g.double()).sum() if L.ACT_DTYPE == torch.float64 else None
+    out2 = K.wfold(g.to(DEV), spec)
+    rhs = (w.double() * out2.cpu().double()).sum()
+    fy, fx, _, _ = [t.double() for t in spec.tables]
+    wp = torch.zeros(k, k, spec.Ipad, spec.Opad, dtype=torch.float64)
+    wp[:, :, :I, :O] = w.double() * spec.coef
+    lhs = (torch.einsum("ptk,qul,klio->pqotui", fy, fx, wp).reshape(g.shape) * g.double()).sum()
+    assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
+
+
 def _product(cfg, GP, DP, with_ocr=True):
     from textboxgan_b200.aster_inferer import AsterInferer
     from textboxgan_b200.discriminator import Discriminator

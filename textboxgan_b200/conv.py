@@ -326,3 +326,73 @@ def down_wmat(w_hwio: torch.Tensor) -> torch.Tensor:
     g = torch.einsum("ut,vs,tsio->ouvi", s, s, w_hwio)
     O, I = w_hwio.shape[3], w_hwio.shape[2]
     return g.reshape(O, (k + 3) * (k + 3) * I)
+
+
+# ----------------------------------------------------------------------------------------------
+# WeightSpec: the linear map master weight -> GEMM matrices of a geometry, as per-axis tables for
+# the tbg_wprep / tbg_wfold kernels
+# ----------------------------------------------------------------------------------------------
+def _axis_fwd_table(kind: str, k_master: int) -> torch.Tensor:
+    """F[phase, tap, master_tap] of one axis."""
+    if kind == "plain":
+        return torch.eye(k_master).reshape(1, k_master, k_master)
+    if kind == "up":
+        assert k_master == 3
+        return _up_coef().clone()
+    if kind == "down":
+        return _fold_table(k_master).reshape(1, k_master + 3, k_master).clone()
+    raise ValueError(kind)
+
+
+def _axis_adj_table(F: torch.Tensor, ax: Axis) -> torch.Tensor:
+    idx, mask = _axis_adjoint_map(ax.kind, ax.k, ax.pad)
+    a = ax.adjoint()
+    flat = F.reshape(F.shape[0] * F.shape[1], F.shape[2])
+    return (flat[idx] * mask[:, None]).reshape(a.phases, a.k, F.shape[2])
+
+
+class WeightSpec:
+    """Everything tbg_wprep / tbg_wfold need for one (geometry, master-weight shape) pair."""
+
+    def __init__(self, geom: ConvGeom, kind_h: str, kind_w: str, KH: int, KW: int, I: int, O: int, coef: float):
+        import ctypes
+
+        self.geom, self.KH, self.KW, self.I, self.O, self.coef = geom, KH, KW, I, O, float(coef)
+        self.Ipad, self.Opad = geom.cin, geom.cout
+        fy, fx = _axis_fwd_table(kind_h, KH), _axis_fwd_table(kind_w, KW)
+        ay, ax = _axis_adj_table(fy, geom.ah), _axis_adj_table(fx, geom.aw)
+        assert fy.shape[:2] == (geom.ah.phases, geom.ah.k) and fx.shape[:2] == (geom.aw.phases, geom.aw.k)
+        self.tables = (fy, fx, ay, ax)
+
+        def pack(ts):
+            buf = []
+            for t in ts:
+                blk = [float(t.shape[0]), float(t.shape[1]), float(t.shape[2])] + [float(v) for v in t.flatten()]
+                buf += blk + [0.0] * (39 - len(blk))
+            return (ctypes.c_float * len(buf))(*buf)
+
+        zero = torch.zeros(0, 1, max(KH, 1))
+        self.ctable = pack([fy, fx, ay, ax])
+        self.ctable_noadj = pack([fy, fx, torch.zeros(0, 0, KH), torch.zeros(0, 0, KW)])
+        a = geom.adjoint()
+        self.fwd_rows, self.fwd_cols = geom.n_total, geom.k_total
+        self.adj_rows, self.adj_cols = a.n_total, a.k_total
+
+
+@lru_cache(maxsize=None)
+def weight_spec(kind: str, H: int, W: int, I: int, O: int, k: int, reduce_height: bool = True, tag: str = "",
+                scale: float = 1.0) -> WeightSpec:
+    """kind: 'plain' | 'up' | 'down'.  Channel counts are padded to multiples of 64 (K blocks of the
+    tensor-core kernels); coef = equalised-LR runtime coefficient 1/sqrt(k*k*I) (commons.py:4-12) x scale."""
+    Ip, Op = (I + 63) // 64 * 64, (O + 63) // 64 * 64
+    coef = scale / math.sqrt(k * k * I)
+    if kind == "plain":
+        g = plain_geom(H, W, Ip, Op, k, tag=tag, algo_frac=(I * O) / float(Ip * Op))
+        return WeightSpec(g, "plain", "plain", k, k, I, O, coef)
+    if kind == "up":
+        g = up_geom(H, W, Ip, Op, tag=tag)
+        return WeightSpec(g, "up", "up", k, k, I, O, coef)
+    if kind == "down":
+        g = down_geom(H, W, Ip, Op, k, reduce_height, tag=tag)
+        return WeightSpec(g, "down" if reduce_height else "down", "down", k, k, I, O, coef)
+    raise ValueError(kind)

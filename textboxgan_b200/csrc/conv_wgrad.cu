@@ -12,6 +12,8 @@
 //
 // Replaces cuDNN's backward-filter behind tape.gradient (training_step.py:224-235) for
 // ModulatedConv2D / Conv2D weights (modulated_conv2d.py:63, conv.py:49).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -217,9 +219,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
             float* dst = p.gw + static_cast<size_t>(n) * p.ktot + tap * p.cin + ct * p.block_c + j * 32;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              float4 val = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
-                                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-              atomicAdd(reinterpret_cast<float4*>(dst + g * 4), val);
+              // one 16-byte vector reduction per 4 accumulators (sm_90+ red.global.add.v4.f32)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                           "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                           "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                           : "memory");
             }
           }
         }
@@ -307,7 +311,19 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int base_items = p.m_tiles * p.groups;
-  int splits = (2 * sms + base_items - 1) / base_items;  // ~2 items per SM
+  static int items_override = -1;
+  if (items_override < 0) {
+    const char* e = getenv("TBG_WGRAD_ITEMS_PER_SM");
+    items_override = e ? atoi(e) : 0;
+  }
+  // Two work items per SM hide the accumulator drain behind the next item's MMAs, but only pay off
+  // when each item still owns >= 16 pixel blocks (measured on B200, profiles/r01_layer_perf.log).
+  int items_per_sm = items_override > 0 ? items_override : 2;
+  int splits = (items_per_sm * sms + base_items - 1) / base_items;
+  if (items_override <= 0 && k_tiles / (splits > 0 ? splits : 1) < 16) {
+    items_per_sm = 1;
+    splits = (sms + base_items - 1) / base_items;
+  }
   if (splits > k_tiles) splits = k_tiles;
   if (splits < 1) splits = 1;
   // every split must own at least one pixel tile

@@ -65,8 +65,17 @@ class Discriminator(Model):
         P = self.params
         w_raw = P[name]
         k, _, I, O = w_raw.shape
-        w = (L.runtime_coef(w_raw.shape) * scale) * w_raw
         B, H, W_, _ = x.shape
+        if L.use_fused():
+            from .fused import ConvAct
+
+            spec = C.weight_spec("down" if down else "plain", H, W_, I, O, k, reduce_height, "dconv", scale)
+            if residual is not None:
+                # (lrelu(v)*sqrt2 + skip)/sqrt2 == lrelu(v) + skip/sqrt2: the caller pre-scales the
+                # (linear) skip branch, so the merge is a plain residual add in the epilogue
+                return ConvAct.apply(x, w_raw, P[bias], residual, spec, 1.0)
+            return ConvAct.apply(x, w_raw, P[bias] if bias else None, None, spec, L.SQRT2)
+        w = (L.runtime_coef(w_raw.shape) * scale) * w_raw
         if down:
             geom = C.down_geom(H, W_, I, O, k, reduce_height, tag="dconv")
             wmat = C.down_wmat(w)
@@ -79,14 +88,6 @@ class Discriminator(Model):
                        residual=residual.contiguous() if residual is not None else None,
                        res_scale=INV_SQRT2 if residual is not None else 1.0)
             return C.conv(x, wmat, geom, epi)
-        if L.use_fused():
-            from .fused import ConvAct
-
-            if residual is not None:
-                # (lrelu(v)*sqrt2 + skip)/sqrt2 == lrelu(v) + skip/sqrt2: the caller pre-scales the
-                # (linear) skip branch, so the merge is a plain residual add in the epilogue
-                return ConvAct.apply(x, wmat, P[bias], residual, geom, 1.0)
-            return ConvAct.apply(x, wmat, P[bias] if bias else None, None, geom, L.SQRT2)
         y = C.conv(x, wmat, geom)
         if bias is None and residual is None:
             return y
@@ -124,10 +125,17 @@ class Discriminator(Model):
         xcat = torch.cat([x, std.to(x.dtype)[:, None, None, :].expand(B, H, W_, 1),
                           x.new_zeros(B, H, W_, cpad - Cc - 1)], dim=3).contiguous()
         w_raw = P[pl + "/conv_0/w"]                                          # [3,3,C+1,C]
-        w = L.runtime_coef(w_raw.shape) * w_raw
-        wpad = torch.cat([w, w.new_zeros(3, 3, cpad - Cc - 1, w.shape[3])], dim=2)
-        y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3, tag="dconv", algo_frac=(Cc + 1) / cpad)).float()
-        y = L.lrelu(y + P[pl + "/bias_0/b"])
+        if L.use_fused():
+            from .fused import ConvAct
+
+            spec = C.weight_spec("plain", H, W_, Cc + 1, w_raw.shape[3], 3, True, "dconv")   # K padded 513 -> 576
+            y = ConvAct.apply(xcat, w_raw, P[pl + "/bias_0/b"], None, spec, L.SQRT2).float()
+        else:
+            w = L.runtime_coef(w_raw.shape) * w_raw
+            wpad = torch.cat([w, w.new_zeros(3, 3, cpad - Cc - 1, w.shape[3])], dim=2)
+            y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3, tag="dconv",
+                                                              algo_frac=(Cc + 1) / cpad)).float()
+            y = L.lrelu(y + P[pl + "/bias_0/b"])
         # flatten in the reference's NCHW order (dense.py:26-27 on an NCHW tensor)
         y = y.permute(0, 3, 1, 2).reshape(B, -1)
         y = L.lrelu(L.dense(y, P[pl + "/dense_1/w"]) + P[pl + "/bias_1/b"])

@@ -31,59 +31,69 @@ def _act_dtype():
 
 
 class ModConvAct(torch.autograd.Function):
+    """x, style scale s, MASTER weight -> lrelu(demod(conv(x*s, w)) + noise*ns + bias)*gain."""
+
     @staticmethod
-    def forward(ctx, x, s, d, wmat, noise, ns, bias, geom: ConvGeom, gain: float):
-        act = _act_dtype()
+    def forward(ctx, x, s, w_raw, noise, ns, bias, spec, gain: float):
+        geom = spec.geom
         x = x.contiguous()
         s = s.contiguous()
-        d = d.contiguous()
+        wmat, wadj, q = K.wprep(w_raw, spec, want_adj=True, want_q=True)        # one launch
+        d = torch.rsqrt((s * s) @ q + 1e-8)                                      # modulated_conv2d.py:80-82
         xs = K.modulate(x, s)
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
-        out = K.conv2d_igemm(xs, wmat.to(act).contiguous(), **geom.kernel_kwargs(), col_scale=d,
-                             noise=noise.contiguous(), noise_strength=ns.reshape(1), bias=bias, act=1, act_gain=gain)
-        # adjoint weights once per step (the synthesis layers are back-propagated twice, :194-206)
-        wadj = relayout_for_adjoint(wmat, geom).to(act).contiguous()
-        ctx.save_for_backward(x, xs, out, s, d, wadj, noise, ns, bias)
-        ctx.geom, ctx.gain = geom, gain
+        out = K.conv2d_igemm(xs, wmat, **geom.kernel_kwargs(), col_scale=d, noise=noise.contiguous(),
+                             noise_strength=ns.reshape(1), bias=bias, act=1, act_gain=gain)
+        ctx.save_for_backward(x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias)
+        ctx.spec, ctx.gain = spec, gain
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x, xs, out, s, d, wadj, noise, ns, bias = ctx.saved_tensors
-        g = ctx.geom
+        x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias = ctx.saved_tensors
+        spec = ctx.spec
+        g = spec.geom
         gy0, S1, Spre, Snz = K.bias_act_bwd(g_out.contiguous(), out, noise=noise.contiguous(), d=d, act=True,
                                             gain=ctx.gain)
         gd = (Spre - ns * Snz - bias[None, :] * S1) / d
         gbias = S1.sum(dim=0)
         gns = Snz.sum().reshape(ns.shape)
+        # d = rsqrt(s^2 @ q + eps):  t = dL/d(s^2 @ q)
+        t = -0.5 * gd * d * d * d
+        gq = (s * s).t() @ t
+        gs_d = 2.0 * s * (t @ q.t())
         K.PROFILE_TAG = (g.tag, g.algo_frac)
         gxs = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
-        gw = K.conv2d_wgrad(xs, gy0, **g.kernel_kwargs())
+        gwmat = K.conv2d_wgrad(xs, gy0, **g.kernel_kwargs())
         gx, gs = K.modulate_bwd(gxs, x, s)
-        return gx, gs, gd, gw, None, gns, gbias, None, None
+        gw_raw = K.wfold(gwmat, spec, gq=gq.contiguous(), w_raw=w_raw)
+        return gx, gs + gs_d, gw_raw, None, gns, gbias, None, None
 
 
 class ConvAct(torch.autograd.Function):
-    """out = lrelu(conv(x, W) + bias)*gain (+ residual)   |   out = conv(x, W) when bias is None."""
+    """out = lrelu(conv(x, w) + bias)*gain (+ residual)   |   out = conv(x, w) when bias is None; ``w`` is
+    the fp32 HWIO master weight (equalised-LR coefficient and FIR folding happen in tbg_wprep)."""
 
     @staticmethod
-    def forward(ctx, x, wmat, bias, residual, geom: ConvGeom, gain: float):
-        act = _act_dtype()
+    def forward(ctx, x, w_raw, bias, residual, spec, gain: float):
+        geom = spec.geom
         x = x.contiguous()
         has_act = bias is not None
+        need_gx = ctx.needs_input_grad[0]
+        wmat, wadj, _ = K.wprep(w_raw, spec, want_adj=need_gx, want_q=False)
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
-        out = K.conv2d_igemm(x, wmat.to(act).contiguous(), **geom.kernel_kwargs(), bias=bias, act=1 if has_act else 0,
+        out = K.conv2d_igemm(x, wmat, **geom.kernel_kwargs(), bias=bias, act=1 if has_act else 0,
                              act_gain=gain if has_act else 1.0,
                              residual=residual.contiguous() if residual is not None else None, res_scale=1.0)
-        wadj = relayout_for_adjoint(wmat, geom).to(act).contiguous() if ctx.needs_input_grad[0] else None
         ctx.save_for_backward(x, wadj, out if has_act else None, residual if has_act else None)
-        ctx.geom, ctx.gain, ctx.has_act, ctx.has_res = geom, gain, has_act, residual is not None
+        ctx.spec, ctx.gain, ctx.has_act, ctx.has_res = spec, gain, has_act, residual is not None
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         x, wadj, out, residual = ctx.saved_tensors
-        g = ctx.geom
+        spec = ctx.spec
+        g = spec.geom
         g_out = g_out.contiguous()
         gbias = None
         if ctx.has_act:
@@ -92,11 +102,11 @@ class ConvAct(torch.autograd.Function):
         else:
             gy0 = g_out
         K.PROFILE_TAG = (g.tag, g.algo_frac)
-        gx = None
-        if ctx.needs_input_grad[0]:
-            gx = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
-        gw = K.conv2d_wgrad(x, gy0, **g.kernel_kwargs()) if ctx.needs_input_grad[1] else None
-        return gx, gw, gbias, (g_out if ctx.has_res else None), None, None
+        gx = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs()) if ctx.needs_input_grad[0] else None
+        gw_raw = None
+        if ctx.needs_input_grad[1]:
+            gw_raw = K.wfold(K.conv2d_wgrad(x, gy0, **g.kernel_kwargs()), spec)
+        return gx, gw_raw, gbias, (g_out if ctx.has_res else None), None, None
 
 
 class ToRGB(torch.autograd.Function):

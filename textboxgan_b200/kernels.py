@@ -277,3 +277,28 @@ def torgb_bwd(x: torch.Tensor, ws: torch.Tensor, gy: torch.Tensor):
     st = _lib.load().tbg_torgb_bwd(_ptr(x), _ptr(ws), _ptr(gy), _ptr(gx), _ptr(gws), B, HW, C, _stream())
     _lib.check(st, "tbg_torgb_bwd")
     return gx, gws
+
+
+def wprep(w_raw: torch.Tensor, spec, *, want_adj: bool = True, want_q: bool = False, act_dtype=torch.bfloat16):
+    """Master weight fp32 [KH,KW,I,O] -> (fwd bf16 [n_total, K], adj bf16 | None, q fp32 [I,O] | None)."""
+    _require(w_raw, torch.float32, "w_raw")
+    fwd = torch.empty((spec.fwd_rows, spec.fwd_cols), device=w_raw.device, dtype=torch.bfloat16)
+    adj = torch.empty((spec.adj_rows, spec.adj_cols), device=w_raw.device, dtype=torch.bfloat16) if want_adj else None
+    q = torch.empty((spec.I, spec.O), device=w_raw.device, dtype=torch.float32) if want_q else None
+    tables = spec.ctable if want_adj else spec.ctable_noadj
+    st = _lib.load().tbg_wprep(_ptr(w_raw), tables, spec.coef, spec.KH, spec.KW, spec.I, spec.O, spec.Ipad, spec.Opad,
+                               _ptr(fwd), _ptr(adj), _ptr(q), _stream())
+    _lib.check(st, "tbg_wprep")
+    return fwd, adj, q
+
+
+def wfold(gfwd: torch.Tensor, spec, *, gq: Optional[torch.Tensor] = None, w_raw: Optional[torch.Tensor] = None,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulate the master-weight gradient from the fp32 gradient of the fwd GEMM matrix."""
+    _require(gfwd, torch.float32, "gfwd")
+    if out is None:
+        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
+    st = _lib.load().tbg_wfold(_ptr(gfwd), _ptr(gq), _ptr(w_raw), spec.ctable, spec.coef, spec.KH, spec.KW, spec.I,
+                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _stream())
+    _lib.check(st, "tbg_wfold")
+    return out

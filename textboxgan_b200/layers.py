@@ -82,9 +82,14 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     with differentiable element-wise ops."""
     w_raw = P[prefix + "/w"]
     kh, kw, I, O = w_raw.shape
-    w = runtime_coef(w_raw.shape) * w_raw                                   # :71
     s = style_scale(style, P, prefix)                                       # [B,I]
     B, H, W_, _ = x.shape
+    if use_fused() and act and noise is not None and bias is not None and demodulate and not fused_epilogue:
+        from .fused import ModConvAct
+
+        spec = C.weight_spec("up" if up else "plain", H, W_, I, O, kh, True, "modconv")
+        return ModConvAct.apply(x, s, w_raw, noise, noise_strength, bias, spec, SQRT2)
+    w = runtime_coef(w_raw.shape) * w_raw                                   # :71
     if up:
         geom = C.up_geom(H, W_, I, O, tag="modconv")
         wmat = C.up_wmat(w)
@@ -95,10 +100,6 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     if demodulate:
         q = (w * w).sum(dim=(0, 1))                                         # [I,O]
         d = torch.rsqrt((s * s) @ q + 1e-8)                                 # :80-82  [B,O]
-    if use_fused() and act and noise is not None and bias is not None and d is not None and not fused_epilogue:
-        from .fused import ModConvAct
-
-        return ModConvAct.apply(x, s, d, wmat, noise, noise_strength, bias, geom, SQRT2)
     if fused_epilogue:
         from . import kernels as K
 
