@@ -49,113 +49,142 @@ __device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& t
   }
 }
 
-// grid = (weight tiles of 32 x 32, combinations): CTA (tile, c) writes combination c of the forward
-// matrix and combination c of the adjoint matrix for its tile; CTA (tile, 0) also writes q.
+// cf[c][tap] = Ty[p,t,kh] * Tx[q,u,kw] for combination c = ((p*Px + q)*Ty.T + t)*Tx.T + u, tap = kh*KW + kw.
+__device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& tx, int KH, int KW, float scale,
+                                         float (*cf)[9]) {
+  const int ncomb = ty.P * tx.P * ty.T * tx.T;
+  for (int e = threadIdx.x; e < ncomb * 9; e += blockDim.x) {
+    const int c = e / 9, tap = e - c * 9;
+    float v = 0.f;
+    if (tap < KH * KW) {
+      const int u = c % tx.T, t = (c / tx.T) % ty.T, q = (c / (tx.T * ty.T)) % tx.P, pp = c / (tx.T * ty.T * tx.P);
+      v = tab(ty, pp, t, tap / KW) * tab(tx, q, u, tap % KW) * scale;
+    }
+    cf[c][tap] = v;
+  }
+}
+
+// One CTA per 32(i) x 32(o) tile of the master weight: the tile is read once, each thread keeps the
+// nine taps of its elements in registers and emits every (phase, tap) combination of both matrices.
 __global__ void __launch_bounds__(256)
 wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ adj,
              float* __restrict__ q, const WPrepParams p) {
   __shared__ float sw[9][32][33];  // [kh*KW+kw][i][o]
-  __shared__ float cff[9], cfa[9];
+  __shared__ float cff[36][9], cfa[36][9];
   const int tiles_o = p.Opad / 32;
   const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
   const int taps = p.KH * p.KW;
-  const int c = blockIdx.y;
   const int TTf = p.fy.T * p.fx.T, ncf = p.fy.P * p.fx.P * TTf;
   const int TTa = p.ay.T * p.ax.T, nca = (adj != nullptr) ? p.ay.P * p.ax.P * TTa : 0;
-  if (threadIdx.x < 9) {
-    const int tap = threadIdx.x;
-    float vf = 0.f, va = 0.f;
-    if (tap < taps) {
-      if (c < ncf) {
-        const int u = c % p.fx.T, t = (c / p.fx.T) % p.fy.T, qq = (c / TTf) % p.fx.P, pp = c / (TTf * p.fx.P);
-        vf = tab(p.fy, pp, t, tap / p.KW) * tab(p.fx, qq, u, tap % p.KW);
-      }
-      if (c < nca) {
-        const int u = c % p.ax.T, t = (c / p.ax.T) % p.ay.T, qq = (c / TTa) % p.ax.P, pp = c / (TTa * p.ax.P);
-        va = tab(p.ay, pp, t, tap / p.KW) * tab(p.ax, qq, u, tap % p.KW);
-      }
-    }
-    cff[tap] = vf;
-    cfa[tap] = va;
-  }
-  for (int tp = 0; tp < taps; ++tp)
+  build_cf(p.fy, p.fx, p.KH, p.KW, 1.f, cff);
+  if (adj != nullptr) build_cf(p.ay, p.ax, p.KH, p.KW, 1.f, cfa);
+  for (int tp = 0; tp < 9; ++tp)
     for (int r = ty; r < 32; r += 8) {
       const int i = i0 + r, o = o0 + tx;
-      sw[tp][r][tx] = (i < p.I && o < p.O) ? __ldg(w + (static_cast<size_t>(tp) * p.I + i) * p.O + o) * p.coef : 0.f;
+      sw[tp][r][tx] = (tp < taps && i < p.I && o < p.O)
+                          ? __ldg(w + (static_cast<size_t>(tp) * p.I + i) * p.O + o) * p.coef : 0.f;
     }
   __syncthreads();
-  if (c < ncf) {  // forward matrix: rows (pq, o), cols (tu, i): i contiguous -> lanes over i
-    const int pq = c / TTf, tu = c - pq * TTf;
-    const size_t Kf = static_cast<size_t>(TTf) * p.Ipad;
-    for (int r = ty; r < 32; r += 8) {
-      float acc = 0.f;
-      for (int tp = 0; tp < taps; ++tp) acc = fmaf(cff[tp], sw[tp][tx][r], acc);
-      fwd[(static_cast<size_t>(pq) * p.Opad + o0 + r) * Kf + static_cast<size_t>(tu) * p.Ipad + i0 + tx] =
-          __float2bfloat16_rn(acc);
+  const size_t Kf = static_cast<size_t>(TTf) * p.Ipad, Ka = static_cast<size_t>(TTa) * p.Opad;
+  for (int r = ty; r < 32; r += 8) {
+    float vf[9], va[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      vf[tp] = sw[tp][tx][r];  // element (i = i0+tx, o = o0+r): lanes over i
+      va[tp] = sw[tp][r][tx];  // element (i = i0+r, o = o0+tx): lanes over o
     }
-  }
-  if (c < nca) {  // adjoint matrix: rows (pq, i), cols (tu, o): o contiguous -> lanes over o
-    const int pq = c / TTa, tu = c - pq * TTa;
-    const size_t Ka = static_cast<size_t>(TTa) * p.Opad;
-    for (int r = ty; r < 32; r += 8) {
-      float acc = 0.f;
-      for (int tp = 0; tp < taps; ++tp) acc = fmaf(cfa[tp], sw[tp][r][tx], acc);
-      adj[(static_cast<size_t>(pq) * p.Ipad + i0 + r) * Ka + static_cast<size_t>(tu) * p.Opad + o0 + tx] =
-          __float2bfloat16_rn(acc);
+    {  // forward matrix: rows (pq, o), cols (tu, i)
+      __nv_bfloat16* dst = fwd + static_cast<size_t>(o0 + r) * Kf + i0 + tx;
+      const size_t pq_stride = static_cast<size_t>(p.Opad) * Kf;
+      for (int pq = 0, c = 0; pq < p.fy.P * p.fx.P; ++pq, dst += pq_stride) {
+#pragma unroll 3
+        for (int tu = 0; tu < TTf; ++tu, ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) acc = fmaf(cff[c][tp], vf[tp], acc);
+          dst[static_cast<size_t>(tu) * p.Ipad] = __float2bfloat16_rn(acc);
+        }
+      }
     }
-  }
-  if (q != nullptr && c == 0) {
-    for (int r = ty; r < 32; r += 8) {
+    if (nca > 0) {  // adjoint matrix: rows (pq, i), cols (tu, o)
+      __nv_bfloat16* dst = adj + static_cast<size_t>(i0 + r) * Ka + o0 + tx;
+      const size_t pq_stride = static_cast<size_t>(p.Ipad) * Ka;
+      for (int pq = 0, c = 0; pq < p.ay.P * p.ax.P; ++pq, dst += pq_stride) {
+#pragma unroll 3
+        for (int tu = 0; tu < TTa; ++tu, ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) acc = fmaf(cfa[c][tp], va[tp], acc);
+          dst[static_cast<size_t>(tu) * p.Opad] = __float2bfloat16_rn(acc);
+        }
+      }
+    }
+    if (q != nullptr) {
       const int i = i0 + r, o = o0 + tx;
       if (i < p.I && o < p.O) {
         float acc = 0.f;
-        for (int tp = 0; tp < taps; ++tp) acc += sw[tp][r][tx] * sw[tp][r][tx];
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) acc = fmaf(va[tp], va[tp], acc);
         q[static_cast<size_t>(i) * p.O + o] = acc;
       }
     }
   }
 }
 
-// gw[kh,kw,i,o] += coef * sum_c cf[c][tap] * gfwd_c[o,i]  (+ 2*coef^2*w*gq[i,o]); CTA (tile, c) folds
-// combination c with fp32 reductions into gw (each combination touches at most 9 master taps).
+// gw[tap,i,o] += coef * sum_c cf[c][tap] * gfwd_c[o,i]  (+ 2*coef^2*w*gq[i,o]).  One CTA per weight tile
+// streams the (phase, tap) combinations of the gradient matrix through a 32 x 32 transpose buffer.
 __global__ void __launch_bounds__(256)
 wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const float* __restrict__ w,
              float* __restrict__ gw, const WPrepParams p) {
-  __shared__ float sg[32][33];  // [o][i]
-  __shared__ float cff[9];
+  __shared__ float sg[2][32][33];  // double-buffered [o][i]
+  __shared__ float cff[36][9];
   const int tiles_o = p.Opad / 32;
   const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int TT = p.fy.T * p.fx.T;
   const size_t Kf = static_cast<size_t>(TT) * p.Ipad;
+  const int ncomb = p.fy.P * p.fx.P * TT;
   const int taps = p.KH * p.KW;
-  const int c = blockIdx.y;
-  if (threadIdx.x < 9) {
-    const int tap = threadIdx.x;
-    float v = 0.f;
-    if (tap < taps) {
-      const int u = c % p.fx.T, t = (c / p.fx.T) % p.fy.T, qq = (c / TT) % p.fx.P, pp = c / (TT * p.fx.P);
-      v = tab(p.fy, pp, t, tap / p.KW) * tab(p.fx, qq, u, tap % p.KW);
-    }
-    cff[tap] = v * p.coef;
-  }
-  {
+  build_cf(p.fy, p.fx, p.KH, p.KW, p.coef, cff);
+  float acc[4][9];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) acc[k][tp] = 0.f;
+  auto load_tile = [&](int c, int buf) {
     const int pq = c / TT, tu = c - pq * TT;
-    for (int r = ty; r < 32; r += 8)  // r = o, tx = i (contiguous)
-      sg[r][tx] = __ldg(gfwd + (static_cast<size_t>(pq) * p.Opad + o0 + r) * Kf + static_cast<size_t>(tu) * p.Ipad + i0 + tx);
-  }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // row = o, lanes over i (contiguous)
+      const int r = ty + 8 * k;
+      sg[buf][r][tx] = __ldg(gfwd + (static_cast<size_t>(pq) * p.Opad + o0 + r) * Kf + static_cast<size_t>(tu) * p.Ipad + i0 + tx);
+    }
+  };
+  load_tile(0, 0);
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {  // r = i, tx = o (contiguous in the master weight)
-    const int i = i0 + r, o = o0 + tx;
+  for (int c = 0; c < ncomb; ++c) {
+    if (c + 1 < ncomb) load_tile(c + 1, (c + 1) & 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // element (i = i0 + ty + 8k, o = o0 + tx)
+      const float g = sg[c & 1][tx][ty + 8 * k];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) acc[k][tp] = fmaf(cff[c][tp], g, acc[k][tp]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + ty + 8 * k, o = o0 + tx;
     if (i >= p.I || o >= p.O) continue;
-    const float g = sg[tx][r];
-    const float gqv = (gq != nullptr && c == 0) ? 2.f * p.coef * p.coef * __ldg(gq + static_cast<size_t>(i) * p.O + o) : 0.f;
-    for (int tp = 0; tp < taps; ++tp) {
-      const size_t idx = (static_cast<size_t>(tp) * p.I + i) * p.O + o;
-      float v = cff[tp] * g;
-      if (gq != nullptr && c == 0) v = fmaf(gqv, __ldg(w + idx), v);
-      if (v != 0.f) atomicAdd(gw + idx, v);
+    const float gqv = (gq != nullptr) ? 2.f * p.coef * p.coef * __ldg(gq + static_cast<size_t>(i) * p.O + o) : 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      if (tp < taps) {
+        const size_t idx = (static_cast<size_t>(tp) * p.I + i) * p.O + o;
+        float v = acc[k][tp];
+        if (gq != nullptr) v = fmaf(gqv, __ldg(w + idx), v);
+        gw[idx] += v;
+      }
     }
   }
 }
@@ -194,7 +223,7 @@ extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH
   const int ncf = p.fy.P * p.fx.P * p.fy.T * p.fx.T;
   const int nca = (p.ay.P > 0) ? p.ay.P * p.ax.P * p.ay.T * p.ax.T : 0;
   TBG_CHECK_ARG(ncf <= 36 && nca <= 36, "tbg_wprep: too many (phase, tap) combinations");
-  wprep_kernel<<<dim3((Ipad / 32) * (Opad / 32), ncf > nca ? ncf : nca), 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(fwd),
+  wprep_kernel<<<(Ipad / 32) * (Opad / 32), 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(fwd),
                                                              (p.ay.P > 0) ? reinterpret_cast<__nv_bfloat16*>(adj) : nullptr,
                                                              q, p);
   count_launch();
@@ -213,7 +242,7 @@ extern "C" int tbg_wfold(const float* gfwd, const float* gq, const float* w, con
   TBG_CHECK_ARG(p.fy.P * p.fx.P * p.fy.T * p.fx.T <= 36, "tbg_wfold: too many (phase, tap) combinations");
   p.KH = KH; p.KW = KW; p.I = I; p.O = O; p.Ipad = Ipad; p.Opad = Opad; p.coef = coef;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  wfold_kernel<<<dim3((Ipad / 32) * (Opad / 32), p.fy.P * p.fx.P * p.fy.T * p.fx.T), 256, 0, stream>>>(gfwd, gq, w, gw, p);
+  wfold_kernel<<<(Ipad / 32) * (Opad / 32), 256, 0, stream>>>(gfwd, gq, w, gw, p);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
