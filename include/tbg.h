@@ -181,6 +181,33 @@ int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, i
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
               int I, int O, int Ipad, int Opad, float* gw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Greedy Bahdanau-attention LSTM decoder of the frozen OCR head, all decode steps in one launch,
+ * one CTA per sample (reached through AsterInferer.call, aster_inferer.py:28-37; the head is frozen,
+ * so backward yields only d/d mem and d/d keys).  Dimensions are fixed: hidden = attention units =
+ * embedding = 256, memory features 512, 96 classes, T <= 64.  Weights bf16 (v, b, bd fp32).
+ *   fwd: mem f32 [B,T,512], keys f32 [B,T,256] (= mem Wm, computed by the caller)
+ *        -> logits f32 [B,steps,96] + saved a [B,steps,T], ctx [B,steps,512], gates [B,steps,1024],
+ *           c, h [B,steps,256], prev int32 [B,steps]
+ *   bwd: g_logits f32 [B,steps,96] (+ saved) -> g_mem f32 [B,T,512], g_keys f32 [B,T,256]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tbg_dec_weights {
+  const void *wq, *wqT;   /* bf16 [256,256] query layer and its transpose */
+  const void* v;          /* f32  [256] attention_v */
+  const void* emb;        /* bf16 [96,256] previous-symbol embedding */
+  const void *wg, *wgT;   /* bf16 [1024,1024]: rows [emb | ctx | h] = LSTM W_ih stacked on W_hh (-> i,f,g,o), and its transpose */
+  const void* b;          /* f32  [1024] */
+  const void *wd, *wdT;   /* bf16 [768,96], [96,768]  output dense on [h, ctx] */
+  const void* bd;         /* f32  [96] */
+} tbg_dec_weights;
+
+int tbg_attn_decoder_fwd(const float* mem, const float* keys, const tbg_dec_weights* w, float* logits, float* sv_a,
+                         float* sv_ctx, float* sv_gates, float* sv_c, float* sv_h, int* sv_prev, int B, int T,
+                         int steps, void* stream);
+int tbg_attn_decoder_bwd(const float* mem, const float* keys, const tbg_dec_weights* w, const float* g_logits,
+                         const float* sv_a, const float* sv_ctx, const float* sv_gates, const float* sv_c,
+                         const float* sv_h, float* g_mem, float* g_keys, int B, int T, int steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

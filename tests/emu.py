@@ -214,6 +214,73 @@ def emu_wfold(gfwd, spec, *, gq=None, w_raw=None, out=None):
     return gw
 
 
+def emu_attn_decoder_fwd(mem, keys, w, steps):
+    """Documented semantics of tbg_attn_decoder_fwd == oracle/aster.py::attention_decoder."""
+    B, T, _ = mem.shape
+    f = lambda n: w[n].double()
+    m, ky = mem.double(), keys.double()
+    h = torch.zeros(B, 256, dtype=torch.float64)
+    c = torch.zeros(B, 256, dtype=torch.float64)
+    prev = torch.zeros(B, dtype=torch.long)
+    sv = dict(a=[], ctx=[], gates=[], c=[], h=[], prev=[])
+    logits = []
+    for _ in range(steps):
+        q = h @ f("wq")
+        e = torch.tanh(ky + q[:, None, :]) @ f("v")
+        a = torch.softmax(e, dim=1)
+        ctx = (a[:, :, None] * m).sum(1)
+        gates = torch.cat([f("emb")[prev], ctx, h], 1) @ f("wg") + f("b")
+        i, fg, g, o = gates.chunk(4, dim=1)
+        i, fg, g, o = torch.sigmoid(i), torch.sigmoid(fg), torch.tanh(g), torch.sigmoid(o)
+        c = fg * c + i * g
+        h = o * torch.tanh(c)
+        lg = torch.cat([h, ctx], 1) @ f("wd") + f("bd")
+        sv["prev"].append(prev.clone())
+        prev = lg.argmax(dim=1)
+        for k, v in (("a", a), ("ctx", ctx), ("gates", torch.cat([i, fg, g, o], 1)), ("c", c), ("h", h)):
+            sv[k].append(v)
+        logits.append(lg)
+    out = {k: torch.stack(v, 1).float() if k != "prev" else torch.stack(v, 1).int() for k, v in sv.items()}
+    return torch.stack(logits, 1).float(), out
+
+
+def emu_attn_decoder_bwd(mem, keys, w, g_logits, sv):
+    B, T, _ = mem.shape
+    steps = g_logits.shape[1]
+    f = lambda n: w[n].double()
+    m, ky, gl = mem.double(), keys.double(), g_logits.double()
+    g_mem = torch.zeros_like(m)
+    g_keys = torch.zeros_like(ky)
+    dh = torch.zeros(B, 256, dtype=torch.float64)
+    dc = torch.zeros(B, 256, dtype=torch.float64)
+    for st in range(steps - 1, -1, -1):
+        dcat = gl[:, st] @ f("wd").t()
+        dh = dh + dcat[:, :256]
+        dctx = dcat[:, 256:]
+        i, fg, g, o = sv["gates"][:, st].double().chunk(4, dim=1)
+        cc = sv["c"][:, st].double()
+        cp = sv["c"][:, st - 1].double() if st > 0 else torch.zeros_like(cc)
+        hp = sv["h"][:, st - 1].double() if st > 0 else torch.zeros_like(cc)
+        tc = torch.tanh(cc)
+        do = dh * tc * o * (1 - o)
+        dcc = dh * o * (1 - tc * tc) + dc
+        dg = torch.cat([dcc * g * i * (1 - i), dcc * cp * fg * (1 - fg), dcc * i * (1 - g * g), do], 1)
+        dc = dcc * fg
+        dx = dg @ f("wg").t()
+        dctx = dctx + dx[:, 256:768]
+        dh_prev = dx[:, 768:]
+        a = sv["a"][:, st].double()
+        da = (dctx[:, None, :] * m).sum(2)
+        g_mem += a[:, :, None] * dctx[:, None, :]
+        de = a * (da - (a * da).sum(1, keepdim=True))
+        q = hp @ f("wq")
+        th = torch.tanh(ky + q[:, None, :])
+        dp = de[:, :, None] * f("v")[None, None, :] * (1 - th * th)
+        g_keys += dp
+        dh = dh_prev + dp.sum(1) @ f("wq").t()
+    return g_mem.float(), g_keys.float()
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -225,8 +292,9 @@ def emulated_kernels(act_dtype=torch.float32):
              K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd, K.torgb_bwd)
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
-    saved_w = (K.wprep, K.wfold)
+    saved_w = (K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd)
     K.wprep, K.wfold = emu_wprep, emu_wfold
+    K.attn_decoder_fwd, K.attn_decoder_bwd = emu_attn_decoder_fwd, emu_attn_decoder_bwd
     K.conv2d_igemm = emu_conv2d_igemm
     K.conv2d_wgrad = emu_conv2d_wgrad
     K.upfirdn2d = emu_upfirdn2d
@@ -242,4 +310,4 @@ def emulated_kernels(act_dtype=torch.float32):
         (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
          K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd,
          K.torgb_bwd) = saved
-        K.wprep, K.wfold = saved_w
+        K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd = saved_w

@@ -264,6 +264,40 @@ def test_weight_prep_and_fold_vs_emulated_semantics(kind, k, rh, I, O):
     assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
 
 
+@pytest.mark.parametrize("B,T,steps", [(3, 32, 8), (5, 17, 4)])
+def test_attention_decoder_and_lstm_kernels_vs_emulated_semantics(B, T, steps):
+    import emu
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200.aster_inferer import _LstmLayer, _pack_decoder, init_aster_params
+
+    P = init_aster_params()
+    w_dev = _pack_decoder(P, DEV)
+    w_cpu = {k: v.float().cpu() for k, v in w_dev.items()}          # the same bf16-rounded weights
+    gen = torch.Generator().manual_seed(B * 100 + T)
+    mem = torch.randn(B, T, 512, generator=gen)
+    keys = mem @ P["dec/memory_layer/w"]
+    logits, sv = K.attn_decoder_fwd(mem.to(DEV), keys.to(DEV), w_dev, steps)
+    rl, rsv = emu.emu_attn_decoder_fwd(mem, keys, w_cpu, steps)
+    assert torch.equal(sv["prev"].cpu(), rsv["prev"])                # greedy symbols: integer path, bit-exact
+    assert rel_err(logits, rl) < 1e-4
+    for k in ("a", "ctx", "gates", "c", "h"):
+        assert rel_err(sv[k], rsv[k]) < 1e-4, k
+    gl = torch.randn(B, steps, 96, generator=gen)
+    gm, gk = K.attn_decoder_bwd(mem.to(DEV), keys.to(DEV), w_dev, gl.to(DEV), sv)
+    rgm, rgk = emu.emu_attn_decoder_bwd(mem, keys, w_cpu, gl, rsv)
+    assert rel_err(gm, rgm) < 1e-4 and rel_err(gk, rgk) < 1e-4
+    # LSTM sequence kernels
+    lay = _LstmLayer(P, "rnn/l0", DEV)
+    xp = torch.randn(2, B, T, 1024, generator=gen)
+    h, gates, c = K.lstm_seq_fwd(xp.to(DEV), lay.w_packed)
+    rh, rg, rc = emu.emu_lstm_seq_fwd(xp, lay.w_packed.float().cpu())
+    assert rel_err(h, rh) < 1e-4 and rel_err(gates, rg) < 1e-4 and rel_err(c, rc) < 1e-4
+    gh = torch.randn(2, B, T, 256, generator=gen)
+    gxp = K.lstm_seq_bwd(gh.to(DEV), gates, c, lay.wT_packed)
+    rgxp = emu.emu_lstm_seq_bwd(gh, rg, rc, lay.wT_packed.float().cpu())
+    assert rel_err(gxp, rgxp) < 1e-4
+
+
 def _product(cfg, GP, DP, with_ocr=True):
     from textboxgan_b200.aster_inferer import AsterInferer
     from textboxgan_b200.discriminator import Discriminator

@@ -162,6 +162,33 @@ class _LstmSeq(torch.autograd.Function):
         return K.lstm_seq_bwd(g_h.contiguous(), gates, c, ctx.layer.wT_packed), None
 
 
+class _AttnDecoder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mem, keys, w: dict, steps: int):
+        logits, sv = K.attn_decoder_fwd(mem, keys, w, steps)
+        ctx.w, ctx.sv = w, sv
+        ctx.save_for_backward(mem, keys)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g_logits):
+        mem, keys = ctx.saved_tensors
+        g_mem, g_keys = K.attn_decoder_bwd(mem, keys, ctx.w, g_logits.contiguous().float(), ctx.sv)
+        return g_mem, g_keys, None, None
+
+
+def _pack_decoder(P, device) -> dict:
+    """Frozen decoder weights in the layouts the kernels stream (bf16 matrices + their transposes)."""
+    act = L.ACT_DTYPE
+    m = lambda n: P[n].to(device).float()
+    wq, wih, whh, wd = m("dec/query_layer/w"), m("dec/lstm_cell/w_ih"), m("dec/lstm_cell/w_hh"), m("dec/dense/w")
+    wg = torch.cat([wih, whh], dim=0)                       # rows [emb | ctx | h]
+    return dict(wq=wq.to(act).contiguous(), wqT=wq.t().to(act).contiguous(), v=m("dec/attention_v").contiguous(),
+                emb=m("dec/embedding").to(act).contiguous(), wg=wg.to(act).contiguous(),
+                wgT=wg.t().to(act).contiguous(), b=m("dec/lstm_cell/b").contiguous(), wd=wd.to(act).contiguous(),
+                wdT=wd.t().to(act).contiguous(), bd=m("dec/dense/b").contiguous())
+
+
 class AsterInferer:
     """Reads the word written in a text box (aster_inferer.py:7-37)."""
 
@@ -178,6 +205,7 @@ class AsterInferer:
         self.P = {k: v.to(self.device).float() for k, v in P.items()}
         self._build_encoder(P)
         self.lstm = {n: _LstmLayer(P, n, self.device) for n in ("rnn/l0", "rnn/l1")}
+        self.dec_w = _pack_decoder(P, self.device)
 
     # ------------------------------------------------------------------------------------------
     def _build_encoder(self, P) -> None:
@@ -227,25 +255,9 @@ class AsterInferer:
         return torch.cat([hs[0], hs[1].flip(1)], dim=2)
 
     def _decoder(self, mem: torch.Tensor, steps: int) -> torch.Tensor:
-        P = self.P
-        B = mem.shape[0]
-        keys = mem @ P["dec/memory_layer/w"]
-        h = mem.new_zeros(B, LSTM_HIDDEN)
-        c = mem.new_zeros(B, LSTM_HIDDEN)
-        prev = torch.zeros(B, dtype=torch.long, device=mem.device)
-        logits = []
-        for _ in range(steps):
-            q = h @ P["dec/query_layer/w"]
-            e = torch.tanh(keys + q[:, None, :]) @ P["dec/attention_v"]
-            a = torch.softmax(e, dim=1)
-            ctx = (a[:, :, None] * mem).sum(dim=1)
-            inp = torch.cat([P["dec/embedding"][prev], ctx], dim=1)
-            xp = inp @ P["dec/lstm_cell/w_ih"] + P["dec/lstm_cell/b"]
-            h, c = self._lstm_cell(xp, h, c, P["dec/lstm_cell/w_hh"])
-            lg = torch.cat([h, ctx], dim=1) @ P["dec/dense/w"] + P["dec/dense/b"]
-            logits.append(lg)
-            prev = lg.detach().argmax(dim=1)
-        return torch.stack(logits, dim=1)
+        """All decode steps in one launch (``tbg_attn_decoder_fwd``); ``keys = mem @ W_m`` is a plain GEMM."""
+        keys = mem @ self.P["dec/memory_layer/w"]
+        return _AttnDecoder.apply(mem.contiguous(), keys.contiguous(), self.dec_w, steps)
 
     # -- reference surface -------------------------------------------------------------------------
     def __call__(self, inputs: torch.Tensor) -> torch.Tensor:

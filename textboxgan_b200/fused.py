@@ -24,6 +24,26 @@ from . import kernels as K
 from .conv import ConvGeom, relayout_for_adjoint
 
 
+# Prepared GEMM matrices of a master weight, shared by every use of that weight inside ONE training
+# step (the discriminator runs twice per step, on fake and on real images, training_step.py:260,288;
+# weights only change in the optimiser updates at the end of the step).
+_STEP_CACHE: dict = {}
+
+
+def clear_step_cache() -> None:
+    _STEP_CACHE.clear()
+
+
+def _prepared(w_raw, spec, want_adj: bool, want_q: bool):
+    key = (w_raw.data_ptr(), id(spec))
+    hit = _STEP_CACHE.get(key)
+    if hit is not None and (hit[1] is not None or not want_adj) and (hit[2] is not None or not want_q):
+        return hit
+    out = K.wprep(w_raw, spec, want_adj=want_adj, want_q=want_q)
+    _STEP_CACHE[key] = out
+    return out
+
+
 def _act_dtype():
     from . import layers as L
 
@@ -38,7 +58,7 @@ class ModConvAct(torch.autograd.Function):
         geom = spec.geom
         x = x.contiguous()
         s = s.contiguous()
-        wmat, wadj, q = K.wprep(w_raw, spec, want_adj=True, want_q=True)        # one launch
+        wmat, wadj, q = _prepared(w_raw, spec, True, True)                       # one launch per step
         d = torch.rsqrt((s * s) @ q + 1e-8)                                      # modulated_conv2d.py:80-82
         xs = K.modulate(x, s)
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
@@ -80,7 +100,7 @@ class ConvAct(torch.autograd.Function):
         x = x.contiguous()
         has_act = bias is not None
         need_gx = ctx.needs_input_grad[0]
-        wmat, wadj, _ = K.wprep(w_raw, spec, want_adj=need_gx, want_q=False)
+        wmat, wadj, _ = _prepared(w_raw, spec, need_gx, False)
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
         out = K.conv2d_igemm(x, wmat, **geom.kernel_kwargs(), bias=bias, act=1 if has_act else 0,
                              act_gain=gain if has_act else 1.0,

@@ -49,6 +49,10 @@ class WgradArgs(C.Structure):
     ]
 
 
+class DecWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("wq", "wqT", "v", "emb", "wg", "wgT", "b", "wd", "wdT", "bd")]
+
+
 _lib = None
 
 # every symbol include/tbg.h declares: (name, restype, argtypes)
@@ -72,6 +76,8 @@ _SIGNATURES = [
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
     ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 2),
+    ("tbg_attn_decoder_fwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
+    ("tbg_attn_decoder_bwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
 ]
 
 

@@ -189,7 +189,10 @@ class TrainingStep:
     def _train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
                     ocr_loss_weight: float, draws: Optional[dict] = None):
         """training_step.py:138-222"""
+        from . import fused as _fused
+
         draws = draws or {}
+        _fused.clear_step_cache()
         G, D = self.generator, self.discriminator
         dev = G.device
         z = draws["z"].to(dev) if "z" in draws else torch.randn(self.batch_size_per_gpu, self.z_dim, device=dev)
@@ -221,6 +224,7 @@ class TrainingStep:
                 self.ocr_optimizer.apply_gradients(zip(o_grads, o_vars), model=G, names=self._ocr_names)
             self.d_optimizer.apply_gradients(zip(d_grads, d_vars), model=D, names=self._d_names)
 
+        _fused.clear_step_cache()
         gen_losses = (reg_g_loss.detach(), g_loss.detach(), pl_penalty.detach())
         disc_losses = (reg_d_loss.detach(), d_loss.detach(), r1_penalty.detach())
         ocr_out = (ocr_loss / ocr_loss_weight).detach() if ocr_loss is not None else torch.zeros((), device=dev)
