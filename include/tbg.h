@@ -145,12 +145,15 @@ int tbg_lstm_seq_bwd(const float* g_h, const float* gates, const float* c_saved,
  * Fused HBM-bound passes of the plain (first-order) step.  x/xs/g* activations are bf16
  * [B, HW, C] (NHWC flattened), C % 8 == 0; per-sample vectors are fp32 [B, C].
  *   tbg_modulate       xs = x * s[b,c]                                   (modulated_conv2d.py:96)
- *   tbg_modulate_bwd   gx = gxs * s ;  gs[b,c] += sum_hw gxs*x           (gs must be zeroed)
+ *   tbg_modulate_bwd   gx = gxs * s ;  gs[b,c] += sum_hw gxs*x           (gs zeroed, or initialised by
+ *                      tbg_demod_bwd with the demodulation term of dL/ds)
  *   tbg_bias_act_bwd   backward of out = act(y0*d + noise*ns + bias)*gain (+ residual)
  *                      (modulated_conv2d.py:121, noise.py:21, bias_act.py:25-34, discriminator.py:82):
  *                      gy0 = g_pre*d (bf16) and, when S1 != NULL, the zero-initialised sums
  *                      S1 = sum_hw g_pre, Spre = sum_hw g_pre*pre, Snz = sum_hw g_pre*noise, from
- *                      which d(bias), d(noise strength) and d(d) follow on [B, C] tensors.
+ *                      which d(bias), d(noise strength) and d(d) follow on [B, C] tensors
+ *                      (Spre / Snz may be NULL).  s1_over_batch != 0: S1 is [C], summed over the
+ *                      batch as well (= the bias gradient of Conv2D + BiasAct; Spre, noise NULL).
  *                      act: 0 linear, 1 leaky-relu(0.2), 2 relu.
  *   tbg_torgb_fwd/bwd  y[p,j] = sum_c x[p,c]*ws[b,c,j] (+ bias[j]), j < 3   (to_rgb.py:28-33);
  *                      bwd: gx = gy . ws^T (bf16), gws[b,c,j] += sum_p x*gy (gws must be zeroed)
@@ -160,7 +163,7 @@ int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, void* gx, f
                      void* stream);
 int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise, const float* d,
                      void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C, int act, float gain,
-                     void* stream);
+                     int s1_over_batch, void* stream);
 int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C, void* stream);
 int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
                   void* stream);
@@ -174,12 +177,50 @@ int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, flo
  * `tables` is a HOST array of 4 blocks {P, T, K, 36 floats [P][T][K]} for Ty, Tx, Ty', Tx' (identity
  * for plain convs; FIR-folded tables for upsample_conv_2d / conv_downsample_2d,
  * upfirdn_2d_v2.py:65-113).  coef is the equalised-LR runtime coefficient (commons.py:4-12).
- * tbg_wfold is the transpose: gw += coef * fold(gfwd) (+ 2 coef^2 w gq), gfwd fp32 in fwd layout.
+ * tbg_wfold is the transpose: gw += coef * fold(gfwd) (+ 2 coef^2 w gq), gfwd fp32 in fwd layout;
+ * gq[i,o] = dL/dq is either given or formed in the kernel from (s [nb,I], t [nb,O]) of tbg_demod_bwd as
+ * sum_b s[b,i]^2 t[b,o] (pass gq NULL).
  * ------------------------------------------------------------------------------------------ */
 int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad, int Opad,
               void* fwd, void* adj, float* q, void* stream);
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
-              int I, int O, int Ipad, int Opad, float* gw, void* stream);
+              int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Demodulation coefficient of ModulatedConv2D and its gradient (modulated_conv2d.py:75-82), fp32:
+ *   tbg_demod_coef  d[b,o] = rsqrt(sum_i s[b,i]^2 q[i,o] + eps)           s [B,I], q [I,O] (tbg_wprep)
+ *   tbg_demod_bwd   from S1/Spre/Snz [B,O] of tbg_bias_act_bwd, d, the noise strength ns (device
+ *                   scalar) and bias [O]:
+ *                     t[b,o]   = dL/d(s^2 @ q) = -0.5 (Spre - ns Snz - bias S1) d^2
+ *                     gs[b,i]  = 2 s[b,i] sum_o t[b,o] q[i,o]   (written; tbg_modulate_bwd adds to it)
+ *                     gbias[o] = sum_b S1[b,o],  gns[0] = sum_{b,o} Snz[b,o]
+ * ------------------------------------------------------------------------------------------ */
+int tbg_demod_coef(const float* s, const float* q, float* d, int B, int I, int O, float eps, void* stream);
+int tbg_demod_bwd(const float* S1, const float* Spre, const float* Snz, const float* d, const float* ns,
+                  const float* bias, const float* s, const float* q, float* t, float* gbias, float* gns, float* gs,
+                  int B, int I, int O, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Grouped style projection of the synthesis network: for every modulated convolution l,
+ *   s_l[b,i] = coef * sum_k style[b, idx_l, k] * w_l[k,i] + b_l[i] + 1        (modulated_conv2d.py:75-76,
+ * dense.py:23-29; coef = 1/sqrt(S)), all layers in ONE launch; tbg_style_dense_bwd returns, in two
+ * launches, gw_l = coef * style[:,idx_l]^T gs_l, gb_l = sum_b gs_l and
+ * gstyle[b,j,:] = coef * sum_{l: idx_l = j} gs_l[b,:] w_l^T (rows no layer uses are zeroed).
+ * style / gstyle: fp32 [B, n_style, S]; at most 32 layers; the table is a HOST array.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tbg_style_layer {
+  const float* w;   /* [S, I] */
+  const float* b;   /* [I] */
+  float* s;         /* fwd out [B, I] */
+  const float* gs;  /* bwd in  [B, I] */
+  float* gw;        /* bwd out [S, I] */
+  float* gb;        /* bwd out [I] */
+  int I, idx;
+} tbg_style_layer;
+int tbg_style_dense_fwd(const tbg_style_layer* layers, int n_layers, const float* style, int B, int n_style, int S,
+                        float coef, void* stream);
+int tbg_style_dense_bwd(const tbg_style_layer* layers, int n_layers, const float* style, float* gstyle, int B,
+                        int n_style, int S, float coef, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Greedy Bahdanau-attention LSTM decoder of the frozen OCR head, all decode steps in one launch,

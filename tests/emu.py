@@ -143,14 +143,45 @@ def emu_modulate(x, s):
     return (x.double() * s.double().reshape(s.shape[0], *([1] * (x.dim() - 2)), s.shape[1])).to(x.dtype)
 
 
-def emu_modulate_bwd(gxs, x, s):
+def emu_modulate_bwd(gxs, x, s, gs_init=None):
     sb = s.double().reshape(s.shape[0], *([1] * (x.dim() - 2)), s.shape[1])
     gx = (gxs.double() * sb).to(x.dtype)
     gs = (gxs.double() * x.double()).reshape(x.shape[0], -1, x.shape[-1]).sum(1).to(s.dtype)
+    if gs_init is not None:
+        gs = gs + gs_init
     return gx, gs
 
 
-def emu_bias_act_bwd(g_out, out, *, residual=None, noise=None, d=None, act=True, gain=1.0, want_sums=True):
+def emu_style_dense_fwd(style, ws, bs, idxs, coef):
+    return [(coef * (style[:, i].double() @ w.double()) + b.double() + 1.0).to(style.dtype)
+            for w, b, i in zip(ws, bs, idxs)]
+
+
+def emu_style_dense_bwd(style, ws, gss, idxs, coef):
+    gstyle = torch.zeros_like(style, dtype=torch.float64)
+    gws, gbs = [], []
+    for w, g, i in zip(ws, gss, idxs):
+        gws.append((coef * style[:, i].double().t() @ g.double()).to(style.dtype))
+        gbs.append(g.double().sum(0).to(style.dtype))
+        gstyle[:, i] += coef * g.double() @ w.double().t()
+    return gstyle.to(style.dtype), gws, gbs
+
+
+def emu_demod_coef(s, q, eps=1e-8):
+    return torch.rsqrt((s.double() ** 2) @ q.double() + eps).to(s.dtype)
+
+
+def emu_demod_bwd(S1, Spre, Snz, d, ns, bias, s, q):
+    """Documented semantics of tbg_demod_bwd (include/tbg.h)."""
+    nsv = ns.double().reshape(()) if (ns is not None and Snz is not None) else 0.0
+    snz = Snz.double() if Snz is not None else torch.zeros_like(S1).double()
+    t = -0.5 * (Spre.double() - nsv * snz - bias.double()[None, :] * S1.double()) * d.double() ** 2
+    gs = 2.0 * s.double() * (t @ q.double().t())
+    return t.to(s.dtype), S1.double().sum(0).to(s.dtype), snz.sum().reshape(1).to(s.dtype), gs.to(s.dtype)
+
+
+def emu_bias_act_bwd(g_out, out, *, residual=None, noise=None, d=None, act=True, gain=1.0, want_sums=True,
+                     bias_grad_only=False):
     B, C = out.shape[0], out.shape[-1]
     o = out.double()
     if residual is not None:
@@ -161,6 +192,8 @@ def emu_bias_act_bwd(g_out, out, *, residual=None, noise=None, d=None, act=True,
     pre = torch.where(slope > 0, o / (gain * slope.clamp_min(1e-30)), torch.zeros_like(o))
     dd = d.double().reshape(B, *([1] * (out.dim() - 2)), C) if d is not None else 1.0
     gy0 = (gp * dd).to(out.dtype)
+    if bias_grad_only:
+        return gy0, gp.reshape(-1, C).sum(0).float(), None, None
     if not want_sums:
         return gy0, None, None, None
     S1 = gp.reshape(B, -1, C).sum(1).float()
@@ -201,7 +234,9 @@ def emu_wprep(w_raw, spec, *, want_adj=True, want_q=False, act_dtype=None):
     return fwd, adj, q
 
 
-def emu_wfold(gfwd, spec, *, gq=None, w_raw=None, out=None):
+def emu_wfold(gfwd, spec, *, gq=None, w_raw=None, out=None, s=None, t=None):
+    if s is not None:
+        gq = (s.double() ** 2).t() @ t.double()
     fy, fx, _, _ = [t.double() for t in spec.tables]
     g6 = gfwd.double().reshape(fy.shape[0], fx.shape[0], spec.Opad, fy.shape[1], fx.shape[1], spec.Ipad)
     gw = torch.einsum("ptk,qul,pqotui->klio", fy, fx, g6)[:, :, : spec.I, : spec.O] * spec.coef
@@ -293,6 +328,9 @@ def emulated_kernels(act_dtype=torch.float32):
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
     saved_w = (K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd)
+    saved_d = (K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd)
+    K.demod_coef, K.demod_bwd = emu_demod_coef, emu_demod_bwd
+    K.style_dense_fwd, K.style_dense_bwd = emu_style_dense_fwd, emu_style_dense_bwd
     K.wprep, K.wfold = emu_wprep, emu_wfold
     K.attn_decoder_fwd, K.attn_decoder_bwd = emu_attn_decoder_fwd, emu_attn_decoder_bwd
     K.conv2d_igemm = emu_conv2d_igemm
@@ -311,3 +349,4 @@ def emulated_kernels(act_dtype=torch.float32):
          K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd,
          K.torgb_bwd) = saved
         K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd = saved_w
+        K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd = saved_d

@@ -264,6 +264,76 @@ def test_weight_prep_and_fold_vs_emulated_semantics(kind, k, rh, I, O):
     assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
 
 
+@pytest.mark.parametrize("B,I,O", [(4, 512, 512), (32, 128, 64), (3, 192, 512), (5, 64, 3)])
+def test_demodulation_kernels_vs_emulated_semantics(B, I, O):
+    """tbg_demod_coef / tbg_demod_bwd / tbg_wfold(s, t) / tbg_modulate_bwd(gs_init) / bias-gradient mode of
+    tbg_bias_act_bwd against their documented semantics (fp32: 1e-4 relative, summation order only)."""
+    import emu
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(B + I + O)
+    s = torch.randn(B, I, generator=gen) + 1.0
+    q = torch.rand(I, O, generator=gen) / I
+    d = K.demod_coef(s.to(DEV), q.to(DEV))
+    rd = emu.emu_demod_coef(s, q)
+    assert rel_err(d, rd) < 1e-5
+    S1, Spre, Snz = (torch.randn(B, O, generator=gen) for _ in range(3))
+    ns = torch.randn(1, generator=gen)
+    bias = torch.randn(O, generator=gen)
+    out = K.demod_bwd(*(t.to(DEV) for t in (S1, Spre, Snz, rd, ns, bias, s, q)))
+    ref = emu.emu_demod_bwd(S1, Spre, Snz, rd, ns, bias, s, q)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < 1e-4
+    if O % 32 == 0 and I % 32 == 0:
+        spec = C.weight_spec("plain", 8, 16, I, O, 3, True)
+        w = torch.randn(3, 3, I, O, generator=gen)
+        g = torch.randn(spec.fwd_rows, spec.fwd_cols, generator=gen)
+        t = ref[0]
+        got = K.wfold(g.to(DEV), spec, w_raw=w.to(DEV), s=s.to(DEV), t=t.to(DEV))
+        want = emu.emu_wfold(g, spec, w_raw=w, s=s, t=t)
+        assert rel_err(got, want) < 1e-4
+    if O % 8 == 0:
+        x = _bf16_round(torch.randn(B, 4, 8, O, generator=gen))
+        gy = _bf16_round(torch.randn(B, 4, 8, O, generator=gen))
+        so = torch.randn(B, O, generator=gen)
+        init = torch.randn(B, O, generator=gen)
+        gx, gs = K.modulate_bwd(gy.to(DEV).bfloat16(), x.to(DEV).bfloat16(), so.to(DEV), gs_init=init.to(DEV).clone())
+        rgx, rgs = emu.emu_modulate_bwd(gy, x, so, gs_init=init)
+        assert rel_err(gx.float(), rgx) < 1e-2 and rel_err(gs, rgs) < 1e-4
+        o2 = K.bias_act_bwd(gy.to(DEV).bfloat16(), x.to(DEV).bfloat16(), act=True, gain=1.0, want_sums=False,
+                            bias_grad_only=True)
+        r2 = emu.emu_bias_act_bwd(gy, x, act=True, gain=1.0, want_sums=False, bias_grad_only=True)
+        assert rel_err(o2[0].float(), r2[0]) < 1e-2 and rel_err(o2[1], r2[1]) < 1e-4 and o2[2] is None
+
+
+@pytest.mark.parametrize("B,n,S,Is,idxs", [(4, 9, 128, (128, 512, 512, 3), (0, 0, 1, 2)),
+                                           (32, 12, 512, (128, 128, 512, 512, 256, 64), (0, 0, 1, 2, 5, 11)),
+                                           (37, 3, 96, (40, 200), (2, 0))])
+def test_grouped_style_projection_vs_emulated_semantics(B, n, S, Is, idxs):
+    """tbg_style_dense_fwd/bwd (all style projections of the synthesis network in one launch) against
+    their documented semantics; fp32, 1e-4 relative (summation order only)."""
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(B + S)
+    style = torch.randn(B, n, S, generator=gen)
+    ws = [torch.randn(S, I, generator=gen) for I in Is]
+    bs = [torch.randn(I, generator=gen) for I in Is]
+    gss = [torch.randn(B, I, generator=gen) for I in Is]
+    coef = 1.0 / math.sqrt(S)
+    dv = lambda ts: [t.to(DEV) for t in ts]
+    out = K.style_dense_fwd(style.to(DEV), dv(ws), dv(bs), idxs, coef)
+    ref = emu.emu_style_dense_fwd(style, ws, bs, idxs, coef)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < 1e-4
+    gstyle, gws, gbs = K.style_dense_bwd(style.to(DEV), dv(ws), dv(gss), idxs, coef)
+    rstyle, rws, rbs = emu.emu_style_dense_bwd(style, ws, gss, idxs, coef)
+    assert rel_err(gstyle, rstyle) < 1e-4
+    for a, b in zip(gws + gbs, rws + rbs):
+        assert rel_err(a, b) < 1e-4
+
+
 @pytest.mark.parametrize("B,T,steps", [(3, 32, 8), (5, 17, 4)])
 def test_attention_decoder_and_lstm_kernels_vs_emulated_semantics(B, T, steps):
     import emu

@@ -125,7 +125,7 @@ __global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4
                                     const uint4* __restrict__ res, const float* __restrict__ noise,
                                     const float* __restrict__ d, uint4* __restrict__ gy0, float* __restrict__ S1,
                                     float* __restrict__ Spre, float* __restrict__ Snz, int hw, int c8,
-                                    int pix_per_cta, int act, float gain, int want_sums) {
+                                    int pix_per_cta, int act, float gain, int want_sums, int s1_over_batch) {
   extern __shared__ float red[];  // [rows][c8*8][3]
   const int b = blockIdx.y;
   const int rows = blockDim.x / c8;
@@ -190,11 +190,11 @@ __global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4
         a2[i] += red[(rr * cw + cv * 8 + i) * 3 + 1];
         a3[i] += red[(rr * cw + cv * 8 + i) * 3 + 2];
       }
-    const long long o0 = (static_cast<long long>(b) * c8 + cv) * 8;
+    const long long o0 = (static_cast<long long>(s1_over_batch ? 0 : b) * c8 + cv) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       atomicAdd(S1 + o0 + i, a1[i]);
-      atomicAdd(Spre + o0 + i, a2[i]);
+      if (Spre != nullptr) atomicAdd(Spre + o0 + i, a2[i]);
       if (noise != nullptr) atomicAdd(Snz + o0 + i, a3[i]);
     }
   }
@@ -358,11 +358,12 @@ extern "C" int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, 
 
 extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise,
                                 const float* d, void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C,
-                                int act, float gain, void* stream_v) {
+                                int act, float gain, int s1_over_batch, void* stream_v) {
   TBG_CHECK_ARG(g_out && out && gy0, "tbg_bias_act_bwd: null pointer");
   TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_bias_act_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
   TBG_CHECK_ARG(!noise || Snz, "tbg_bias_act_bwd: noise without Snz");
-  TBG_CHECK_ARG((S1 == nullptr) == (Spre == nullptr), "tbg_bias_act_bwd: S1 and Spre go together");
+  TBG_CHECK_ARG(S1 || !Spre, "tbg_bias_act_bwd: Spre without S1");
+  TBG_CHECK_ARG(!s1_over_batch || (!Spre && !noise), "tbg_bias_act_bwd: s1_over_batch yields S1[C] only");
   TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out) && TBG_ALIGNED16(residual) && TBG_ALIGNED16(d) && TBG_ALIGNED16(gy0),
                 "tbg_bias_act_bwd: 16-byte alignment required");
   TBG_CHECK_ARG(gain > 0.f, "tbg_bias_act_bwd: gain must be positive");
@@ -376,7 +377,8 @@ extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* 
   }
   bias_act_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
       reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), reinterpret_cast<const uint4*>(residual),
-      noise, d, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, HW, C / 8, g.pix_per_cta, act, gain, S1 != nullptr);
+      noise, d, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, HW, C / 8, g.pix_per_cta, act, gain, S1 != nullptr,
+      s1_over_batch);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

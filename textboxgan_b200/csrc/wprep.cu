@@ -64,21 +64,26 @@ __device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& t
   }
 }
 
-// One CTA per 32(i) x 32(o) tile of the master weight: the tile is read once, each thread keeps the
-// nine taps of its elements in registers and emits every (phase, tap) combination of both matrices.
+// One CTA per 32(i) x 32(o) tile of the master weight and per CHUNK of (phase, tap) combinations
+// (blockIdx.y: forward chunks first, then adjoint chunks) so that even a 128 x 128 weight fills the
+// SMs; the tile is re-read by each chunk (L2 hits), each thread keeps the nine taps of its element in
+// registers and emits its chunk's combinations.
 __global__ void __launch_bounds__(256)
 wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ adj,
-             float* __restrict__ q, const WPrepParams p) {
+             float* __restrict__ q, const WPrepParams p, const int chunk, const int fwd_chunks) {
   __shared__ float sw[9][32][33];  // [kh*KW+kw][i][o]
-  __shared__ float cff[36][9], cfa[36][9];
+  __shared__ float cf[36][9];
   const int tiles_o = p.Opad / 32;
   const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
   const int taps = p.KH * p.KW;
-  const int TTf = p.fy.T * p.fx.T, ncf = p.fy.P * p.fx.P * TTf;
-  const int TTa = p.ay.T * p.ax.T, nca = (adj != nullptr) ? p.ay.P * p.ax.P * TTa : 0;
-  build_cf(p.fy, p.fx, p.KH, p.KW, 1.f, cff);
-  if (adj != nullptr) build_cf(p.ay, p.ax, p.KH, p.KW, 1.f, cfa);
+  const bool is_adj = static_cast<int>(blockIdx.y) >= fwd_chunks;
+  const int chunk_id = is_adj ? blockIdx.y - fwd_chunks : blockIdx.y;
+  const AxisTable& ay = is_adj ? p.ay : p.fy;
+  const AxisTable& ax = is_adj ? p.ax : p.fx;
+  const int TT = ay.T * ax.T, ncomb = ay.P * ax.P * TT;
+  const int c_begin = chunk_id * chunk, c_end = min(ncomb, c_begin + chunk);
+  build_cf(ay, ax, p.KH, p.KW, 1.f, cf);
   for (int tp = 0; tp < 9; ++tp)
     for (int r = ty; r < 32; r += 8) {
       const int i = i0 + r, o = o0 + tx;
@@ -86,105 +91,103 @@ wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_
                           ? __ldg(w + (static_cast<size_t>(tp) * p.I + i) * p.O + o) * p.coef : 0.f;
     }
   __syncthreads();
-  const size_t Kf = static_cast<size_t>(TTf) * p.Ipad, Ka = static_cast<size_t>(TTa) * p.Opad;
+  // forward matrix: rows (pq, o), cols (tu, i), lanes over i;  adjoint: rows (pq, i), cols (tu, o), lanes over o
+  const int rows_pad = is_adj ? p.Ipad : p.Opad, cols_pad = is_adj ? p.Opad : p.Ipad;
+  const size_t Kc = static_cast<size_t>(TT) * cols_pad;
+  __nv_bfloat16* const base = is_adj ? adj : fwd;
   for (int r = ty; r < 32; r += 8) {
-    float vf[9], va[9];
+    float v[9];
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) {
-      vf[tp] = sw[tp][tx][r];  // element (i = i0+tx, o = o0+r): lanes over i
-      va[tp] = sw[tp][r][tx];  // element (i = i0+r, o = o0+tx): lanes over o
-    }
-    {  // forward matrix: rows (pq, o), cols (tu, i)
-      __nv_bfloat16* dst = fwd + static_cast<size_t>(o0 + r) * Kf + i0 + tx;
-      const size_t pq_stride = static_cast<size_t>(p.Opad) * Kf;
-      for (int pq = 0, c = 0; pq < p.fy.P * p.fx.P; ++pq, dst += pq_stride) {
+    for (int tp = 0; tp < 9; ++tp) v[tp] = is_adj ? sw[tp][r][tx] : sw[tp][tx][r];
+    const int row = (is_adj ? i0 : o0) + r, colv = (is_adj ? o0 : i0) + tx;
 #pragma unroll 3
-        for (int tu = 0; tu < TTf; ++tu, ++c) {
-          float acc = 0.f;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int pq = c / TT, tu = c - pq * TT;
+      float acc = 0.f;
 #pragma unroll
-          for (int tp = 0; tp < 9; ++tp) acc = fmaf(cff[c][tp], vf[tp], acc);
-          dst[static_cast<size_t>(tu) * p.Ipad] = __float2bfloat16_rn(acc);
-        }
-      }
+      for (int tp = 0; tp < 9; ++tp) acc = fmaf(cf[c][tp], v[tp], acc);
+      base[(static_cast<size_t>(pq) * rows_pad + row) * Kc + static_cast<size_t>(tu) * cols_pad + colv] =
+          __float2bfloat16_rn(acc);
     }
-    if (nca > 0) {  // adjoint matrix: rows (pq, i), cols (tu, o)
-      __nv_bfloat16* dst = adj + static_cast<size_t>(i0 + r) * Ka + o0 + tx;
-      const size_t pq_stride = static_cast<size_t>(p.Ipad) * Ka;
-      for (int pq = 0, c = 0; pq < p.ay.P * p.ax.P; ++pq, dst += pq_stride) {
-#pragma unroll 3
-        for (int tu = 0; tu < TTa; ++tu, ++c) {
-          float acc = 0.f;
-#pragma unroll
-          for (int tp = 0; tp < 9; ++tp) acc = fmaf(cfa[c][tp], va[tp], acc);
-          dst[static_cast<size_t>(tu) * p.Opad] = __float2bfloat16_rn(acc);
-        }
-      }
-    }
-    if (q != nullptr) {
+    if (q != nullptr && blockIdx.y == 0) {   // chunk 0 of the forward matrix also emits q (lanes over o)
       const int i = i0 + r, o = o0 + tx;
       if (i < p.I && o < p.O) {
         float acc = 0.f;
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp) acc = fmaf(va[tp], va[tp], acc);
+        for (int tp = 0; tp < 9; ++tp) acc = fmaf(sw[tp][r][tx], sw[tp][r][tx], acc);
         q[static_cast<size_t>(i) * p.O + o] = acc;
       }
     }
   }
 }
 
-// gw[tap,i,o] += coef * sum_c cf[c][tap] * gfwd_c[o,i]  (+ 2*coef^2*w*gq[i,o]).  One CTA per weight tile
-// streams the (phase, tap) combinations of the gradient matrix through a 32 x 32 transpose buffer.
+// gw[tap,i,o] += coef * sum_c cf[c][tap] * gfwd_c[o,i]  (+ 2*coef^2*w*gq[i,o]).  One CTA per 32(i) x 8(o)
+// weight tile: each thread owns one element, issues the loads of all (phase, tap) combinations
+// back-to-back (lanes over the contiguous i axis of the gradient matrix, no barrier in the loop) and
+// accumulates the nine master taps in registers; the result is transposed through shared memory so the
+// read-modify-write of the o-contiguous master gradient touches whole 32-byte sectors.
 __global__ void __launch_bounds__(256)
 wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const float* __restrict__ w,
-             float* __restrict__ gw, const WPrepParams p) {
-  __shared__ float sg[2][32][33];  // double-buffered [o][i]
+             float* __restrict__ gw, const WPrepParams p, const float* __restrict__ sv, const float* __restrict__ tv,
+             const int nb) {
+  __shared__ float st[9][8][36];  // [tap][o][i]
   __shared__ float cff[36][9];
-  const int tiles_o = p.Opad / 32;
-  const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
+  const int tiles_o = p.Opad / 8;
+  const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 8;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int TT = p.fy.T * p.fx.T;
   const size_t Kf = static_cast<size_t>(TT) * p.Ipad;
-  const int ncomb = p.fy.P * p.fx.P * TT;
+  const int nph = p.fy.P * p.fx.P;
   const int taps = p.KH * p.KW;
   build_cf(p.fy, p.fx, p.KH, p.KW, p.coef, cff);
-  float acc[4][9];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp) acc[k][tp] = 0.f;
-  auto load_tile = [&](int c, int buf) {
-    const int pq = c / TT, tu = c - pq * TT;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {  // row = o, lanes over i (contiguous)
-      const int r = ty + 8 * k;
-      sg[buf][r][tx] = __ldg(gfwd + (static_cast<size_t>(pq) * p.Opad + o0 + r) * Kf + static_cast<size_t>(tu) * p.Ipad + i0 + tx);
-    }
-  };
-  load_tile(0, 0);
   __syncthreads();
-  for (int c = 0; c < ncomb; ++c) {
-    if (c + 1 < ncomb) load_tile(c + 1, (c + 1) & 1);
+  float acc[9];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // element (i = i0 + ty + 8k, o = o0 + tx)
-      const float g = sg[c & 1][tx][ty + 8 * k];
+  for (int tp = 0; tp < 9; ++tp) acc[tp] = 0.f;
+  for (int pq = 0; pq < nph; ++pq) {
+    const float* src = gfwd + (static_cast<size_t>(pq) * p.Opad + o0 + ty) * Kf + i0 + tx;
+    int tu = 0;
+    for (; tu + 4 <= TT; tu += 4) {     // four independent loads in flight per thread before the FMAs
+      float g[4];
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) acc[k][tp] = fmaf(cff[c][tp], g, acc[k][tp]);
+      for (int u = 0; u < 4; ++u) g[u] = __ldg(src + static_cast<size_t>(tu + u) * p.Ipad);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* cfr = cff[pq * TT + tu + u];
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) acc[tp] = fmaf(cfr[tp], g[u], acc[tp]);
+      }
     }
-    __syncthreads();
+    for (; tu < TT; ++tu) {
+      const float g = __ldg(src + static_cast<size_t>(tu) * p.Ipad);
+      const float* cfr = cff[pq * TT + tu];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) acc[tp] = fmaf(cfr[tp], g, acc[tp]);
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = i0 + ty + 8 * k, o = o0 + tx;
-    if (i >= p.I || o >= p.O) continue;
-    const float gqv = (gq != nullptr) ? 2.f * p.coef * p.coef * __ldg(gq + static_cast<size_t>(i) * p.O + o) : 0.f;
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp) {
-      if (tp < taps) {
-        const size_t idx = (static_cast<size_t>(tp) * p.I + i) * p.O + o;
-        float v = acc[k][tp];
-        if (gq != nullptr) v = fmaf(gqv, __ldg(w + idx), v);
-        gw[idx] += v;
+  for (int tp = 0; tp < 9; ++tp) st[tp][ty][tx] = acc[tp];
+  __syncthreads();
+  const int il = threadIdx.x >> 3, ol = threadIdx.x & 7;
+  const int i = i0 + il, o = o0 + ol;
+  if (i < p.I && o < p.O) {
+    // dL/dq[i,o]: given, or formed here from the demodulation gradient t: sum_b s[b,i]^2 t[b,o]
+    float gqv = 0.f;
+    if (gq != nullptr) {
+      gqv = __ldg(gq + static_cast<size_t>(i) * p.O + o);
+    } else if (sv != nullptr) {
+      for (int b = 0; b < nb; ++b) {
+        const float s1 = __ldg(sv + static_cast<size_t>(b) * p.I + i);
+        gqv = fmaf(s1 * s1, __ldg(tv + static_cast<size_t>(b) * p.O + o), gqv);
       }
+    }
+    gqv *= 2.f * p.coef * p.coef;
+    const bool has_q = (gq != nullptr) || (sv != nullptr);
+    for (int tp = 0; tp < taps; ++tp) {
+      const size_t idx = (static_cast<size_t>(tp) * p.I + i) * p.O + o;
+      float v = st[tp][ol][il];
+      if (has_q) v = fmaf(gqv, __ldg(w + idx), v);
+      gw[idx] += v;
     }
   }
 }
@@ -223,18 +226,29 @@ extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH
   const int ncf = p.fy.P * p.fx.P * p.fy.T * p.fx.T;
   const int nca = (p.ay.P > 0) ? p.ay.P * p.ax.P * p.ay.T * p.ax.T : 0;
   TBG_CHECK_ARG(ncf <= 36 && nca <= 36, "tbg_wprep: too many (phase, tap) combinations");
-  wprep_kernel<<<(Ipad / 32) * (Opad / 32), 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(fwd),
-                                                             (p.ay.P > 0) ? reinterpret_cast<__nv_bfloat16*>(adj) : nullptr,
-                                                             q, p);
+  TBG_CHECK_ARG(nca == 0 || adj, "tbg_wprep: adjoint tables without an adjoint output");
+  // split the (phase, tap) combinations into chunks until the grid covers the SMs about twice
+  const int tiles = (Ipad / 32) * (Opad / 32);
+  int nchunks = (296 + tiles - 1) / tiles;
+  if (nchunks > 4) nchunks = 4;
+  if (nchunks < 1) nchunks = 1;
+  const int nmax = ncf > nca ? ncf : nca;
+  const int chunk = (nmax + nchunks - 1) / nchunks;
+  const int fwd_chunks = (ncf + chunk - 1) / chunk;
+  const int adj_chunks = (nca + chunk - 1) / chunk;
+  wprep_kernel<<<dim3(tiles, fwd_chunks + adj_chunks), 256, 0, stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(fwd), reinterpret_cast<__nv_bfloat16*>(adj), q, p, chunk, fwd_chunks);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
 }
 
 extern "C" int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH,
-                         int KW, int I, int O, int Ipad, int Opad, float* gw, void* stream_v) {
+                         int KW, int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb,
+                         void* stream_v) {
   TBG_CHECK_ARG(gfwd && tables && gw, "tbg_wfold: null pointer");
-  TBG_CHECK_ARG(!gq || w, "tbg_wfold: gq needs the master weight");
+  TBG_CHECK_ARG(!(gq || s) || w, "tbg_wfold: gq / (s, t) need the master weight");
+  TBG_CHECK_ARG((s == nullptr) == (t == nullptr) && !(s && gq) && (!s || nb >= 1), "tbg_wfold: pass gq or (s, t, nb)");
   TBG_CHECK_ARG(KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3, "tbg_wfold: master kernel must be at most 3x3");
   TBG_CHECK_ARG(Ipad % 32 == 0 && Opad % 32 == 0 && Ipad >= I && Opad >= O, "tbg_wfold: bad channel counts");
   WPrepParams p;
@@ -242,7 +256,7 @@ extern "C" int tbg_wfold(const float* gfwd, const float* gq, const float* w, con
   TBG_CHECK_ARG(p.fy.P * p.fx.P * p.fy.T * p.fx.T <= 36, "tbg_wfold: too many (phase, tap) combinations");
   p.KH = KH; p.KW = KW; p.I = I; p.O = O; p.Ipad = Ipad; p.Opad = Opad; p.coef = coef;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  wfold_kernel<<<(Ipad / 32) * (Opad / 32), 256, 0, stream>>>(gfwd, gq, w, gw, p);
+  wfold_kernel<<<(Ipad / 32) * (Opad / 8), 256, 0, stream>>>(gfwd, gq, w, gw, p, s, t, nb);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -44,6 +44,32 @@ def _prepared(w_raw, spec, want_adj: bool, want_q: bool):
     return out
 
 
+def _aligned_vec(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# Tags ("dconv", ...) whose weight gradients are not wanted by the running backward pass: the
+# generator pass of training_step.py:194-199 differentiates through the discriminator but only asks
+# for generator variables, which a static ``needs_input_grad`` cannot express.
+_SKIP_WGRAD_TAGS: frozenset = frozenset()
+
+
+class skip_weight_grads:
+    def __init__(self, *tags: str):
+        self.tags = frozenset(tags)
+
+    def __enter__(self):
+        global _SKIP_WGRAD_TAGS
+        self.prev = _SKIP_WGRAD_TAGS
+        _SKIP_WGRAD_TAGS = self.tags
+        return self
+
+    def __exit__(self, *exc):
+        global _SKIP_WGRAD_TAGS
+        _SKIP_WGRAD_TAGS = self.prev
+        return False
+
+
 def _act_dtype():
     from . import layers as L
 
@@ -59,7 +85,7 @@ class ModConvAct(torch.autograd.Function):
         x = x.contiguous()
         s = s.contiguous()
         wmat, wadj, q = _prepared(w_raw, spec, True, True)                       # one launch per step
-        d = torch.rsqrt((s * s) @ q + 1e-8)                                      # modulated_conv2d.py:80-82
+        d = K.demod_coef(s, q)                                                   # modulated_conv2d.py:80-82
         xs = K.modulate(x, s)
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
         out = K.conv2d_igemm(xs, wmat, **geom.kernel_kwargs(), col_scale=d, noise=noise.contiguous(),
@@ -75,19 +101,15 @@ class ModConvAct(torch.autograd.Function):
         g = spec.geom
         gy0, S1, Spre, Snz = K.bias_act_bwd(g_out.contiguous(), out, noise=noise.contiguous(), d=d, act=True,
                                             gain=ctx.gain)
-        gd = (Spre - ns * Snz - bias[None, :] * S1) / d
-        gbias = S1.sum(dim=0)
-        gns = Snz.sum().reshape(ns.shape)
-        # d = rsqrt(s^2 @ q + eps):  t = dL/d(s^2 @ q)
-        t = -0.5 * gd * d * d * d
-        gq = (s * s).t() @ t
-        gs_d = 2.0 * s * (t @ q.t())
+        # dL/d(d) -> t = dL/d(s^2 @ q), the bias / noise-strength gradients and the demodulation term
+        # of dL/ds in one launch (d = rsqrt(s^2 @ q + eps))
+        t, gbias, gns, gs = K.demod_bwd(S1, Spre, Snz, d, ns.reshape(1), _aligned_vec(bias), s, q)
         K.PROFILE_TAG = (g.tag, g.algo_frac)
         gxs = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
         gwmat = K.conv2d_wgrad(xs, gy0, **g.kernel_kwargs())
-        gx, gs = K.modulate_bwd(gxs, x, s)
-        gw_raw = K.wfold(gwmat, spec, gq=gq.contiguous(), w_raw=w_raw)
-        return gx, gs + gs_d, gw_raw, None, gns, gbias, None, None
+        gx, gs = K.modulate_bwd(gxs, x, s, gs_init=gs)
+        gw_raw = K.wfold(gwmat, spec, w_raw=w_raw, s=s, t=t)                   # + dL/dq = (s^2)^T t
+        return gx, gs, gw_raw, None, gns.reshape(ns.shape), gbias, None, None
 
 
 class ConvAct(torch.autograd.Function):
@@ -115,18 +137,45 @@ class ConvAct(torch.autograd.Function):
         spec = ctx.spec
         g = spec.geom
         g_out = g_out.contiguous()
+        want_w = ctx.needs_input_grad[1] and g.tag not in _SKIP_WGRAD_TAGS
         gbias = None
         if ctx.has_act:
-            gy0, S1, _, _ = K.bias_act_bwd(g_out, out, residual=residual, act=True, gain=ctx.gain)
-            gbias = S1.sum(dim=0)
+            gy0, gbias, _, _ = K.bias_act_bwd(g_out, out, residual=residual, act=True, gain=ctx.gain,
+                                              want_sums=False, bias_grad_only=want_w)
         else:
             gy0 = g_out
         K.PROFILE_TAG = (g.tag, g.algo_frac)
         gx = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs()) if ctx.needs_input_grad[0] else None
         gw_raw = None
-        if ctx.needs_input_grad[1]:
+        if want_w:
             gw_raw = K.wfold(K.conv2d_wgrad(x, gy0, **g.kernel_kwargs()), spec)
         return gx, gw_raw, gbias, (g_out if ctx.has_res else None), None, None
+
+
+class StyleScales(torch.autograd.Function):
+    """All style projections of the synthesis network at once: for layer l,
+    s_l = mod_bias(mod_dense(style[:, idx_l])) + 1 (modulated_conv2d.py:75-76).  Inputs after the
+    layout arguments are w_0, b_0, w_1, b_1, ...; outputs one [B, I_l] tensor per layer."""
+
+    @staticmethod
+    def forward(ctx, style, idxs, coef, *wb):
+        style = style.contiguous()
+        ws, bs = [w.contiguous() for w in wb[0::2]], [b.contiguous() for b in wb[1::2]]
+        outs = K.style_dense_fwd(style, ws, bs, idxs, coef)
+        ctx.save_for_backward(style, *ws)
+        ctx.idxs, ctx.coef = idxs, coef
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gss):
+        style, *ws = ctx.saved_tensors
+        gss = [g.contiguous() if g is not None else torch.zeros((style.shape[0], w.shape[1]), device=style.device)
+               for g, w in zip(gss, ws)]
+        gstyle, gws, gbs = K.style_dense_bwd(style, ws, gss, ctx.idxs, ctx.coef)
+        out = [gstyle, None, None]
+        for gw, gb in zip(gws, gbs):
+            out += [gw, gb]
+        return tuple(out)
 
 
 class ToRGB(torch.autograd.Function):

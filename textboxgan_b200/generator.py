@@ -142,16 +142,29 @@ class Generator(Model):
         """synthesis_block.py:137-156; x NHWC bf16, returns NCHW fp32 image."""
         cfg, P = self.cfg, self.params
         res = cfg.generator_resolutions
-        y = L.to_rgb(x, style[:, 0], P, f"synthesis/{res[0][0]}x{res[0][1]}/ToRGB")
+        # style rows: ToRGB_0 <- 0; block i: conv_0 <- 3i, conv_1 <- 3i+1, ToRGB <- 3i+2 (:140,143-147)
+        prefixes = [f"synthesis/{res[0][0]}x{res[0][1]}/ToRGB/conv"]
+        idxs = [0]
+        for i, (h, w) in enumerate(res[1:]):
+            prefixes += [f"synthesis/{h}x{w}/block/conv_0", f"synthesis/{h}x{w}/block/conv_1",
+                         f"synthesis/{h}x{w}/ToRGB/conv"]
+            idxs += [3 * i, 3 * i + 1, 3 * i + 2]
+        if L.use_fused():
+            sc = L.all_style_scales(style.float(), P, prefixes, idxs)        # one launch for all layers
+        else:
+            sc = [None] * len(prefixes)
+        y = L.to_rgb(x, style[:, 0], P, f"synthesis/{res[0][0]}x{res[0][1]}/ToRGB", s_pre=sc[0])
         for i, (h, w) in enumerate(res[1:]):
             pb = f"synthesis/{h}x{w}/block"
             s0, s1, s2 = style[:, 3 * i], style[:, 3 * i + 1], style[:, 3 * i + 2]
             n0, n1 = noises[2 * i], noises[2 * i + 1]
             x = L.modulated_conv2d(x, s0, P, pb + "/conv_0", up=True, noise=n0, noise_strength=P[pb + "/noise_0/w"],
-                                   bias=P[pb + "/bias_0/b"], act=True, fused_epilogue=fused_epilogue)
+                                   bias=P[pb + "/bias_0/b"], act=True, fused_epilogue=fused_epilogue,
+                                   s_pre=sc[3 * i + 1])
             x = L.modulated_conv2d(x, s1, P, pb + "/conv_1", up=False, noise=n1, noise_strength=P[pb + "/noise_1/w"],
-                                   bias=P[pb + "/bias_1/b"], act=True, fused_epilogue=fused_epilogue)
-            y = L.upsample_rgb(y) + L.to_rgb(x, s2, P, f"synthesis/{h}x{w}/ToRGB")
+                                   bias=P[pb + "/bias_1/b"], act=True, fused_epilogue=fused_epilogue,
+                                   s_pre=sc[3 * i + 2])
+            y = L.upsample_rgb(y) + L.to_rgb(x, s2, P, f"synthesis/{h}x{w}/ToRGB", s_pre=sc[3 * i + 3])
         return y.permute(0, 3, 1, 2).contiguous()
 
     def _noises(self, batch: int, draws: dict):

@@ -233,32 +233,40 @@ def modulate(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     return xs
 
 
-def modulate_bwd(gxs: torch.Tensor, x: torch.Tensor, s: torch.Tensor):
+def modulate_bwd(gxs: torch.Tensor, x: torch.Tensor, s: torch.Tensor, gs_init: Optional[torch.Tensor] = None):
+    """gx = gxs*s; gs = (gs_init or 0) + sum_hw gxs*x (gs_init is accumulated into, in place)."""
     _require(gxs, torch.bfloat16, "gxs")
     _require(x, torch.bfloat16, "x")
     _require(s, torch.float32, "s")
     B, HW, C = _bhwc(x)
     gx = torch.empty_like(x)
-    gs = torch.zeros_like(s)
+    if gs_init is not None:
+        _require(gs_init, torch.float32, "gs_init")
+        gs = gs_init
+    else:
+        gs = torch.zeros_like(s)
     st = _lib.load().tbg_modulate_bwd(_ptr(gxs), _ptr(x), _ptr(s), _ptr(gx), _ptr(gs), B, HW, C, _stream())
     _lib.check(st, "tbg_modulate_bwd")
     return gx, gs
 
 
 def bias_act_bwd(g_out: torch.Tensor, out: torch.Tensor, *, residual=None, noise=None, d=None, act=True,
-                 gain: float = 1.0, want_sums: bool = True):
-    """Returns (gy0 bf16, S1, Spre, Snz) — see include/tbg.h."""
+                 gain: float = 1.0, want_sums: bool = True, bias_grad_only: bool = False):
+    """Returns (gy0 bf16, S1, Spre, Snz) — see include/tbg.h.  ``bias_grad_only``: S1 is the [C]
+    bias gradient (summed over the batch too), Spre / Snz are None."""
     _require(g_out, torch.bfloat16, "g_out")
     _require(out, torch.bfloat16, "out")
     B, HW, C = _bhwc(out)
     gy0 = torch.empty_like(out)
     S1 = Spre = Snz = None
-    if want_sums:
+    if bias_grad_only:
+        S1 = torch.zeros((C,), device=out.device, dtype=torch.float32)
+    elif want_sums:
         sums = torch.zeros((3, B, C), device=out.device, dtype=torch.float32)
         S1, Spre, Snz = sums[0], sums[1], sums[2]
     st = _lib.load().tbg_bias_act_bwd(_ptr(g_out), _ptr(out), _ptr(residual), _ptr(noise), _ptr(d), _ptr(gy0),
-                                      _ptr(S1), _ptr(Spre), _ptr(Snz) if noise is not None or want_sums else None,
-                                      B, HW, C, int(act), float(gain), _stream())
+                                      _ptr(S1), _ptr(Spre), _ptr(Snz),
+                                      B, HW, C, int(act), float(gain), int(bias_grad_only), _stream())
     _lib.check(st, "tbg_bias_act_bwd")
     return gy0, S1, Spre, Snz
 
@@ -300,15 +308,84 @@ def wprep(w_raw: torch.Tensor, spec, *, want_adj: bool = True, want_q: bool = Fa
 
 
 def wfold(gfwd: torch.Tensor, spec, *, gq: Optional[torch.Tensor] = None, w_raw: Optional[torch.Tensor] = None,
-          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Accumulate the master-weight gradient from the fp32 gradient of the fwd GEMM matrix."""
+          out: Optional[torch.Tensor] = None, s: Optional[torch.Tensor] = None,
+          t: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulate the master-weight gradient from the fp32 gradient of the fwd GEMM matrix; the
+    demodulation term comes from ``gq`` [I,O] or from (``s`` [B,I], ``t`` [B,O]) of demod_bwd."""
     _require(gfwd, torch.float32, "gfwd")
     if out is None:
         out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
+    nb = 0
+    if s is not None:
+        _require(s, torch.float32, "s")
+        _require(t, torch.float32, "t")
+        nb = s.shape[0]
     st = _lib.load().tbg_wfold(_ptr(gfwd), _ptr(gq), _ptr(w_raw), spec.ctable, spec.coef, spec.KH, spec.KW, spec.I,
-                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _stream())
+                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _ptr(s), _ptr(t), nb, _stream())
     _lib.check(st, "tbg_wfold")
     return out
+
+
+def demod_coef(s: torch.Tensor, q: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """d[b,o] = rsqrt(sum_i s[b,i]^2 q[i,o] + eps)   (modulated_conv2d.py:80-82)."""
+    _require(s, torch.float32, "s")
+    _require(q, torch.float32, "q")
+    B, I = s.shape
+    O = q.shape[1]
+    d = torch.empty((B, O), device=s.device, dtype=torch.float32)
+    _lib.check(_lib.load().tbg_demod_coef(_ptr(s), _ptr(q), _ptr(d), B, I, O, float(eps), _stream()), "tbg_demod_coef")
+    return d
+
+
+def demod_bwd(S1, Spre, Snz, d, ns, bias, s, q):
+    """-> (t [B,O], gbias [O], gns [1], gs_demod [B,I]) — see include/tbg.h."""
+    for tn, n in ((S1, "S1"), (Spre, "Spre"), (d, "d"), (s, "s"), (q, "q")):
+        _require(tn, torch.float32, n)
+    B, I = s.shape
+    O = q.shape[1]
+    dev = s.device
+    t = torch.empty((B, O), device=dev, dtype=torch.float32)
+    gbias = torch.empty((O,), device=dev, dtype=torch.float32)
+    gns = torch.empty((1,), device=dev, dtype=torch.float32)
+    gs = torch.empty((B, I), device=dev, dtype=torch.float32)
+    st = _lib.load().tbg_demod_bwd(_ptr(S1), _ptr(Spre), _ptr(Snz), _ptr(d), _ptr(ns), _ptr(bias), _ptr(s), _ptr(q),
+                                   _ptr(t), _ptr(gbias), _ptr(gns), _ptr(gs), B, I, O, _stream())
+    _lib.check(st, "tbg_demod_bwd")
+    return t, gbias, gns, gs
+
+
+def style_dense_fwd(style: torch.Tensor, ws, bs, idxs, coef: float):
+    """style fp32 [B,n,S]; per layer w [S,I_l], b [I_l], style row idx_l -> list of s_l [B,I_l]
+    (= coef * style[:,idx_l] @ w_l + b_l + 1), one launch."""
+    _require(style, torch.float32, "style")
+    B, n, S = style.shape
+    outs = [torch.empty((B, w.shape[1]), device=style.device, dtype=torch.float32) for w in ws]
+    arr = (_lib.StyleLayer * len(ws))()
+    for a, w, b, o, i in zip(arr, ws, bs, outs, idxs):
+        _require(w, torch.float32, "w")
+        _require(b, torch.float32, "b")
+        a.w, a.b, a.s, a.I, a.idx = _ptr(w), _ptr(b), _ptr(o), w.shape[1], int(i)
+    st = _lib.load().tbg_style_dense_fwd(arr, len(ws), _ptr(style), B, n, S, float(coef), _stream())
+    _lib.check(st, "tbg_style_dense_fwd")
+    return outs
+
+
+def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
+    """-> (gstyle [B,n,S], [gw_l [S,I_l]], [gb_l [I_l]]), two launches."""
+    _require(style, torch.float32, "style")
+    B, n, S = style.shape
+    dev = style.device
+    gstyle = torch.empty_like(style)
+    gws = [torch.empty_like(w) for w in ws]
+    gbs = [torch.empty((w.shape[1],), device=dev, dtype=torch.float32) for w in ws]
+    arr = (_lib.StyleLayer * len(ws))()
+    dummy = gbs[0]
+    for a, w, g, gw, gb, i in zip(arr, ws, gss, gws, gbs, idxs):
+        _require(g, torch.float32, "gs")
+        a.w, a.b, a.gs, a.gw, a.gb, a.I, a.idx = _ptr(w), _ptr(dummy), _ptr(g), _ptr(gw), _ptr(gb), w.shape[1], int(i)
+    st = _lib.load().tbg_style_dense_bwd(arr, len(ws), _ptr(style), _ptr(gstyle), B, n, S, float(coef), _stream())
+    _lib.check(st, "tbg_style_dense_bwd")
+    return gstyle, gws, gbs
 
 
 def _dec_struct(w: dict):

@@ -74,7 +74,8 @@ def style_scale(style: torch.Tensor, P: Params, prefix: str) -> torch.Tensor:
 def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str, *, up: bool,
                      demodulate: bool = True, noise: Optional[torch.Tensor] = None,
                      noise_strength: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                     act: bool = False, fused_epilogue: bool = False) -> torch.Tensor:
+                     act: bool = False, fused_epilogue: bool = False,
+                     s_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [B,H,W,I] bf16 -> [B,H',W',O] bf16, including (optionally) noise, bias and activation.
 
     ``fused_epilogue`` applies demod/noise/bias/lrelu inside the GEMM epilogue; it is only legal
@@ -82,7 +83,7 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     with differentiable element-wise ops."""
     w_raw = P[prefix + "/w"]
     kh, kw, I, O = w_raw.shape
-    s = style_scale(style, P, prefix)                                       # [B,I]
+    s = s_pre if s_pre is not None else style_scale(style, P, prefix)       # [B,I]
     B, H, W_, _ = x.shape
     if use_fused() and act and noise is not None and bias is not None and demodulate and not fused_epilogue:
         from .fused import ModConvAct
@@ -124,11 +125,24 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     return y.to(ACT_DTYPE)
 
 
-def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str) -> torch.Tensor:
+def all_style_scales(style: torch.Tensor, P: Params, prefixes, idxs):
+    """s_l for every modulated convolution ``prefixes[l]`` fed by style row ``idxs[l]``, in one launch
+    (fused.StyleScales); style [B, n_style, S]."""
+    from .fused import StyleScales
+
+    wb = []
+    for pf in prefixes:
+        wb += [P[pf + "/mod_dense/w"], P[pf + "/mod_bias/b"]]
+    coef = runtime_coef(P[prefixes[0] + "/mod_dense/w"].shape)
+    return StyleScales.apply(style, tuple(int(i) for i in idxs), coef, *wb)
+
+
+def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str,
+           s_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
     """1x1 modulated conv without demodulation + bias, fp32 [B,H,W,3] (to_rgb.py:28-33)."""
     w_raw = P[prefix + "/conv/w"]                                           # [1,1,C,3]
     w = runtime_coef(w_raw.shape) * w_raw[0, 0]
-    s = style_scale(style, P, prefix + "/conv")
+    s = s_pre if s_pre is not None else style_scale(style, P, prefix + "/conv")
     ws = s[:, :, None] * w[None]                                            # [B,C,3]
     if use_fused():
         from .fused import ToRGB

@@ -49,6 +49,11 @@ class WgradArgs(C.Structure):
     ]
 
 
+class StyleLayer(C.Structure):
+    _fields_ = [("w", c_void_p), ("b", c_void_p), ("s", c_void_p), ("gs", c_void_p), ("gw", c_void_p), ("gb", c_void_p),
+                ("I", c_int), ("idx", c_int)]
+
+
 class DecWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("wq", "wqT", "v", "emb", "wg", "wgT", "b", "wd", "wdT", "bd")]
 
@@ -71,11 +76,16 @@ _SIGNATURES = [
     ("tbg_lstm_seq_bwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     ("tbg_modulate", c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     ("tbg_modulate_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
-    ("tbg_bias_act_bwd", c_int, [c_void_p] * 9 + [c_int] * 4 + [c_float, c_void_p]),
+    ("tbg_bias_act_bwd", c_int, [c_void_p] * 9 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     ("tbg_torgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
-    ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 2),
+    ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
+    ("tbg_style_dense_fwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    ("tbg_style_dense_bwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                    c_void_p]),
+    ("tbg_demod_coef", c_int, [c_void_p] * 3 + [c_int] * 3 + [c_float, c_void_p]),
+    ("tbg_demod_bwd", c_int, [c_void_p] * 12 + [c_int] * 3 + [c_void_p]),
     ("tbg_attn_decoder_fwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
     ("tbg_attn_decoder_bwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
 ]

@@ -212,7 +212,8 @@ class TrainingStep:
         o_vars = [G.params[n] for n in self._ocr_names]
         d_vars = [D.params[n] for n in self._d_names]
         # three tape.gradient calls on one persistent tape (:194-213): all at pre-update weights
-        g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
+        with _fused.skip_weight_grads("dconv"):       # only generator variables are wanted from this pass
+            g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
         o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
             if ocr_loss is not None else None
         d_grads = torch.autograd.grad(reg_d_loss, d_vars, allow_unused=True)
