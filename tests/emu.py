@@ -51,7 +51,11 @@ def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_s
     y = y * act_gain
     if residual is not None and not res_first:
         y = (y + residual.double()) * res_scale
-    return y.to(torch.float32 if out_fp32 else x.dtype)
+    y = y.to(torch.float32 if out_fp32 else x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def emu_conv2d_wgrad(x, gy, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), gw=None):

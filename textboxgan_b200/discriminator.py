@@ -98,8 +98,10 @@ class Discriminator(Model):
             y = (y + residual.float()) * INV_SQRT2
         return y.to(L.ACT_DTYPE)
 
-    def __call__(self, images: torch.Tensor) -> torch.Tensor:
-        """discriminator.py:202-214: [B,3,H,W] fp32 -> [B,1] fp32."""
+    def __call__(self, images: torch.Tensor, n_calls: int = 1) -> torch.Tensor:
+        """discriminator.py:202-214: [B,3,H,W] fp32 -> [B,1] fp32.  ``n_calls`` > 1 evaluates that many
+        independent calls concatenated on the batch axis in one pass (every layer is per-sample except
+        the minibatch statistic, which is then taken per call)."""
         P = self.params
         res = self.resolutions
         r0 = res[0]
@@ -120,7 +122,7 @@ class Discriminator(Model):
         # minibatch-std feature (mini_batch_std.py): one extra constant channel per sample; padded
         # with zero channels up to a multiple of 64 so that K stays TMA/UMMA aligned
         B, H, W_, Cc = x.shape
-        std = L.minibatch_std(x)                                             # [B,1]
+        std = L.minibatch_std(x, n_calls=n_calls)                            # [B,1]
         cpad = (Cc + 1 + 63) // 64 * 64
         xcat = torch.cat([x, std.to(x.dtype)[:, None, None, :].expand(B, H, W_, 1),
                           x.new_zeros(B, H, W_, cpad - Cc - 1)], dim=3).contiguous()

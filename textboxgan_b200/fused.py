@@ -70,6 +70,29 @@ class skip_weight_grads:
         return False
 
 
+# Leading-batch limit per tag for the running backward pass: when the discriminator evaluated fake and
+# real images in one concatenated pass, the generator pass only carries a cotangent on the fake half, so
+# its input-gradient kernels run on that half and the rest of the gradient is zero by construction.
+_BATCH_LIMIT: dict = {}
+
+
+class backward_batch_limit:
+    def __init__(self, tag: str, limit: int):
+        self.tag, self.limit = tag, int(limit)
+
+    def __enter__(self):
+        self.prev = _BATCH_LIMIT.get(self.tag)
+        _BATCH_LIMIT[self.tag] = self.limit
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is None:
+            _BATCH_LIMIT.pop(self.tag, None)
+        else:
+            _BATCH_LIMIT[self.tag] = self.prev
+        return False
+
+
 def _act_dtype():
     from . import layers as L
 
@@ -139,6 +162,19 @@ class ConvAct(torch.autograd.Function):
         g_out = g_out.contiguous()
         want_w = ctx.needs_input_grad[1] and g.tag not in _SKIP_WGRAD_TAGS
         gbias = None
+        lim = _BATCH_LIMIT.get(g.tag)
+        if lim is not None and g_out.shape[0] > lim and not want_w:
+            # cotangent is zero beyond the first ``lim`` samples: run on that slice only
+            gy0 = g_out[:lim]
+            if ctx.has_act:
+                gy0, _, _, _ = K.bias_act_bwd(gy0, out[:lim], residual=residual[:lim] if residual is not None else None,
+                                              act=True, gain=ctx.gain, want_sums=False)
+            gx = None
+            if ctx.needs_input_grad[0]:
+                gx = torch.zeros_like(x)
+                K.PROFILE_TAG = (g.tag, g.algo_frac)
+                K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs(), out=gx[:lim])
+            return gx, None, None, (g_out if ctx.has_res else None), None, None
         if ctx.has_act:
             gy0, gbias, _, _ = K.bias_act_bwd(g_out, out, residual=residual, act=True, gain=ctx.gain,
                                               want_sums=False, bias_grad_only=want_w)

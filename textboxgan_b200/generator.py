@@ -104,26 +104,34 @@ class Generator(Model):
         return x.reshape(batch_size, out_w, out_c, out_h).permute(0, 3, 1, 2).contiguous().to(L.ACT_DTYPE)
 
     def _mapping(self, z: torch.Tensor) -> torch.Tensor:
-        """mapping_block.py:35-45"""
+        """mapping_block.py:35-45.  lrelu(v)*sqrt2 == lrelu(sqrt2*v) (positive homogeneity), so each
+        layer is one addmm (equalised-LR coefficient and sqrt2 folded into alpha) + one leaky-relu."""
         P = self.params
         x = z * torch.rsqrt(torch.mean(z * z, dim=1, keepdim=True) + 1e-8)
         for i in range(self.cfg.n_mapping):
-            x = L.dense(x, P[f"latent_encoder/g_mapping/dense_{i}/w"], 1.0, 0.01)
-            x = L.lrelu(x + 0.01 * P[f"latent_encoder/g_mapping/bias_{i}/b"])
+            w = P[f"latent_encoder/g_mapping/dense_{i}/w"]
+            b = P[f"latent_encoder/g_mapping/bias_{i}/b"]
+            pre = torch.addmm(b * (0.01 * L.SQRT2), x, w, alpha=L.runtime_coef(w.shape, 1.0, 0.01) * L.SQRT2)
+            x = torch.nn.functional.leaky_relu(pre, 0.2)
         return x
 
     def _latent_encoder(self, z, training: bool, truncation_psi: float, draws: dict):
         """latent_encoder.py:80-99"""
         P = self.params
         n = self.n_style
-        wb = self._mapping(z)[:, None, :].expand(-1, n, -1)
+        if training:
+            # both latents of the style-mixing pair go through the mapping network as one batch
+            z2 = draws["z2"].to(z.device) if "z2" in draws else torch.randn_like(z)   # :49
+            w12 = self._mapping(torch.cat([z, z2], dim=0))
+            wb = w12[: z.shape[0], None, :].expand(-1, n, -1)
+        else:
+            wb = self._mapping(z)[:, None, :].expand(-1, n, -1)
         if training:
             with torch.no_grad():                                            # :39-45
                 batch_avg = wb[:, 0].mean(dim=0)
                 w_avg = P["latent_encoder/w_avg"]
                 w_avg.copy_(batch_avg + (w_avg - batch_avg) * self.w_ema_decay)
-            z2 = draws["z2"].to(z.device) if "z2" in draws else torch.randn_like(z)   # :49
-            wb2 = self._mapping(z2)[:, None, :].expand(-1, n, -1)
+            wb2 = w12[z.shape[0]:, None, :].expand(-1, n, -1)
             # :55-60 — one scalar coin / cutoff per batch, drawn on the device (no host sync, so the
             # whole step can be replayed from a CUDA graph)
             coin = torch.as_tensor(draws["mix_coin"], device=z.device, dtype=torch.float32) if "mix_coin" in draws \

@@ -159,12 +159,15 @@ def upsample_rgb(y: torch.Tensor) -> torch.Tensor:
     return U.upsample_2d_nhwc(y.contiguous())
 
 
-def minibatch_std(x: torch.Tensor, group_size: int = 4) -> torch.Tensor:
-    """mini_batch_std.py:10-35 on NHWC: returns the [B,1] per-sample statistic (fp32)."""
-    B = x.shape[0]
+def minibatch_std(x: torch.Tensor, group_size: int = 4, n_calls: int = 1) -> torch.Tensor:
+    """mini_batch_std.py:10-35 on NHWC: returns the [B,1] per-sample statistic (fp32).  ``n_calls`` > 1:
+    ``x`` is the concatenation of that many independent discriminator calls; the statistic is taken
+    inside each call's own batch, exactly as if the calls were separate."""
+    Bt = x.shape[0]
+    B = Bt // n_calls
     g = min(group_size, B)
-    y = x.float().reshape(g, B // g, -1)
-    y = y - y.mean(dim=0, keepdim=True)
-    y = torch.sqrt((y * y).mean(dim=0) + 1e-8)
-    y = y.mean(dim=1, keepdim=True)                                         # [B/g, 1]
-    return y.repeat(g, 1)
+    y = x.float().reshape(n_calls, g, B // g, -1)
+    y = y - y.mean(dim=1, keepdim=True)
+    y = torch.sqrt((y * y).mean(dim=1) + 1e-8)                              # [n_calls, B/g, F]
+    y = y.mean(dim=2, keepdim=True)                                         # [n_calls, B/g, 1]
+    return y[:, None].expand(n_calls, g, B // g, 1).reshape(Bt, 1)

@@ -78,6 +78,7 @@ class TrainingStep:
         # CUDA-graph replay of the step (one graph per (do_r1_reg, do_pl_reg) variant — the
         # reference's tf.function likewise retraces per Python bool, train.py:182-183)
         self.use_cuda_graph = False
+        self.batch_d_calls = True       # evaluate D(fake) and D(real) as one concatenated pass
         self._graphs = {}
         self._static = None
 
@@ -199,9 +200,20 @@ class TrainingStep:
         fake_images = G((input_words, z), training=True, draws=draws)                        # :178
         fake_images = mask_text_box(fake_images, input_words, self.char_width)              # :180
 
+        # D(fake) and D(real) (training_step.py:260,288) as ONE concatenated pass when no R1 penalty is due:
+        # every discriminator layer is per-sample except the minibatch statistic, taken per call.
+        self._batched_d = bool(self.batch_d_calls and L.use_fused() and not do_r1_reg)
+        real_scores = None
+        if self._batched_d:
+            nb = fake_images.shape[0]
+            scores = D(torch.cat([fake_images, real_images.detach().to(fake_images.dtype)], dim=0), n_calls=2)
+            fake_scores, real_scores = scores[:nb], scores[nb:]
+        else:
+            fake_scores = None
         fake_scores, reg_g_loss, g_loss, pl_penalty = self._get_generator_losses(fake_images, do_pl_reg,
-                                                                                 input_words, draws)
-        reg_d_loss, d_loss, r1_penalty = self._get_discriminator_losses(fake_scores, real_images, do_r1_reg)
+                                                                                 input_words, draws, fake_scores)
+        reg_d_loss, d_loss, r1_penalty = self._get_discriminator_losses(fake_scores, real_images, do_r1_reg,
+                                                                        real_scores)
         if self.aster_ocr is not None:
             ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
             ocr_loss = ocr_loss_weight * ocr_loss                                            # :191-192
@@ -212,7 +224,9 @@ class TrainingStep:
         o_vars = [G.params[n] for n in self._ocr_names]
         d_vars = [D.params[n] for n in self._d_names]
         # three tape.gradient calls on one persistent tape (:194-213): all at pre-update weights
-        with _fused.skip_weight_grads("dconv"):       # only generator variables are wanted from this pass
+        with _fused.skip_weight_grads("dconv"), \
+                _fused.backward_batch_limit("dconv", fake_images.shape[0] if self._batched_d else 1 << 30):
+            # only generator variables are wanted from this pass
             g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
         o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
             if ocr_loss is not None else None
@@ -232,20 +246,22 @@ class TrainingStep:
         return gen_losses, disc_losses, ocr_out
 
     # ------------------------------------------------------------------------------------------
-    def _get_discriminator_losses(self, fake_scores, real_images, do_r1_reg: bool):
+    def _get_discriminator_losses(self, fake_scores, real_images, do_r1_reg: bool, real_scores=None):
         """training_step.py:237-266"""
         if do_r1_reg:
             real_scores, r1_penalty = self._r1_reg(real_images)
         else:
-            real_scores = self.discriminator(real_images)
+            if real_scores is None:
+                real_scores = self.discriminator(real_images)
             r1_penalty = torch.zeros((), device=real_scores.device)
         d_loss = discriminator_loss(fake_scores, real_scores, self.batch_size)
         reg_d_loss = d_loss + r1_penalty
         return reg_d_loss, d_loss, r1_penalty
 
-    def _get_generator_losses(self, fake_images, do_pl_reg: bool, input_words, draws: dict):
+    def _get_generator_losses(self, fake_images, do_pl_reg: bool, input_words, draws: dict, fake_scores=None):
         """training_step.py:268-298"""
-        fake_scores = self.discriminator(fake_images)
+        if fake_scores is None:
+            fake_scores = self.discriminator(fake_images)
         g_loss = generator_loss(fake_scores, self.batch_size)
         pl_penalty = self._path_length_reg(input_words, draws) if do_pl_reg \
             else torch.zeros((), device=fake_scores.device)
