@@ -316,7 +316,7 @@ def run_ours(args) -> None:
             oh, ow = recipe["Ho"] * (1 + up_[0]), recipe["Wo"] * (1 + up_[1])
             kw = dict(Ho=recipe["Ho"], Wo=recipe["Wo"], taps=recipe["taps"], pad=recipe["pad"], stride=recipe["stride"],
                       up=up_, act=recipe["act"], act_gain=recipe["act_gain"], res_scale=recipe["res_scale"],
-                      res_first=recipe["res_first"], out_fp32=recipe["out_fp32"])
+                      res_first=recipe["res_first"], out_fp32=recipe["out_fp32"], tap_mask=recipe.get("tap_mask"))
             if recipe["has_scale"]:
                 kw["col_scale"] = torch.rand(Bq, cout, device=dev) + 0.5
             if recipe["has_bias"]:

@@ -79,6 +79,9 @@ typedef struct tbg_conv_args {
   int act;         /* 0 linear, 1 leaky-relu(0.2), 2 relu */
   float act_gain;  /* multiplies after act (sqrt(2) for lrelu) */
   int out_fp32;    /* 0: bf16 output, 1: fp32 output */
+  unsigned long long tap_mask[4]; /* per output phase (py*2+px along up axes, else [0]): bit (th*taps_w+tw) set = the tap's
+                           weight block is non-zero and is computed; 0 = all taps.  Lets a transposed
+                           stride-2 convolution skip the taps a phase does not have. */
 } tbg_conv_args;
 
 int tbg_conv2d_igemm(const tbg_conv_args* args, void* stream);
@@ -164,6 +167,16 @@ int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, void* gx, f
 int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise, const float* d,
                      void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C, int act, float gain,
                      int s1_over_batch, void* stream);
+/* 4x4 separable FIR k = [1,3,3,1] (x) [1,3,3,1] on NHWC bf16 — the resample kernel upfirdn_2d applies after
+ * the transposed convolution of upsample_conv_2d and before the strided convolution of
+ * conv_downsample_2d (upfirdn_2d_v2.py:65-113):
+ *   out[b,y,x,c] = scale * sum_{m,n<4} k[m] k[n] in[b, y+m+offy, x+n+offx, c]      (in = 0 out of bounds)
+ * optionally followed by v = act(v*d[b,c] + noise[b,y,x]*ns + bias[c]) * gain (d, noise, bias may be NULL;
+ * act: 0 linear, 1 leaky-relu(0.2)).  k is symmetric: the adjoint is the same call with
+ * off' = -3 - off and the roles of in/out exchanged. */
+int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
+             const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
+             void* stream);
 int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C, void* stream);
 int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
                   void* stream);
@@ -185,6 +198,13 @@ int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, i
               void* fwd, void* adj, float* q, void* stream);
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
               int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, void* stream);
+
+/* Fold of a gradient held in the adjoint-matrix layout [Ipad, (tap, Opad)] of an identity-table geometry
+ * (role-swapped weight gradient of a transposed convolution): gw[tap,i,o] += coef*gadj[i, tap'*Opad+o], tap' =
+ * tap, or the spatially mirrored tap when flip != 0 (upsample_conv_2d flips w, upfirdn_2d_v2.py:80)
+ * (+ 2 coef^2 w dL/dq with dL/dq formed from (s, t) as in tbg_wfold). */
+int tbg_wfold_adj(const float* gadj, const float* w, float coef, int KH, int KW, int I, int O, int Opad, float* gw,
+                  const float* s, const float* t, int nb, int flip, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Demodulation coefficient of ModulatedConv2D and its gradient (modulated_conv2d.py:75-82), fp32:

@@ -47,3 +47,36 @@ run("d down 16x64 128->256", B, C.down_geom(16, 64, 128, 256, 3, True))
 run("d 8x32 256->256", B, C.plain_geom(8, 32, 256, 256, 3))
 run("d 4x8 512->512", B, C.plain_geom(4, 8, 512, 512, 3))
 run("big 64x256 128->128", B, C.plain_geom(64, 256, 128, 128, 3))
+
+
+def run_upT(name, B, h, w, I, O):
+    """Unfolded upsample_conv_2d: transposed conv (tap masks) + FIR pass; dgrad = stride-2 conv; wgrad role-swapped."""
+    dev = "cuda"
+    spec = C.weight_spec("upT", h, w, I, O, 3, True, "modconv")
+    n_rot = min(64, max(2, int(300e6 // (B * h * w * I * 2)) + 1))
+    xs = [torch.randn(B, h, w, I, device=dev).bfloat16() for _ in range(n_rot)]
+    th, tw = spec.t_hw
+    gTs = [torch.randn(B, th, tw, O, device=dev).bfloat16() for _ in range(min(n_rot, 8))]
+    wf = (torch.randn(spec.fwd_rows, spec.fwd_cols, device=dev) / (9 * I) ** 0.5).bfloat16()
+    wa = (torch.randn(spec.adj_rows, spec.adj_cols, device=dev) / (9 * I) ** 0.5).bfloat16()
+    T = torch.empty(B, th, tw, O, device=dev, dtype=torch.bfloat16)
+    d = torch.rand(B, O, device=dev) + 0.5
+    nz = torch.randn(B, 2 * h, 2 * w, device=dev)
+    ns = torch.ones(1, device=dev)
+    bias = torch.randn(O, device=dev)
+    gx = torch.empty(B, h, w, I, device=dev, dtype=torch.bfloat16)
+    gw = torch.zeros(spec.adj_rows, spec.adj_cols, device=dev)
+    t_c = bench(lambda i: K.conv2d_igemm(xs[i], wf, out=T, **spec.fwd_kwargs), n_rot)
+    t_f = bench(lambda i: K.fir4(gTs[i % len(gTs)], spec.out_hw, (-1, -1), 1 / 16, d=d, noise=nz, noise_strength=ns, bias=bias, act=1, gain=1.4), n_rot)
+    t_d = bench(lambda i: K.conv2d_igemm(gTs[i % len(gTs)], wa, out=gx, **spec.s2_kwargs), n_rot)
+    t_w = bench(lambda i: K.conv2d_wgrad(gTs[i % len(gTs)], xs[i], gw=gw, **spec.s2_kwargs), n_rot)
+    algo = 2.0 * B * h * w * 9 * I * O
+    print(f"{name:28s} B={B} convT {t_c:6.1f} us (algo {algo/t_c/1e6:6.1f} TF/s) fir {t_f:6.1f} us | dgrad {t_d:6.1f} us "
+          f"(algo {algo/t_d/1e6:6.1f}) | wgrad {t_w:6.1f} us (algo {algo/t_w/1e6:6.1f})", flush=True)
+
+
+run_upT("modT up 2x8 128->512", B, 2, 8, 128, 512)
+run_upT("modT up 4x16 512->256", B, 4, 16, 512, 256)
+run_upT("modT up 8x32 256->256", B, 8, 32, 256, 256)
+run_upT("modT up 16x64 256->128", B, 16, 64, 256, 128)
+run_upT("modT up 32x128 128->128", B, 32, 128, 128, 128)

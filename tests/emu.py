@@ -19,7 +19,8 @@ def _gather_tap(xp, PH, PW, ty, tx, pad, stride, Ho, Wo):
 
 
 def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_scale=None, bias=None, noise=None,
-                     noise_strength=None, residual=None, res_scale=1.0, res_first=False, act=0, act_gain=1.0, out_fp32=False, out=None):
+                     noise_strength=None, residual=None, res_scale=1.0, res_first=False, act=0, act_gain=1.0, out_fp32=False, out=None,
+                     tap_mask=None):
     if isinstance(up, bool):
         up = (int(up), int(up))
     B, H, W_, Cin = x.shape
@@ -27,6 +28,15 @@ def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_s
     n_total = w.shape[0]
     cout = n_total // (ph * pw)
     w6 = w.reshape(ph, pw, cout, taps[0], taps[1], Cin).to(torch.float64)
+    if tap_mask is not None:      # masked taps are not computed (their weight blocks are treated as zero)
+        keep = torch.zeros(ph, pw, 1, taps[0], taps[1], 1, dtype=torch.float64)
+        for p_ in range(ph):
+            for q_ in range(pw):
+                m = int(tap_mask[p_ * pw + q_])
+                for t_ in range(taps[0] * taps[1]):
+                    if m == 0 or (m >> t_) & 1:
+                        keep[p_, q_, 0, t_ // taps[1], t_ % taps[1], 0] = 1.0
+        w6 = w6 * keep
     PH = taps[0] + pad[0] + stride[0] * Ho + 2
     PW = taps[1] + pad[1] + stride[1] * Wo + 2
     xp = F.pad(x.to(torch.float64), (0, 0, PW, PW, PH, PH))
@@ -154,6 +164,48 @@ def emu_modulate_bwd(gxs, x, s, gs_init=None):
     if gs_init is not None:
         gs = gs + gs_init
     return gx, gs
+
+
+def emu_fir4(x, out_hw, off, scale, *, d=None, noise=None, noise_strength=None, bias=None, act=0, gain=1.0):
+    """Documented semantics of tbg_fir4 (include/tbg.h)."""
+    B, IH, IW, C = x.shape
+    OH, OW = out_hw
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    # zero-extend so that every index y+m+off lands inside the padded tensor
+    lo_y, lo_x = max(0, -off[0]), max(0, -off[1])
+    hi_y, hi_x = max(0, OH + 3 + off[0] - IH), max(0, OW + 3 + off[1] - IW)
+    xp = torch.nn.functional.pad(x.double(), (0, 0, lo_x, hi_x, lo_y, hi_y))
+    acc = torch.zeros(B, OH, OW, C, dtype=torch.float64)
+    for m in range(4):
+        for n in range(4):
+            y0, x0 = m + off[0] + lo_y, n + off[1] + lo_x
+            acc += k[m] * k[n] * xp[:, y0:y0 + OH, x0:x0 + OW]
+    acc = acc * scale
+    if d is not None:
+        acc = acc * d.double()[:, None, None, :]
+    if noise is not None:
+        acc = acc + noise.double()[..., None] * noise_strength.double().reshape(())
+    if bias is not None:
+        acc = acc + bias.double()
+    if act == 1:
+        acc = torch.where(acc > 0, acc, 0.2 * acc)
+    return (acc * gain).to(x.dtype)
+
+
+def emu_wfold_adj(gadj, spec, *, w_raw=None, s=None, t=None, out=None, flip=False):
+    taps = spec.KH * spec.KW
+    g = gadj.double().reshape(spec.Ipad, taps, spec.Opad)[: spec.I, :, : spec.O]
+    if flip:
+        g = g.flip(1)
+    gw = (g.permute(1, 0, 2) * spec.coef).reshape(spec.KH, spec.KW, spec.I, spec.O)
+    if s is not None:
+        gq = (s.double() ** 2).t() @ t.double()
+        gw = gw + 2.0 * spec.coef * spec.coef * w_raw.double() * gq[None, None]
+    gw = gw.float()
+    if out is not None:
+        out += gw
+        return out
+    return gw
 
 
 def emu_style_dense_fwd(style, ws, bs, idxs, coef):
@@ -332,6 +384,8 @@ def emulated_kernels(act_dtype=torch.float32):
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
     saved_w = (K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd)
+    saved_f = (K.fir4, K.wfold_adj)
+    K.fir4, K.wfold_adj = emu_fir4, emu_wfold_adj
     saved_d = (K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd)
     K.demod_coef, K.demod_bwd = emu_demod_coef, emu_demod_bwd
     K.style_dense_fwd, K.style_dense_bwd = emu_style_dense_fwd, emu_style_dense_bwd
@@ -354,3 +408,4 @@ def emulated_kernels(act_dtype=torch.float32):
          K.torgb_bwd) = saved
         K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd = saved_w
         K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd = saved_d
+        K.fir4, K.wfold_adj = saved_f

@@ -7,6 +7,7 @@ whole-model quantities in bf16 activations 5e-2 (losses) — stated next to each
 """
 import copy
 import math
+import zlib
 
 import pytest
 import torch
@@ -23,6 +24,11 @@ DEV = "cuda"
 
 def _bf16_round(t):
     return t.to(torch.bfloat16).float()
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
 def _geoms():
@@ -50,7 +56,7 @@ def test_conv_forward_adjoint_wgrad_vs_emulated_semantics(name, batch):
     from textboxgan_b200 import kernels as K
 
     g = _geoms()[name]
-    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    gen = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)    # str hash() is salted per process
     x = _bf16_round(torch.randn(batch, g.H, g.W, g.cin, generator=gen))
     w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
     kw = g.kernel_kwargs()
@@ -71,7 +77,8 @@ def test_conv_forward_adjoint_wgrad_vs_emulated_semantics(name, batch):
     # <conv(x), gy> == <x, conv^T(gy)>  (size-independent property, exact up to fp32 rounding)
     lhs = (y.double().cpu() * gy.double()).sum()
     rhs = (x.double() * gx.double().cpu()).sum()
-    assert abs(lhs - rhs) <= 1e-4 * (abs(lhs) + 1.0)
+    # (both sides are sums with cancellation: the bound is relative to the sum of magnitudes)
+    assert abs(lhs - rhs) <= 1e-5 * ((y.double().cpu() * gy.double()).abs().sum() + 1.0)
     # weight gradient
     gw = K.conv2d_wgrad(x.to(DEV).bfloat16(), gy.to(DEV).bfloat16(), **kw)
     gwref = emu_conv2d_wgrad(x, gy, **kw)
@@ -332,6 +339,120 @@ def test_grouped_style_projection_vs_emulated_semantics(B, n, S, Is, idxs):
     assert rel_err(gstyle, rstyle) < 1e-4
     for a, b in zip(gws + gbs, rws + rbs):
         assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("B,h,w,I,O", [(3, 4, 16, 128, 64), (32, 2, 8, 128, 512), (5, 16, 64, 64, 128), (2, 8, 32, 256, 256)])
+def test_unfolded_upsample_conv_kernels_vs_emulated_semantics(B, h, w, I, O):
+    """upsample_conv_2d as transposed conv (tap masks, (h+1) x (w+1) non-power-of-two tile grid) + tbg_fir4:
+    every kernel against its documented semantics, and the whole layer (forward and all gradients)
+    against the FIR-folded formulation of the same layer."""
+    import emu
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import fused as F
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(B * 7 + h + I)
+    spec = C.weight_spec("upT", h, w, I, O, 3, True, "modconv")
+    x = _bf16_round(torch.randn(B, h, w, I, generator=gen))
+    wr = torch.randn(3, 3, I, O, generator=gen)
+    fwd, adj, q = K.wprep(wr.to(DEV), spec, want_adj=True, want_q=True)
+    rf, ra, rq = emu.emu_wprep(wr, spec, want_adj=True, want_q=True)
+    assert rel_err(fwd.float(), rf.float()) < 4e-3 and rel_err(adj.float(), ra.float()) < 4e-3
+    # transposed conv with masked taps, fp32 out: accumulation order only
+    T = K.conv2d_igemm(x.to(DEV).bfloat16(), fwd, out_fp32=True, **spec.fwd_kwargs)
+    rT = emu.emu_conv2d_igemm(x, fwd.float().cpu(), out_fp32=True, **spec.fwd_kwargs)
+    assert T.shape == (B, 2 * h + 2, 2 * w + 2, O) and rel_err(T, rT) < 2e-5
+    # FIR pass (+ epilogue) and its adjoint
+    Tb = _bf16_round(rT)
+    d = torch.rand(B, O, generator=gen) + 0.5
+    nz = torch.randn(B, 2 * h, 2 * w, generator=gen)
+    ns = torch.tensor([0.3])
+    bias = torch.randn(O, generator=gen)
+    kw = dict(d=d, noise=nz, noise_strength=ns, bias=bias, act=1, gain=math.sqrt(2))
+    o = K.fir4(Tb.to(DEV).bfloat16(), spec.out_hw, (-1, -1), 1 / 16, **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()})
+    ro = emu.emu_fir4(Tb, spec.out_hw, (-1, -1), 1 / 16, **kw)
+    assert rel_err(o.float(), ro) < 1e-2
+    gy = _bf16_round(torch.randn(B, 2 * h, 2 * w, O, generator=gen))
+    gT = K.fir4(gy.to(DEV).bfloat16(), spec.t_hw, (-2, -2), 1 / 16)
+    rgT = emu.emu_fir4(gy, spec.t_hw, (-2, -2), 1 / 16)
+    assert rel_err(gT.float(), rgT) < 1e-2
+    # adjoint identity <fir(T), gy> == <T, fir_adj(gy)> on the emulated semantics (fp64)
+    lhs = (emu.emu_fir4(Tb.double(), spec.out_hw, (-1, -1), 1 / 16).double() * gy.double()).sum()
+    rhs = (Tb.double() * emu.emu_fir4(gy.double(), spec.t_hw, (-2, -2), 1 / 16).double()).sum()
+    assert abs(lhs - rhs) < 1e-6 * (abs(lhs) + 1)
+    # adjoint-layout fold
+    g = torch.randn(spec.adj_rows, spec.adj_cols, generator=gen)
+    s = torch.randn(B, I, generator=gen)
+    t = torch.randn(B, O, generator=gen)
+    got = K.wfold_adj(g.to(DEV), spec, w_raw=wr.to(DEV), s=s.to(DEV), t=t.to(DEV), flip=True)
+    want = emu.emu_wfold_adj(g, spec, w_raw=wr, s=s, t=t, flip=True)
+    assert rel_err(got, want) < 1e-4
+    # whole layer: unfolded vs folded formulation on the GPU (bf16 activations: 2e-2 of the tensor maximum)
+    sc = torch.randn(B, I, generator=gen) * 0.2 + 1.0
+    outs = []
+    for kind, Fn in (("up", F.ModConvAct), ("upT", F.ModUpConvAct)):
+        F.clear_step_cache()
+        xa = x.to(DEV).bfloat16().requires_grad_(True)
+        sa = sc.to(DEV).requires_grad_(True)
+        wa = wr.to(DEV).requires_grad_(True)
+        y = Fn.apply(xa, sa, wa, nz.to(DEV), ns.to(DEV).reshape(()), bias.to(DEV), C.weight_spec(kind, h, w, I, O, 3, True, "modconv"),
+                     math.sqrt(2))
+        y.backward(gy.to(DEV).bfloat16())
+        outs.append((y.float(), xa.grad.float(), sa.grad, wa.grad))
+    F.clear_step_cache()
+    # outputs: one bf16 rounding (2e-2 of the maximum).  Gradients: the leaky-ReLU slope is recovered from
+    # the bf16 output, so the two formulations pick different slopes where |pre-activation| is below their
+    # rounding difference; compare in relative L2 norm (5e-2).
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-2
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert _rel_l2(a, b) < 5e-2
+
+
+@pytest.mark.parametrize("B,H,W,I,O,k,rh", [(4, 16, 64, 128, 128, 3, True), (6, 8, 32, 256, 256, 3, False),
+                                             (4, 16, 64, 128, 256, 1, True), (3, 8, 16, 256, 512, 1, False),
+                                             (64, 4, 8, 512, 512, 3, False)])
+def test_unfolded_downsample_conv_layer_matches_folded(B, H, W, I, O, k, rh):
+    """conv_downsample_2d as FIR pre-pass + strided k x k conv (forward, weight gradient) against the
+    FIR-folded single convolution, whole layer incl. bias/lrelu/residual (bf16 activations: 2e-2)."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import fused as F
+
+    gen = torch.Generator().manual_seed(B + H + I + k)
+    x = _bf16_round(torch.randn(B, H, W, I, generator=gen))
+    wr = torch.randn(k, k, I, O, generator=gen)
+    bias = torch.randn(O, generator=gen) * 0.1 if k == 3 else None
+    oh, ow = (H // 2 if rh else H), W // 2
+    res = _bf16_round(torch.randn(B, oh, ow, O, generator=gen)) if k == 3 else None
+    gy = _bf16_round(torch.randn(B, oh, ow, O, generator=gen))
+    outs = []
+    for kind in ("down", "downU"):
+        F.clear_step_cache()
+        xa = x.to(DEV).bfloat16().requires_grad_(True)
+        wa = wr.to(DEV).requires_grad_(True)
+        ba = bias.to(DEV).requires_grad_(True) if bias is not None else None
+        ra = res.to(DEV).bfloat16().requires_grad_(True) if res is not None else None
+        y = F.ConvAct.apply(xa, wa, ba, ra, C.weight_spec(kind, H, W, I, O, k, rh, "dconv"), 1.0)
+        assert y.shape == (B, oh, ow, O)
+        y.backward(gy.to(DEV).bfloat16())
+        outs.append([y.float(), xa.grad.float(), wa.grad] + ([ba.grad, ra.grad.float()] if k == 3 else []))
+    F.clear_step_cache()
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-2
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert _rel_l2(a, b) < 5e-2          # see test_unfolded_upsample_conv_kernels_vs_emulated_semantics
+
+
+@pytest.mark.parametrize("Ho,Wo,B", [(5, 17, 3), (17, 65, 2), (3, 9, 32), (33, 129, 1), (7, 5, 9)])
+def test_conv_forward_non_power_of_two_grids(Ho, Wo, B):
+    """Tile boxes are chosen per grid (any bw x bh x bn <= 128): plain 3x3 SAME conv on odd-sized grids."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    g = C.plain_geom(Ho, Wo, 64, 96, 3)
+    gen = torch.Generator().manual_seed(Ho * 100 + Wo)
+    x = _bf16_round(torch.randn(B, Ho, Wo, 64, generator=gen))
+    w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
+    y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), out_fp32=True, **g.kernel_kwargs())
+    assert rel_err(y, emu_conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs())) < 2e-5
 
 
 @pytest.mark.parametrize("B,T,steps", [(3, 32, 8), (5, 17, 4)])

@@ -354,13 +354,17 @@ def _axis_adj_table(F: torch.Tensor, ax: Axis) -> torch.Tensor:
 class WeightSpec:
     """Everything tbg_wprep / tbg_wfold need for one (geometry, master-weight shape) pair."""
 
-    def __init__(self, geom: ConvGeom, kind_h: str, kind_w: str, KH: int, KW: int, I: int, O: int, coef: float):
+    def __init__(self, geom: ConvGeom, kind_h: str, kind_w: str, KH: int, KW: int, I: int, O: int, coef: float,
+                 tables=None, adj_shape=None):
         import ctypes
 
         self.geom, self.KH, self.KW, self.I, self.O, self.coef = geom, KH, KW, I, O, float(coef)
         self.Ipad, self.Opad = geom.cin, geom.cout
-        fy, fx = _axis_fwd_table(kind_h, KH), _axis_fwd_table(kind_w, KW)
-        ay, ax = _axis_adj_table(fy, geom.ah), _axis_adj_table(fx, geom.aw)
+        if tables is not None:
+            fy, fx, ay, ax = tables
+        else:
+            fy, fx = _axis_fwd_table(kind_h, KH), _axis_fwd_table(kind_w, KW)
+            ay, ax = _axis_adj_table(fy, geom.ah), _axis_adj_table(fx, geom.aw)
         assert fy.shape[:2] == (geom.ah.phases, geom.ah.k) and fx.shape[:2] == (geom.aw.phases, geom.aw.k)
         self.tables = (fy, fx, ay, ax)
 
@@ -374,9 +378,19 @@ class WeightSpec:
         zero = torch.zeros(0, 1, max(KH, 1))
         self.ctable = pack([fy, fx, ay, ax])
         self.ctable_noadj = pack([fy, fx, torch.zeros(0, 0, KH), torch.zeros(0, 0, KW)])
-        a = geom.adjoint()
+        self.fir = None                      # optional FIR pre-pass of the forward input (tbg_fir4 arguments)
+        self.fwd_kwargs = geom.kernel_kwargs()
+        self.adj_frac = geom.algo_frac
+        try:
+            self.adj_kwargs = geom.adjoint().kernel_kwargs() if adj_shape is None else None
+        except AssertionError:
+            self.adj_kwargs = None
         self.fwd_rows, self.fwd_cols = geom.n_total, geom.k_total
-        self.adj_rows, self.adj_cols = a.n_total, a.k_total
+        if adj_shape is not None:
+            self.adj_rows, self.adj_cols = adj_shape
+        else:
+            a = geom.adjoint()
+            self.adj_rows, self.adj_cols = a.n_total, a.k_total
 
 
 @lru_cache(maxsize=None)
@@ -395,4 +409,73 @@ def weight_spec(kind: str, H: int, W: int, I: int, O: int, k: int, reduce_height
     if kind == "down":
         g = down_geom(H, W, Ip, Op, k, reduce_height, tag=tag)
         return WeightSpec(g, "down" if reduce_height else "down", "down", k, k, I, O, coef)
+    if kind == "upT":
+        return _upT_spec(H, W, I, O, Ip, Op, k, coef, tag)
+    if kind == "downU":
+        return _downU_spec(H, W, I, O, Ip, Op, k, reduce_height, coef, scale, tag)
     raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------------------------
+# conv_downsample_2d with the FIR unfolded in the FORWARD and WEIGHT-GRADIENT directions
+# (upfirdn_2d_v2.py:106-113 in the reference's order): xb = FIR(x) once (tbg_fir4, saved for backward), then the
+# VALID k x k stride-(2|1, 2) convolution and its weight gradient run at their algorithmic cost (k*k taps
+# instead of (k+3)^2).  The INPUT gradient keeps the folded form (one 4-phase GEMM straight from the output
+# gradient to the input gradient, no FIR-adjoint pass).
+#   k = 3: xb[j] = sum_m kf[m] x[j+m-2], (H+2) x (W+2);  y[p] = sum_t xb[s*p + t] w[t]
+#   k = 1: xb[j] = sum_m kf[m] x[j+m-1],  H x W;          y[p] = xb[s*p] w
+# ----------------------------------------------------------------------------------------------
+def _downU_spec(H: int, W: int, I: int, O: int, Ip: int, Op: int, k: int, reduce_height: bool, coef: float,
+                scale: float, tag: str) -> "WeightSpec":
+    folded = weight_spec("down", H, W, I, O, k, reduce_height, tag, scale)
+    ext = 2 if k == 3 else 0
+    sh = 2 if reduce_height else 1
+    g = ConvGeom(H + ext, W + ext, Ip, Op, Axis("s2" if reduce_height else "s1", k, 0), Axis("s2", k, 0), tag,
+                 (I * O) / float(Ip * Op))
+    ident = torch.eye(k).reshape(1, k, k)
+    a = folded.geom.adjoint()
+    spec = WeightSpec(g, "plain", "plain", k, k, I, O, coef, tables=(ident, ident.clone(), folded.tables[2], folded.tables[3]),
+                      adj_shape=(a.n_total, a.k_total))
+    spec.fwd_kwargs = dict(Ho=H // sh, Wo=W // 2, taps=(k, k), pad=(0, 0), stride=(sh, 2), up=(0, 0))
+    spec.adj_kwargs = a.kernel_kwargs()
+    spec.adj_frac = folded.geom.algo_frac
+    spec.fir = dict(out_hw=(H + ext, W + ext), off=(-2, -2) if k == 3 else (-1, -1), scale=1.0 / 64.0)
+    return spec
+
+
+# ----------------------------------------------------------------------------------------------
+# upsample_conv_2d WITHOUT folding the FIR (upfirdn_2d_v2.py:65-103 as the reference orders it): the
+# stride-2 transposed 3x3 convolution runs at its algorithmic cost (9 tap blocks), the 4x4 FIR is a
+# separate bandwidth-bound pass (tbg_fir4) that also applies the layer epilogue.
+#   T[2a+py, 2c+px] = sum_{ty,tx} x[a+ty-1, c+tx-1] * Wt[(py,px), (ty,tx)]      a in [0,h], c in [0,w]
+# conv2d_transpose runs on the spatially flipped kernel (upfirdn_2d_v2.py:80), T[Y] = sum_i x[i] w[2-(Y-2i)], so
+# per axis  phase 0 (even rows): taps t=0 -> w[0] (input a-1), t=1 -> w[2] (input a);
+#           phase 1 (odd rows):  tap  t=1 -> w[1] (input a); t=0 is structurally zero (masked).
+# Its adjoint (input gradient) is the plain stride-2 VALID 3x3 convolution of the (2h+2) x (2w+2)
+# tensor, and its weight gradient is that convolution's weight gradient with the roles of input and
+# output gradient exchanged — both run on the power-of-two h x w grid with exactly 9 taps.
+# ----------------------------------------------------------------------------------------------
+UPT_TAP_MASK = (0b1111, 0b1010, 0b1100, 0b1000)   # phases (py,px) = (0,0), (0,1), (1,0), (1,1); bit = ty*2+tx
+
+
+def _upT_table() -> torch.Tensor:
+    f = torch.zeros(2, 2, 3)
+    f[0, 0, 0] = 1.0
+    f[0, 1, 2] = 1.0
+    f[1, 1, 1] = 1.0
+    return f
+
+
+def _upT_spec(h: int, w: int, I: int, O: int, Ip: int, Op: int, k: int, coef: float, tag: str) -> "WeightSpec":
+    assert k == 3
+    algo = 9.0 * h * w / (16.0 * (h + 1) * (w + 1))
+    g = ConvGeom(h, w, Ip, Op, Axis("up", 2, 1), Axis("up", 2, 1), tag, algo)
+    f, ident = _upT_table(), torch.eye(3).flip(0).reshape(1, 3, 3)     # adjoint: stride-2 conv with the flipped kernel
+    spec = WeightSpec(g, "upT", "upT", 3, 3, I, O, coef, tables=(f, f.clone(), ident, ident.clone()),
+                      adj_shape=(Ip, 9 * Op))
+    # kernel launch descriptions of the three convolutions
+    spec.fwd_kwargs = dict(Ho=h + 1, Wo=w + 1, taps=(2, 2), pad=(1, 1), stride=(1, 1), up=(1, 1), tap_mask=UPT_TAP_MASK)
+    spec.s2_kwargs = dict(Ho=h, Wo=w, taps=(3, 3), pad=(0, 0), stride=(2, 2), up=(0, 0))
+    spec.t_hw = (2 * h + 2, 2 * w + 2)
+    spec.out_hw = (2 * h, 2 * w)
+    return spec

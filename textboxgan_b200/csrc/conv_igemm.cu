@@ -15,7 +15,8 @@ namespace tbg {
 
 struct ConvKernelParams {
   int B;
-  int bw_log2, bh_log2, bn_log2;  // M-tile box (output pixels): bw*bh*bn == 128
+  int bw, bh, bn;  // M-tile box (output pixels): bw*bh*bn <= 128 (any sizes; rows beyond the box are ignored)
+  uint64_t tap_mask[4];  // per output phase: bit (ty*taps_w+tx) set = that tap's K blocks are computed
   int tiles_w, tiles_h, tiles_b, tiles_n;
   int block_n;  // columns per N tile (multiple of 32, <= 256)
   int n_total;
@@ -93,8 +94,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
   const int total_tiles = tiles_m * p.tiles_n;
-  const int k_blocks = p.taps_h * p.taps_w * p.cin_chunks;
-  const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2, bn = 1 << p.bn_log2;
+  const int bw = p.bw, bh = p.bh, bn = p.bn;
+  const uint32_t a_bytes = static_cast<uint32_t>(bw * bh * bn) * 128u;  // bytes one activation box delivers
+  // output phase of an N tile (up-sampling geometries put the phases side by side along N)
+  auto tile_mask = [&](int n_tile) -> uint64_t {
+    const int ph = (p.up_h | p.up_w) ? (n_tile * p.block_n) / p.cout : 0;
+    return p.tap_mask[ph & 3];
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -110,12 +116,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int w_base = tw * bw * p.stride_w + p.in_off_w;
         const int h_base = th * bh * p.stride_h + p.in_off_h;
         const int n_base = tb * bn;
-        int kcol = 0;
+        const uint64_t mask = tile_mask(n_tile);
         for (int ty = 0; ty < p.taps_h; ++ty) {
           for (int tx = 0; tx < p.taps_w; ++tx) {
+            if (!((mask >> (ty * p.taps_w + tx)) & 1ull)) continue;   // structurally zero weight block
+            int kcol = (ty * p.taps_w + tx) * p.cin;
             for (int ch = 0; ch < p.cin_chunks; ++ch, kcol += 64) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
+              mbar_arrive_expect_tx(&full[stage], a_bytes + b_bytes);
               tma_load_4d(smA + stage * kABytes, &tmA, &full[stage], ch * 64, w_base + tx, h_base + ty, n_base);
               tma_load_2d(smB + stage * b_bytes, &tmB, &full[stage], kcol, n_tile * p.block_n);
               if (++stage == stages) {
@@ -140,6 +148,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty[acc_stage], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
+        const uint64_t mask = tile_mask(tile % p.tiles_n);
+        const int k_blocks = __popcll(mask) * p.cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -164,9 +174,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================================ epilogue ================================
     const int e = warp - 4;
     const int r = e * 32 + lane;
-    const int w_in = r & (bw - 1);
-    const int h_in = (r >> p.bw_log2) & (bh - 1);
-    const int n_in = r >> (p.bw_log2 + p.bh_log2);
+    const int w_in = r % bw;
+    const int h_in = (r / bw) % bh;
+    const int n_in = r / (bw * bh);
     const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -178,7 +188,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int b = tb * bn + n_in;
       const int ho = th * bh + h_in;
       const int wo = tw * bw + w_in;
-      const bool valid = (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
+      const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc_stage], acc_phase);
@@ -311,7 +321,8 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
                 "tbg_conv2d_igemm: n_total=%d inconsistent with cout=%d up=(%d,%d)", a->n_total, a->cout, a->up_h, a->up_w);
   TBG_CHECK_ARG(!(a->up_h && a->stride_h != 1) && !(a->up_w && a->stride_w != 1), "tbg_conv2d_igemm: up with stride on one axis");
   TBG_CHECK_ARG(a->act >= 0 && a->act <= 2, "tbg_conv2d_igemm: act must be 0 (linear), 1 (lrelu) or 2 (relu)");
-  TBG_CHECK_ARG(a->taps_h >= 1 && a->taps_w >= 1 && a->taps_h <= 8 && a->taps_w <= 8, "tbg_conv2d_igemm: bad taps");
+  TBG_CHECK_ARG(a->taps_h >= 1 && a->taps_w >= 1 && a->taps_h <= 8 && a->taps_w <= 8 && a->taps_h * a->taps_w <= 36,
+                "tbg_conv2d_igemm: bad taps");
   TBG_CHECK_ARG((a->stride_h == 1 || a->stride_h == 2) && (a->stride_w == 1 || a->stride_w == 2),
                 "tbg_conv2d_igemm: strides must be 1 or 2");
   TBG_CHECK_ARG(!a->noise || a->noise_strength, "tbg_conv2d_igemm: noise without noise_strength");
@@ -324,16 +335,35 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 
   ConvKernelParams p{};
   p.B = a->B;
-  const int wo_p2 = 1 << ilog2(a->Wo), ho_p2 = 1 << ilog2(a->Ho);  // next powers of two
-  const int bw = wo_p2 < 128 ? wo_p2 : 128;
-  int bh = 128 / bw;
-  if (bh > ho_p2) bh = ho_p2;
-  const int bn = 128 / (bw * bh);
-  // with a stride-2 load the TMA box spans 2*b elements and must stay <= 256
-  TBG_CHECK_ARG(bw * a->stride_w <= 256 && bh * a->stride_h <= 256, "tbg_conv2d_igemm: tile box too large");
-  p.bw_log2 = ilog2(bw);
-  p.bh_log2 = ilog2(bh);
-  p.bn_log2 = ilog2(bn);
+  // M-tile box: bw x bh x bn output pixels (<= 128) maximising the fraction of useful GEMM rows;
+  // ties go to the widest box (longest contiguous TMA rows).  Power-of-two grids get full tiles.
+  int bw = 1, bh = 1, bn = 1;
+  {
+    double best = -1.0;
+    const int wmax = a->Wo < 128 ? a->Wo : 128;
+    for (int cw = wmax; cw >= 1; --cw) {
+      if (cw * a->stride_w > 256) continue;
+      const int tw = (a->Wo + cw - 1) / cw;
+      const int hmax = (128 / cw) < a->Ho ? (128 / cw) : a->Ho;
+      for (int ch = hmax; ch >= 1; --ch) {
+        if (ch * a->stride_h > 256) continue;
+        const int th = (a->Ho + ch - 1) / ch;
+        int cn = 128 / (cw * ch);
+        if (cn > a->B) cn = a->B;
+        if (cn > 1 && (tw > 1 || th > 1)) cn = 1;      // batch several images per tile only when one tile covers an image
+        if (cn < 1) cn = 1;
+        const int tb = (a->B + cn - 1) / cn;
+        const double eff = (double)a->Wo * a->Ho * a->B / ((double)tw * th * tb * 128.0);
+        if (eff > best + 1e-9) {
+          best = eff;
+          bw = cw; bh = ch; bn = cn;
+        }
+      }
+    }
+  }
+  p.bw = bw;
+  p.bh = bh;
+  p.bn = bn;
   p.tiles_w = (a->Wo + bw - 1) / bw;
   p.tiles_h = (a->Ho + bh - 1) / bh;
   p.Ho = a->Ho;
@@ -346,7 +376,19 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   // prefer >= 2 N tiles' worth of parallelism only when M tiles are scarce
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
   while (block_n > 64 && tiles_m * (a->n_total / block_n) < num_sms() && (a->n_total % (block_n / 2)) == 0) block_n >>= 1;
+  // up-sampling geometries: an N tile must not straddle two output phases (tap masks are per phase)
+  if (a->up_h | a->up_w)
+    while (block_n > 32 && (block_n > a->cout || a->cout % block_n != 0)) block_n >>= 1;
   p.block_n = block_n;
+  {
+    const uint64_t all = (1ull << (a->taps_h * a->taps_w)) - 1ull;   // taps_h * taps_w <= 36
+    const int nph = (1 + a->up_h) * (1 + a->up_w);
+    for (int i = 0; i < 4; ++i) {
+      p.tap_mask[i] = (a->tap_mask[i] ? a->tap_mask[i] : all) & all;
+      if (i < nph)
+        TBG_CHECK_ARG(p.tap_mask[i] != 0, "tbg_conv2d_igemm: phase %d has no taps", i);
+    }
+  }
   p.tiles_n = (a->n_total + block_n - 1) / block_n;
   p.n_total = a->n_total;
   p.cin = a->Cin;

@@ -295,6 +295,86 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4x4 separable FIR [1,3,3,1] x [1,3,3,1] on NHWC bf16 (the resample kernel of synthesis_block.py:36 /
+// discriminator.py:44 as applied by upfirdn_2d, upfirdn_2d_v2.py:116-163):
+//   out[b,y,x,c] = scale * sum_{m,n<4} k[m] k[n] in[b, y+m+offy, x+n+offx, c]     (in = 0 out of bounds)
+// optionally followed by the layer epilogue  v = act(v*d[b,c] + noise[b,y,x]*ns + bias[c]) * gain.
+// The kernel is symmetric, so the adjoint is the same call with off' = -3 - off and in/out swapped.
+// One thread per (pixel, 8 channels); neighbouring pixels are re-read from L1/L2.
+// ---------------------------------------------------------------------------------------------
+// One thread per (image, output column, 8 channels) and strip of kFirRows output rows: the horizontally
+// filtered input rows are kept in a 4-deep register window, so every output costs 4 (not 16) 16-byte loads.
+static constexpr int kFirRows = 8;
+
+__global__ void __launch_bounds__(256)
+fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int IW, int OH, int OW, int c8, int offy,
+            int offx, float scale, const float* __restrict__ d, const float* __restrict__ noise,
+            const float* __restrict__ ns, const float* __restrict__ bias, int act, float gain, long long n_items,
+            int strips) {
+  const float nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_items;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(e % c8);
+    long long r = e / c8;
+    const int x = static_cast<int>(r % OW);
+    r /= OW;
+    const int strip = static_cast<int>(r % strips);
+    const int b = static_cast<int>(r / strips);
+    const int y0 = strip * kFirRows;
+    const int y1 = min(OH, y0 + kFirRows);
+    float dv[8], bv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) : 1.f;
+      bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+    }
+    // h(iy)[i] = sum_n k[n] * in[b, iy, x+n+offx, cv*8+i]  (zero outside the input)
+    float win[4][8];
+    auto hrow = [&](int iy, float (&h)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = 0.f;
+      if (iy < 0 || iy >= IH) return;
+      const uint4* rowp = in + (static_cast<long long>(b) * IH + iy) * IW * c8 + cv;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int ix = x + n + offx;
+        if (ix < 0 || ix >= IW) continue;
+        float v[8];
+        unpack8(__ldg(rowp + static_cast<long long>(ix) * c8), v);
+        const float kn = (n == 0 || n == 3) ? 1.f : 3.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = fmaf(kn, v[i], h[i]);
+      }
+    };
+    hrow(y0 + offy + 0, win[0]);
+    hrow(y0 + offy + 1, win[1]);
+    hrow(y0 + offy + 2, win[2]);
+#pragma unroll
+    for (int yy = 0; yy < kFirRows; ++yy) {
+      const int y = y0 + yy;
+      if (y >= y1) break;
+      hrow(y + offy + 3, win[(yy + 3) & 3]);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        acc[i] = (win[yy & 3][i] + win[(yy + 3) & 3][i] + 3.f * (win[(yy + 1) & 3][i] + win[(yy + 2) & 3][i])) * scale * dv[i];
+      if (noise != nullptr) {
+        const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += nz;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = acc[i] + bv[i];
+        if (act == 1) v = v > 0.f ? v : 0.2f * v;
+        acc[i] = v * gain;
+      }
+      out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
+    }
+  }
+}
+
 // launch geometry for the (chunks, B) reduction kernels
 struct RedGeom {
   int threads, rows, pix_per_cta, chunks;
@@ -415,6 +495,29 @@ extern "C" int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, vo
   torgb_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(reinterpret_cast<const uint4*>(x), ws, gy,
                                                                       reinterpret_cast<uint4*>(gx), gws, HW, C / 8,
                                                                       g.pix_per_cta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx,
+                        float scale, const float* d, const float* noise, const float* noise_strength, const float* bias,
+                        int act, float gain, void* stream_v) {
+  TBG_CHECK_ARG(in && out, "tbg_fir4: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && IH >= 1 && IW >= 1 && OH >= 1 && OW >= 1,
+                "tbg_fir4: bad shape B=%d in=%dx%d out=%dx%d C=%d", B, IH, IW, OH, OW, C);
+  TBG_CHECK_ARG(!noise || noise_strength, "tbg_fir4: noise without noise_strength");
+  TBG_CHECK_ARG(act == 0 || act == 1, "tbg_fir4: act must be 0 (linear) or 1 (lrelu)");
+  TBG_CHECK_ARG(TBG_ALIGNED16(in) && TBG_ALIGNED16(out) && TBG_ALIGNED16(d), "tbg_fir4: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int strips = (OH + kFirRows - 1) / kFirRows;
+  const long long n_items = static_cast<long long>(B) * strips * OW * (C / 8);
+  long long blocks = (n_items + 255) / 256;
+  const long long cap = static_cast<long long>(sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  fir4_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+                                                            IH, IW, OH, OW, C / 8, offy, offx, scale, d, noise,
+                                                            noise_strength, bias, act, gain, n_items, strips);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -192,9 +192,51 @@ wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const
   }
 }
 
+// Fold of a gradient held in the ADJOINT matrix layout of a plain (identity-table) geometry:
+//   gw[tap,i,o] += coef * gadj[i, tap'*Opad + o]  (+ 2 coef^2 w[tap,i,o] * dL/dq[i,o]),  tap' = tap or, with
+//   flip, the spatially mirrored tap (conv2d_transpose of upsample_conv_2d uses w[::-1, ::-1])
+// (the role-swapped weight gradient of a transposed convolution lands in this layout).  o-contiguous on
+// both sides: one thread per (i, o), loop over taps.
+__global__ void __launch_bounds__(256)
+wfold_adj_kernel(const float* __restrict__ gadj, const float* __restrict__ w, float* __restrict__ gw, int taps, int I,
+                 int O, int Opad, float coef, const float* __restrict__ sv, const float* __restrict__ tv, int nb,
+                 int flip) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= static_cast<long long>(I) * O) return;
+  const int i = static_cast<int>(e / O), o = static_cast<int>(e % O);
+  float gqv = 0.f;
+  if (sv != nullptr) {
+    for (int b = 0; b < nb; ++b) {
+      const float s1 = __ldg(sv + static_cast<size_t>(b) * I + i);
+      gqv = fmaf(s1 * s1, __ldg(tv + static_cast<size_t>(b) * O + o), gqv);
+    }
+    gqv *= 2.f * coef * coef;
+  }
+  for (int tp = 0; tp < taps; ++tp) {
+    const size_t idx = (static_cast<size_t>(tp) * I + i) * O + o;
+    const int ta = flip ? taps - 1 - tp : tp;   // the matrix holds the spatially flipped kernel
+    float v = coef * __ldg(gadj + (static_cast<size_t>(i) * taps + ta) * Opad + o);
+    if (sv != nullptr) v = fmaf(gqv, __ldg(w + idx), v);
+    gw[idx] += v;
+  }
+}
+
 }  // namespace tbg
 
 using namespace tbg;
+
+extern "C" int tbg_wfold_adj(const float* gadj, const float* w, float coef, int KH, int KW, int I, int O, int Opad,
+                             float* gw, const float* s, const float* t, int nb, int flip, void* stream_v) {
+  TBG_CHECK_ARG(gadj && gw, "tbg_wfold_adj: null pointer");
+  TBG_CHECK_ARG(KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3 && I >= 1 && O >= 1 && Opad >= O, "tbg_wfold_adj: bad shape");
+  TBG_CHECK_ARG((s == nullptr) == (t == nullptr) && (!s || (w && nb >= 1)), "tbg_wfold_adj: (s, t, nb) need the master weight");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n = static_cast<long long>(I) * O;
+  wfold_adj_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(gadj, w, gw, KH * KW, I, O, Opad, coef, s, t, nb, flip);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
 
 // tables: 4 blocks of [P, T, K, then P*T*K floats] for fy, fx, ay, ax (ay/ax may have P = 0)
 static int load_tables(const float* tables, WPrepParams& p) {

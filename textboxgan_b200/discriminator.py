@@ -69,7 +69,8 @@ class Discriminator(Model):
         if L.use_fused():
             from .fused import ConvAct
 
-            spec = C.weight_spec("down" if down else "plain", H, W_, I, O, k, reduce_height, "dconv", scale)
+            kind = ("downU" if L.UNFOLD_DOWN else "down") if down else "plain"
+            spec = C.weight_spec(kind, H, W_, I, O, k, reduce_height, "dconv", scale)
             if residual is not None:
                 # (lrelu(v)*sqrt2 + skip)/sqrt2 == lrelu(v) + skip/sqrt2: the caller pre-scales the
                 # (linear) skip branch, so the merge is a plain residual add in the epilogue

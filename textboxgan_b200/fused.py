@@ -135,9 +135,50 @@ class ModConvAct(torch.autograd.Function):
         return gx, gs, gw_raw, None, gns.reshape(ns.shape), gbias, None, None
 
 
+class ModUpConvAct(torch.autograd.Function):
+    """ModulatedConv2D(up=True) + Noise + BiasAct with upsample_conv_2d in the reference's own order
+    (upfirdn_2d_v2.py:65-103): transposed stride-2 3x3 convolution on the tensor cores at its algorithmic
+    cost, then the 4x4 FIR as one bandwidth-bound pass that also applies demodulation, noise, bias and
+    leaky-ReLU.  ``spec`` is weight_spec("upT", ...)."""
+
+    @staticmethod
+    def forward(ctx, x, s, w_raw, noise, ns, bias, spec, gain: float):
+        g = spec.geom
+        x = x.contiguous()
+        s = s.contiguous()
+        wmat, wadj, q = _prepared(w_raw, spec, True, True)
+        d = K.demod_coef(s, q)
+        xs = K.modulate(x, s)
+        K.PROFILE_TAG = (g.tag, g.algo_frac)
+        T = K.conv2d_igemm(xs, wmat, **spec.fwd_kwargs)                           # [B, 2h+2, 2w+2, O]
+        out = K.fir4(T, spec.out_hw, (-1, -1), 1.0 / 16.0, d=d, noise=noise.contiguous(), noise_strength=ns.reshape(1),
+                     bias=_aligned_vec(bias), act=1, gain=gain)
+        ctx.save_for_backward(x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias)
+        ctx.spec, ctx.gain = spec, gain
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias = ctx.saved_tensors
+        spec = ctx.spec
+        g = spec.geom
+        gy0, S1, Spre, Snz = K.bias_act_bwd(g_out.contiguous(), out, noise=noise.contiguous(), d=d, act=True,
+                                            gain=ctx.gain)
+        t, gbias, gns, gs = K.demod_bwd(S1, Spre, Snz, d, ns.reshape(1), _aligned_vec(bias), s, q)
+        gT = K.fir4(gy0, spec.t_hw, (-2, -2), 1.0 / 16.0)                        # adjoint of the FIR pass
+        K.PROFILE_TAG = (g.tag, 1.0)
+        gxs = K.conv2d_igemm(gT, wadj, **spec.s2_kwargs)                          # stride-2 3x3 VALID conv
+        gwadj = K.conv2d_wgrad(gT, xs, **spec.s2_kwargs)                          # roles exchanged: [I, 9*O]
+        gx, gs = K.modulate_bwd(gxs, x, s, gs_init=gs)
+        gw_raw = K.wfold_adj(gwadj, spec, w_raw=w_raw, s=s, t=t, flip=True)
+        return gx, gs, gw_raw, None, gns.reshape(ns.shape), gbias, None, None
+
+
 class ConvAct(torch.autograd.Function):
     """out = lrelu(conv(x, w) + bias)*gain (+ residual)   |   out = conv(x, w) when bias is None; ``w`` is
-    the fp32 HWIO master weight (equalised-LR coefficient and FIR folding happen in tbg_wprep)."""
+    the fp32 HWIO master weight (equalised-LR coefficient and FIR folding happen in tbg_wprep).  A spec
+    with a ``fir`` pre-pass (conv_downsample_2d, weight_spec("downU")) filters x once, convolves and takes
+    the weight gradient on the filtered tensor, and keeps the folded form for the input gradient."""
 
     @staticmethod
     def forward(ctx, x, w_raw, bias, residual, spec, gain: float):
@@ -146,8 +187,10 @@ class ConvAct(torch.autograd.Function):
         has_act = bias is not None
         need_gx = ctx.needs_input_grad[0]
         wmat, wadj, _ = _prepared(w_raw, spec, need_gx, False)
+        if spec.fir is not None:
+            x = K.fir4(x, spec.fir["out_hw"], spec.fir["off"], spec.fir["scale"])
         K.PROFILE_TAG = (geom.tag, geom.algo_frac)
-        out = K.conv2d_igemm(x, wmat, **geom.kernel_kwargs(), bias=bias, act=1 if has_act else 0,
+        out = K.conv2d_igemm(x, wmat, **spec.fwd_kwargs, bias=bias, act=1 if has_act else 0,
                              act_gain=gain if has_act else 1.0,
                              residual=residual.contiguous() if residual is not None else None, res_scale=1.0)
         ctx.save_for_backward(x, wadj, out if has_act else None, residual if has_act else None)
@@ -156,14 +199,17 @@ class ConvAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        x, wadj, out, residual = ctx.saved_tensors
+        x, wadj, out, residual = ctx.saved_tensors          # x: the (filtered) tensor the convolution read
         spec = ctx.spec
         g = spec.geom
         g_out = g_out.contiguous()
         want_w = ctx.needs_input_grad[1] and g.tag not in _SKIP_WGRAD_TAGS
         gbias = None
+        nb = g_out.shape[0]
+        gx_shape = (nb, g.H, g.W, g.cin) if spec.fir is None else \
+            (nb, spec.fir["out_hw"][0] - (2 if spec.KH == 3 else 0), spec.fir["out_hw"][1] - (2 if spec.KH == 3 else 0), g.cin)
         lim = _BATCH_LIMIT.get(g.tag)
-        if lim is not None and g_out.shape[0] > lim and not want_w:
+        if lim is not None and nb > lim and not want_w:
             # cotangent is zero beyond the first ``lim`` samples: run on that slice only
             gy0 = g_out[:lim]
             if ctx.has_act:
@@ -171,20 +217,21 @@ class ConvAct(torch.autograd.Function):
                                               act=True, gain=ctx.gain, want_sums=False)
             gx = None
             if ctx.needs_input_grad[0]:
-                gx = torch.zeros_like(x)
-                K.PROFILE_TAG = (g.tag, g.algo_frac)
-                K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs(), out=gx[:lim])
+                gx = torch.zeros(gx_shape, device=g_out.device, dtype=g_out.dtype)
+                K.PROFILE_TAG = (g.tag, spec.adj_frac)
+                K.conv2d_igemm(gy0, wadj, **spec.adj_kwargs, out=gx[:lim])
             return gx, None, None, (g_out if ctx.has_res else None), None, None
         if ctx.has_act:
             gy0, gbias, _, _ = K.bias_act_bwd(g_out, out, residual=residual, act=True, gain=ctx.gain,
                                               want_sums=False, bias_grad_only=want_w)
         else:
             gy0 = g_out
-        K.PROFILE_TAG = (g.tag, g.algo_frac)
-        gx = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs()) if ctx.needs_input_grad[0] else None
+        K.PROFILE_TAG = (g.tag, spec.adj_frac)
+        gx = K.conv2d_igemm(gy0, wadj, **spec.adj_kwargs) if ctx.needs_input_grad[0] else None
         gw_raw = None
         if want_w:
-            gw_raw = K.wfold(K.conv2d_wgrad(x, gy0, **g.kernel_kwargs()), spec)
+            K.PROFILE_TAG = (g.tag, g.algo_frac)
+            gw_raw = K.wfold(K.conv2d_wgrad(x, gy0, **spec.fwd_kwargs), spec)
         return gx, gw_raw, gbias, (g_out if ctx.has_res else None), None, None
 
 

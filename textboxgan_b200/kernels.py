@@ -83,6 +83,7 @@ def conv2d_igemm(
     act_gain: float = 1.0,
     out_fp32: bool = False,
     out: Optional[torch.Tensor] = None,
+    tap_mask: Optional[tuple] = None,           # per output phase: bit (th*taps_w+tw) = tap computed (None: all)
 ) -> torch.Tensor:
     _require(x, torch.bfloat16, "x")
     _require(w, torch.bfloat16, "w")
@@ -110,6 +111,9 @@ def conv2d_igemm(
         col_scale=_ptr(col_scale), bias=_ptr(bias), noise=_ptr(noise), noise_strength=_ptr(noise_strength),
         residual=_ptr(residual), res_scale=res_scale, res_first=int(res_first), act=act, act_gain=act_gain, out_fp32=int(out_fp32),
     )
+    if tap_mask is not None:
+        for i, m in enumerate(tap_mask):
+            a.tap_mask[i] = int(m)
     with _Timed("conv_igemm", 2.0 * B * Ho * Wo * n_total * taps[0] * taps[1] * Cin):
         _lib.check(_lib.load().tbg_conv2d_igemm(C.byref(a), _stream()), "tbg_conv2d_igemm")
     if PROFILE is not None:
@@ -118,7 +122,7 @@ def conv2d_igemm(
             x_shape=tuple(x.shape), w_shape=tuple(w.shape), Ho=Ho, Wo=Wo, taps=taps, pad=pad, stride=stride, up=up,
             has_scale=col_scale is not None, has_bias=bias is not None, has_noise=noise is not None,
             has_res=residual is not None, res_scale=res_scale, res_first=res_first, act=act, act_gain=act_gain,
-            out_fp32=out_fp32),)
+            out_fp32=out_fp32, tap_mask=tap_mask),)
     return out
 
 
@@ -386,6 +390,36 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     st = _lib.load().tbg_style_dense_bwd(arr, len(ws), _ptr(style), _ptr(gstyle), B, n, S, float(coef), _stream())
     _lib.check(st, "tbg_style_dense_bwd")
     return gstyle, gws, gbs
+
+
+def fir4(x: torch.Tensor, out_hw: tuple[int, int], off: tuple[int, int], scale: float, *, d=None, noise=None,
+         noise_strength=None, bias=None, act: int = 0, gain: float = 1.0) -> torch.Tensor:
+    """4x4 FIR [1,3,3,1]^2 on NHWC bf16 with the optional layer epilogue — see include/tbg.h (tbg_fir4)."""
+    _require(x, torch.bfloat16, "x")
+    B, IH, IW, C_ = x.shape
+    out = torch.empty((B, out_hw[0], out_hw[1], C_), device=x.device, dtype=torch.bfloat16)
+    for t, n in ((d, "d"), (noise, "noise"), (noise_strength, "noise_strength"), (bias, "bias")):
+        if t is not None:
+            _require(t, torch.float32, n)
+    st = _lib.load().tbg_fir4(_ptr(x), _ptr(out), B, IH, IW, out_hw[0], out_hw[1], C_, int(off[0]), int(off[1]),
+                              float(scale), _ptr(d), _ptr(noise), _ptr(noise_strength), _ptr(bias), int(act),
+                              float(gain), _stream())
+    _lib.check(st, "tbg_fir4")
+    return out
+
+
+def wfold_adj(gadj: torch.Tensor, spec, *, w_raw: Optional[torch.Tensor] = None, s: Optional[torch.Tensor] = None,
+              t: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, flip: bool = False) -> torch.Tensor:
+    """Master-weight gradient from a gradient in the adjoint-matrix layout [Ipad, taps*Opad] (identity tables,
+    or the spatially flipped kernel when ``flip``)."""
+    _require(gadj, torch.float32, "gadj")
+    if out is None:
+        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gadj.device, dtype=torch.float32)
+    nb = s.shape[0] if s is not None else 0
+    st = _lib.load().tbg_wfold_adj(_ptr(gadj), _ptr(w_raw), spec.coef, spec.KH, spec.KW, spec.I, spec.O, spec.Opad,
+                                   _ptr(out), _ptr(s), _ptr(t), nb, int(flip), _stream())
+    _lib.check(st, "tbg_wfold_adj")
+    return out
 
 
 def _dec_struct(w: dict):

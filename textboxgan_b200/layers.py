@@ -30,6 +30,12 @@ ACT_DTYPE = torch.bfloat16
 # that needs gradients of gradients (path-length / R1 regularisers) wraps its forward pass in
 # ``double_backward()`` to get the composable, arbitrarily differentiable primitives instead.
 FUSED = True
+# upsample_conv_2d as transposed conv + separate FIR pass (algorithmic FLOPs) instead of the FIR folded into
+# a 4-phase 3x3 GEMM (4x the tensor work, no intermediate)
+UNFOLD_UP = True
+# conv_downsample_2d: FIR pre-pass + k x k strided conv (forward, weight gradient) instead of the folded
+# (k+3) x (k+3) convolution; the input gradient stays folded
+UNFOLD_DOWN = True
 _DOUBLE_BACKWARD = False
 
 
@@ -86,8 +92,11 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     s = s_pre if s_pre is not None else style_scale(style, P, prefix)       # [B,I]
     B, H, W_, _ = x.shape
     if use_fused() and act and noise is not None and bias is not None and demodulate and not fused_epilogue:
-        from .fused import ModConvAct
+        from .fused import ModConvAct, ModUpConvAct
 
+        if up and UNFOLD_UP:
+            spec = C.weight_spec("upT", H, W_, I, O, kh, True, "modconv")
+            return ModUpConvAct.apply(x, s, w_raw, noise, noise_strength, bias, spec, SQRT2)
         spec = C.weight_spec("up" if up else "plain", H, W_, I, O, kh, True, "modconv")
         return ModConvAct.apply(x, s, w_raw, noise, noise_strength, bias, spec, SQRT2)
     w = runtime_coef(w_raw.shape) * w_raw                                   # :71
