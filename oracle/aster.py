@@ -195,7 +195,7 @@ def convert_inputs(fake_images: torch.Tensor, labels: torch.Tensor, blank_label:
         img = fake_images[b: b + 1]
         idx = (labels[b] == blank_label).nonzero()
         if idx.numel() > 0:
-            w_crop = int(idx[0, 0]) * cfg.char_width
+            w_crop = int(int(idx[0, 0]) * cfg.char_width)     # floor for the fractional-width extension (see mask_text_box)
             img = img[:, :, :, :w_crop]
         out.append(F.interpolate(img, size=(oh, ow), mode="bilinear", align_corners=False, antialias=False))
     return torch.cat(out, dim=0).permute(0, 2, 3, 1)

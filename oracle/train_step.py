@@ -22,7 +22,16 @@ Params = Dict[str, torch.Tensor]
 def mask_text_box(fake_images: torch.Tensor, input_words: torch.Tensor, char_width: int) -> torch.Tensor:
     """utils/utils.py:11-45"""
     keep = torch.where(input_words == 0, 0.0, 1.0).to(fake_images.dtype)
-    mask = torch.repeat_interleave(keep, char_width, dim=1)[:, None, None, :]
+    if isinstance(char_width, int):
+        mask = torch.repeat_interleave(keep, char_width, dim=1)[:, None, None, :]
+    else:
+        # EXTENSION (outside the reference's domain: tf.repeat needs integer repeats): for a fractional
+        # char_width = W/mcn, column x belongs to character floor(x / char_width); equals the line above for ints
+        from fractions import Fraction
+
+        cw = Fraction(char_width)
+        idx = (torch.arange(fake_images.shape[3]) * cw.denominator) // cw.numerator
+        mask = keep[:, idx][:, None, None, :]
     return fake_images * mask
 
 

@@ -16,6 +16,16 @@ def small_cfg(batch=4):
     return cfg
 
 
+def fractional_cfg(batch=4):
+    """Tiny ladder (64x16) with max_char_number=12: char_width = 16/3, the BASELINE configs[2]/[3] situation."""
+    from fractions import Fraction
+
+    from textboxgan_b200.config import Config
+
+    return Config(char_height=16, char_width=Fraction(64, 12), max_char_number=12, z_dim=128, style_dim=128,
+                  batch_size_per_gpu=batch, num_replicas=1)
+
+
 def perturbed_params(cfg, seed=1, noise_strength=0.2):
     """Reference-initialised parameters with non-zero biases / noise strengths / w_avg so that
     every term of the forward pass is exercised (the reference initialises them to zero)."""

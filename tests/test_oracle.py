@@ -205,3 +205,35 @@ def test_adam_state_tf_semantics():
                                    "reg_interval": 8})
     assert abs(p["learning_rate"] - 0.002 * 8 / 9) < 1e-12 and p["beta1"] == 0.0
     assert abs(p["beta2"] - 0.99 ** (8 / 9)) < 1e-12
+
+
+def test_fractional_char_width_extension_reduces_to_reference_for_integer_widths():
+    """mask / crop for char_width = W/mcn (BASELINE configs[2], [3]): floor(x / char_width) in exact integer
+    arithmetic; for integer widths it is the reference's repeat (utils/utils.py:30-36) and crop
+    (aster_inferer.py:182) bit for bit."""
+    from fractions import Fraction
+
+    from textboxgan_b200 import utils as U
+    from textboxgan_b200.config import baseline_config
+
+    words = torch.tensor([[5, 3, 0, 0, 0, 0, 0, 0], [1, 2, 3, 4, 5, 6, 7, 8], [9, 0, 0, 0, 0, 0, 0, 0]], dtype=torch.int32)
+    img = torch.rand(3, 3, 4, 128)
+    a = T.mask_text_box(img, words, 16)
+    b = T.mask_text_box(img, words, Fraction(128, 8))
+    c = U.mask_text_box(img, words, Fraction(16))
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(U.crop_width(torch.tensor([0, 1, 5, 8]), 16), torch.tensor([0, 16, 80, 128]))
+    # 256 columns, 12 characters: boundaries at floor(n * 64/3); every character gets 21 or 22 columns
+    idx = U.column_char_index(256, Fraction(256, 12))
+    counts = torch.bincount(idx, minlength=12)
+    assert idx.min() == 0 and idx.max() == 11 and set(counts.tolist()) == {21, 22} and int(counts.sum()) == 256
+    assert torch.equal(U.crop_width(torch.tensor([1, 3, 12]), Fraction(256, 12)), torch.tensor([21, 64, 256]))
+    w12 = torch.zeros(2, 12, dtype=torch.int32)
+    w12[0, :3] = 7
+    w12[1, :] = 7
+    im = torch.ones(2, 3, 2, 256)
+    m = U.mask_text_box(im, w12, Fraction(256, 12))
+    assert torch.equal(m, T.mask_text_box(im, w12, Fraction(256, 12)))
+    assert float(m[0, 0, 0].sum()) == 64 and float(m[1, 0, 0].sum()) == 256
+    c2 = baseline_config(2)
+    assert c2.image_width == 256 and c2.max_char_number == 12 and c2.generator_feat_maps[0] == 192 and c2.n_style == 15

@@ -295,7 +295,9 @@ class AsterInferer:
         is_blank = labels == blank_label
         has_blank = is_blank.any(dim=1)
         first = torch.where(has_blank, is_blank.int().argmax(dim=1), torch.full_like(labels[:, 0], 10 ** 6))
-        w_crop = torch.clamp(first.long() * cfg.char_width, min=1, max=W)           # [B]
+        from .utils import crop_width
+
+        w_crop = torch.clamp(crop_width(first, cfg.char_width), min=1, max=W)       # [B]
 
         def interp_matrix(out_size: int, in_size: torch.Tensor, in_max: int) -> torch.Tensor:
             # rows: output index; tf.image.resize(bilinear): src = (o + 0.5) * in/out - 0.5

@@ -7,14 +7,15 @@ attached explicitly with :func:`Config.attach_strategy`.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, List, Optional, Tuple
+from fractions import Fraction
+from typing import Any, List, Optional, Tuple, Union
 
 
 @dataclass
 class Config:
     # Text boxes specs (config/config.py:40-43)
     char_height: int = 64
-    char_width: int = 32
+    char_width: Union[int, Fraction] = 32   # Fraction: BASELINE shapes whose width is not a multiple of max_char_number
     max_char_number: int = 8
     # Model (config/config.py:45-78)
     embedding_out_dim: int = 32
@@ -51,7 +52,11 @@ class Config:
 
     def __post_init__(self) -> None:
         assert self.ocr_loss_type in ["softmax_crossentropy", "mse"]  # config/config.py:111
-        self.image_width = self.char_width * self.max_char_number  # config/config.py:122
+        iw = self.char_width * self.max_char_number                 # config/config.py:122
+        assert iw == int(iw), "char_width * max_char_number must be an integer image width"
+        self.image_width = int(iw)
+        if isinstance(self.char_width, Fraction) and self.char_width.denominator == 1:
+            self.char_width = int(self.char_width)
         if not self.generator_resolutions:
             g_res, g_fm, d_res, d_fm = derive_ladders(self.char_height, self.image_width)
             self.generator_resolutions, self.generator_feat_maps = g_res, g_fm
@@ -113,11 +118,12 @@ def baseline_config(index: int, n_gpus: int = 1) -> Config:
         3: dict(batch=256, mcn=12, z=512, h=64, w=256),
         4: dict(batch=512, mcn=16, z=512, h=128, w=512),
     }[index]
-    if table["w"] % table["mcn"] != 0:
-        # mcn=12 @ 256: char_width is fractional in the reference (undefined there, App. B).
-        raise ValueError("config with fractional char_width: use make_config(..., allow_fractional=True)")
+    # mcn=12 @ 256 (configs 2, 3): 256/12 is not an integer.  The reference derives image_width from an integer
+    # char_width (config/config.py:122) and tf.repeat needs integer repeats (utils/utils.py:30-36), so that
+    # shape is outside its domain; here char_width becomes the exact fraction W/mcn and column x belongs to
+    # character floor(x*mcn/W) (identical to x // char_width whenever char_width is an integer).
     per_gpu = table["batch"] // n_gpus
-    return Config(char_height=table["h"], char_width=table["w"] // table["mcn"], max_char_number=table["mcn"],
+    return Config(char_height=table["h"], char_width=Fraction(table["w"], table["mcn"]), max_char_number=table["mcn"],
                   z_dim=table["z"], style_dim=table["z"], batch_size_per_gpu=per_gpu, num_replicas=n_gpus)
 
 

@@ -303,75 +303,73 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
 // The kernel is symmetric, so the adjoint is the same call with off' = -3 - off and in/out swapped.
 // One thread per (pixel, 8 channels); neighbouring pixels are re-read from L1/L2.
 // ---------------------------------------------------------------------------------------------
-// One thread per (image, output column, 8 channels) and strip of kFirRows output rows: the horizontally
-// filtered input rows are kept in a 4-deep register window, so every output costs 4 (not 16) 16-byte loads.
-static constexpr int kFirRows = 8;
+// One CTA per (8 rows x 32 columns x 64 channels) output tile: the (8+3) x (32+3) input patch is staged in
+// shared memory with fully independent coalesced 16-byte loads (each input element leaves L2 once per
+// tile), then every thread slides a 4-row window of horizontally filtered values down its column.
+static constexpr int kFirRows = 8, kFirCols = 32;
 
 __global__ void __launch_bounds__(256)
 fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int IW, int OH, int OW, int c8, int offy,
             int offx, float scale, const float* __restrict__ d, const float* __restrict__ noise,
-            const float* __restrict__ ns, const float* __restrict__ bias, int act, float gain, long long n_items,
-            int strips) {
+            const float* __restrict__ ns, const float* __restrict__ bias, int act, float gain, int cgroups) {
+  extern __shared__ uint4 tile[];  // [kFirRows+3][kFirCols+3][8]
+  constexpr int TR = kFirRows + 3, TC = kFirCols + 3;
+  const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirRows;
+  const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
+  const int nv = min(8, c8 - cg * 8);  // 8-channel vectors of this channel group
+  for (int e = threadIdx.x; e < TR * TC * 8; e += 256) {
+    const int v = e & 7, c = (e >> 3) % TC, r = (e >> 3) / TC;
+    const int iy = y0 + offy + r, ix = x0 + offx + c;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (v < nv && iy >= 0 && iy < IH && ix >= 0 && ix < IW)
+      val = __ldg(in + ((static_cast<long long>(b) * IH + iy) * IW + ix) * c8 + cg * 8 + v);
+    tile[e] = val;
+  }
+  __syncthreads();
+  const int v = threadIdx.x & 7, xl = threadIdx.x >> 3;
+  const int x = x0 + xl, cv = cg * 8 + v;
+  if (x >= OW || v >= nv) return;
   const float nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_items;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(e % c8);
-    long long r = e / c8;
-    const int x = static_cast<int>(r % OW);
-    r /= OW;
-    const int strip = static_cast<int>(r % strips);
-    const int b = static_cast<int>(r / strips);
-    const int y0 = strip * kFirRows;
-    const int y1 = min(OH, y0 + kFirRows);
-    float dv[8], bv[8];
+  float dv[8], bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) * scale : scale;
+    bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+  }
+  float win[4][8];
+  auto hrow = [&](int r, float (&h)[8]) {
+    float v0[8], v1[8], v2[8], v3[8];
+    unpack8(tile[(r * TC + xl) * 8 + v], v0);
+    unpack8(tile[(r * TC + xl + 1) * 8 + v], v1);
+    unpack8(tile[(r * TC + xl + 2) * 8 + v], v2);
+    unpack8(tile[(r * TC + xl + 3) * 8 + v], v3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = v0[i] + v3[i] + 3.f * (v1[i] + v2[i]);
+  };
+  hrow(0, win[0]);
+  hrow(1, win[1]);
+  hrow(2, win[2]);
+#pragma unroll
+  for (int yy = 0; yy < kFirRows; ++yy) {
+    const int y = y0 + yy;
+    if (y >= OH) break;
+    hrow(yy + 3, win[(yy + 3) & 3]);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      acc[i] = (win[yy & 3][i] + win[(yy + 3) & 3][i] + 3.f * (win[(yy + 1) & 3][i] + win[(yy + 2) & 3][i])) * dv[i];
+    if (noise != nullptr) {
+      const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += nz;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) : 1.f;
-      bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+      float o = acc[i] + bv[i];
+      if (act == 1) o = o > 0.f ? o : 0.2f * o;
+      acc[i] = o * gain;
     }
-    // h(iy)[i] = sum_n k[n] * in[b, iy, x+n+offx, cv*8+i]  (zero outside the input)
-    float win[4][8];
-    auto hrow = [&](int iy, float (&h)[8]) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) h[i] = 0.f;
-      if (iy < 0 || iy >= IH) return;
-      const uint4* rowp = in + (static_cast<long long>(b) * IH + iy) * IW * c8 + cv;
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int ix = x + n + offx;
-        if (ix < 0 || ix >= IW) continue;
-        float v[8];
-        unpack8(__ldg(rowp + static_cast<long long>(ix) * c8), v);
-        const float kn = (n == 0 || n == 3) ? 1.f : 3.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = fmaf(kn, v[i], h[i]);
-      }
-    };
-    hrow(y0 + offy + 0, win[0]);
-    hrow(y0 + offy + 1, win[1]);
-    hrow(y0 + offy + 2, win[2]);
-#pragma unroll
-    for (int yy = 0; yy < kFirRows; ++yy) {
-      const int y = y0 + yy;
-      if (y >= y1) break;
-      hrow(y + offy + 3, win[(yy + 3) & 3]);
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        acc[i] = (win[yy & 3][i] + win[(yy + 3) & 3][i] + 3.f * (win[(yy + 1) & 3][i] + win[(yy + 2) & 3][i])) * scale * dv[i];
-      if (noise != nullptr) {
-        const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += nz;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = acc[i] + bv[i];
-        if (act == 1) v = v > 0.f ? v : 0.2f * v;
-        acc[i] = v * gain;
-      }
-      out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
-    }
+    out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
   }
 }
 
@@ -510,14 +508,17 @@ extern "C" int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH
   TBG_CHECK_ARG(act == 0 || act == 1, "tbg_fir4: act must be 0 (linear) or 1 (lrelu)");
   TBG_CHECK_ARG(TBG_ALIGNED16(in) && TBG_ALIGNED16(out) && TBG_ALIGNED16(d), "tbg_fir4: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const int strips = (OH + kFirRows - 1) / kFirRows;
-  const long long n_items = static_cast<long long>(B) * strips * OW * (C / 8);
-  long long blocks = (n_items + 255) / 256;
-  const long long cap = static_cast<long long>(sms()) * 32;
-  if (blocks > cap) blocks = cap;
-  fir4_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
-                                                            IH, IW, OH, OW, C / 8, offy, offx, scale, d, noise,
-                                                            noise_strength, bias, act, gain, n_items, strips);
+  const int cgroups = (C / 8 + 7) / 8;
+  const size_t smem = static_cast<size_t>(kFirRows + 3) * (kFirCols + 3) * 8 * sizeof(uint4);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fir4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr = true;
+  }
+  TBG_CHECK_ARG(static_cast<long long>(B) * cgroups <= 65535, "tbg_fir4: B * channel groups exceeds the grid limit");
+  const dim3 grid((OW + kFirCols - 1) / kFirCols, (OH + kFirRows - 1) / kFirRows, B * cgroups);
+  fir4_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW, OH, OW,
+                                           C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain, cgroups);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -79,6 +79,8 @@ class TrainingStep:
         # reference's tf.function likewise retraces per Python bool, train.py:182-183)
         self.use_cuda_graph = False
         self.batch_d_calls = True       # evaluate D(fake) and D(real) as one concatenated pass
+        self.overlap_ocr = True         # OCR branch on a second CUDA stream (parallel sub-graph when captured)
+        self._side = None
         self._graphs = {}
         self._static = None
 
@@ -175,6 +177,11 @@ class TrainingStep:
         r = res.unbind(0)
         return (r[0], r[1], r[2]), (r[3], r[4], r[5]), r[6]
 
+    def _side_stream(self, dev):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
     def graph_launches(self, do_r1_reg: bool = False, do_pl_reg: bool = False) -> int:
         """Number of this repo's kernel launches inside the captured graph of a step variant."""
         e = self._graphs.get((bool(do_r1_reg), bool(do_pl_reg)))
@@ -200,6 +207,19 @@ class TrainingStep:
         fake_images = G((input_words, z), training=True, draws=draws)                        # :178
         fake_images = mask_text_box(fake_images, input_words, self.char_width)              # :180
 
+        # The OCR branch (convert_inputs -> ASTER -> loss, :375-402) only shares ``fake_images`` with the
+        # discriminator branch: it is issued on a second stream so that its latency-bound kernels (whole-sequence
+        # LSTM, attention decoder, small ResNet convolutions) overlap the discriminator's; inside the captured
+        # CUDA graph the two branches become parallel sub-graphs.
+        main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+        side = self._side_stream(dev) if (main is not None and self.overlap_ocr and self.aster_ocr is not None) else None
+        ocr_loss = None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
+                ocr_loss = ocr_loss_weight * ocr_loss                                        # :191-192
+
         # D(fake) and D(real) (training_step.py:260,288) as ONE concatenated pass when no R1 penalty is due:
         # every discriminator layer is per-sample except the minibatch statistic, taken per call.
         self._batched_d = bool(self.batch_d_calls and L.use_fused() and not do_r1_reg)
@@ -214,22 +234,32 @@ class TrainingStep:
                                                                                  input_words, draws, fake_scores)
         reg_d_loss, d_loss, r1_penalty = self._get_discriminator_losses(fake_scores, real_images, do_r1_reg,
                                                                         real_scores)
-        if self.aster_ocr is not None:
+        if self.aster_ocr is not None and side is None:
             ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
             ocr_loss = ocr_loss_weight * ocr_loss                                            # :191-192
-        else:
-            ocr_loss = None
 
         g_vars = [G.params[n] for n in self._g_names]
         o_vars = [G.params[n] for n in self._ocr_names]
         d_vars = [D.params[n] for n in self._d_names]
         # three tape.gradient calls on one persistent tape (:194-213): all at pre-update weights
+        g_fake_ocr = None
+        if side is not None:
+            # first half of the OCR pass (chain rule split at fake_images): back through the frozen recogniser on
+            # the second stream, concurrently with the generator pass below
+            with torch.cuda.stream(side):
+                (g_fake_ocr,) = torch.autograd.grad(ocr_loss, [fake_images], retain_graph=True)
         with _fused.skip_weight_grads("dconv"), \
                 _fused.backward_batch_limit("dconv", fake_images.shape[0] if self._batched_d else 1 << 30):
             # only generator variables are wanted from this pass
             g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
-        o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
-            if ocr_loss is not None else None
+        if g_fake_ocr is not None:
+            main.wait_stream(side)
+            g_fake_ocr.record_stream(main)
+            o_grads = torch.autograd.grad(fake_images, o_vars, grad_outputs=g_fake_ocr, retain_graph=True,
+                                          allow_unused=True)
+        else:
+            o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
+                if ocr_loss is not None else None
         d_grads = torch.autograd.grad(reg_d_loss, d_vars, allow_unused=True)
         self.last_grads = (g_grads, o_grads, d_grads) if draws.get("keep_grads") else None
 
