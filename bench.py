@@ -197,7 +197,8 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    cfg = baseline_config(args.config)          # per-GPU batch fixed (weak scaling)
+    # per-GPU batch fixed (weak scaling): configs 3 and 4 are quoted on 8 GPUs, i.e. batch/8 per GPU
+    cfg = baseline_config(args.config, n_gpus=8 if args.config in (3, 4) else 1)
     cfg.attach_strategy(strategy)
     B = cfg.batch_size_per_gpu
 
@@ -363,6 +364,9 @@ def run_ours(args) -> None:
         }
 
     if rank != 0:
+        if world > 1 and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -384,6 +388,9 @@ def run_ours(args) -> None:
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    if world > 1 and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

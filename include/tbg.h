@@ -79,6 +79,8 @@ typedef struct tbg_conv_args {
   int act;         /* 0 linear, 1 leaky-relu(0.2), 2 relu */
   float act_gain;  /* multiplies after act (sqrt(2) for lrelu) */
   int out_fp32;    /* 0: bf16 output, 1: fp32 output */
+  const void* relu_mask;  /* bf16, same shape as out, or NULL: the final value is zeroed where relu_mask <= 0 — the
+                             backward of a ReLU whose output is relu_mask, fused into the input-gradient conv */
   unsigned long long tap_mask[4]; /* per output phase (py*2+px along up axes, else [0]): bit (th*taps_w+tw) set = the tap's
                            weight block is non-zero and is computed; 0 = all taps.  Lets a transposed
                            stride-2 convolution skip the taps a phase does not have. */
@@ -177,6 +179,14 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
+/* FromRGB (from_rgb.py:26-29): 1x1 conv 3 -> C of the NCHW fp32 image + bias + leaky-ReLU(0.2)*gain -> NHWC bf16:
+ *   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] w[j,c] + bias[c]) * gain,   w fp32 [3, C]
+ * bwd: gpre = g_out*gain*slope(out); gimg[b,j,p] = coef sum_c gpre w[j,c] (NCHW fp32, may be NULL);
+ *      gw[j,c] += coef sum_{b,p} img gpre, gb[c] += sum_{b,p} gpre (zeroed by the caller; both NULL to skip). */
+int tbg_fromrgb_fwd(const float* img, const float* w, const float* bias, void* out, int B, int HW, int C, float coef,
+                    float gain, void* stream);
+int tbg_fromrgb_bwd(const float* img, const float* w, const void* g_out, const void* out, float* gimg, float* gw, float* gb,
+                    int B, int HW, int C, float coef, float gain, void* stream);
 int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C, void* stream);
 int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
                   void* stream);

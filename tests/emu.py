@@ -20,7 +20,7 @@ def _gather_tap(xp, PH, PW, ty, tx, pad, stride, Ho, Wo):
 
 def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_scale=None, bias=None, noise=None,
                      noise_strength=None, residual=None, res_scale=1.0, res_first=False, act=0, act_gain=1.0, out_fp32=False, out=None,
-                     tap_mask=None):
+                     tap_mask=None, relu_mask=None):
     if isinstance(up, bool):
         up = (int(up), int(up))
     B, H, W_, Cin = x.shape
@@ -61,6 +61,8 @@ def emu_conv2d_igemm(x, w, *, Ho, Wo, taps, pad, stride=(1, 1), up=(0, 0), col_s
     y = y * act_gain
     if residual is not None and not res_first:
         y = (y + residual.double()) * res_scale
+    if relu_mask is not None:
+        y = torch.where(relu_mask.double() > 0, y, torch.zeros_like(y))
     y = y.to(torch.float32 if out_fp32 else x.dtype)
     if out is not None:
         out.copy_(y)
@@ -164,6 +166,22 @@ def emu_modulate_bwd(gxs, x, s, gs_init=None):
     if gs_init is not None:
         gs = gs + gs_init
     return gx, gs
+
+
+def emu_fromrgb_fwd(img, w, bias, coef, gain):
+    y = torch.einsum("bjhw,jc->bhwc", img.double(), w.double()) * coef + bias.double()
+    y = torch.where(y > 0, y, 0.2 * y) * gain
+    from textboxgan_b200 import layers as L
+
+    return y.to(L.ACT_DTYPE)
+
+
+def emu_fromrgb_bwd(img, w, g_out, out, coef, gain, *, want_img=True, want_w=True):
+    gp = g_out.double() * gain * torch.where(out.double() > 0, 1.0, 0.2)
+    gimg = (torch.einsum("bhwc,jc->bjhw", gp, w.double()) * coef).float() if want_img else None
+    gw = (torch.einsum("bjhw,bhwc->jc", img.double(), gp) * coef).float() if want_w else None
+    gb = gp.sum(dim=(0, 1, 2)).float() if want_w else None
+    return gimg, gw, gb
 
 
 def emu_fir4(x, out_hw, off, scale, *, d=None, noise=None, noise_strength=None, bias=None, act=0, gain=1.0):
@@ -384,8 +402,9 @@ def emulated_kernels(act_dtype=torch.float32):
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
     saved_w = (K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd)
-    saved_f = (K.fir4, K.wfold_adj)
+    saved_f = (K.fir4, K.wfold_adj, K.fromrgb_fwd, K.fromrgb_bwd)
     K.fir4, K.wfold_adj = emu_fir4, emu_wfold_adj
+    K.fromrgb_fwd, K.fromrgb_bwd = emu_fromrgb_fwd, emu_fromrgb_bwd
     saved_d = (K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd)
     K.demod_coef, K.demod_bwd = emu_demod_coef, emu_demod_bwd
     K.style_dense_fwd, K.style_dense_bwd = emu_style_dense_fwd, emu_style_dense_bwd
@@ -408,4 +427,4 @@ def emulated_kernels(act_dtype=torch.float32):
          K.torgb_bwd) = saved
         K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd = saved_w
         K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd = saved_d
-        K.fir4, K.wfold_adj = saved_f
+        K.fir4, K.wfold_adj, K.fromrgb_fwd, K.fromrgb_bwd = saved_f

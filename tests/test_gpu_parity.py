@@ -455,6 +455,67 @@ def test_conv_forward_non_power_of_two_grids(Ho, Wo, B):
     assert rel_err(y, emu_conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs())) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,W,C", [(4, 16, 64, 128), (3, 5, 7, 64), (64, 32, 128, 128), (2, 64, 256, 64)])
+def test_fromrgb_kernels_vs_emulated_semantics(B, H, W, C):
+    """tbg_fromrgb_fwd / bwd against their documented semantics (bf16 output 1e-2; fp32 gradients 1e-4)."""
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(B + H + C)
+    img = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
+    w = torch.randn(3, C, generator=gen)
+    bias = torch.randn(C, generator=gen) * 0.1
+    coef, gain = 1 / math.sqrt(3.0), math.sqrt(2.0)
+    out = K.fromrgb_fwd(img.to(DEV), w.to(DEV), bias.to(DEV), coef, gain)
+    with emu.emulated_kernels(act_dtype=torch.float32):
+        ref = emu.emu_fromrgb_fwd(img, w, bias, coef, gain)
+    assert rel_err(out.float(), ref) < 1e-2
+    g = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    ob = out.float().cpu()
+    gi, gw, gb = K.fromrgb_bwd(img.to(DEV), w.to(DEV), g.to(DEV).bfloat16(), out, coef, gain)
+    ri, rw, rb = emu.emu_fromrgb_bwd(img, w, g, ob, coef, gain)
+    assert rel_err(gi, ri) < 1e-4 and rel_err(gw, rw) < 1e-4 and rel_err(gb, rb) < 1e-4
+    gi2, gw2, gb2 = K.fromrgb_bwd(img.to(DEV), w.to(DEV), g.to(DEV).bfloat16(), out, coef, gain, want_w=False)
+    assert gw2 is None and gb2 is None and rel_err(gi2, ri) < 1e-4
+
+
+def test_relu_mask_epilogue_and_fused_encoder_backward():
+    """relu_mask epilogue of tbg_conv2d_igemm (fused ReLU backward) against its documented semantics, and the
+    one-node ResNet encoder (masks and residual sums folded into the input-gradient convs) against the
+    layer-by-layer autograd formulation (bf16 activations, identical kernels: 2e-2)."""
+    from textboxgan_b200 import aster_inferer as AI
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200.config import baseline_config
+
+    g = C.ConvGeom(8, 32, 128, 64, C.Axis("s2", 1, 0), C.Axis("s1", 1, 0))
+    gen = torch.Generator().manual_seed(11)
+    x = _bf16_round(torch.randn(3, 8, 32, 128, generator=gen))
+    w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
+    res = _bf16_round(torch.randn(3, 4, 32, 64, generator=gen))
+    m = _bf16_round(torch.randn(3, 4, 32, 64, generator=gen))
+    kw = dict(g.kernel_kwargs(), res_scale=1.0, res_first=True, out_fp32=True)
+    y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), residual=res.to(DEV).bfloat16(),
+                       relu_mask=m.to(DEV).bfloat16(), **kw)
+    ref = emu_conv2d_igemm(x, w, residual=res, relu_mask=m, **kw)
+    assert rel_err(y, ref) < 2e-5 and float((y.cpu()[m <= 0]).abs().max()) == 0.0
+
+    cfg = baseline_config(0)
+    aster = AI.AsterInferer(cfg, device=DEV)
+    img = torch.randn(4, 64, 256, 3, generator=gen).to(DEV)
+    gm = torch.randn(4, 64, 512, generator=gen).to(DEV)       # T = 256 / 4 feature columns
+    outs = []
+    for fused in (False, True):
+        AI.FUSED_ENCODER = fused
+        xi = img.clone().requires_grad_(True)
+        mem = aster._encoder(xi)
+        (gi,) = torch.autograd.grad((mem * gm[:, : mem.shape[1]]).sum(), xi)
+        outs.append((mem, gi))
+    AI.FUSED_ENCODER = True
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-6          # same forward kernels
+    assert _rel_l2(outs[1][1], outs[0][1]) < 2e-2
+
+
 @pytest.mark.parametrize("B,T,steps", [(3, 32, 8), (5, 17, 4)])
 def test_attention_decoder_and_lstm_kernels_vs_emulated_semantics(B, T, steps):
     import emu

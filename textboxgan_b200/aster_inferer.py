@@ -82,6 +82,10 @@ def init_aster_params(seed: int = 1234) -> Dict[str, torch.Tensor]:
     return P
 
 
+# the ResNet encoder as one autograd node with ReLU masks / residual sums fused into the input-gradient convs
+FUSED_ENCODER = True
+
+
 def _pad_c(n: int) -> int:
     return (n + 63) // 64 * 64
 
@@ -112,6 +116,51 @@ class _FrozenConv(torch.autograd.Function):
         K.PROFILE_TAG = (layer.geom.tag, layer.geom.algo_frac)
         gx = K.conv2d_igemm(g, layer.wmat_adj, **layer.geom.adjoint().kernel_kwargs())
         return gx, None, (g if ctx.has_res else None), None
+
+
+class _EncoderFn(torch.autograd.Function):
+    """The whole frozen ResNet encoder as one node: forward = the fused conv+bias+(residual)+ReLU launches;
+    backward = one input-gradient launch per convolution with the ReLU masks and the residual-branch sums
+    folded into the epilogues (no stand-alone ReLU-backward or add kernels):
+        unit:  y = relu(c1(x));  out = relu(c2(y) + sc(x))          (sc = 1x1 conv, or identity)
+        gz given (gradient w.r.t. the unit's pre-activation):
+            gy  = c2^T(gz) masked by y ;   gx = (c1^T(gy) + sc^T(gz)) masked by x   -> gz of the unit below."""
+
+    @staticmethod
+    def forward(ctx, x, enc: "AsterInferer"):
+        x = x.contiguous()
+        run = lambda layer, t, residual=None, relu=True: K.conv2d_igemm(
+            t, layer.wmat, **layer.geom.kernel_kwargs(), bias=layer.bias, residual=residual, res_scale=1.0,
+            res_first=True, act=2 if relu else 0)
+        K.PROFILE_TAG = ("aster", 1.0)
+        saved = [x]
+        h = run(enc.stem, x)
+        for c1, c2, sc in enc.units:
+            y = run(c1, h)
+            shortcut = run(sc, h, relu=False) if sc is not None else h
+            out = run(c2, y, residual=shortcut)
+            saved += [h, y]
+            h = out
+        saved.append(h)
+        ctx.enc = enc
+        ctx.save_for_backward(*saved)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        enc = ctx.enc
+        saved = ctx.saved_tensors
+        out = saved[-1]
+        K.PROFILE_TAG = ("aster", 1.0)
+        dgrad = lambda layer, t, **kw: K.conv2d_igemm(t, layer.wmat_adj, **layer.geom.adjoint().kernel_kwargs(), **kw)
+        gz = K.bias_act_bwd(g.contiguous(), out, act=2, gain=1.0, want_sums=False)[0]     # mask of the last ReLU
+        for ui in range(len(enc.units) - 1, -1, -1):
+            c1, c2, sc = enc.units[ui]
+            h, y = saved[1 + 2 * ui], saved[2 + 2 * ui]
+            gy = dgrad(c2, gz, relu_mask=y)
+            gsc = dgrad(sc, gz) if sc is not None else gz
+            gz = dgrad(c1, gy, residual=gsc, res_scale=1.0, res_first=True, relu_mask=h)
+        return dgrad(enc.stem, gz), None
 
 
 class _ConvLayer:
@@ -229,11 +278,14 @@ class AsterInferer:
         B = x_nhwc.shape[0]
         x = F.avg_pool2d(x_nhwc.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)          # rectifier stand-in
         x = F.pad(x, (0, 64 - x.shape[3])).to(L.ACT_DTYPE).contiguous()           # channels 3 -> 64
-        x = self.stem(x)
-        for c1, c2, sc in self.units:
-            y = c1(x)
-            shortcut = sc(x, relu=False) if sc is not None else x
-            x = c2(y, residual=shortcut, relu=True)
+        if FUSED_ENCODER and torch.is_grad_enabled():
+            x = _EncoderFn.apply(x, self)
+        else:
+            x = self.stem(x)
+            for c1, c2, sc in self.units:
+                y = c1(x)
+                shortcut = sc(x, relu=False) if sc is not None else x
+                x = c2(y, residual=shortcut, relu=True)
         return x.reshape(B, x.shape[2], x.shape[3]).float()[:, :, :512]
 
     # -- recurrent part (plain batched GEMMs + element-wise gates) -------------------------------

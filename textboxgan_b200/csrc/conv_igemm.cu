@@ -36,6 +36,7 @@ struct ConvKernelParams {
   const float* noise;
   const float* noise_strength;
   const __nv_bfloat16* residual;
+  const __nv_bfloat16* relu_mask;  // optional: output zeroed where this tensor (shape of out) is <= 0
   float res_scale;
   int res_first;  // 1: residual is added before the activation (ResNet unit), 0: after (D block)
   int act;
@@ -264,6 +265,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
             }
+            if (p.relu_mask) {   // gradient of a ReLU whose output is relu_mask (fused ReLU backward)
+              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + off + g * 8));
+              const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 mf = __bfloat1622float2(mh[i]);
+                if (!(mf.x > 0.f)) f[2 * i] = 0.f;
+                if (!(mf.y > 0.f)) f[2 * i + 1] = 0.f;
+              }
+            }
             if (p.out_fp32) {
               float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
               *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -330,7 +341,7 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
                     (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                 "tbg_conv2d_igemm: tensors must be 16-byte aligned");
   TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->col_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
+                    (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->relu_mask) & 15) == 0,
                 "tbg_conv2d_igemm: col_scale / bias / residual must be 16-byte aligned (vector loads in the epilogue)");
 
   ConvKernelParams p{};
@@ -409,6 +420,7 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.noise = a->noise;
   p.noise_strength = a->noise_strength;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.relu_mask = reinterpret_cast<const __nv_bfloat16*>(a->relu_mask);
   p.res_scale = a->res_scale;
   p.res_first = a->res_first;
   p.act = a->act;

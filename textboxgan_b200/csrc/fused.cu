@@ -373,6 +373,115 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FromRGB (from_rgb.py:26-29): 1x1 convolution 3 -> C on the NCHW fp32 image + bias + leaky-ReLU*gain,
+// written as NHWC bf16.  K = 3 makes it bandwidth-bound: one thread per (pixel, 8 channels).
+//   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] * w[j,c] + bias[c]) * gain
+// backward: gpre = g*gain*slope(out);  gimg[b,j,p] = coef * sum_c gpre*w[j,c];
+//           gw[j,c] += coef * sum_{b,p} img*gpre;  gb[c] += sum_{b,p} gpre            (gw, gb zeroed by the caller)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fromrgb_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                   uint4* __restrict__ out, int hw, int c8, float coef, float gain, long long n_vec) {
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_vec;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(e % c8);
+    const long long pix = e / c8;
+    const long long b = pix / hw, p = pix - b * hw;
+    const float* ip = img + b * 3 * hw + p;
+    const float x0 = __ldg(ip) * coef, x1 = __ldg(ip + hw) * coef, x2 = __ldg(ip + 2 * static_cast<long long>(hw)) * coef;
+    const int C = c8 * 8;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = cv * 8 + i;
+      float v = fmaf(x0, __ldg(w + c), fmaf(x1, __ldg(w + C + c), fmaf(x2, __ldg(w + 2 * C + c), __ldg(bias + c))));
+      v = v > 0.f ? v : 0.2f * v;
+      f[i] = v * gain;
+    }
+    out[e] = pack8(f);
+  }
+}
+
+// grid (chunks, B); block = c8 * rows threads (c8 <= 32, a power of two): thread (r, cv) walks pixels r, r+rows, ...
+__global__ void fromrgb_bwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const uint4* __restrict__ g_out,
+                                   const uint4* __restrict__ out, float* __restrict__ gimg, float* __restrict__ gw,
+                                   float* __restrict__ gb, int hw, int c8, int pix_per_cta, float coef, float gain,
+                                   int want_w) {
+  extern __shared__ float red[];  // [rows][c8*8][4]
+  const int b = blockIdx.y;
+  const int rows = blockDim.x / c8;
+  const int cv = threadIdx.x % c8;
+  const int r = threadIdx.x / c8;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  const int C = c8 * 8;
+  float wv[3][8], acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wv[j][i] = __ldg(w + j * C + cv * 8 + i) * coef;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][i] = 0.f;
+  }
+  // uniform trip count for every thread of the CTA: the per-pixel shuffle reduction below needs whole warps
+  for (int pp = p0; pp < p1; pp += rows) {
+    const int p = pp + r;
+    const bool valid = (r < rows) && (p < p1);
+    const long long pix = static_cast<long long>(b) * hw + (valid ? p : p0);
+    float g[8], o[8];
+    unpack8(__ldg(g_out + pix * c8 + cv), g);
+    unpack8(__ldg(out + pix * c8 + cv), o);
+    const float* ip = img + static_cast<long long>(b) * 3 * hw + (valid ? p : p0);
+    const float x0 = __ldg(ip), x1 = __ldg(ip + hw), x2 = __ldg(ip + 2 * static_cast<long long>(hw));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gp = valid ? g[i] * gain * (o[i] > 0.f ? 1.f : 0.2f) : 0.f;
+      s0 = fmaf(gp, wv[0][i], s0);
+      s1 = fmaf(gp, wv[1][i], s1);
+      s2 = fmaf(gp, wv[2][i], s2);
+      acc[0][i] = fmaf(gp, x0, acc[0][i]);
+      acc[1][i] = fmaf(gp, x1, acc[1][i]);
+      acc[2][i] = fmaf(gp, x2, acc[2][i]);
+      acc[3][i] += gp;
+    }
+    // sum over the c8 threads of this pixel (consecutive lanes; c8 is a power of two <= 32)
+    for (int sh = c8 >> 1; sh > 0; sh >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, sh);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+    }
+    if (valid && cv == 0 && gimg != nullptr) {
+      float* gp = gimg + static_cast<long long>(b) * 3 * hw + p;
+      gp[0] = s0;
+      gp[hw] = s1;
+      gp[2 * static_cast<long long>(hw)] = s2;
+    }
+  }
+  if (!want_w) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[((r * c8 + cv) * 8 + i) * 4 + j] = acc[j][i];
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] += red[((rr * c8 + cv) * 8 + i) * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = cv * 8 + i;
+      atomicAdd(gw + c, acc[0][i] * coef);
+      atomicAdd(gw + C + c, acc[1][i] * coef);
+      atomicAdd(gw + 2 * C + c, acc[2][i] * coef);
+      atomicAdd(gb + c, acc[3][i]);
+    }
+  }
+}
+
 // launch geometry for the (chunks, B) reduction kernels
 struct RedGeom {
   int threads, rows, pix_per_cta, chunks;
@@ -519,6 +628,46 @@ extern "C" int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH
   const dim3 grid((OW + kFirCols - 1) / kFirCols, (OH + kFirRows - 1) / kFirRows, B * cgroups);
   fir4_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW, OH, OW,
                                            C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain, cgroups);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_fromrgb_fwd(const float* img, const float* w, const float* bias, void* out, int B, int HW, int C,
+                               float coef, float gain, void* stream_v) {
+  TBG_CHECK_ARG(img && w && bias && out, "tbg_fromrgb_fwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && HW >= 1, "tbg_fromrgb_fwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(out), "tbg_fromrgb_fwd: out must be 16-byte aligned");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n_vec = static_cast<long long>(B) * HW * (C / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = static_cast<long long>(sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  fromrgb_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(img, w, bias, reinterpret_cast<uint4*>(out), HW, C / 8,
+                                                                   coef, gain, n_vec);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_fromrgb_bwd(const float* img, const float* w, const void* g_out, const void* out, float* gimg, float* gw,
+                               float* gb, int B, int HW, int C, float coef, float gain, void* stream_v) {
+  TBG_CHECK_ARG(img && w && g_out && out, "tbg_fromrgb_bwd: null pointer");
+  TBG_CHECK_ARG((gw == nullptr) == (gb == nullptr), "tbg_fromrgb_bwd: gw and gb go together");
+  const int c8 = C / 8;
+  TBG_CHECK_ARG(C % 8 == 0 && c8 >= 1 && c8 <= 32 && (c8 & (c8 - 1)) == 0 && B >= 1 && HW >= 1,
+                "tbg_fromrgb_bwd: C=%d must be 8 * a power of two <= 256", C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out), "tbg_fromrgb_bwd: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, c8, 4);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fromrgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  fromrgb_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
+      img, w, reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), gimg, gw, gb, HW, c8, g.pix_per_cta,
+      coef, gain, gw != nullptr);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

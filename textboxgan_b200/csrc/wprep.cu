@@ -36,25 +36,14 @@ __device__ __forceinline__ float tab(const AxisTable& t, int p, int tt, int k) {
 
 // cf[c][tap] = Ty[p,t,kh] * Tx[q,u,kw] for combination c = ((p*Px + q)*Ty.T + t)*Tx.T + u, tap = kh*KW + kw;
 // built once per CTA in shared memory so that the hot loops index shared memory, not kernel parameters.
-__device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& tx, int KH, int KW, float (*cf)[9]) {
-  const int ncomb = ty.P * tx.P * ty.T * tx.T;
-  for (int e = threadIdx.x; e < ncomb * 9; e += blockDim.x) {
-    const int c = e / 9, tap = e - c * 9;
-    float v = 0.f;
-    if (tap < KH * KW) {
-      const int u = c % tx.T, t = (c / tx.T) % ty.T, q = (c / (tx.T * ty.T)) % tx.P, pp = c / (tx.T * ty.T * tx.P);
-      v = tab(ty, pp, t, tap / KW) * tab(tx, q, u, tap % KW);
-    }
-    cf[c][tap] = v;
-  }
-}
 
 // cf[c][tap] = Ty[p,t,kh] * Tx[q,u,kw] for combination c = ((p*Px + q)*Ty.T + t)*Tx.T + u, tap = kh*KW + kw.
 __device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& tx, int KH, int KW, float scale,
-                                         float (*cf)[9]) {
+                                         float (*cf)[12]) {
+  // rows padded to 12 floats (48 B) so that a combination's nine coefficients are three 16-byte loads
   const int ncomb = ty.P * tx.P * ty.T * tx.T;
-  for (int e = threadIdx.x; e < ncomb * 9; e += blockDim.x) {
-    const int c = e / 9, tap = e - c * 9;
+  for (int e = threadIdx.x; e < ncomb * 12; e += blockDim.x) {
+    const int c = e / 12, tap = e - c * 12;
     float v = 0.f;
     if (tap < KH * KW) {
       const int u = c % tx.T, t = (c / tx.T) % ty.T, q = (c / (tx.T * ty.T)) % tx.P, pp = c / (tx.T * ty.T * tx.P);
@@ -66,16 +55,17 @@ __device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& t
 
 // One CTA per 32(i) x 32(o) tile of the master weight and per CHUNK of (phase, tap) combinations
 // (blockIdx.y: forward chunks first, then adjoint chunks) so that even a 128 x 128 weight fills the
-// SMs; the tile is re-read by each chunk (L2 hits), each thread keeps the nine taps of its element in
-// registers and emits its chunk's combinations.
+// SMs; the tile is re-read by each chunk (L2 hits).  A thread owns two neighbouring elements along the
+// contiguous axis of the output matrix, keeps their nine taps in registers and emits one packed
+// bf16x2 store per combination; per-combination offsets and coefficients come from shared memory.
 __global__ void __launch_bounds__(256)
 wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ adj,
              float* __restrict__ q, const WPrepParams p, const int chunk, const int fwd_chunks) {
   __shared__ float sw[9][32][33];  // [kh*KW+kw][i][o]
-  __shared__ float cf[36][9];
+  __shared__ __align__(16) float cf[36][12];
+  __shared__ unsigned coff[36];    // element offset of combination c inside the output matrix
   const int tiles_o = p.Opad / 32;
   const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
   const int taps = p.KH * p.KW;
   const bool is_adj = static_cast<int>(blockIdx.y) >= fwd_chunks;
   const int chunk_id = is_adj ? blockIdx.y - fwd_chunks : blockIdx.y;
@@ -83,40 +73,63 @@ wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_
   const AxisTable& ax = is_adj ? p.ax : p.fx;
   const int TT = ay.T * ax.T, ncomb = ay.P * ax.P * TT;
   const int c_begin = chunk_id * chunk, c_end = min(ncomb, c_begin + chunk);
-  build_cf(ay, ax, p.KH, p.KW, 1.f, cf);
-  for (int tp = 0; tp < 9; ++tp)
-    for (int r = ty; r < 32; r += 8) {
-      const int i = i0 + r, o = o0 + tx;
-      sw[tp][r][tx] = (tp < taps && i < p.I && o < p.O)
-                          ? __ldg(w + (static_cast<size_t>(tp) * p.I + i) * p.O + o) * p.coef : 0.f;
-    }
-  __syncthreads();
-  // forward matrix: rows (pq, o), cols (tu, i), lanes over i;  adjoint: rows (pq, i), cols (tu, o), lanes over o
+  // forward matrix: rows (pq, o), cols (tu, i), contiguous over i;  adjoint: rows (pq, i), cols (tu, o), contiguous over o
   const int rows_pad = is_adj ? p.Ipad : p.Opad, cols_pad = is_adj ? p.Opad : p.Ipad;
-  const size_t Kc = static_cast<size_t>(TT) * cols_pad;
-  __nv_bfloat16* const base = is_adj ? adj : fwd;
-  for (int r = ty; r < 32; r += 8) {
-    float v[9];
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp) v[tp] = is_adj ? sw[tp][r][tx] : sw[tp][tx][r];
-    const int row = (is_adj ? i0 : o0) + r, colv = (is_adj ? o0 : i0) + tx;
-#pragma unroll 3
-    for (int c = c_begin; c < c_end; ++c) {
-      const int pq = c / TT, tu = c - pq * TT;
-      float acc = 0.f;
-#pragma unroll
-      for (int tp = 0; tp < 9; ++tp) acc = fmaf(cf[c][tp], v[tp], acc);
-      base[(static_cast<size_t>(pq) * rows_pad + row) * Kc + static_cast<size_t>(tu) * cols_pad + colv] =
-          __float2bfloat16_rn(acc);
-    }
-    if (q != nullptr && blockIdx.y == 0) {   // chunk 0 of the forward matrix also emits q (lanes over o)
-      const int i = i0 + r, o = o0 + tx;
-      if (i < p.I && o < p.O) {
-        float acc = 0.f;
-#pragma unroll
-        for (int tp = 0; tp < 9; ++tp) acc = fmaf(sw[tp][r][tx], sw[tp][r][tx], acc);
-        q[static_cast<size_t>(i) * p.O + o] = acc;
+  const unsigned Kc = static_cast<unsigned>(TT) * cols_pad;
+  build_cf(ay, ax, p.KH, p.KW, 1.f, cf);
+  if (threadIdx.x < ncomb) {
+    const int c = threadIdx.x, pq = c / TT, tu = c - pq * TT;
+    coff[c] = static_cast<unsigned>(pq) * rows_pad * Kc + static_cast<unsigned>(tu) * cols_pad;
+  }
+  {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int tp = 0; tp < 9; ++tp)
+      for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, o = o0 + tx;
+        sw[tp][r][tx] = (tp < taps && i < p.I && o < p.O)
+                            ? __ldg(w + (static_cast<size_t>(tp) * p.I + i) * p.O + o) * p.coef : 0.f;
       }
+  }
+  __syncthreads();
+  __nv_bfloat16* const base = is_adj ? adj : fwd;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 column pairs x 16 rows, two row passes
+#pragma unroll
+  for (int rp = 0; rp < 2; ++rp) {
+    const int r = ty + 16 * rp;
+    float v0[9], v1[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      v0[tp] = is_adj ? sw[tp][r][2 * tx] : sw[tp][2 * tx][r];
+      v1[tp] = is_adj ? sw[tp][r][2 * tx + 1] : sw[tp][2 * tx + 1][r];
+    }
+    const int row = (is_adj ? i0 : o0) + r, colv = (is_adj ? o0 : i0) + 2 * tx;
+    __nv_bfloat16* const dst = base + static_cast<size_t>(row) * Kc + colv;
+#pragma unroll 2
+    for (int c = c_begin; c < c_end; ++c) {
+      const float4 c0 = *reinterpret_cast<const float4*>(&cf[c][0]);
+      const float4 c1 = *reinterpret_cast<const float4*>(&cf[c][4]);
+      const float c2 = cf[c][8];
+      float a0 = c0.x * v0[0], a1 = c0.x * v1[0];
+      a0 = fmaf(c0.y, v0[1], a0); a1 = fmaf(c0.y, v1[1], a1);
+      a0 = fmaf(c0.z, v0[2], a0); a1 = fmaf(c0.z, v1[2], a1);
+      a0 = fmaf(c0.w, v0[3], a0); a1 = fmaf(c0.w, v1[3], a1);
+      a0 = fmaf(c1.x, v0[4], a0); a1 = fmaf(c1.x, v1[4], a1);
+      a0 = fmaf(c1.y, v0[5], a0); a1 = fmaf(c1.y, v1[5], a1);
+      a0 = fmaf(c1.z, v0[6], a0); a1 = fmaf(c1.z, v1[6], a1);
+      a0 = fmaf(c1.w, v0[7], a0); a1 = fmaf(c1.w, v1[7], a1);
+      a0 = fmaf(c2, v0[8], a0);   a1 = fmaf(c2, v1[8], a1);
+      *reinterpret_cast<uint32_t*>(dst + coff[c]) = pack_bf16x2(a0, a1);
+    }
+    if (q != nullptr && blockIdx.y == 0) {   // chunk 0 of the forward matrix also emits q[i, o]
+      const int i = i0 + r, o = o0 + 2 * tx;
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        q0 = fmaf(sw[tp][r][2 * tx], sw[tp][r][2 * tx], q0);
+        q1 = fmaf(sw[tp][r][2 * tx + 1], sw[tp][r][2 * tx + 1], q1);
+      }
+      if (i < p.I && o < p.O) q[static_cast<size_t>(i) * p.O + o] = q0;
+      if (i < p.I && o + 1 < p.O) q[static_cast<size_t>(i) * p.O + o + 1] = q1;
     }
   }
 }
@@ -131,7 +144,7 @@ wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const
              float* __restrict__ gw, const WPrepParams p, const float* __restrict__ sv, const float* __restrict__ tv,
              const int nb) {
   __shared__ float st[9][8][36];  // [tap][o][i]
-  __shared__ float cff[36][9];
+  __shared__ __align__(16) float cff[36][12];
   const int tiles_o = p.Opad / 8;
   const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 8;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -154,8 +167,12 @@ wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float* cfr = cff[pq * TT + tu + u];
-#pragma unroll
-        for (int tp = 0; tp < 9; ++tp) acc[tp] = fmaf(cfr[tp], g[u], acc[tp]);
+        const float4 c0 = *reinterpret_cast<const float4*>(cfr);
+        const float4 c1 = *reinterpret_cast<const float4*>(cfr + 4);
+        const float c2 = cfr[8];
+        acc[0] = fmaf(c0.x, g[u], acc[0]); acc[1] = fmaf(c0.y, g[u], acc[1]); acc[2] = fmaf(c0.z, g[u], acc[2]);
+        acc[3] = fmaf(c0.w, g[u], acc[3]); acc[4] = fmaf(c1.x, g[u], acc[4]); acc[5] = fmaf(c1.y, g[u], acc[5]);
+        acc[6] = fmaf(c1.z, g[u], acc[6]); acc[7] = fmaf(c1.w, g[u], acc[7]); acc[8] = fmaf(c2, g[u], acc[8]);
       }
     }
     for (; tu < TT; ++tu) {
@@ -269,13 +286,12 @@ extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH
   const int nca = (p.ay.P > 0) ? p.ay.P * p.ax.P * p.ay.T * p.ax.T : 0;
   TBG_CHECK_ARG(ncf <= 36 && nca <= 36, "tbg_wprep: too many (phase, tap) combinations");
   TBG_CHECK_ARG(nca == 0 || adj, "tbg_wprep: adjoint tables without an adjoint output");
-  // split the (phase, tap) combinations into chunks until the grid covers the SMs about twice
+  // split the (phase, tap) combinations into equal chunks of at most 9 (one CTA each): every CTA then does the
+  // same amount of work, so partial waves cost little, and even a 128 x 128 weight fills the SMs
   const int tiles = (Ipad / 32) * (Opad / 32);
-  int nchunks = (296 + tiles - 1) / tiles;
-  if (nchunks > 4) nchunks = 4;
-  if (nchunks < 1) nchunks = 1;
   const int nmax = ncf > nca ? ncf : nca;
-  const int chunk = (nmax + nchunks - 1) / nchunks;
+  int chunk = nmax < 9 ? nmax : 9;
+  if (tiles * ((ncf + chunk - 1) / chunk + (nca + chunk - 1) / chunk) < 296 && chunk > 3) chunk = 3;
   const int fwd_chunks = (ncf + chunk - 1) / chunk;
   const int adj_chunks = (nca + chunk - 1) / chunk;
   wprep_kernel<<<dim3(tiles, fwd_chunks + adj_chunks), 256, 0, stream>>>(

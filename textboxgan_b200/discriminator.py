@@ -106,11 +106,16 @@ class Discriminator(Model):
         P = self.params
         res = self.resolutions
         r0 = res[0]
-        x = images.permute(0, 2, 3, 1).float()                               # NHWC
-        # FromRGB (from_rgb.py:26-29): 1x1 conv with K = 3 -> plain small GEMM
         w0 = P[f"{r0[0]}x{r0[1]}/FromRGB/conv/w"]
-        x = x @ (L.runtime_coef(w0.shape) * w0[0, 0]) + P[f"{r0[0]}x{r0[1]}/FromRGB/bias/b"]
-        x = L.lrelu(x).to(L.ACT_DTYPE)
+        if L.use_fused():
+            from .fused import FromRGB
+
+            # FromRGB (from_rgb.py:26-29): K = 3 -> bandwidth-bound, one fused launch (NCHW fp32 -> NHWC bf16)
+            x = FromRGB.apply(images.float(), w0, P[f"{r0[0]}x{r0[1]}/FromRGB/bias/b"], L.runtime_coef(w0.shape), L.SQRT2)
+        else:
+            x = images.permute(0, 2, 3, 1).float()                           # NHWC
+            x = x @ (L.runtime_coef(w0.shape) * w0[0, 0]) + P[f"{r0[0]}x{r0[1]}/FromRGB/bias/b"]
+            x = L.lrelu(x).to(L.ACT_DTYPE)
         for (h, w), (nh, nw) in zip(res[:-1], res[1:]):
             pb = f"{h}x{w}"
             rh = h != nh

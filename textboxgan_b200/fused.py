@@ -235,6 +235,36 @@ class ConvAct(torch.autograd.Function):
         return gx, gw_raw, gbias, (g_out if ctx.has_res else None), None, None
 
 
+class FromRGB(torch.autograd.Function):
+    """FromRGB.call (from_rgb.py:26-29) + BiasAct on the NCHW fp32 image -> NHWC bf16, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, img, w_raw, bias, coef: float, gain: float):
+        img = img.contiguous()
+        w2 = w_raw.reshape(3, -1).contiguous()
+        out = K.fromrgb_fwd(img, w2, _aligned_vec(bias), coef, gain)
+        ctx.save_for_backward(img, w2, out)
+        ctx.coef, ctx.gain, ctx.wshape = coef, gain, w_raw.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, w2, out = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        want_w = ctx.needs_input_grad[1] and "dconv" not in _SKIP_WGRAD_TAGS
+        lim = _BATCH_LIMIT.get("dconv")
+        if lim is not None and g_out.shape[0] > lim and not want_w:
+            gimg = None
+            if ctx.needs_input_grad[0]:
+                gimg = torch.zeros_like(img)
+                gi, _, _ = K.fromrgb_bwd(img[:lim], w2, g_out[:lim], out[:lim], ctx.coef, ctx.gain, want_img=True, want_w=False)
+                gimg[:lim].copy_(gi)
+            return gimg, None, None, None, None
+        gimg, gw, gb = K.fromrgb_bwd(img, w2, g_out, out, ctx.coef, ctx.gain, want_img=ctx.needs_input_grad[0],
+                                     want_w=want_w)
+        return gimg, (gw.reshape(ctx.wshape) if gw is not None else None), gb, None, None
+
+
 class StyleScales(torch.autograd.Function):
     """All style projections of the synthesis network at once: for layer l,
     s_l = mod_bias(mod_dense(style[:, idx_l])) + 1 (modulated_conv2d.py:75-76).  Inputs after the

@@ -84,6 +84,7 @@ def conv2d_igemm(
     out_fp32: bool = False,
     out: Optional[torch.Tensor] = None,
     tap_mask: Optional[tuple] = None,           # per output phase: bit (th*taps_w+tw) = tap computed (None: all)
+    relu_mask: Optional[torch.Tensor] = None,   # bf16, shape of out: result zeroed where relu_mask <= 0
 ) -> torch.Tensor:
     _require(x, torch.bfloat16, "x")
     _require(w, torch.bfloat16, "w")
@@ -102,6 +103,8 @@ def conv2d_igemm(
             _require(t, torch.float32, n)
     if residual is not None:
         _require(residual, torch.bfloat16, "residual")
+    if relu_mask is not None:
+        _require(relu_mask, torch.bfloat16, "relu_mask")
     col_scale, bias = _aligned(col_scale), _aligned(bias)
     a = _lib.ConvArgs(
         x=_ptr(x), w=_ptr(w), out=_ptr(out),
@@ -110,6 +113,7 @@ def conv2d_igemm(
         stride_h=stride[0], stride_w=stride[1], up_h=up[0], up_w=up[1],
         col_scale=_ptr(col_scale), bias=_ptr(bias), noise=_ptr(noise), noise_strength=_ptr(noise_strength),
         residual=_ptr(residual), res_scale=res_scale, res_first=int(res_first), act=act, act_gain=act_gain, out_fp32=int(out_fp32),
+        relu_mask=_ptr(relu_mask),
     )
     if tap_mask is not None:
         for i, m in enumerate(tap_mask):
@@ -390,6 +394,37 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     st = _lib.load().tbg_style_dense_bwd(arr, len(ws), _ptr(style), _ptr(gstyle), B, n, S, float(coef), _stream())
     _lib.check(st, "tbg_style_dense_bwd")
     return gstyle, gws, gbs
+
+
+def fromrgb_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coef: float, gain: float) -> torch.Tensor:
+    """img fp32 NCHW [B,3,H,W], w fp32 [3,C], bias [C] -> lrelu(coef*img.w + bias)*gain, bf16 NHWC [B,H,W,C]."""
+    _require(img, torch.float32, "img")
+    _require(w, torch.float32, "w")
+    _require(bias, torch.float32, "bias")
+    B, _, H, W_ = img.shape
+    C_ = w.shape[1]
+    out = torch.empty((B, H, W_, C_), device=img.device, dtype=torch.bfloat16)
+    st = _lib.load().tbg_fromrgb_fwd(_ptr(img), _ptr(w), _ptr(bias), _ptr(out), B, H * W_, C_, float(coef), float(gain),
+                                     _stream())
+    _lib.check(st, "tbg_fromrgb_fwd")
+    return out
+
+
+def fromrgb_bwd(img: torch.Tensor, w: torch.Tensor, g_out: torch.Tensor, out: torch.Tensor, coef: float, gain: float,
+                *, want_img: bool = True, want_w: bool = True):
+    """-> (gimg fp32 NCHW | None, gw fp32 [3,C] | None, gb fp32 [C] | None)."""
+    _require(img, torch.float32, "img")
+    _require(g_out, torch.bfloat16, "g_out")
+    _require(out, torch.bfloat16, "out")
+    B, _, H, W_ = img.shape
+    C_ = w.shape[1]
+    gimg = torch.empty_like(img) if want_img else None
+    gwb = torch.zeros((4, C_), device=img.device, dtype=torch.float32) if want_w else None
+    st = _lib.load().tbg_fromrgb_bwd(_ptr(img), _ptr(w), _ptr(g_out), _ptr(out), _ptr(gimg),
+                                     _ptr(gwb[:3]) if want_w else None, _ptr(gwb[3]) if want_w else None, B, H * W_, C_,
+                                     float(coef), float(gain), _stream())
+    _lib.check(st, "tbg_fromrgb_bwd")
+    return gimg, (gwb[:3] if want_w else None), (gwb[3] if want_w else None)
 
 
 def fir4(x: torch.Tensor, out_hw: tuple[int, int], off: tuple[int, int], scale: float, *, d=None, noise=None,

@@ -34,6 +34,7 @@ class ConvArgs(C.Structure):
         ("col_scale", c_void_p), ("bias", c_void_p), ("noise", c_void_p), ("noise_strength", c_void_p),
         ("residual", c_void_p), ("res_scale", c_float), ("res_first", c_int),
         ("act", c_int), ("act_gain", c_float), ("out_fp32", c_int),
+        ("relu_mask", c_void_p),
         ("tap_mask", C.c_uint64 * 4),
     ]
 
@@ -82,6 +83,8 @@ _SIGNATURES = [
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
     ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
+    ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
+    ("tbg_fromrgb_bwd", c_int, [c_void_p] * 7 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fir4", c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] + [c_void_p] * 4 + [c_int, c_float, c_void_p]),
     ("tbg_wfold_adj", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 5 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     ("tbg_style_dense_fwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),

@@ -10,6 +10,8 @@ import torch
 
 
 class Model:
+    ALIGN = 64   # floats; start alignment of every variable inside the flat buffer
+
     def __init__(self, name: str = ""):
         self.name = name
         self.params: Dict[str, torch.Tensor] = {}
@@ -72,7 +74,10 @@ class Model:
         # Non-trainable state (w_avg is assigned during the forward pass, latent_encoder.py:39-45)
         # lives outside the flat buffer: views share their base's autograd version counter, so an
         # in-place state update would invalidate every saved parameter of the step.
-        total = sum(p.numel() for k, p in self.params.items() if k not in self._non_trainable)
+        # every variable starts on a 256-byte boundary (ALIGN floats): vectorised kernel paths and the library
+        # GEMMs' aligned kernels apply to each view; the padding stays zero forever (zero gradient => Adam no-op)
+        A = self.ALIGN
+        total = sum((p.numel() + A - 1) // A * A for k, p in self.params.items() if k not in self._non_trainable)
         flat = torch.zeros(total, dtype=torch.float32, device=device)
         off = 0
         self.segments = {}
@@ -86,17 +91,18 @@ class Model:
             q.requires_grad_(True)
             self.params[k] = q
             self.segments[k] = (off, n)
-            off += n
+            off += (n + A - 1) // A * A
         self.flat = flat
         return self
 
     def flat_range(self, names: Sequence[str]):
         """(start, end) of the flat buffer covered by ``names``; they must be contiguous."""
+        A = self.ALIGN
         segs = sorted(self.segments[n] for n in names)
         for (o0, n0), (o1, _) in zip(segs[:-1], segs[1:]):
-            if o0 + n0 != o1:
+            if (o0 + n0 + A - 1) // A * A != o1:
                 raise ValueError("variables are not contiguous in the flat buffer")
-        return segs[0][0], segs[-1][0] + segs[-1][1]
+        return segs[0][0], (segs[-1][0] + segs[-1][1] + A - 1) // A * A
 
 
 class Submodel:

@@ -91,10 +91,19 @@ class Adam:
             phase = start % 4
             self._slots[key] = tuple(self._aligned_like(end - start, phase, p.device) for _ in range(3))
         g, m, v = self._slots[key]
-        parts = []
+        # gather the per-variable gradients into the flat buffer with one multi-tensor copy (padding between
+        # variables stays zero)
+        dsts, srcs = [], []
         for n, gr in zip(names, grads):
-            parts.append(gr.reshape(-1).float() if gr is not None else p.new_zeros(model.segments[n][1]))
-        torch.cat(parts, out=g)
+            o, cnt = model.segments[n]
+            view = g[o - start: o - start + cnt]
+            if gr is None:
+                view.zero_()
+            else:
+                dsts.append(view)
+                srcs.append(gr.detach().reshape(-1))
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)      # SUM: every loss already carries 1/global_batch
         K.adam_step(p, g, m, v, self._lr_arg(), self.beta_1, self.beta_2, self.epsilon)
