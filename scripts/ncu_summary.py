@@ -11,10 +11,12 @@ KEYS = [
     ("dram__bytes_read.sum", "dram_rd"),
     ("dram__bytes_write.sum", "dram_wr"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-    ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "hmma_cyc"),
     ("sm__cycles_elapsed.max", "sm_cyc"),
     ("sm__cycles_active.avg", "sm_cyc_active"),
-    ("sm__inst_executed_pipe_uniform.sum", "uinst"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_mem_pipe%"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2_to_sm_bytes"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed", "l2_to_sm%"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
     ("launch__registers_per_thread", "regs"),
     ("lts__t_sector_hit_rate.pct", "l2hit%"),
@@ -43,12 +45,6 @@ def main(path):
                 continue
             vals[short] = (r[i], units[i])
             parts.append(f"{short}={r[i]}{units[i] if units[i] not in ('', '%') else ''}")
-        try:
-            h = float(vals["hmma_cyc"][0].replace(",", ""))
-            c = float(vals["sm_cyc"][0].replace(",", ""))
-            parts.append(f"tensor_pipe_active={100.0 * h / c:.1f}%_of_elapsed")
-        except Exception:
-            pass
         print("  ".join(parts))
 
 
