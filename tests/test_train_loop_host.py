@@ -69,3 +69,32 @@ def test_trainer_schedule_checkpoints_and_resume(tmp_path):
         assert torch.equal(tr2.generator.flat, tr.generator.flat) and torch.equal(tr2.g_clone.flat, tr.g_clone.flat)
         assert torch.equal(tr2.discriminator.flat, tr.discriminator.flat)
         assert float(tr2.pl_mean) == float(tr.pl_mean) != 0.0
+
+
+def test_infer_generates_cropped_pngs_and_scores_a_corpus(tmp_path):
+    """Row f3 (infer.py:26-134) on the CPU with emulated kernels."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    from textboxgan_b200.generator import Generator
+    from textboxgan_b200.infer import Infer
+
+    cfg = small_cfg(2)
+    lines = []
+    with emulated_kernels():
+        G = Generator(cfg, device="cpu", seed=0)
+        inf = Infer(cfg, device="cpu", generator=G, printer=lines.append)
+        z = torch.randn(1, cfg.z_dim, generator=torch.Generator().manual_seed(0))
+        a = inf.generate(["ab", "hello"], z=z)
+        b = inf.generate(["ab", "hello"], z=z, truncation_psi=0.5)
+        assert a.shape == (2, cfg.char_height, cfg.image_width, 3) and a.dtype.name == "uint8"
+        assert (a != b).any()                                                # truncation moves the style
+        paths = inf.genererate_chosen_words(["ab", "hello"], "t", str(tmp_path), do_sentence=False)
+        im = cv2.imread(paths[1])
+        assert im.shape == (cfg.char_height, cfg.char_width * 5, 3)          # cropped to len(word) characters
+        (sp,) = inf.genererate_chosen_words(["ab", "hello"], "t", str(tmp_path), do_sentence=True)
+        assert cv2.imread(sp).shape == (cfg.char_height, cfg.char_width * 7, 3)
+        w = torch.randn(cfg.style_dim)
+        c = inf.generate(["ab"], w_latents=w)
+        assert c.shape == (1, cfg.char_height, cfg.image_width, 3)
+        (tmp_path / "test_corpus.txt").write_text("one\ntwo\nthree\nfour\n")
+        loss = inf.infer_test_set(2, str(tmp_path))
+        assert loss > 0 and any("AVERAGE TEST LOSS" in l for l in lines)
