@@ -14,7 +14,10 @@ One JSON line on rank 0 with the contract keys plus
                 host cores on a bounded sample (rank 0, N = 1 only),
   e2e           the same metric through the public API with pinned-host inputs copied in and
                 the seven loss scalars read back every step,
-  gpu_launches  launches of this repo's kernels inside the timed region.
+  gpu_launches  launches of this repo's kernels inside the timed region,
+  mix16         (N = 1) images/s over the 16-step lazy-regularisation schedule of train.py:182-183 (14 plain steps, one
+                path-length step, one path-length + R1 step), measured by a child process (`--mix16-child`) after the
+                main measurements so that it cannot affect them; `{"error": ...}` if the child fails.
 ``--impl reference`` times the oracle port of the reference's CPU path (TensorFlow 2.8 is not
 installable offline — see DESIGN.md) with all host threads on a bounded sample.
 """
@@ -153,6 +156,73 @@ def synthetic_inputs(cfg, batch: int, seed: int):
     real = torch.rand(batch, 3, cfg.char_height, cfg.image_width, generator=g) * 2 - 1
     real = mask_text_box(real, words, cfg.char_width)
     return real.contiguous(), words, labels
+
+
+def run_mix16_child(args) -> None:
+    """`--mix16-child` (spawned by the main arm on one GPU): the 16-step schedule of train.py:182-183 — 14 plain steps,
+    one path-length step (step 8) and one path-length + R1 step (step 16) — each variant replayed from its own CUDA
+    graph.  Prints one JSON object; runs in its own process so that nothing here can take the headline line down."""
+    import torch
+
+    from textboxgan_b200 import lib
+    from textboxgan_b200.aster_inferer import AsterInferer
+    from textboxgan_b200.config import baseline_config
+    from textboxgan_b200.discriminator import Discriminator
+    from textboxgan_b200.generator import Generator
+    from textboxgan_b200.optimizers import Adam, update_optimizer_params
+    from textboxgan_b200.training_step import TrainingStep
+
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    lib.load()
+    dev = torch.device("cuda", 0)
+    cfg = baseline_config(args.config, n_gpus=8 if args.config in (3, 4) else 1)
+    B = cfg.batch_size_per_gpu
+    G, D, g_clone = Generator(cfg, device=dev, seed=1), Discriminator(cfg, device=dev, seed=2), Generator(cfg, device=dev, seed=1)
+    aster = AsterInferer(cfg, device=dev)
+    go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
+    mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
+    ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), cfg.g_opt["reg_interval"], cfg.d_opt["reg_interval"],
+                      torch.zeros((), device=dev), cfg)
+    ts.use_cuda_graph = True
+    real_h, words_h, labels_h = synthetic_inputs(cfg, B, 4444)
+    real, words, labels = real_h.to(dev), words_h.to(dev), labels_h.to(dev)
+    zero = torch.zeros((), device=dev)
+
+    def step(i):
+        do_r1 = (i + 1) % cfg.d_opt["reg_interval"] == 0
+        do_pl = (i + 1) % cfg.g_opt["reg_interval"] == 0
+        ts.dist_train_step(real, zero, words, labels, do_r1, do_pl, cfg.ocr_loss_weight)
+        g_clone.set_as_moving_average_of(G)
+
+    for i in range(48):                 # three cycles: eager first use, capture, replay of every variant
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cycles = 2
+    e0.record()
+    for i in range(16 * cycles):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms16 = e0.elapsed_time(e1) / cycles
+    print(json.dumps({"value": 16 * B / (ms16 * 1e-3), "unit": UNIT, "ms_per_16_steps": ms16,
+                      "schedule": "14 plain + 1 path-length + 1 path-length+R1 step (train.py:182-183), CUDA-graph replay"}),
+          flush=True)
+
+
+def mix16_subprocess(config: int, timeout_s: int = 240) -> dict:
+    """Run :func:`run_mix16_child` in a child process and return its JSON (or ``{"error": ...}``)."""
+    import subprocess
+
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--mix16-child", "--config", str(config)],
+                           capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+        return json.loads(lines[-1])
+    except Exception as ex:   # timeout, JSON error, ...
+        return {"error": repr(ex)[:300]}
 
 
 def run_reference(args) -> None:
@@ -393,6 +463,10 @@ def run_ours(args) -> None:
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"1 timed plain training step (after 1 warm-up) at batch 4 of the config-{args.config} shape, "
                          f"oracle restatement of the reference cpu_only path, {threads} host threads"}
+    # the 16-step weighted mix of SURVEY 8d, measured in a child process after this process has finished with the GPU
+    mix16 = None
+    if world == 1 and not args.no_mix16:
+        mix16 = mix16_subprocess(args.config)
     gb = B * world
     line = {
         "metric": METRIC, "value": gb / (ms_eff * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -404,6 +478,7 @@ def run_ours(args) -> None:
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "mix16": mix16,
     }
     print(json.dumps(line), flush=True)
     # NOTE: no dist.destroy_process_group() here — with NCCL collectives captured inside CUDA graphs it hung the
@@ -419,8 +494,12 @@ def main():
     ap.add_argument("--config", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--no-mix16", action="store_true", help="skip the 16-step schedule measurement (child process)")
+    ap.add_argument("--mix16-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.mix16_child:
+        run_mix16_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -102,3 +102,13 @@ def test_bench_synthetic_inputs_follow_the_loader_contract():
     src = open(os.path.join(ROOT, "bench.py")).read()
     body = src[src.index("def run_ours"):src.index("def main")]
     assert "from oracle" not in body and "import oracle" not in body        # only the cpu_baseline leg calls it
+
+
+def test_bench_mix16_child_failures_never_reach_the_headline_line():
+    """The 16-step schedule measurement runs in a child process; without a GPU the child fails and the parent-side
+    helper must return an error record instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    rec = bench.mix16_subprocess(1, timeout_s=300)
+    assert set(rec) == {"error"} and "CUDA" in rec["error"]
