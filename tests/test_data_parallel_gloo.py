@@ -62,15 +62,24 @@ def _run(rank, world, port, ret, shard=None):
         dist.destroy_process_group()
 
 
+def _free_port() -> int:
+    """A port nobody listens on right now (a fixed port can collide with a socket of an earlier run in TIME_WAIT)."""
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def test_two_ranks_sum_gradients_of_their_shards():
     """The gradient buffer each optimiser consumes on 2 ranks == the SUM of the gradients two
     independent single-rank runs compute on the two shards (losses carry 1/global_batch), and the
     reported losses are the SUM of the per-shard losses (training_step.py:106-134)."""
     mgr = mp.Manager()
     r2, s0, s1 = mgr.dict(), mgr.dict(), mgr.dict()
-    mp.spawn(_run, args=(2, 29541, r2), nprocs=2, join=True)
-    mp.spawn(_run, args=(1, 29542, s0, 0), nprocs=1, join=True)
-    mp.spawn(_run, args=(1, 29543, s1, 1), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, _free_port(), r2), nprocs=2, join=True)
+    mp.spawn(_run, args=(1, _free_port(), s0, 0), nprocs=1, join=True)
+    mp.spawn(_run, args=(1, _free_port(), s1, 1), nprocs=1, join=True)
     for key in ("gG", "gD"):
         want = s0[key] + s1[key]
         err = ((r2[key] - want).abs().max() / (want.abs().max() + 1e-30)).item()
