@@ -202,19 +202,20 @@ int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, flo
  * upfirdn_2d_v2.py:65-113).  coef is the equalised-LR runtime coefficient (commons.py:4-12).
  * tbg_wfold is the transpose: gw += coef * fold(gfwd) (+ 2 coef^2 w gq), gfwd fp32 in fwd layout;
  * gq[i,o] = dL/dq is either given or formed in the kernel from (s [nb,I], t [nb,O]) of tbg_demod_bwd as
- * sum_b s[b,i]^2 t[b,o] (pass gq NULL).
+ * sum_b s[b,i]^2 t[b,o] (pass gq NULL).  accumulate != 0: gw += ...; 0: gw = ... (no zero-initialisation needed).
  * ------------------------------------------------------------------------------------------ */
 int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad, int Opad,
               void* fwd, void* adj, float* q, void* stream);
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
-              int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, void* stream);
+              int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, int accumulate,
+              void* stream);
 
 /* Fold of a gradient held in the adjoint-matrix layout [Ipad, (tap, Opad)] of an identity-table geometry
  * (role-swapped weight gradient of a transposed convolution): gw[tap,i,o] += coef*gadj[i, tap'*Opad+o], tap' =
  * tap, or the spatially mirrored tap when flip != 0 (upsample_conv_2d flips w, upfirdn_2d_v2.py:80)
  * (+ 2 coef^2 w dL/dq with dL/dq formed from (s, t) as in tbg_wfold). */
 int tbg_wfold_adj(const float* gadj, const float* w, float coef, int KH, int KW, int I, int O, int Opad, float* gw,
-                  const float* s, const float* t, int nb, int flip, void* stream);
+                  const float* s, const float* t, int nb, int flip, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Demodulation coefficient of ModulatedConv2D and its gradient (modulated_conv2d.py:75-82), fp32:

@@ -47,6 +47,11 @@ struct ConvKernelParams {
 
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
+// Epilogue staging: each epilogue warp transposes its 32 accumulator rows through shared memory, 256 bytes
+// of a row at a time (+16 bytes of padding: conflict-free 16-byte accesses), so that global stores go out as
+// whole 128-byte lines of two pixels per instruction instead of one 16-byte piece of 32 different pixels.
+static constexpr uint32_t kStgRow = 256 + 16;
+static constexpr uint32_t kStgBytes = 4 * 32 * kStgRow;
 
 __global__ void __launch_bounds__(256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -65,6 +70,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars + 2 * kMaxStages + 6);   // epilogue staging, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,6 +185,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
     const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    uint8_t* const stg = stg_base + e * (32 * kStgRow);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
@@ -196,6 +203,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
                              static_cast<uint32_t>(acc_stage * p.block_n);
+      const int esize = p.out_fp32 ? 4 : 2;
+      const int chunk_cols = min(p.block_n, 256 / esize);   // columns staged per flush (<= 256 bytes per row)
+      const int j_per_chunk = chunk_cols / 32;
+      uint8_t* const my_row = stg + lane * kStgRow;
+      long long row_off = -1;                                 // element offset of this row's chunk in out, or -1
       for (int j = 0; j < p.block_n / 32; ++j) {
         const int col0 = n_tile * p.block_n + j * 32;
         uint32_t v[32];
@@ -213,9 +225,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
           const size_t off = pix * p.cout + c0;
+          if (j % j_per_chunk == 0) row_off = static_cast<long long>(off);
           const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
           const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
           const float* bs = p.bias ? p.bias + c0 : nullptr;
+          uint8_t* const srow = my_row + (j % j_per_chunk) * 32 * esize;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
@@ -276,19 +290,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              float4* o = reinterpret_cast<float4*>(srow + g * 32);
+              o[0] = make_float4(f[0], f[1], f[2], f[3]);
+              o[1] = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
               uint4 pk;
               pk.x = pack_bf16x2(f[0], f[1]);
               pk.y = pack_bf16x2(f[2], f[3]);
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(o) = pk;
+              *reinterpret_cast<uint4*>(srow + g * 16) = pk;
             }
           }
+        } else if (j % j_per_chunk == 0) {
+          row_off = -1;
+        }
+        if ((j + 1) % j_per_chunk == 0) {
+          // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
+          __syncwarp();
+          const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4, 8 or 16
+          const int rows_per_pass = 32 / lanes_per_row;
+          const int sub = lane % lanes_per_row;
+          for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+            const int rr = r0 + lane / lanes_per_row;
+            const long long o_el = __shfl_sync(0xffffffffu, row_off, rr);
+            if (o_el >= 0) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRow + sub * 16);
+              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * esize + sub * 16;
+              *reinterpret_cast<uint4*>(dst) = val;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -430,11 +462,11 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/;
+  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + kStgBytes;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;

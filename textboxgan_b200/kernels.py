@@ -321,15 +321,16 @@ def wfold(gfwd: torch.Tensor, spec, *, gq: Optional[torch.Tensor] = None, w_raw:
     """Accumulate the master-weight gradient from the fp32 gradient of the fwd GEMM matrix; the
     demodulation term comes from ``gq`` [I,O] or from (``s`` [B,I], ``t`` [B,O]) of demod_bwd."""
     _require(gfwd, torch.float32, "gfwd")
+    accumulate = out is not None
     if out is None:
-        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
+        out = torch.empty((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
     nb = 0
     if s is not None:
         _require(s, torch.float32, "s")
         _require(t, torch.float32, "t")
         nb = s.shape[0]
     st = _lib.load().tbg_wfold(_ptr(gfwd), _ptr(gq), _ptr(w_raw), spec.ctable, spec.coef, spec.KH, spec.KW, spec.I,
-                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _ptr(s), _ptr(t), nb, _stream())
+                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _ptr(s), _ptr(t), nb, int(accumulate), _stream())
     _lib.check(st, "tbg_wfold")
     return out
 
@@ -448,11 +449,12 @@ def wfold_adj(gadj: torch.Tensor, spec, *, w_raw: Optional[torch.Tensor] = None,
     """Master-weight gradient from a gradient in the adjoint-matrix layout [Ipad, taps*Opad] (identity tables,
     or the spatially flipped kernel when ``flip``)."""
     _require(gadj, torch.float32, "gadj")
+    accumulate = out is not None
     if out is None:
-        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gadj.device, dtype=torch.float32)
+        out = torch.empty((spec.KH, spec.KW, spec.I, spec.O), device=gadj.device, dtype=torch.float32)
     nb = s.shape[0] if s is not None else 0
     st = _lib.load().tbg_wfold_adj(_ptr(gadj), _ptr(w_raw), spec.coef, spec.KH, spec.KW, spec.I, spec.O, spec.Opad,
-                                   _ptr(out), _ptr(s), _ptr(t), nb, int(flip), _stream())
+                                   _ptr(out), _ptr(s), _ptr(t), nb, int(flip), int(accumulate), _stream())
     _lib.check(st, "tbg_wfold_adj")
     return out
 
