@@ -153,7 +153,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config_dict(cfg, args, n_gpus=1),
+        "config": _config_dict(cfg, args, n_gpus=max(1, args.gpus)),     # same workload description as our arm
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port of the reference cpu_only path (TensorFlow 2.8 not installable offline)",
@@ -364,9 +364,6 @@ def run_ours(args) -> None:
         }
 
     if rank != 0:
-        if world > 1 and dist.is_initialized():
-            dist.barrier()
-            dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -388,9 +385,8 @@ def run_ours(args) -> None:
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1 and dist.is_initialized():
-        dist.barrier()
-        dist.destroy_process_group()
+    # NOTE: no dist.destroy_process_group() here — with NCCL collectives captured inside CUDA graphs it hung the
+    # 8-GPU run at exit (round 1); the process group is torn down by interpreter exit.
 
 
 def main():
