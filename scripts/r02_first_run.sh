@@ -1,0 +1,12 @@
+#!/bin/bash
+# Round-2 first GPU call for the kernels parked on branch wip/r02-unvalidated-kernels (none of them has run on
+# a GPU yet): validate, then measure against the round-1 numbers in profiles/r01d_*.
+#   gpurun --timeout 1200 -- 'bash scripts/r02_first_run.sh'
+set -x
+mkdir -p gpurun_out
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I textboxgan_b200/csrc -o gpurun_out/exp_halo \
+     scripts/exp_halo_umma.cu textboxgan_b200/csrc/host_util.cu && timeout 120 gpurun_out/exp_halo 2>&1 | tee gpurun_out/r02_exp_halo.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r02_pytest.log
+timeout 300 python scripts/perf_layers.py 32 2>&1 | tee gpurun_out/r02_layer_perf.log | tail -25
+timeout 300 python scripts/step_timing.py 1 ocr graph noprof 2>&1 | tail -5
+timeout 300 python scripts/graph_timeline.py 1 3 2>&1 | sed -n 3,30p
