@@ -46,6 +46,46 @@ def test_invalid_arguments_return_status_not_exceptions():
     assert st == -1 and b"upx" in h.tbg_last_error()
 
 
+def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
+    """Each entry point called through the ctypes binding with its full argument list and invalid contents returns
+    TBG_ERR_INVALID_ARG (-1) with a message — exercises the marshalling of every signature on a CPU-only box."""
+    from textboxgan_b200 import lib
+
+    h = lib.load()
+    P = 1 << 20          # a non-null, 16-byte aligned fake pointer (never dereferenced: validation fails first)
+    calls = {
+        "tbg_conv2d_wgrad": lambda: h.tbg_conv2d_wgrad(None, None),
+        "tbg_adam_step": lambda: h.tbg_adam_step(None, P, P, P, 8, 0.1, None, 0.0, 0.99, 1e-8, None),
+        "tbg_ema_step": lambda: h.tbg_ema_step(None, P, 8, 0.99, None),
+        "tbg_lstm_seq_fwd": lambda: h.tbg_lstm_seq_fwd(None, P, P, P, P, 2, 1, 4, 256, None),
+        "tbg_lstm_seq_bwd": lambda: h.tbg_lstm_seq_bwd(None, P, P, P, P, 2, 1, 4, 256, None),
+        "tbg_modulate": lambda: h.tbg_modulate(P, P, P, 1, 4, 12, None),
+        "tbg_modulate_bwd": lambda: h.tbg_modulate_bwd(P, P, P, P, P, 1, 4, 12, None),
+        "tbg_bias_act_bwd": lambda: h.tbg_bias_act_bwd(P, P, None, None, None, P, None, P, None, 1, 4, 64, 1, 1.0, 0, None),
+        "tbg_torgb_fwd": lambda: h.tbg_torgb_fwd(P, P, None, P, 1, 4, 12, None),
+        "tbg_torgb_bwd": lambda: h.tbg_torgb_bwd(P, P, P, P, P, 1, 4, 12, None),
+        "tbg_fromrgb_fwd": lambda: h.tbg_fromrgb_fwd(P, P, P, P, 1, 4, 12, 1.0, 1.0, None),
+        "tbg_fromrgb_bwd": lambda: h.tbg_fromrgb_bwd(P, P, P, P, P, P, None, 1, 4, 64, 1.0, 1.0, None),
+        "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),
+        "tbg_wprep": lambda: h.tbg_wprep(P, None, 1.0, 3, 3, 64, 64, 64, 64, P, P, None, None),
+        "tbg_wfold": lambda: h.tbg_wfold(P, None, None, None, 1.0, 3, 3, 64, 64, 64, 64, P, None, None, 0, None),
+        "tbg_wfold_adj": lambda: h.tbg_wfold_adj(None, None, 1.0, 3, 3, 64, 64, 64, P, None, None, 0, 0, None),
+        "tbg_demod_coef": lambda: h.tbg_demod_coef(None, P, P, 1, 64, 64, 1e-8, None),
+        "tbg_demod_bwd": lambda: h.tbg_demod_bwd(None, P, P, P, P, P, P, P, P, P, P, P, 1, 64, 64, None),
+        "tbg_style_dense_fwd": lambda: h.tbg_style_dense_fwd(None, 0, P, 1, 3, 64, 1.0, None),
+        "tbg_style_dense_bwd": lambda: h.tbg_style_dense_bwd(None, 0, P, P, 1, 3, 64, 1.0, None),
+        "tbg_attn_decoder_fwd": lambda: h.tbg_attn_decoder_fwd(None, P, None, P, P, P, P, P, P, P, 1, 8, 4, None),
+        "tbg_attn_decoder_bwd": lambda: h.tbg_attn_decoder_bwd(None, P, None, P, P, P, P, P, P, P, P, 1, 8, 4, None),
+    }
+    covered = set(calls) | {"tbg_conv2d_igemm", "tbg_upfirdn2d", "tbg_last_error", "tbg_version", "tbg_launch_count",
+                            "tbg_reset_launch_count"}
+    assert covered == set(lib.exported_symbols()), set(lib.exported_symbols()) ^ covered
+    for name, call in calls.items():
+        st = call()
+        assert st == -1, (name, st)
+        assert len(h.tbg_last_error()) > 0, name
+
+
 def test_product_does_not_import_the_oracle():
     for f in (ROOT / "textboxgan_b200").glob("*.py"):
         src = f.read_text()

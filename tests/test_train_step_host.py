@@ -34,7 +34,8 @@ def _build(cfg, GP, DP, with_ocr):
 
 
 @pytest.mark.parametrize("do_r1,do_pl,with_ocr,frac", [(False, False, True, False), (True, True, False, False),
-                                                        (False, False, True, True)])
+                                                        (False, False, True, True), (True, True, True, False),
+                                                        (False, True, True, False)])
 def test_train_step_matches_oracle(do_r1, do_pl, with_ocr, frac):
     cfg = fractional_cfg(4) if frac else small_cfg(4)
     GP, DP, g = perturbed_params(cfg)

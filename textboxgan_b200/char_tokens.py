@@ -43,6 +43,16 @@ class CharTokenizer:
         self.aster = _CharLevelTokenizer(ASTER_CHAR_VECTOR)
 
 
+def main_to_aster_ids(main_ids: np.ndarray) -> np.ndarray:
+    """Main-vocabulary ids (0 = pad/OOV, '0' = 1 ... '"' = 69; utils/utils.py:80-85) -> ASTER ids of the same
+    characters (1 = pad, '0' = 2 ... '~' = 95; utils/utils.py:102-105)."""
+    tok = CharTokenizer()
+    lut = np.ones(len(MAIN_CHAR_VECTOR) + 1, dtype=np.int32)
+    for i, ch in enumerate(MAIN_CHAR_VECTOR):
+        lut[i + 1] = tok.aster.word_index[ch]
+    return lut[np.asarray(main_ids, dtype=np.int64)]
+
+
 def pad_sequences(seqs: List[List[int]], maxlen: int, value: int) -> np.ndarray:
     """keras ``pad_sequences(..., padding="post")`` with the default ``truncating="pre"``."""
     out = np.full((len(seqs), maxlen), value, dtype=np.int32)

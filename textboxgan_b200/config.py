@@ -38,6 +38,12 @@ class Config:
     ocr_loss_type: str = "softmax_crossentropy"
     aster_image_dims: Tuple[int, int] = (64, 256)
     aster_weights: Optional[str] = None
+    # Summaries / checkpoints (config/config.py:97-103)
+    summary_steps_frequency: dict = field(default_factory=lambda: {"print_steps": [50, 500], "log_losses": [False, True]})
+    image_summary_step_frequency: int = 500
+    validation_step_frequency: int = 10000
+    save_step_frequency: int = 10000
+    num_ckpts_to_keep: int = 5
     # Others
     shuffle_seed: int = 4444
     max_steps: int = 130000
