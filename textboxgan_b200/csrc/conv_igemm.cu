@@ -30,6 +30,7 @@ struct ConvKernelParams {
   int cout;
   int out_H, out_W;
   int stages;
+  int msub;  // M sub-tiles per work item (1 or 2): two 128-pixel tiles share every weight box (halves weight traffic)
   // epilogue
   const float* col_scale;
   const float* bias;
@@ -62,8 +63,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int stages = p.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const int msub = p.msub;
+  const uint32_t a_stage = static_cast<uint32_t>(msub) * kABytes;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + stages * kABytes;
+  uint8_t* smB = smem + stages * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + stages * b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
@@ -100,8 +103,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int tiles_ms = (tiles_m + msub - 1) / msub;       // work items along M (each = msub adjacent M tiles)
+  const int total_tiles = tiles_ms * p.tiles_n;
   const int bw = p.bw, bh = p.bh, bn = p.bn;
+  // M tile -> (tw, th, tb); a tile index past the end maps to tb = tiles_b, i.e. fully out of bounds (TMA zero fill,
+  // epilogue rows invalid)
+  auto decode_m = [&](int m_tile, int& tw, int& th, int& tb) {
+    if (m_tile >= tiles_m) {
+      tw = 0; th = 0; tb = p.tiles_b;
+    } else {
+      tw = m_tile % p.tiles_w;
+      th = (m_tile / p.tiles_w) % p.tiles_h;
+      tb = m_tile / (p.tiles_w * p.tiles_h);
+    }
+  };
   const uint32_t a_bytes = static_cast<uint32_t>(bw * bh * bn) * 128u;  // bytes one activation box delivers
   // output phase of an N tile (up-sampling geometries put the phases side by side along N)
   auto tile_mask = [&](int n_tile) -> uint64_t {
@@ -116,13 +131,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.tiles_n;
-        const int m_tile = tile / p.tiles_n;
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tb = m_tile / (p.tiles_w * p.tiles_h);
-        const int w_base = tw * bw * p.stride_w + p.in_off_w;
-        const int h_base = th * bh * p.stride_h + p.in_off_h;
-        const int n_base = tb * bn;
+        const int ms_tile = tile / p.tiles_n;
+        int w_base[2], h_base[2], n_base[2];
+        for (int sub = 0; sub < msub; ++sub) {
+          int tw, th, tb;
+          decode_m(ms_tile * msub + sub, tw, th, tb);
+          w_base[sub] = tw * bw * p.stride_w + p.in_off_w;
+          h_base[sub] = th * bh * p.stride_h + p.in_off_h;
+          n_base[sub] = tb * bn;
+        }
         const uint64_t mask = tile_mask(n_tile);
         for (int ty = 0; ty < p.taps_h; ++ty) {
           for (int tx = 0; tx < p.taps_w; ++tx) {
@@ -130,8 +147,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int kcol = (ty * p.taps_w + tx) * p.cin;
             for (int ch = 0; ch < p.cin_chunks; ++ch, kcol += 64) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full[stage], a_bytes + b_bytes);
-              tma_load_4d(smA + stage * kABytes, &tmA, &full[stage], ch * 64, w_base + tx, h_base + ty, n_base);
+              mbar_arrive_expect_tx(&full[stage], msub * a_bytes + b_bytes);
+              for (int sub = 0; sub < msub; ++sub)
+                tma_load_4d(smA + stage * a_stage + sub * kABytes, &tmA, &full[stage], ch * 64, w_base[sub] + tx,
+                            h_base[sub] + ty, n_base[sub]);
               tma_load_2d(smB + stage * b_bytes, &tmB, &full[stage], kcol, n_tile * p.block_n);
               if (++stage == stages) {
                 stage = 0;
@@ -154,19 +173,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc_stage], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * msub * p.block_n);
         const uint64_t mask = tile_mask(tile % p.tiles_n);
         const int k_blocks = __popcll(mask) * p.cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
+          const uint32_t a_addr = smem_u32(smA + stage * a_stage);
           const uint32_t b_addr = smem_u32(smB + stage * b_bytes);
+          for (int sub = 0; sub < msub; ++sub) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc_sw128(a_addr + sub * kABytes + k * 32, 0, 1024);
+              const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              umma_bf16(d_tmem + static_cast<uint32_t>(sub * p.block_n), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (kb == k_blocks - 1) umma_commit(&tfull[acc_stage]);
@@ -189,20 +210,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
-      const int m_tile = tile / p.tiles_n;
-      const int tw = m_tile % p.tiles_w;
-      const int th = (m_tile / p.tiles_w) % p.tiles_h;
-      const int tb = m_tile / (p.tiles_w * p.tiles_h);
-      const int b = tb * bn + n_in;
-      const int ho = th * bh + h_in;
-      const int wo = tw * bw + w_in;
-      const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
+      const int ms_tile = tile / p.tiles_n;
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
+      for (int sub = 0; sub < msub; ++sub) {
+      int tw, th, tb;
+      decode_m(ms_tile * msub + sub, tw, th, tb);
+      const int b = tb * bn + n_in;
+      const int ho = th * bh + h_in;
+      const int wo = tw * bw + w_in;
+      const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
-                             static_cast<uint32_t>(acc_stage * p.block_n);
+                             static_cast<uint32_t>((acc_stage * msub + sub) * p.block_n);
       const int esize = p.out_fp32 ? 4 : 2;
       const int chunk_cols = min(p.block_n, 256 / esize);   // columns staged per flush (<= 256 bytes per row)
       const int j_per_chunk = chunk_cols / 32;
@@ -323,6 +344,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
         }
       }
+      }  // sub
       tc_fence_before();
       mbar_arrive(&tempty[acc_stage]);
     }
@@ -460,8 +482,12 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.out_fp32 = a->out_fp32;
   p.out = a->out;
 
+  // two M tiles per work item when both accumulator sets still double-buffer in TMEM (2 x 2 x block_n <= 512) and
+  // there is enough work to keep every SM busy with the larger items
+  // (>= 4 items per SM: with fewer, the static round-robin's last partial wave costs more than the traffic saves)
+  p.msub = (block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.msub) * kABytes + b_bytes;
   const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -493,7 +519,7 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
     TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int total_tiles = ((tiles_m + p.msub - 1) / p.msub) * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
   count_launch();
