@@ -357,6 +357,9 @@ def run_ours(args) -> None:
             "launches_per_step": iso_launches / 2, "avg_launch_us": iso_secs / max(iso_launches, 1) * 1e6,
             "in_step_event_tflops": algo / secs / 1e12,
             "traffic": None,
+            "traffic_note": "achieved aggregates 24 launch shapes, so no single per-launch DRAM figure applies; ncu --set "
+                            "full of the top-layer launches (profiles/r01d_ncu_full_conv_kernels_summary.txt): 33.9 MB DRAM "
+                            "read for 33.6 MB of activations (32x128x128ch, batch 32), 604 MB delivered L2->SM",
             "by_kernel_in_step": {f"{k[0]}:{k[1]}": {"launches_per_step": v[0] / 2, "ms_per_step": v[1] * 1e3 / 2,
                                                      "algorithmic_tflops": v[2] / max(v[1], 1e-12) / 1e12,
                                                      "executed_tflops": v[3] / max(v[1], 1e-12) / 1e12}

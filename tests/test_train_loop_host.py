@@ -98,3 +98,18 @@ def test_infer_generates_cropped_pngs_and_scores_a_corpus(tmp_path):
         (tmp_path / "test_corpus.txt").write_text("one\ntwo\nthree\nfour\n")
         loss = inf.infer_test_set(2, str(tmp_path))
         assert loss > 0 and any("AVERAGE TEST LOSS" in l for l in lines)
+
+
+def test_tensorboard_writer_logs_scalars_and_config(tmp_path):
+    import os
+
+    from textboxgan_b200.tensorboard_writer import TensorboardWriter
+
+    w = TensorboardWriter(str(tmp_path), small_cfg(2))
+    t = LossTracker(["a"])
+    t.increment_losses({"a": 2.0})
+    w.log_scalars(t.losses, 3)
+    w.log_scalars({"b": 1.5}, 4)
+    w.log_config_file(0)
+    files = [f for f in os.listdir(tmp_path) if "tfevents" in f]
+    assert files and os.path.getsize(os.path.join(tmp_path, files[0])) > 0
