@@ -135,6 +135,26 @@ def _cpu_oracle_rate(cfg_index: int, sample_batch: int, steps: int, threads: int
     return sample_batch / per_step, per_step
 
 
+def synthetic_inputs(cfg, batch: int, seed: int):
+    """Seeded synthetic word batch with the loader's tensor contract (dataset_utils/training_data_loader.py:56-97,
+    SURVEY.md §8d): words of length U{1..mcn} over the 69 main characters (pad 0), their ASTER labels (pad 1), uniform
+    "real" images zeroed right of the word.  Product code only (the oracle is not involved in the measured arm)."""
+    import torch
+
+    from textboxgan_b200.char_tokens import main_to_aster_ids
+    from textboxgan_b200.utils import mask_text_box
+
+    g = torch.Generator().manual_seed(seed)
+    mcn = cfg.max_char_number
+    lens = torch.randint(1, mcn + 1, (batch,), generator=g)
+    chars = torch.randint(1, 70, (batch, mcn), generator=g)
+    words = torch.where(torch.arange(mcn)[None, :] < lens[:, None], chars, torch.zeros_like(chars)).to(torch.int32)
+    labels = torch.from_numpy(main_to_aster_ids(words.numpy())).to(torch.int32)
+    real = torch.rand(batch, 3, cfg.char_height, cfg.image_width, generator=g) * 2 - 1
+    real = mask_text_box(real, words, cfg.char_width)
+    return real.contiguous(), words, labels
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,7 +198,6 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from oracle import train_step as OT  # synthetic-input generator only (shapes/seeds of SURVEY §8d)
     from textboxgan_b200 import kernels as K
     from textboxgan_b200 import lib
     from textboxgan_b200.aster_inferer import AsterInferer
@@ -212,8 +231,7 @@ def run_ours(args) -> None:
                       torch.zeros((), device=dev), cfg)
     ts.use_cuda_graph = not args.eager      # whole iteration replayed from a CUDA graph
 
-    gen = torch.Generator().manual_seed(4444 + rank)
-    real_h, words_h, labels_h = OT.synthetic_batch(cfg, B, gen)
+    real_h, words_h, labels_h = synthetic_inputs(cfg, B, 4444 + rank)          # reference shuffle_seed, config.py:114
     real_h, words_h, labels_h = real_h.pin_memory(), words_h.pin_memory(), labels_h.pin_memory()
     real, words, labels = real_h.to(dev), words_h.to(dev), labels_h.to(dev)
     zero = torch.zeros((), device=dev)

@@ -76,3 +76,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["unit"] == "images/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_synthetic_inputs_follow_the_loader_contract():
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import train_step as OT
+    from textboxgan_b200.config import baseline_config
+
+    for idx in (1, 2):
+        cfg = baseline_config(idx)
+        real, words, labels = bench.synthetic_inputs(cfg, 8, 4444)
+        assert real.shape == (8, 3, cfg.char_height, cfg.image_width) and real.dtype == torch.float32 and real.is_contiguous()
+        assert words.shape == (8, cfg.max_char_number) and words.dtype == torch.int32 and labels.dtype == torch.int32
+        lens = (words != 0).sum(1)
+        assert int(lens.min()) >= 1 and int(words.max()) <= 69
+        for b in range(8):
+            n = int(lens[b])
+            assert (words[b, :n] > 0).all() and (words[b, n:] == 0).all() and (labels[b, n:] == 1).all()
+            assert (labels[b, :n] >= 2).all() and (labels[b, :n] <= 95).all()
+        # zero right of the word, exactly like the training step's own mask (and the oracle's)
+        assert torch.equal(real, OT.mask_text_box(real, words, cfg.char_width))
+        assert float(real.abs().max()) <= 1.0
+    # the measured arm of bench.py does not touch the oracle
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    body = src[src.index("def run_ours"):src.index("def main")]
+    assert "from oracle" not in body and "import oracle" not in body        # only the cpu_baseline leg calls it
