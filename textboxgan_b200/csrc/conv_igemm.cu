@@ -8,6 +8,8 @@
 // algebra), upsample_conv_2d (upfirdn_2d_v2.py:65-103, as a 4-phase GEMM), Conv2D.call
 // (conv.py:51-73), Noise.call (noise.py:12-22), BiasAct.call (bias_act.py:25-34), the residual
 // merge of DiscriminatorBlock.call (discriminator.py:82).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -486,6 +488,14 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   // there is enough work to keep every SM busy with the larger items
   // (>= 4 items per SM: with fewer, the static round-robin's last partial wave costs more than the traffic saves)
   p.msub = (block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
+  {
+    static int msub_override = -1;      // TBG_IGEMM_MSUB=1|2 forces the choice (tests, tuning); 2 needs block_n <= 128
+    if (msub_override < 0) {
+      const char* e = getenv("TBG_IGEMM_MSUB");
+      msub_override = e ? atoi(e) : 0;
+    }
+    if (msub_override == 1 || (msub_override == 2 && block_n <= 128)) p.msub = msub_override;
+  }
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
   const uint32_t stage_bytes = static_cast<uint32_t>(p.msub) * kABytes + b_bytes;
   const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/;
