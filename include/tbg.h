@@ -179,6 +179,15 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
+/* AsterInferer.convert_inputs (aster_inferer.py:153-190): NCHW fp32 image [B,3,H,W] -> per-sample crop at
+ * floor(first_blank * cw_num / cw_den) columns (clamped to [1, W]; W when `labels` [B, mcn] has no `blank`) ->
+ * bilinear resize (half-pixel centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].  bwd scatters into gimg (zeroed by
+ * the caller) with fp32 atomics. */
+int tbg_crop_resize_fwd(const float* img, const int* labels, float* out, int B, int H, int W, int oh, int ow, int mcn,
+                        int blank, int cw_num, int cw_den, void* stream);
+int tbg_crop_resize_bwd(const float* g, const int* labels, float* gimg, int B, int H, int W, int oh, int ow, int mcn,
+                        int blank, int cw_num, int cw_den, void* stream);
+
 /* FromRGB (from_rgb.py:26-29): 1x1 conv 3 -> C of the NCHW fp32 image + bias + leaky-ReLU(0.2)*gain -> NHWC bf16:
  *   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] w[j,c] + bias[c]) * gain,   w fp32 [3, C]
  * bwd: gpre = g_out*gain*slope(out); gimg[b,j,p] = coef sum_c gpre w[j,c] (NCHW fp32, may be NULL);

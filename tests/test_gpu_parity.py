@@ -516,6 +516,35 @@ def test_fromrgb_kernels_vs_emulated_semantics(B, H, W, C):
     assert gw2 is None and gb2 is None and rel_err(gi2, ri) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W,mcn,cw", [(5, 16, 64, 8, 8), (4, 32, 128, 8, 16), (3, 64, 256, 12, "64/3")])
+def test_crop_resize_kernels_vs_emulated_semantics(B, H, W, mcn, cw):
+    """tbg_crop_resize_fwd / bwd (convert_inputs) against the crop + tf.image.resize semantics (fp32, 1e-5), incl.
+    words without a blank label, a blank in the first position (clamped to one column) and a fractional char_width."""
+    from fractions import Fraction
+
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    cw = Fraction(cw)
+    gen = torch.Generator().manual_seed(B + H)
+    img = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
+    labels = torch.randint(2, 96, (B, mcn), generator=gen, dtype=torch.int32)
+    labels[0, 3:] = 1
+    labels[1, :] = 1
+    if B > 3:
+        labels[3, mcn - 1:] = 1
+    out = K.crop_resize_fwd(img.to(DEV), labels.to(DEV), 1, cw, (64, 256))
+    ref = emu.emu_crop_resize_fwd(img, labels, 1, cw, (64, 256))
+    assert rel_err(out, ref) < 1e-5
+    g = torch.randn(B, 64, 256, 3, generator=gen)
+    gi = K.crop_resize_bwd(g.to(DEV), labels.to(DEV), 1, cw, (H, W))
+    ri = emu.emu_crop_resize_bwd(g, labels, 1, cw, (H, W))
+    assert rel_err(gi, ri) < 1e-4
+    # adjoint identity on the device results
+    lhs, rhs = (out.cpu().double() * g.double()).sum(), (img.double() * gi.cpu().double()).sum()
+    assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
+
+
 def test_relu_mask_epilogue_and_fused_encoder_backward():
     """relu_mask epilogue of tbg_conv2d_igemm (fused ReLU backward) against its documented semantics, and the
     one-node ResNet encoder (masks and residual sums folded into the input-gradient convs) against the

@@ -397,6 +397,35 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     return gstyle, gws, gbs
 
 
+def crop_resize_fwd(img: torch.Tensor, labels: torch.Tensor, blank: int, char_width, out_hw) -> torch.Tensor:
+    """convert_inputs forward — see include/tbg.h (tbg_crop_resize_fwd)."""
+    from fractions import Fraction
+
+    _require(img, torch.float32, "img")
+    _require(labels, torch.int32, "labels")
+    B, _, H, W_ = img.shape
+    cw = Fraction(char_width)
+    out = torch.empty((B, out_hw[0], out_hw[1], 3), device=img.device, dtype=torch.float32)
+    st = _lib.load().tbg_crop_resize_fwd(_ptr(img), _ptr(labels), _ptr(out), B, H, W_, out_hw[0], out_hw[1], labels.shape[1],
+                                         int(blank), cw.numerator, cw.denominator, _stream())
+    _lib.check(st, "tbg_crop_resize_fwd")
+    return out
+
+
+def crop_resize_bwd(g: torch.Tensor, labels: torch.Tensor, blank: int, char_width, img_hw) -> torch.Tensor:
+    from fractions import Fraction
+
+    _require(g, torch.float32, "g")
+    _require(labels, torch.int32, "labels")
+    B, oh, ow, _ = g.shape
+    cw = Fraction(char_width)
+    gimg = torch.zeros((B, 3, img_hw[0], img_hw[1]), device=g.device, dtype=torch.float32)
+    st = _lib.load().tbg_crop_resize_bwd(_ptr(g), _ptr(labels), _ptr(gimg), B, img_hw[0], img_hw[1], oh, ow, labels.shape[1],
+                                         int(blank), cw.numerator, cw.denominator, _stream())
+    _lib.check(st, "tbg_crop_resize_bwd")
+    return gimg
+
+
 def fromrgb_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coef: float, gain: float) -> torch.Tensor:
     """img fp32 NCHW [B,3,H,W], w fp32 [3,C], bias [C] -> lrelu(coef*img.w + bias)*gain, bf16 NHWC [B,H,W,C]."""
     _require(img, torch.float32, "img")
