@@ -6,7 +6,9 @@ set -x
 mkdir -p gpurun_out
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I textboxgan_b200/csrc -o gpurun_out/exp_halo \
      scripts/exp_halo_umma.cu textboxgan_b200/csrc/host_util.cu && timeout 120 gpurun_out/exp_halo 2>&1 | tee gpurun_out/r02_exp_halo.log
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r02_pytest.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee gpurun_out/r02_pytest.log
+# if the line above shows conv failures, these isolate the two staged epilogues (round-1 store paths):
+TBG_IGEMM_STAGED=0 TBG_WGRAD_STAGED=0 TBG_IGEMM_MSUB=1 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/r02_pytest_unstaged.log
 TBG_LSTM_CLUSTER=1 timeout 300 python -m pytest tests -m gpu -q -k "lstm or train_step" 2>&1 | tail -5 | tee gpurun_out/r02_pytest_lstm_cluster.log
 TBG_LSTM_CLUSTER=1 timeout 300 python scripts/step_timing.py 1 ocr graph noprof 2>&1 | tail -5
 timeout 300 python scripts/perf_layers.py 32 2>&1 | tee gpurun_out/r02_layer_perf.log | tail -25

@@ -32,6 +32,7 @@ struct ConvKernelParams {
   int cout;
   int out_H, out_W;
   int stages;
+  int staged;  // 1: epilogue stores go through the shared-memory transpose (TBG_IGEMM_STAGED=0 restores direct stores)
   int msub;  // M sub-tiles per work item (1 or 2): two 128-pixel tiles share every weight box (halves weight traffic)
   // epilogue
   const float* col_scale;
@@ -313,7 +314,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.out_fp32) {
-              float4* o = reinterpret_cast<float4*>(srow + g * 32);
+              float4* o = p.staged ? reinterpret_cast<float4*>(srow + g * 32)
+                                   : reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + g * 8);
               o[0] = make_float4(f[0], f[1], f[2], f[3]);
               o[1] = make_float4(f[4], f[5], f[6], f[7]);
             } else {
@@ -322,13 +324,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               pk.y = pack_bf16x2(f[2], f[3]);
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(srow + g * 16) = pk;
+              uint4* o = p.staged ? reinterpret_cast<uint4*>(srow + g * 16)
+                                  : reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8);
+              *o = pk;
             }
           }
         } else if (j % j_per_chunk == 0) {
           row_off = -1;
         }
-        if ((j + 1) % j_per_chunk == 0) {
+        if (p.staged && (j + 1) % j_per_chunk == 0) {
           // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
           __syncwarp();
           const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4, 8 or 16
@@ -487,6 +491,14 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   // two M tiles per work item when both accumulator sets still double-buffer in TMEM (2 x 2 x block_n <= 512) and
   // there is enough work to keep every SM busy with the larger items
   // (>= 4 items per SM: with fewer, the static round-robin's last partial wave costs more than the traffic saves)
+  {
+    static int staged = -1;
+    if (staged < 0) {
+      const char* e = getenv("TBG_IGEMM_STAGED");
+      staged = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    p.staged = staged;
+  }
   p.msub = (block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
   {
     static int msub_override = -1;      // TBG_IGEMM_MSUB=1|2 forces the choice (tests, tuning); 2 needs block_n <= 128

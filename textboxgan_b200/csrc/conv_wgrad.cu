@@ -36,6 +36,7 @@ struct WgradParams {
   int stages;
   int ktot;                       // taps * cin
   float* gw;
+  int staged;   // 1: vector atomics go out line-coalesced through shared memory (TBG_WGRAD_STAGED=0: one row per thread)
 };
 
 static constexpr int kWgMaxStages = 8;
@@ -220,6 +221,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32(t_row + j * 32, v);
           tmem_ld_wait();
+          if (!p.staged) {      // round-1 path: every thread reduces 16-byte pieces of its own output-channel row
+            const int nn = m_tile * 128 + e * 32 + lane;
+            if (nn < p.n_total && kt1 > kt0) {
+              float* dst = p.gw + static_cast<size_t>(nn) * p.ktot + tap * p.cin + ct * p.block_c + j * 32;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                             "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                             "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                             : "memory");
+            }
+            continue;
+          }
           float4* srow = reinterpret_cast<float4*>(stg + lane * kWgStgRow + (j & 1) * 128);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -304,6 +318,14 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   p.stride_w = a->stride_w;
   p.ktot = a->taps_h * a->taps_w * a->Cin;
   p.gw = a->gw;
+  {
+    static int staged = -1;
+    if (staged < 0) {
+      const char* e = getenv("TBG_WGRAD_STAGED");
+      staged = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    p.staged = staged;
+  }
 
   // pixel block: 64 pixels unless a stage would not leave room for >= 3 stages
   int P = 64;
