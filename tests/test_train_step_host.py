@@ -111,3 +111,49 @@ def test_adam_is_tf_keras_adam():
         ref = p - lr_t * m / (vv.sqrt() + 1e-8)
         assert torch.allclose(v.detach(), ref, rtol=1e-6, atol=1e-9)
         assert opt.iterations.numpy() == 1
+
+
+def test_four_consecutive_steps_follow_the_oracle_loss_curve():
+    """State carried across iterations (Adam moments and step counters of all three optimisers, pl_mean, w_avg, EMA
+    clone) — four steps with the lazy-regularisation schedule of train.py:182-183 (intervals 2 / 3 so that a PL step, an
+    R1 step and a second PL step occur), every random draw injected on both sides.  The first step agrees to 5e-4; later
+    steps to 2e-2: with beta1 = 0 the Adam update is lr * g / (|g| + eps), i.e. +-lr for every element however small
+    its gradient, so fp32 rounding of near-zero gradients (and leaky-ReLU slope choices at |pre| ~ 1e-7) moves a few
+    weights by 2*lr per step and the trajectories separate slowly — the reference's own runs differ from each other
+    in the same way.  Weights after the fourth step stay within 4 steps * 2 * lr of the oracle's."""
+    cfg = small_cfg(4)
+    GP, DP, g = perturbed_params(cfg)
+    st = OT.StepState(copy.deepcopy(GP), copy.deepcopy(DP), OA.init_aster_params(), OT.make_adam(cfg.g_opt),
+                      OT.make_adam(cfg.g_opt), OT.make_adam(cfg.d_opt), torch.zeros(()), g_reg_interval=2,
+                      d_reg_interval=3)
+    with emulated_kernels():
+        G = Generator(cfg, device="cpu", seed=0)
+        G.load_state_dict(GP)
+        clone = Generator(cfg, device="cpu", seed=0)
+        clone.load_state_dict(GP)
+        D = Discriminator(cfg, device="cpu", seed=0)
+        D.load_state_dict(DP)
+        aster = AsterInferer(cfg, device="cpu")
+        g_opt, d_opt = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
+        mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
+        pl_mean = torch.zeros(())
+        ts = TrainingStep(G, D, aster, mk(g_opt), mk(g_opt), mk(d_opt), 2, 3, pl_mean, cfg)
+        for step in range(4):
+            do_r1, do_pl = (step + 1) % 3 == 0, (step + 1) % 2 == 0
+            real, words, labels = OT.synthetic_batch(cfg, 4, g)
+            draws = OT.make_draws(cfg, 4, g, with_pl=do_pl)
+            ref = OT.train_step(st, cfg, real, torch.zeros(()), words, labels, do_r1, do_pl, 1e-4, draws, fused=False)
+            out = ts.dist_train_step(real, torch.zeros(()), words, labels, do_r1, do_pl, 1e-4, draws=dict(draws))
+            clone.set_as_moving_average_of(G)
+            flat = lambda o: [float(v) for v in (*o[0], *o[1], o[2])]
+            tol = 5e-4 if step == 0 else 2e-2
+            for a, b in zip(flat(out), flat(ref)):
+                assert abs(a - b) <= tol * max(1.0, abs(b)), (step, flat(out), flat(ref))
+            assert (flat(out)[2] > 0) == do_pl and (flat(out)[5] > 0) == do_r1
+        bound = 4 * 2 * 0.002 * 1.01        # steps * 2 * lr (synthesis weights get two updates per step: x2 below)
+        for n, p in G.params.items():
+            assert float((p.detach() - st.G[n]).abs().max()) <= 2 * bound, n
+        for n, p in D.params.items():
+            assert float((p.detach() - st.D[n]).abs().max()) <= bound, n
+        assert abs(float(pl_mean) - float(st.pl_mean)) < 1e-4 * max(1.0, abs(float(st.pl_mean)))
+        assert ts.g_optimizer.iterations.numpy() == 4 and ts.ocr_optimizer.iterations.numpy() == 4

@@ -1,64 +1,62 @@
-"""LossTracker — running means of the training losses between two prints (mirror of
-utils/loss_tracker.py:11-82).  Values ``<= 0`` are skipped exactly like the reference's ``if loss_value > 0``
-(:41-43), so the regularisation penalties — identically 0.0 on the steps that do not compute them
-(training_step.py:115,261,294) — average over regularised steps only."""
+"""Running means of the training losses between two prints — the service utils/loss_tracker.py:11-82 gives train.py.
+
+Semantics kept from the reference:
+* a value is accumulated only when it is strictly positive (:41-43): the regularisation penalties are identically
+  0.0 on the steps that do not compute them (training_step.py:115,261,294), so their mean runs over regularised steps;
+* every ``increment_losses`` call also records the wall time since the previous call; ``print_losses`` reports the
+  mean step time and the number of steps (per replica) since the last ``reinitialize_tracker``;
+* the printed line has the reference's exact format.
+"""
 from __future__ import annotations
 
-from time import time
-from typing import Dict, List, Optional
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional, Sequence
 
 
-class _Mean:
-    """tf.keras.metrics.Mean for scalars: ``m(value)`` accumulates, ``result()`` is the mean (0.0 when empty)."""
+@dataclass
+class RunningMean:
+    """Scalar stand-in for ``tf.keras.metrics.Mean``: call to add a value, ``result()`` is 0.0 while empty."""
 
-    def __init__(self, name: str):
-        self.name = name
-        self.total = 0.0
-        self.count = 0
+    name: str
+    total: float = 0.0
+    count: int = 0
 
     def __call__(self, value) -> None:
-        self.total += float(value)
         self.count += 1
+        self.total += float(value)
 
     def result(self) -> float:
         return self.total / self.count if self.count else 0.0
 
 
 class LossTracker:
-    """Tracks the different losses to monitor the performance of the model."""
-
-    def __init__(self, loss_names: List[str], print_step: Optional[int] = None, log_losses: Optional[bool] = None,
-                 num_replicas: int = 1, printer=print):
-        self.print_step = print_step
-        self.log_losses = log_losses
-        self.loss_names = loss_names
-        self.num_replicas = num_replicas
-        self._print = printer
-        self._initiate_loss_tracking()
-
-    def _initiate_loss_tracking(self) -> None:
-        self.losses: Dict[str, _Mean] = {n: _Mean(n) for n in self.loss_names}
-        self.timer = _Mean("timer")
-        self.start_time = time()
-
-    def increment_losses(self, losses: dict) -> None:
-        """utils/loss_tracker.py:32-46.  ``float(loss) > 0`` reads a device scalar: one host sync per tracked
-        value, as in the reference (``.numpy()`` behind ``if loss_value > 0``)."""
-        for loss_name, loss_value in losses.items():
-            v = float(loss_value)
-            if v > 0:
-                self.losses[loss_name](v)
-        self.timer(time() - self.start_time)
-        self.start_time = time()
-
-    def print_losses(self, step) -> str:
-        """utils/loss_tracker.py:48-79"""
-        start_print = "Step: {}. Avg over the last {:d} steps. {:.2f} s/step. Losses:".format(
-            step, int(self.timer.count / self.num_replicas), self.timer.result())
-        loss_print = ", ".join("- {:s}: {:.4f}".format(n, self.losses[n].result()) for n in self.loss_names)
-        line = start_print + loss_print
-        self._print(line)
-        return line
+    def __init__(self, loss_names: Sequence[str], print_step: Optional[int] = None, log_losses: Optional[bool] = None,
+                 num_replicas: int = 1, printer: Callable[[str], None] = print):
+        self.loss_names = list(loss_names)
+        self.print_step, self.log_losses = print_step, log_losses
+        self.num_replicas = max(1, int(num_replicas))
+        self._emit = printer
+        self.reinitialize_tracker()
 
     def reinitialize_tracker(self) -> None:
-        self._initiate_loss_tracking()
+        self.losses: Dict[str, RunningMean] = {name: RunningMean(name) for name in self.loss_names}
+        self.timer = RunningMean("timer")
+        self._last = time.time()
+
+    def increment_losses(self, losses: dict) -> None:
+        """``float(v)`` on a device scalar is one host read per tracked loss, like the reference's ``loss_value > 0``."""
+        for name, value in losses.items():
+            value = float(value)
+            if value > 0.0:
+                self.losses[name](value)
+        now = time.time()
+        self.timer(now - self._last)
+        self._last = now
+
+    def print_losses(self, step) -> str:
+        n_steps = self.timer.count // self.num_replicas
+        head = f"Step: {step}. Avg over the last {n_steps:d} steps. {self.timer.result():.2f} s/step. Losses:"
+        body = ", ".join(f"- {name}: {self.losses[name].result():.4f}" for name in self.loss_names)
+        self._emit(head + body)
+        return head + body

@@ -95,50 +95,58 @@ class Trainer:
         if self.manager is not None and self.strategy.rank == 0:
             self.manager.save(checkpoint_number=step)
 
+    # -- pieces of the loop body (train.py:178-256) ---------------------------------------------------------------
+    def _one_step(self, batch) -> dict:
+        """One generator/discriminator/OCR update + EMA; returns the seven tracked losses by name."""
+        real_images, ocr_image, input_words, ocr_labels = batch
+        step = self.g_optimizer.iterations.numpy()
+        r1, pl = self.regularisation_flags(step)
+        (reg_g, g, pl_pen), (reg_d, d, r1_pen), ocr = self.training_step.dist_train_step(
+            real_images, ocr_image, input_words, ocr_labels, r1, pl, self.ocr_weight(step))
+        self.g_clone.set_as_moving_average_of(self.generator)                                      # train.py:208
+        return dict(zip(TRAIN_LOSSES, (reg_g, g, pl_pen, ocr, reg_d, d, r1_pen)))
+
+    def _validate(self, tracker: LossTracker, step: int) -> None:
+        for words, labels in self.strategy.experimental_distribute_dataset(self.validation_dataset):
+            tracker.increment_losses({"validation_ocr_loss": self.validation_step.dist_validation_step(words, labels)})
+        self._log(tracker, step)
+        tracker.print_losses(step)
+        tracker.reinitialize_tracker()
+
+    def _log(self, tracker: LossTracker, step: int) -> None:
+        if self.scalar_writer is not None:
+            self.scalar_writer({name: mean.result() for name, mean in tracker.losses.items()}, step)
+
     def train(self) -> int:
         """Main training loop (train.py:131-261).  Returns the number of generator updates done."""
-        assert self.training_dataset is not None, "Trainer.train() needs a train_dataset iterable"
-        train_dataset = self.strategy.experimental_distribute_dataset(self.training_dataset)
+        if self.training_dataset is None:
+            raise ValueError("Trainer.train() needs a train_dataset iterable")
         self._print("Start Training")
-        nrep = self.strategy.num_replicas_in_sync
-        loss_trackers = [LossTracker(TRAIN_LOSSES, ps, ll, num_replicas=nrep, printer=self._print)
-                         for ps, ll in zip(self.summary_steps_frequency["print_steps"],
-                                           self.summary_steps_frequency["log_losses"])]
-        validation_tracker = LossTracker(["validation_ocr_loss"], num_replicas=nrep, printer=self._print)
-        for real_images, ocr_image, input_words, ocr_labels in train_dataset:
-            step = self.g_optimizer.iterations.numpy()
-            do_r1_reg, do_pl_reg = self.regularisation_flags(step)
-            gen_losses, disc_losses, ocr_loss = self.training_step.dist_train_step(
-                real_images, ocr_image, input_words, ocr_labels, do_r1_reg, do_pl_reg, self.ocr_weight(step))
-            reg_g_loss, g_loss, pl_penalty = gen_losses
-            reg_d_loss, d_loss, r1_penalty = disc_losses
-            self.g_clone.set_as_moving_average_of(self.generator)                                  # train.py:208
-            step = self.g_optimizer.iterations.numpy()
-            losses_dict = {"reg_g_loss": reg_g_loss, "g_loss": g_loss, "pl_penalty": pl_penalty, "ocr_loss": ocr_loss,
-                           "reg_d_loss": reg_d_loss, "d_loss": d_loss, "r1_penalty": r1_penalty}
-            for loss_tracker in loss_trackers:
-                loss_tracker.increment_losses(losses_dict)
+        replicas = self.strategy.num_replicas_in_sync
+        freq = self.summary_steps_frequency
+        trackers = [LossTracker(TRAIN_LOSSES, every, log, num_replicas=replicas, printer=self._print)
+                    for every, log in zip(freq["print_steps"], freq["log_losses"])]
+        val_tracker = LossTracker(["validation_ocr_loss"], num_replicas=replicas, printer=self._print)
+        for batch in self.strategy.experimental_distribute_dataset(self.training_dataset):
+            losses = self._one_step(batch)
+            step = self.g_optimizer.iterations.numpy()                     # counts generator updates (train.py:211)
+            for tracker in trackers:
+                tracker.increment_losses(losses)
             if step % self.save_step_frequency == 0:
                 self._save(step)
             if self.validation_dataset is not None and step % self.validation_step_frequency == 0:
-                for v_words, v_labels in self.strategy.experimental_distribute_dataset(self.validation_dataset):
-                    v_loss = self.validation_step.dist_validation_step(v_words, v_labels)
-                    validation_tracker.increment_losses({"validation_ocr_loss": v_loss})
-                if self.scalar_writer is not None:
-                    self.scalar_writer({k: m.result() for k, m in validation_tracker.losses.items()}, step)
-                validation_tracker.print_losses(step)
-                validation_tracker.reinitialize_tracker()
-            for loss_tracker in loss_trackers:
-                if step % loss_tracker.print_step == 0:
-                    loss_tracker.print_losses(step)
-                    if loss_tracker.log_losses and self.scalar_writer is not None:
-                        self.scalar_writer({k: m.result() for k, m in loss_tracker.losses.items()}, step)
-                    loss_tracker.reinitialize_tracker()
+                self._validate(val_tracker, step)
+            for tracker in trackers:
+                if step % tracker.print_step == 0:
+                    tracker.print_losses(step)
+                    if tracker.log_losses:
+                        self._log(tracker, step)
+                    tracker.reinitialize_tracker()
             if step == self.max_steps:
                 break
-        step = self.g_optimizer.iterations.numpy()
-        self._save(step)                                                                           # train.py:259-261
-        return step
+        last = self.g_optimizer.iterations.numpy()
+        self._save(last)                                                   # train.py:259-261
+        return last
 
 
 def synthetic_dataset(cfg: Config, n_batches: int, device="cuda", seed: Optional[int] = None):
