@@ -179,6 +179,14 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
+/* EXPERIMENTAL: 3x3 stride-1 SAME convolution (same tensors and epilogue subset as tbg_conv2d_igemm) whose nine taps
+ * read shifted windows of ONE activation halo box per 64-channel block (csrc/conv_halo.cu).  H, W multiples of 16,
+ * Cin % 64 == 0, Cout in {32, 64, 128}.  use_base_offset selects the descriptor addressing variant that
+ * scripts/exp_halo_umma.cu finds to work. */
+int tbg_conv3x3_halo(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                     const float* col_scale, const float* bias, const float* noise, const float* noise_strength, int act,
+                     float act_gain, int use_base_offset, void* stream);
+
 /* AsterInferer.convert_inputs (aster_inferer.py:153-190): NCHW fp32 image [B,3,H,W] -> per-sample crop at
  * floor(first_blank * cw_num / cw_den) columns (clamped to [1, W]; W when `labels` [B, mcn] has no `blank`) ->
  * bilinear resize (half-pixel centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].  bwd scatters into gimg (zeroed by

@@ -16,3 +16,6 @@ timeout 300 python scripts/step_timing.py 1 ocr graph noprof 2>&1 | tail -5
 timeout 300 python scripts/graph_timeline.py 1 3 2>&1 | sed -n 3,30p
 # last: a wrong addressing variant can trap the context
 timeout 300 python scripts/perf_halo.py 32 2>&1 | tee gpurun_out/r02_perf_halo.log | tail -6
+# if a halo variant works (v = 1: base_offset 0, v = 2: base_offset from the start address), the whole suite and the step
+# with the 3x3 convolutions routed through it:
+for v in 1 2; do TBG_CONV_HALO=$v timeout 600 python -m pytest tests -m gpu -q -k "train_step or fused or conv" 2>&1 | tail -3; done

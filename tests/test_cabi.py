@@ -66,6 +66,7 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_torgb_bwd": lambda: h.tbg_torgb_bwd(P, P, P, P, P, 1, 4, 12, None),
         "tbg_fromrgb_fwd": lambda: h.tbg_fromrgb_fwd(P, P, P, P, 1, 4, 12, 1.0, 1.0, None),
         "tbg_fromrgb_bwd": lambda: h.tbg_fromrgb_bwd(P, P, P, P, P, P, None, 1, 4, 64, 1.0, 1.0, None),
+        "tbg_conv3x3_halo": lambda: h.tbg_conv3x3_halo(None, P, P, 1, 16, 16, 64, 64, None, None, None, None, 0, 1.0, 0, None),
         "tbg_crop_resize_fwd": lambda: h.tbg_crop_resize_fwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_crop_resize_bwd": lambda: h.tbg_crop_resize_bwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),

@@ -229,7 +229,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 using namespace tbg;
 
-// Experimental entry (not part of include/tbg.h until validated): same tensors as tbg_conv2d_igemm for a 3x3 SAME conv.
+// Experimental entry: same tensors as tbg_conv2d_igemm for a 3x3 SAME conv (include/tbg.h).
 extern "C" int tbg_conv3x3_halo(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
                                 const float* col_scale, const float* bias, const float* noise, const float* noise_strength,
                                 int act, float act_gain, int use_base_offset, void* stream_v) {

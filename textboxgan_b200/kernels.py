@@ -90,6 +90,12 @@ def conv2d_igemm(
     _require(w, torch.bfloat16, "w")
     if isinstance(up, bool):
         up = (int(up), int(up))
+    if (HALO > 0 and residual is None and relu_mask is None and not out_fp32 and tap_mask is None and act in (0, 1)
+            and x.shape[1] == Ho and x.shape[2] == Wo and halo_applicable(x, w, taps, pad, stride, up)):
+        flops = 2.0 * x.shape[0] * Ho * Wo * w.shape[0] * 9 * x.shape[3]
+        with _Timed("conv_igemm", flops):      # same profiling bucket: it computes the same convolution
+            return conv3x3_halo(x, w, col_scale=col_scale, bias=bias, noise=noise, noise_strength=noise_strength, act=act,
+                                act_gain=act_gain, out=out)
     B, H, W_, Cin = x.shape
     n_total = w.shape[0]
     cout = n_total // ((1 + up[0]) * (1 + up[1]))
@@ -395,6 +401,34 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     st = _lib.load().tbg_style_dense_bwd(arr, len(ws), _ptr(style), _ptr(gstyle), B, n, S, float(coef), _stream())
     _lib.check(st, "tbg_style_dense_bwd")
     return gstyle, gws, gbs
+
+
+# Experimental halo-reuse 3x3 convolution (csrc/conv_halo.cu).  HALO = 0: off; 1 / 2: on with descriptor base_offset 0 /
+# (start >> 7) & 7 — whichever variant scripts/exp_halo_umma.cu validates on the device.
+HALO = int(__import__("os").environ.get("TBG_CONV_HALO", "0"))
+
+
+def halo_applicable(x: torch.Tensor, w: torch.Tensor, taps, pad, stride, up) -> bool:
+    B, H, W_, Cin = x.shape
+    return (HALO > 0 and tuple(taps) == (3, 3) and tuple(pad) == (1, 1) and tuple(stride) == (1, 1) and not any(up)
+            and H % 16 == 0 and W_ % 16 == 0 and Cin % 64 == 0 and w.shape[0] in (32, 64, 128))
+
+
+def conv3x3_halo(x: torch.Tensor, w: torch.Tensor, *, col_scale=None, bias=None, noise=None, noise_strength=None,
+                 act: int = 0, act_gain: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 SAME conv, bf16 NHWC in/out — see include/tbg.h (tbg_conv3x3_halo)."""
+    _require(x, torch.bfloat16, "x")
+    _require(w, torch.bfloat16, "w")
+    B, H, W_, Cin = x.shape
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W_, cout), device=x.device, dtype=torch.bfloat16)
+    col_scale, bias = _aligned(col_scale), _aligned(bias)
+    st = _lib.load().tbg_conv3x3_halo(_ptr(x), _ptr(w), _ptr(out), B, H, W_, Cin, cout, _ptr(col_scale), _ptr(bias),
+                                      _ptr(noise), _ptr(noise_strength), int(act), float(act_gain), int(HALO == 2),
+                                      _stream())
+    _lib.check(st, "tbg_conv3x3_halo")
+    return out
 
 
 def crop_resize_fwd(img: torch.Tensor, labels: torch.Tensor, blank: int, char_width, out_hw) -> torch.Tensor:

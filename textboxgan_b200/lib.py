@@ -83,6 +83,7 @@ _SIGNATURES = [
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
     ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
+    ("tbg_conv3x3_halo", c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 4 + [c_int, c_float, c_int, c_void_p]),
     ("tbg_crop_resize_fwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_crop_resize_bwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
