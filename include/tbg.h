@@ -179,6 +179,23 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
+/* EXPERIMENTAL: 3x3 stride-1 SAME convolution (same tensors and epilogue subset as tbg_conv2d_igemm) whose nine taps
+ * read shifted windows of ONE activation halo box per 64-channel block (csrc/conv_halo.cu).  H, W multiples of 16,
+ * Cin % 64 == 0, Cout in {32, 64, 128}.  use_base_offset selects the descriptor addressing variant that
+ * scripts/exp_halo_umma.cu finds to work. */
+int tbg_conv3x3_halo(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                     const float* col_scale, const float* bias, const float* noise, const float* noise_strength, int act,
+                     float act_gain, int use_base_offset, void* stream);
+
+/* AsterInferer.convert_inputs (aster_inferer.py:153-190): NCHW fp32 image [B,3,H,W] -> per-sample crop at
+ * floor(first_blank * cw_num / cw_den) columns (clamped to [1, W]; W when `labels` [B, mcn] has no `blank`) ->
+ * bilinear resize (half-pixel centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].  bwd scatters into gimg (zeroed by
+ * the caller) with fp32 atomics. */
+int tbg_crop_resize_fwd(const float* img, const int* labels, float* out, int B, int H, int W, int oh, int ow, int mcn,
+                        int blank, int cw_num, int cw_den, void* stream);
+int tbg_crop_resize_bwd(const float* g, const int* labels, float* gimg, int B, int H, int W, int oh, int ow, int mcn,
+                        int blank, int cw_num, int cw_den, void* stream);
+
 /* FromRGB (from_rgb.py:26-29): 1x1 conv 3 -> C of the NCHW fp32 image + bias + leaky-ReLU(0.2)*gain -> NHWC bf16:
  *   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] w[j,c] + bias[c]) * gain,   w fp32 [3, C]
  * bwd: gpre = g_out*gain*slope(out); gimg[b,j,p] = coef sum_c gpre w[j,c] (NCHW fp32, may be NULL);
@@ -202,19 +219,20 @@ int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, flo
  * upfirdn_2d_v2.py:65-113).  coef is the equalised-LR runtime coefficient (commons.py:4-12).
  * tbg_wfold is the transpose: gw += coef * fold(gfwd) (+ 2 coef^2 w gq), gfwd fp32 in fwd layout;
  * gq[i,o] = dL/dq is either given or formed in the kernel from (s [nb,I], t [nb,O]) of tbg_demod_bwd as
- * sum_b s[b,i]^2 t[b,o] (pass gq NULL).
+ * sum_b s[b,i]^2 t[b,o] (pass gq NULL).  accumulate != 0: gw += ...; 0: gw = ... (no zero-initialisation needed).
  * ------------------------------------------------------------------------------------------ */
 int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad, int Opad,
               void* fwd, void* adj, float* q, void* stream);
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
-              int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, void* stream);
+              int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, int accumulate,
+              void* stream);
 
 /* Fold of a gradient held in the adjoint-matrix layout [Ipad, (tap, Opad)] of an identity-table geometry
  * (role-swapped weight gradient of a transposed convolution): gw[tap,i,o] += coef*gadj[i, tap'*Opad+o], tap' =
  * tap, or the spatially mirrored tap when flip != 0 (upsample_conv_2d flips w, upfirdn_2d_v2.py:80)
  * (+ 2 coef^2 w dL/dq with dL/dq formed from (s, t) as in tbg_wfold). */
 int tbg_wfold_adj(const float* gadj, const float* w, float coef, int KH, int KW, int I, int O, int Opad, float* gw,
-                  const float* s, const float* t, int nb, int flip, void* stream);
+                  const float* s, const float* t, int nb, int flip, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Demodulation coefficient of ModulatedConv2D and its gradient (modulated_conv2d.py:75-82), fp32:

@@ -168,6 +168,45 @@ def emu_modulate_bwd(gxs, x, s, gs_init=None):
     return gx, gs
 
 
+def _emu_interp(out_size, in_size, in_max):
+    o = torch.arange(out_size, dtype=torch.float64)[None, :]
+    src = (o + 0.5) * (in_size.double()[:, None] / out_size) - 0.5
+    f0 = torch.floor(src)
+    lerp = src - f0
+    hi = in_size[:, None] - 1
+    i0 = torch.minimum(torch.clamp(f0.long(), min=0), hi)
+    i1 = torch.minimum(torch.clamp(torch.ceil(src).long(), min=0), hi)
+    m = torch.zeros(in_size.shape[0], out_size, in_max, dtype=torch.float64)
+    m.scatter_add_(2, i0[..., None], (1.0 - lerp)[..., None])
+    m.scatter_add_(2, i1[..., None], lerp[..., None])
+    return m
+
+
+def _emu_crop_mats(labels, blank, char_width, H, W, out_hw):
+    from fractions import Fraction
+
+    cw = Fraction(char_width)
+    is_blank = labels == blank
+    first = torch.where(is_blank.any(1), is_blank.int().argmax(1), torch.full_like(labels[:, 0], 10 ** 6)).long()
+    wc = torch.clamp((first * cw.numerator) // cw.denominator, min=1, max=W)
+    my = _emu_interp(out_hw[0], torch.full((1,), H, dtype=torch.long), H)[0]
+    mx = _emu_interp(out_hw[1], wc, W)
+    return my, mx
+
+
+def emu_crop_resize_fwd(img, labels, blank, char_width, out_hw):
+    """Documented semantics of tbg_crop_resize_fwd (= the reference's crop + tf.image.resize, aster_inferer.py:153-190)."""
+    my, mx = _emu_crop_mats(labels, blank, char_width, img.shape[2], img.shape[3], out_hw)
+    x = torch.einsum("yh,bchw->bcyw", my, img.double())
+    return torch.einsum("bcyw,bxw->byxc", x, mx).to(img.dtype)
+
+
+def emu_crop_resize_bwd(g, labels, blank, char_width, img_hw):
+    my, mx = _emu_crop_mats(labels, blank, char_width, img_hw[0], img_hw[1], (g.shape[1], g.shape[2]))
+    t = torch.einsum("byxc,bxw->bcyw", g.double(), mx)
+    return torch.einsum("yh,bcyw->bchw", my, t).to(g.dtype)
+
+
 def emu_fromrgb_fwd(img, w, bias, coef, gain):
     y = torch.einsum("bjhw,jc->bhwc", img.double(), w.double()) * coef + bias.double()
     y = torch.where(y > 0, y, 0.2 * y) * gain
@@ -402,6 +441,8 @@ def emulated_kernels(act_dtype=torch.float32):
     K.modulate, K.modulate_bwd, K.bias_act_bwd = emu_modulate, emu_modulate_bwd, emu_bias_act_bwd
     K.torgb_fwd, K.torgb_bwd = emu_torgb_fwd, emu_torgb_bwd
     saved_w = (K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd)
+    saved_c = (K.crop_resize_fwd, K.crop_resize_bwd)
+    K.crop_resize_fwd, K.crop_resize_bwd = emu_crop_resize_fwd, emu_crop_resize_bwd
     saved_f = (K.fir4, K.wfold_adj, K.fromrgb_fwd, K.fromrgb_bwd)
     K.fir4, K.wfold_adj = emu_fir4, emu_wfold_adj
     K.fromrgb_fwd, K.fromrgb_bwd = emu_fromrgb_fwd, emu_fromrgb_bwd
@@ -428,3 +469,4 @@ def emulated_kernels(act_dtype=torch.float32):
         K.wprep, K.wfold, K.attn_decoder_fwd, K.attn_decoder_bwd = saved_w
         K.demod_coef, K.demod_bwd, K.style_dense_fwd, K.style_dense_bwd = saved_d
         K.fir4, K.wfold_adj, K.fromrgb_fwd, K.fromrgb_bwd = saved_f
+        K.crop_resize_fwd, K.crop_resize_bwd = saved_c

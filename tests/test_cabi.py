@@ -66,10 +66,13 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_torgb_bwd": lambda: h.tbg_torgb_bwd(P, P, P, P, P, 1, 4, 12, None),
         "tbg_fromrgb_fwd": lambda: h.tbg_fromrgb_fwd(P, P, P, P, 1, 4, 12, 1.0, 1.0, None),
         "tbg_fromrgb_bwd": lambda: h.tbg_fromrgb_bwd(P, P, P, P, P, P, None, 1, 4, 64, 1.0, 1.0, None),
+        "tbg_conv3x3_halo": lambda: h.tbg_conv3x3_halo(None, P, P, 1, 16, 16, 64, 64, None, None, None, None, 0, 1.0, 0, None),
+        "tbg_crop_resize_fwd": lambda: h.tbg_crop_resize_fwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
+        "tbg_crop_resize_bwd": lambda: h.tbg_crop_resize_bwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),
         "tbg_wprep": lambda: h.tbg_wprep(P, None, 1.0, 3, 3, 64, 64, 64, 64, P, P, None, None),
-        "tbg_wfold": lambda: h.tbg_wfold(P, None, None, None, 1.0, 3, 3, 64, 64, 64, 64, P, None, None, 0, None),
-        "tbg_wfold_adj": lambda: h.tbg_wfold_adj(None, None, 1.0, 3, 3, 64, 64, 64, P, None, None, 0, 0, None),
+        "tbg_wfold": lambda: h.tbg_wfold(P, None, None, None, 1.0, 3, 3, 64, 64, 64, 64, P, None, None, 0, 0, None),
+        "tbg_wfold_adj": lambda: h.tbg_wfold_adj(None, None, 1.0, 3, 3, 64, 64, 64, P, None, None, 0, 0, 0, None),
         "tbg_demod_coef": lambda: h.tbg_demod_coef(None, P, P, 1, 64, 64, 1e-8, None),
         "tbg_demod_bwd": lambda: h.tbg_demod_bwd(None, P, P, P, P, P, P, P, P, P, P, P, 1, 64, 64, None),
         "tbg_style_dense_fwd": lambda: h.tbg_style_dense_fwd(None, 0, P, 1, 3, 64, 1.0, None),

@@ -441,6 +441,43 @@ def test_unfolded_downsample_conv_layer_matches_folded(B, H, W, I, O, k, rh):
         assert _rel_l2(a, b) < 5e-2          # see test_unfolded_upsample_conv_kernels_vs_emulated_semantics
 
 
+def test_conv_two_m_tile_work_items_are_bit_identical_to_single_tiles():
+    """conv_igemm work items of two M tiles sharing each weight box (msub = 2) run the same MMA sequence per tile as
+    single-tile items, so the outputs must be bit-identical; each mode in its own process (the choice is read once
+    from TBG_IGEMM_MSUB).  Odd tile counts exercise the out-of-range second sub-tile."""
+    import os
+    import subprocess
+    import sys
+
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from textboxgan_b200 import conv as C, kernels as K
+outs = []
+for (B, H, W, I, O, k) in [(3, 16, 64, 64, 64, 3), (5, 8, 40, 128, 128, 1), (2, 32, 128, 64, 32, 3)]:
+    g = C.plain_geom(H, W, I, O, k)
+    gen = torch.Generator().manual_seed(B + H)
+    x = torch.randn(B, H, W, I, generator=gen).cuda().bfloat16()
+    w = (torch.randn(g.n_total, g.k_total, generator=gen) / g.k_total ** 0.5).cuda().bfloat16()
+    bias = torch.randn(O, generator=gen).cuda()
+    outs.append(K.conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.4, **g.kernel_kwargs()).float().cpu())
+    outs.append(K.conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs()).cpu())
+torch.save(outs, sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for m in ("1", "2"):
+            path = os.path.join(td, f"o{m}.pt")
+            env = dict(os.environ, TBG_IGEMM_MSUB=m)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[m] = torch.load(path)
+    for a, b in zip(res["1"], res["2"]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("Ho,Wo,B", [(5, 17, 3), (17, 65, 2), (3, 9, 32), (33, 129, 1), (7, 5, 9)])
 def test_conv_forward_non_power_of_two_grids(Ho, Wo, B):
     """Tile boxes are chosen per grid (any bw x bh x bn <= 128): plain 3x3 SAME conv on odd-sized grids."""
@@ -477,6 +514,35 @@ def test_fromrgb_kernels_vs_emulated_semantics(B, H, W, C):
     assert rel_err(gi, ri) < 1e-4 and rel_err(gw, rw) < 1e-4 and rel_err(gb, rb) < 1e-4
     gi2, gw2, gb2 = K.fromrgb_bwd(img.to(DEV), w.to(DEV), g.to(DEV).bfloat16(), out, coef, gain, want_w=False)
     assert gw2 is None and gb2 is None and rel_err(gi2, ri) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,mcn,cw", [(5, 16, 64, 8, 8), (4, 32, 128, 8, 16), (3, 64, 256, 12, "64/3")])
+def test_crop_resize_kernels_vs_emulated_semantics(B, H, W, mcn, cw):
+    """tbg_crop_resize_fwd / bwd (convert_inputs) against the crop + tf.image.resize semantics (fp32, 1e-5), incl.
+    words without a blank label, a blank in the first position (clamped to one column) and a fractional char_width."""
+    from fractions import Fraction
+
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    cw = Fraction(cw)
+    gen = torch.Generator().manual_seed(B + H)
+    img = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
+    labels = torch.randint(2, 96, (B, mcn), generator=gen, dtype=torch.int32)
+    labels[0, 3:] = 1
+    labels[1, :] = 1
+    if B > 3:
+        labels[3, mcn - 1:] = 1
+    out = K.crop_resize_fwd(img.to(DEV), labels.to(DEV), 1, cw, (64, 256))
+    ref = emu.emu_crop_resize_fwd(img, labels, 1, cw, (64, 256))
+    assert rel_err(out, ref) < 1e-5
+    g = torch.randn(B, 64, 256, 3, generator=gen)
+    gi = K.crop_resize_bwd(g.to(DEV), labels.to(DEV), 1, cw, (H, W))
+    ri = emu.emu_crop_resize_bwd(g, labels, 1, cw, (H, W))
+    assert rel_err(gi, ri) < 1e-4
+    # adjoint identity on the device results
+    lhs, rhs = (out.cpu().double() * g.double()).sum(), (img.double() * gi.cpu().double()).sum()
+    assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
 
 
 def test_relu_mask_epilogue_and_fused_encoder_backward():

@@ -84,6 +84,8 @@ def init_aster_params(seed: int = 1234) -> Dict[str, torch.Tensor]:
 
 # the ResNet encoder as one autograd node with ReLU masks / residual sums fused into the input-gradient convs
 FUSED_ENCODER = True
+# convert_inputs as the tbg_crop_resize kernels (first order) instead of two batched interpolation GEMMs
+FUSED_CONVERT_INPUTS = True
 
 
 def _pad_c(n: int) -> int:
@@ -161,6 +163,24 @@ class _EncoderFn(torch.autograd.Function):
             gsc = dgrad(sc, gz) if sc is not None else gz
             gz = dgrad(c1, gy, residual=gsc, res_scale=1.0, res_first=True, relu_mask=h)
         return dgrad(enc.stem, gz), None
+
+
+class _CropResize(torch.autograd.Function):
+    """convert_inputs as one gather launch forward and one scatter launch backward (first order only)."""
+
+    @staticmethod
+    def forward(ctx, images, labels, blank_label, char_width, out_hw):
+        images = images.float().contiguous()
+        labels = labels.to(torch.int32).contiguous()
+        ctx.save_for_backward(labels)
+        ctx.args = (int(blank_label), char_width, (images.shape[2], images.shape[3]))
+        return K.crop_resize_fwd(images, labels, int(blank_label), char_width, out_hw)
+
+    @staticmethod
+    def backward(ctx, g):
+        (labels,) = ctx.saved_tensors
+        blank, cw, hw = ctx.args
+        return K.crop_resize_bwd(g.float().contiguous(), labels, blank, cw, hw), None, None, None, None
 
 
 class _ConvLayer:
@@ -344,6 +364,8 @@ class AsterInferer:
         B, Cc, H, W = fake_images.shape
         oh, ow = cfg.aster_image_dims
         dev = fake_images.device
+        if L.use_fused() and FUSED_CONVERT_INPUTS and Cc == 3:
+            return _CropResize.apply(fake_images, labels, blank_label, cfg.char_width, (oh, ow))
         is_blank = labels == blank_label
         has_blank = is_blank.any(dim=1)
         first = torch.where(has_blank, is_blank.int().argmax(dim=1), torch.full_like(labels[:, 0], 10 ** 6))

@@ -8,6 +8,8 @@
 // algebra), upsample_conv_2d (upfirdn_2d_v2.py:65-103, as a 4-phase GEMM), Conv2D.call
 // (conv.py:51-73), Noise.call (noise.py:12-22), BiasAct.call (bias_act.py:25-34), the residual
 // merge of DiscriminatorBlock.call (discriminator.py:82).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -30,6 +32,8 @@ struct ConvKernelParams {
   int cout;
   int out_H, out_W;
   int stages;
+  int staged;  // 1: epilogue stores go through the shared-memory transpose (TBG_IGEMM_STAGED=0 restores direct stores)
+  int msub;  // M sub-tiles per work item (1 or 2): two 128-pixel tiles share every weight box (halves weight traffic)
   // epilogue
   const float* col_scale;
   const float* bias;
@@ -47,6 +51,11 @@ struct ConvKernelParams {
 
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
+// Epilogue staging: each epilogue warp transposes its 32 accumulator rows through shared memory, 256 bytes
+// of a row at a time (+16 bytes of padding: conflict-free 16-byte accesses), so that global stores go out as
+// whole 128-byte lines of two pixels per instruction instead of one 16-byte piece of 32 different pixels.
+static constexpr uint32_t kStgRow = 256 + 16;
+static constexpr uint32_t kStgBytes = 4 * 32 * kStgRow;
 
 __global__ void __launch_bounds__(256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -57,14 +66,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int stages = p.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const int msub = p.msub;
+  const uint32_t a_stage = static_cast<uint32_t>(msub) * kABytes;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + stages * kABytes;
+  uint8_t* smB = smem + stages * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + stages * b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars + 2 * kMaxStages + 6);   // epilogue staging, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,8 +106,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int tiles_ms = (tiles_m + msub - 1) / msub;       // work items along M (each = msub adjacent M tiles)
+  const int total_tiles = tiles_ms * p.tiles_n;
   const int bw = p.bw, bh = p.bh, bn = p.bn;
+  // M tile -> (tw, th, tb); a tile index past the end maps to tb = tiles_b, i.e. fully out of bounds (TMA zero fill,
+  // epilogue rows invalid)
+  auto decode_m = [&](int m_tile, int& tw, int& th, int& tb) {
+    if (m_tile >= tiles_m) {
+      tw = 0; th = 0; tb = p.tiles_b;
+    } else {
+      tw = m_tile % p.tiles_w;
+      th = (m_tile / p.tiles_w) % p.tiles_h;
+      tb = m_tile / (p.tiles_w * p.tiles_h);
+    }
+  };
   const uint32_t a_bytes = static_cast<uint32_t>(bw * bh * bn) * 128u;  // bytes one activation box delivers
   // output phase of an N tile (up-sampling geometries put the phases side by side along N)
   auto tile_mask = [&](int n_tile) -> uint64_t {
@@ -110,13 +134,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.tiles_n;
-        const int m_tile = tile / p.tiles_n;
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tb = m_tile / (p.tiles_w * p.tiles_h);
-        const int w_base = tw * bw * p.stride_w + p.in_off_w;
-        const int h_base = th * bh * p.stride_h + p.in_off_h;
-        const int n_base = tb * bn;
+        const int ms_tile = tile / p.tiles_n;
+        int w_base[2], h_base[2], n_base[2];
+        for (int sub = 0; sub < msub; ++sub) {
+          int tw, th, tb;
+          decode_m(ms_tile * msub + sub, tw, th, tb);
+          w_base[sub] = tw * bw * p.stride_w + p.in_off_w;
+          h_base[sub] = th * bh * p.stride_h + p.in_off_h;
+          n_base[sub] = tb * bn;
+        }
         const uint64_t mask = tile_mask(n_tile);
         for (int ty = 0; ty < p.taps_h; ++ty) {
           for (int tx = 0; tx < p.taps_w; ++tx) {
@@ -124,8 +150,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int kcol = (ty * p.taps_w + tx) * p.cin;
             for (int ch = 0; ch < p.cin_chunks; ++ch, kcol += 64) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full[stage], a_bytes + b_bytes);
-              tma_load_4d(smA + stage * kABytes, &tmA, &full[stage], ch * 64, w_base + tx, h_base + ty, n_base);
+              mbar_arrive_expect_tx(&full[stage], msub * a_bytes + b_bytes);
+              for (int sub = 0; sub < msub; ++sub)
+                tma_load_4d(smA + stage * a_stage + sub * kABytes, &tmA, &full[stage], ch * 64, w_base[sub] + tx,
+                            h_base[sub] + ty, n_base[sub]);
               tma_load_2d(smB + stage * b_bytes, &tmB, &full[stage], kcol, n_tile * p.block_n);
               if (++stage == stages) {
                 stage = 0;
@@ -148,19 +176,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc_stage], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * msub * p.block_n);
         const uint64_t mask = tile_mask(tile % p.tiles_n);
         const int k_blocks = __popcll(mask) * p.cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
+          const uint32_t a_addr = smem_u32(smA + stage * a_stage);
           const uint32_t b_addr = smem_u32(smB + stage * b_bytes);
+          for (int sub = 0; sub < msub; ++sub) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc_sw128(a_addr + sub * kABytes + k * 32, 0, 1024);
+              const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              umma_bf16(d_tmem + static_cast<uint32_t>(sub * p.block_n), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (kb == k_blocks - 1) umma_commit(&tfull[acc_stage]);
@@ -179,23 +209,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
     const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    uint8_t* const stg = stg_base + e * (32 * kStgRow);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
-      const int m_tile = tile / p.tiles_n;
-      const int tw = m_tile % p.tiles_w;
-      const int th = (m_tile / p.tiles_w) % p.tiles_h;
-      const int tb = m_tile / (p.tiles_w * p.tiles_h);
-      const int b = tb * bn + n_in;
-      const int ho = th * bh + h_in;
-      const int wo = tw * bw + w_in;
-      const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
+      const int ms_tile = tile / p.tiles_n;
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
+      for (int sub = 0; sub < msub; ++sub) {
+      int tw, th, tb;
+      decode_m(ms_tile * msub + sub, tw, th, tb);
+      const int b = tb * bn + n_in;
+      const int ho = th * bh + h_in;
+      const int wo = tw * bw + w_in;
+      const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
-                             static_cast<uint32_t>(acc_stage * p.block_n);
+                             static_cast<uint32_t>((acc_stage * msub + sub) * p.block_n);
+      const int esize = p.out_fp32 ? 4 : 2;
+      const int chunk_cols = min(p.block_n, 256 / esize);   // columns staged per flush (<= 256 bytes per row)
+      const int j_per_chunk = chunk_cols / 32;
+      uint8_t* const my_row = stg + lane * kStgRow;
+      long long row_off = -1;                                 // element offset of this row's chunk in out, or -1
       for (int j = 0; j < p.block_n / 32; ++j) {
         const int col0 = n_tile * p.block_n + j * 32;
         uint32_t v[32];
@@ -213,9 +249,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
           const size_t off = pix * p.cout + c0;
+          if (j % j_per_chunk == 0) row_off = static_cast<long long>(off);
           const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
           const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
           const float* bs = p.bias ? p.bias + c0 : nullptr;
+          uint8_t* const srow = my_row + (j % j_per_chunk) * 32 * esize;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
@@ -276,21 +314,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              float4* o = p.staged ? reinterpret_cast<float4*>(srow + g * 32)
+                                   : reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + g * 8);
+              o[0] = make_float4(f[0], f[1], f[2], f[3]);
+              o[1] = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
               uint4 pk;
               pk.x = pack_bf16x2(f[0], f[1]);
               pk.y = pack_bf16x2(f[2], f[3]);
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(o) = pk;
+              uint4* o = p.staged ? reinterpret_cast<uint4*>(srow + g * 16)
+                                  : reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8);
+              *o = pk;
             }
           }
+        } else if (j % j_per_chunk == 0) {
+          row_off = -1;
+        }
+        if (p.staged && (j + 1) % j_per_chunk == 0) {
+          // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
+          __syncwarp();
+          const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4, 8 or 16
+          const int rows_per_pass = 32 / lanes_per_row;
+          const int sub = lane % lanes_per_row;
+          for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+            const int rr = r0 + lane / lanes_per_row;
+            const long long o_el = __shfl_sync(0xffffffffu, row_off, rr);
+            if (o_el >= 0) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRow + sub * 16);
+              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * esize + sub * 16;
+              *reinterpret_cast<uint4*>(dst) = val;
+            }
+          }
+          __syncwarp();
         }
       }
+      }  // sub
       tc_fence_before();
       mbar_arrive(&tempty[acc_stage]);
     }
@@ -428,13 +488,33 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.out_fp32 = a->out_fp32;
   p.out = a->out;
 
+  // two M tiles per work item when both accumulator sets still double-buffer in TMEM (2 x 2 x block_n <= 512) and
+  // there is enough work to keep every SM busy with the larger items
+  // (>= 4 items per SM: with fewer, the static round-robin's last partial wave costs more than the traffic saves)
+  {
+    static int staged = -1;
+    if (staged < 0) {
+      const char* e = getenv("TBG_IGEMM_STAGED");
+      staged = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    p.staged = staged;
+  }
+  p.msub = (block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
+  {
+    static int msub_override = -1;      // TBG_IGEMM_MSUB=1|2 forces the choice (tests, tuning); 2 needs block_n <= 128
+    if (msub_override < 0) {
+      const char* e = getenv("TBG_IGEMM_MSUB");
+      msub_override = e ? atoi(e) : 0;
+    }
+    if (msub_override == 1 || (msub_override == 2 && block_n <= 128)) p.msub = msub_override;
+  }
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.msub) * kABytes + b_bytes;
+  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + kStgBytes;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;
@@ -461,7 +541,7 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
     TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int total_tiles = ((tiles_m + p.msub - 1) / p.msub) * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
   count_launch();

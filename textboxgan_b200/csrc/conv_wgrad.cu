@@ -36,9 +36,15 @@ struct WgradParams {
   int stages;
   int ktot;                       // taps * cin
   float* gw;
+  int staged;   // 1: vector atomics go out line-coalesced through shared memory (TBG_WGRAD_STAGED=0: one row per thread)
 };
 
 static constexpr int kWgMaxStages = 8;
+// Epilogue staging (as in conv_igemm.cu): each epilogue warp transposes 32 accumulator rows x 64 fp32 columns
+// through shared memory so that one red.global.add.v4 instruction covers two rows x 256 contiguous bytes
+// instead of 16 bytes of 32 different rows.
+static constexpr uint32_t kWgStgRow = 256 + 16;
+static constexpr uint32_t kWgStgBytes = 4 * 32 * kWgStgRow;
 
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constant__ CUtensorMap tmX,
@@ -61,6 +67,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
   uint64_t* tfull = bars + 2 * kWgMaxStages;
   uint64_t* tempty = bars + 2 * kWgMaxStages + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 2);
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars + 2 * kWgMaxStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,10 +209,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
       const int s_begin = group * p.G;
       int s_end = s_begin + p.G;
       if (s_end > p.subtiles) s_end = p.subtiles;
-      const int n = m_tile * 128 + e * 32 + lane;
-      const bool valid = (n < p.n_total) && (kt1 > kt0);
       mbar_wait(tfull, it & 1);
       tc_fence_after();
+      uint8_t* const stg = stg_base + e * (32 * kWgStgRow);
       for (int s = s_begin; s < s_end; ++s) {
         const int tap = s / p.c_tiles;
         const int ct = s - tap * p.c_tiles;
@@ -215,16 +221,45 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32(t_row + j * 32, v);
           tmem_ld_wait();
-          if (valid) {
-            float* dst = p.gw + static_cast<size_t>(n) * p.ktot + tap * p.cin + ct * p.block_c + j * 32;
+          if (!p.staged) {      // round-1 path: every thread reduces 16-byte pieces of its own output-channel row
+            const int nn = m_tile * 128 + e * 32 + lane;
+            if (nn < p.n_total && kt1 > kt0) {
+              float* dst = p.gw + static_cast<size_t>(nn) * p.ktot + tap * p.cin + ct * p.block_c + j * 32;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              // one 16-byte vector reduction per 4 accumulators (sm_90+ red.global.add.v4.f32)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
-                           "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
-                           "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
-                           : "memory");
+              for (int g = 0; g < 8; ++g)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                             "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                             "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                             : "memory");
             }
+            continue;
+          }
+          float4* srow = reinterpret_cast<float4*>(stg + lane * kWgStgRow + (j & 1) * 128);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            srow[g] = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                  __uint_as_float(v[g * 4 + 3]));
+          const bool last = (j + 1 == p.block_c / 32);
+          if ((j & 1) || last) {
+            // flush 64 (or the last 32) columns of the warp's 32 rows
+            __syncwarp();
+            const int cols = (j & 1) ? 64 : 32;
+            const int lanes_per_row = cols / 4;               // 16 or 8 lanes x 16 bytes
+            const int rows_per_pass = 32 / lanes_per_row;
+            const int sub = lane % lanes_per_row;
+            const int jc0 = (j & 1) ? j - 1 : j;              // first 32-column block of this chunk
+            for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+              const int rr = r0 + lane / lanes_per_row;
+              const int nn = m_tile * 128 + e * 32 + rr;
+              if (nn < p.n_total && kt1 > kt0) {
+                const float4 val = *reinterpret_cast<const float4*>(stg + rr * kWgStgRow + sub * 16);
+                float* dst = p.gw + static_cast<size_t>(nn) * p.ktot + tap * p.cin + ct * p.block_c + jc0 * 32 + sub * 4;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
+                             "f"(val.z), "f"(val.w)
+                             : "memory");
+              }
+            }
+            __syncwarp();
           }
         }
       }
@@ -283,12 +318,20 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   p.stride_w = a->stride_w;
   p.ktot = a->taps_h * a->taps_w * a->Cin;
   p.gw = a->gw;
+  {
+    static int staged = -1;
+    if (staged < 0) {
+      const char* e = getenv("TBG_WGRAD_STAGED");
+      staged = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    p.staged = staged;
+  }
 
   // pixel block: 64 pixels unless a stage would not leave room for >= 3 stages
   int P = 64;
   {
     const uint32_t stage64 = 2u * 64 * 128 + (uint32_t)p.G * (p.block_c / 64) * 64 * 128;
-    if (stage64 * 3 > 225u * 1024u) P = 32;
+    if (stage64 * 3 > 225u * 1024u - kWgStgBytes) P = 32;
   }
   const int npix = a->Ho * a->Wo;
   while (P > 1 && (int64_t)P > (int64_t)npix * a->B) P >>= 1;  // tiny problems
@@ -335,12 +378,12 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
 
   const uint32_t chunk_bytes = (uint32_t)P * 128u;
   const uint32_t stage_bytes = 2u * chunk_bytes + (uint32_t)p.G * (p.block_c / 64) * chunk_bytes;
-  const uint32_t budget = 227u * 1024u - 1024u - 256u;
+  const uint32_t budget = 227u * 1024u - 1024u - 256u - kWgStgBytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   TBG_CHECK_ARG(stages >= 2, "tbg_conv2d_wgrad: stage too large (%u bytes)", stage_bytes);
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + kWgStgBytes;
 
   CUtensorMap tmGY, tmX;
   {

@@ -91,6 +91,7 @@ __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (r < rows) {
+#pragma unroll 2
     for (int p = p0 + r; p < p1; p += rows) {
       const long long idx = (static_cast<long long>(b) * hw + p) * c8 + cv;
       float g[8], xv[8];
@@ -146,6 +147,7 @@ __global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4
   for (int i = 0; i < 8; ++i) a1[i] = a2[i] = a3[i] = 0.f;
   const float inv_gain = 1.f / gain;
   if (r < rows) {
+#pragma unroll 2
     for (int p = p0 + r; p < p1; p += rows) {
       const long long pix = static_cast<long long>(b) * hw + p;
       const long long idx = pix * c8 + cv;
@@ -260,6 +262,7 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
       }
   }
   if (r < rows) {
+#pragma unroll 2
     for (int p = p0 + r; p < p1; p += rows) {
       const long long pix = static_cast<long long>(b) * hw + p;
       const float g0 = __ldg(gy + pix * 3 + 0), g1 = __ldg(gy + pix * 3 + 1), g2 = __ldg(gy + pix * 3 + 2);
@@ -425,6 +428,7 @@ __global__ void fromrgb_bwd_kernel(const float* __restrict__ img, const float* _
     for (int j = 0; j < 4; ++j) acc[j][i] = 0.f;
   }
   // uniform trip count for every thread of the CTA: the per-pixel shuffle reduction below needs whole warps
+#pragma unroll 2
   for (int pp = p0; pp < p1; pp += rows) {
     const int p = pp + r;
     const bool valid = (r < rows) && (p < p1);

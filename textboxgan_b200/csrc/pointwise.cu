@@ -236,3 +236,115 @@ extern "C" int tbg_upfirdn2d(const void* x, const float* k, void* y, int dtype_b
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// UNVALIDATED (branch wip/r02-unvalidated-kernels): AsterInferer.convert_inputs (aster_inferer.py:153-190) as one
+// gather kernel forward and one scatter kernel backward: NCHW fp32 image -> crop at first_blank * char_width ->
+// bilinear resize (tf.image.resize: half-pixel centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].
+//   src = (o + 0.5) * in / out - 0.5 ; i0 = clamp(floor(src)), i1 = clamp(ceil(src)), weights (1 - frac, frac)
+// The crop width of sample b is floor(first_blank(b) * cw_num / cw_den) clamped to [1, W] (W when no blank label).
+// ---------------------------------------------------------------------------------------------
+namespace tbg {
+
+__device__ __forceinline__ int crop_width_of(const int* __restrict__ labels, int b, int mcn, int blank, int cw_num,
+                                             int cw_den, int W) {
+  int first = -1;
+  for (int i = 0; i < mcn; ++i)
+    if (__ldg(labels + static_cast<size_t>(b) * mcn + i) == blank) {
+      first = i;
+      break;
+    }
+  if (first < 0) return W;
+  long long wc = (static_cast<long long>(first) * cw_num) / cw_den;
+  if (wc < 1) wc = 1;
+  if (wc > W) wc = W;
+  return static_cast<int>(wc);
+}
+
+__device__ __forceinline__ void resize_taps(int o, int in_size, int out_size, int& i0, int& i1, float& w0, float& w1) {
+  const float src = (o + 0.5f) * (static_cast<float>(in_size) / static_cast<float>(out_size)) - 0.5f;
+  const float f0 = floorf(src);
+  const float lerp = src - f0;
+  const int hi = in_size - 1;
+  i0 = min(max(static_cast<int>(f0), 0), hi);
+  i1 = min(max(static_cast<int>(ceilf(src)), 0), hi);
+  w0 = 1.f - lerp;
+  w1 = lerp;
+}
+
+__global__ void __launch_bounds__(256)
+crop_resize_fwd_kernel(const float* __restrict__ img, const int* __restrict__ labels, float* __restrict__ out, int B, int H,
+                       int W, int oh, int ow, int mcn, int blank, int cw_num, int cw_den) {
+  const long long n = static_cast<long long>(B) * oh * ow;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(e % ow), y = static_cast<int>((e / ow) % oh), b = static_cast<int>(e / (static_cast<long long>(ow) * oh));
+    const int wc = crop_width_of(labels, b, mcn, blank, cw_num, cw_den, W);
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    resize_taps(y, H, oh, y0, y1, wy0, wy1);
+    resize_taps(x, wc, ow, x0, x1, wx0, wx1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = img + (static_cast<size_t>(b) * 3 + c) * H * W;
+      const float v = wy0 * (wx0 * __ldg(pl + y0 * W + x0) + wx1 * __ldg(pl + y0 * W + x1)) +
+                      wy1 * (wx0 * __ldg(pl + y1 * W + x0) + wx1 * __ldg(pl + y1 * W + x1));
+      out[e * 3 + c] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+crop_resize_bwd_kernel(const float* __restrict__ g, const int* __restrict__ labels, float* __restrict__ gimg, int B, int H,
+                       int W, int oh, int ow, int mcn, int blank, int cw_num, int cw_den) {
+  const long long n = static_cast<long long>(B) * oh * ow;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(e % ow), y = static_cast<int>((e / ow) % oh), b = static_cast<int>(e / (static_cast<long long>(ow) * oh));
+    const int wc = crop_width_of(labels, b, mcn, blank, cw_num, cw_den, W);
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    resize_taps(y, H, oh, y0, y1, wy0, wy1);
+    resize_taps(x, wc, ow, x0, x1, wx0, wx1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gv = __ldg(g + e * 3 + c);
+      float* pl = gimg + (static_cast<size_t>(b) * 3 + c) * H * W;
+      atomicAdd(pl + y0 * W + x0, gv * wy0 * wx0);
+      atomicAdd(pl + y0 * W + x1, gv * wy0 * wx1);
+      atomicAdd(pl + y1 * W + x0, gv * wy1 * wx0);
+      atomicAdd(pl + y1 * W + x1, gv * wy1 * wx1);
+    }
+  }
+}
+
+}  // namespace tbg
+
+extern "C" int tbg_crop_resize_fwd(const float* img, const int* labels, float* out, int B, int H, int W, int oh, int ow,
+                                   int mcn, int blank, int cw_num, int cw_den, void* stream_v) {
+  TBG_CHECK_ARG(img && labels && out, "tbg_crop_resize_fwd: null pointer");
+  TBG_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && oh >= 1 && ow >= 1 && mcn >= 1 && cw_num >= 1 && cw_den >= 1,
+                "tbg_crop_resize_fwd: bad shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n = static_cast<long long>(B) * oh * ow;
+  tbg::crop_resize_fwd_kernel<<<static_cast<int>((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(
+      img, labels, out, B, H, W, oh, ow, mcn, blank, cw_num, cw_den);
+  tbg::count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_crop_resize_bwd(const float* g, const int* labels, float* gimg, int B, int H, int W, int oh, int ow,
+                                   int mcn, int blank, int cw_num, int cw_den, void* stream_v) {
+  TBG_CHECK_ARG(g && labels && gimg, "tbg_crop_resize_bwd: null pointer");
+  TBG_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && oh >= 1 && ow >= 1 && mcn >= 1 && cw_num >= 1 && cw_den >= 1,
+                "tbg_crop_resize_bwd: bad shape");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n = static_cast<long long>(B) * oh * ow;
+  tbg::crop_resize_bwd_kernel<<<static_cast<int>((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(
+      g, labels, gimg, B, H, W, oh, ow, mcn, blank, cw_num, cw_den);
+  tbg::count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}

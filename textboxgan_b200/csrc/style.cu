@@ -156,40 +156,59 @@ __device__ __forceinline__ int find_layer(const StyleParams& p, int tile) {
   return l;
 }
 
-// grid (total i-tiles, ceil(B/32)); block 256 = 32 i-lanes x 8 row groups (4 batch rows each)
+static constexpr int kStRow = 36;   // floats per staged row: 32 batch rows + padding, 16-byte aligned
+
+// grid (total i-tiles, ceil(B/32)); block 256 = 32 i-lanes x 8 K-groups: the reduction axis is split over the
+// eight warps (each thread accumulates all 32 batch rows for its share of K, weights read coalesced, the
+// staged style rows broadcast as float4), partial sums meet in shared memory.
 __global__ void __launch_bounds__(256)
 style_dense_fwd_kernel(const __grid_constant__ StyleParams p, const float* __restrict__ style) {
-  __shared__ float st[32][129];  // [b][k chunk]
+  extern __shared__ __align__(16) float sm_style[];   // st[S][kStRow] | red[8][32][33]
+  float* st = sm_style;
+  float* red = sm_style + static_cast<size_t>(p.S) * kStRow;
   const int li = find_layer(p, blockIdx.x);
   const StyleLayer& L = p.l[li];
-  const int i = (blockIdx.x - L.tile0) * 32 + (threadIdx.x & 31);
-  const int rg = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  const int i = (blockIdx.x - L.tile0) * 32 + lane;
   const int b0 = blockIdx.y * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < p.S; k0 += 128) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 128; e += 256) {
-      const int bb = e >> 7, kk = e & 127;
-      const int b = b0 + bb, k = k0 + kk;
-      st[bb][kk] = (b < p.B && k < p.S) ? __ldg(style + (static_cast<size_t>(b) * p.n_style + L.idx) * p.S + k) : 0.f;
-    }
-    __syncthreads();
-    if (i < L.I) {
-      const int kn = min(128, p.S - k0);
-#pragma unroll 8
-      for (int kk = 0; kk < kn; ++kk) {
-        const float wv = __ldg(L.w + static_cast<size_t>(k0 + kk) * L.I + i);
+  for (int e = threadIdx.x; e < 32 * p.S; e += 256) {     // lanes over k: contiguous in style
+    const int bb = e / p.S, k = e - bb * p.S;
+    const int b = b0 + bb;
+    st[k * kStRow + bb] = (b < p.B) ? __ldg(style + (static_cast<size_t>(b) * p.n_style + L.idx) * p.S + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[32];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(st[rg * 4 + r][kk], wv, acc[r]);
+  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+  const int kper = (p.S + 7) / 8;
+  const int k_begin = kg * kper, k_end = min(p.S, k_begin + kper);
+  if (i < L.I) {
+#pragma unroll 4
+    for (int k = k_begin; k < k_end; ++k) {
+      const float wv = __ldg(L.w + static_cast<size_t>(k) * L.I + i);
+      const float4* sr = reinterpret_cast<const float4*>(st + k * kStRow);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 sv = sr[q];
+        acc[4 * q + 0] = fmaf(sv.x, wv, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(sv.y, wv, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(sv.z, wv, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(sv.w, wv, acc[4 * q + 3]);
       }
     }
   }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) red[(kg * 32 + r) * 33 + lane] = acc[r];
+  __syncthreads();
   if (i < L.I) {
     const float bv = __ldg(L.b + i) + 1.f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int b = b0 + rg * 4 + r;
-      if (b < p.B) L.s[static_cast<size_t>(b) * L.I + i] = fmaf(acc[r], p.coef, bv);
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = kg * 4 + rr, b = b0 + r;
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += red[(g * 32 + r) * 33 + lane];
+      if (b < p.B) L.s[static_cast<size_t>(b) * L.I + i] = fmaf(sum, p.coef, bv);
     }
   }
 }
@@ -235,40 +254,70 @@ style_dense_wgrad_kernel(const __grid_constant__ StyleParams p, const float* __r
 }
 
 // gstyle[b,j,k] = coef * sum_{l: idx_l == j} sum_i gs_l[b,i] * w_l[k,i]   (zero when no layer uses row j)
-// grid (ceil(S/32), n_style, ceil(B/32)); block 256 = 32 k-lanes x 8 row groups (4 batch rows each)
+// grid (ceil(S/32), n_style, ceil(B/32)); block 256 = 32 k-lanes x 8 i-groups: the reduction axis (the layer's
+// input channels) is split over the eight warps, each thread accumulates all 32 batch rows; the layer's
+// gradient rows are staged transposed in shared memory and broadcast as float4.
 __global__ void __launch_bounds__(256)
-style_dense_dgrad_kernel(const __grid_constant__ StyleParams p, float* __restrict__ gstyle) {
-  __shared__ float wt[32][33];  // [k][i chunk]
-  __shared__ float gt[32][33];  // [b][i chunk]
+style_dense_dgrad_kernel(const __grid_constant__ StyleParams p, float* __restrict__ gstyle, int max_I) {
+  extern __shared__ __align__(16) float sm_style[];   // gt[max_I][kStRow] | red[8][32][33]
+  float* gt = sm_style;
+  float* red = sm_style + static_cast<size_t>(max_I) * kStRow;
   const int k0 = blockIdx.x * 32, j = blockIdx.y, b0 = blockIdx.z * 32;
-  const int kl = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int lane = threadIdx.x & 31, ig = threadIdx.x >> 5;
+  const int k = k0 + lane;
+  float acc[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
   for (int li = 0; li < p.n_layers; ++li) {
     const StyleLayer& L = p.l[li];
     if (L.idx != j) continue;
-    for (int i0 = 0; i0 < L.I; i0 += 32) {
-      __syncthreads();
-      for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-        const int r = e >> 5, c = e & 31;  // lanes over i: contiguous in w and gs
-        const int i = i0 + c;
-        wt[r][c] = (k0 + r < p.S && i < L.I) ? __ldg(L.w + static_cast<size_t>(k0 + r) * L.I + i) : 0.f;
-        gt[r][c] = (b0 + r < p.B && i < L.I) ? __ldg(L.gs + static_cast<size_t>(b0 + r) * L.I + i) : 0.f;
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int c = 0; c < 32; ++c) {
-        const float wv = wt[kl][c];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * L.I; e += 256) {   // lanes over i: contiguous in gs
+      const int bb = e / L.I, i = e - bb * L.I;
+      gt[i * kStRow + bb] = (b0 + bb < p.B) ? __ldg(L.gs + static_cast<size_t>(b0 + bb) * L.I + i) : 0.f;
+    }
+    __syncthreads();
+    const int iper = (((L.I + 7) / 8) + 3) & ~3;         // per-warp share of i, multiple of 4
+    const int i_begin = ig * iper, i_end = min(L.I, i_begin + iper);
+    if (k < p.S) {
+      const float* wr = L.w + static_cast<size_t>(k) * L.I;
+      for (int i = i_begin; i < i_end; i += 4) {
+        float wv[4];
+        if (i + 3 < i_end && ((reinterpret_cast<uintptr_t>(wr + i) & 15) == 0)) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + i));
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(gt[rg * 4 + r][c], wv, acc[r]);
+          for (int u = 0; u < 4; ++u) wv[u] = (i + u < i_end) ? __ldg(wr + i + u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i + u >= i_end) break;
+          const float4* gr = reinterpret_cast<const float4*>(gt + (i + u) * kStRow);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 gv = gr[q];
+            acc[4 * q + 0] = fmaf(gv.x, wv[u], acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(gv.y, wv[u], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(gv.z, wv[u], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(gv.w, wv[u], acc[4 * q + 3]);
+          }
+        }
       }
     }
   }
-  const int k = k0 + kl;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; ++r) red[(ig * 32 + r) * 33 + lane] = acc[r];
+  __syncthreads();
   if (k < p.S) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int b = b0 + rg * 4 + r;
-      if (b < p.B) gstyle[(static_cast<size_t>(b) * p.n_style + j) * p.S + k] = acc[r] * p.coef;
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = ig * 4 + rr, b = b0 + r;
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += red[(g * 32 + r) * 33 + lane];
+      if (b < p.B) gstyle[(static_cast<size_t>(b) * p.n_style + j) * p.S + k] = sum * p.coef;
     }
   }
 }
@@ -308,7 +357,14 @@ extern "C" int tbg_style_dense_fwd(const tbg_style_layer* layers, int n_layers, 
   TBG_CHECK_ARG(fill_style_params(p, layers, n_layers, B, n_style, S, coef) == 0, "tbg_style_dense_fwd: bad layer table");
   for (int l = 0; l < n_layers; ++l) TBG_CHECK_ARG(layers[l].s, "tbg_style_dense_fwd: null output");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  tbg::style_dense_fwd_kernel<<<dim3(p.total_tiles, (B + 31) / 32), 256, 0, stream>>>(p, style);
+  TBG_CHECK_ARG(S <= 1024, "tbg_style_dense_fwd: S=%d exceeds the shared-memory staging (1024)", S);
+  const size_t smem = (static_cast<size_t>(S) * tbg::kStRow + 8 * 32 * 33) * sizeof(float);
+  static bool attr_f = false;
+  if (!attr_f) {
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(tbg::style_dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_f = true;
+  }
+  tbg::style_dense_fwd_kernel<<<dim3(p.total_tiles, (B + 31) / 32), 256, smem, stream>>>(p, style);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
@@ -324,7 +380,16 @@ extern "C" int tbg_style_dense_bwd(const tbg_style_layer* layers, int n_layers, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   tbg::style_dense_wgrad_kernel<<<dim3(p.total_tiles, (S + 31) / 32), 256, 0, stream>>>(p, style);
   count_launch();
-  tbg::style_dense_dgrad_kernel<<<dim3((S + 31) / 32, n_style, (B + 31) / 32), 256, 0, stream>>>(p, gstyle);
+  int max_I = 1;
+  for (int l = 0; l < n_layers; ++l) max_I = layers[l].I > max_I ? layers[l].I : max_I;
+  TBG_CHECK_ARG(max_I <= 1024, "tbg_style_dense_bwd: layer width %d exceeds the shared-memory staging (1024)", max_I);
+  const size_t smem = (static_cast<size_t>(max_I) * tbg::kStRow + 8 * 32 * 33) * sizeof(float);
+  static bool attr_d = false;
+  if (!attr_d) {
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(tbg::style_dense_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_d = true;
+  }
+  tbg::style_dense_dgrad_kernel<<<dim3((S + 31) / 32, n_style, (B + 31) / 32), 256, smem, stream>>>(p, gstyle, max_I);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -142,7 +142,7 @@ wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_
 __global__ void __launch_bounds__(256)
 wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const float* __restrict__ w,
              float* __restrict__ gw, const WPrepParams p, const float* __restrict__ sv, const float* __restrict__ tv,
-             const int nb) {
+             const int nb, const int accumulate) {
   __shared__ float st[9][8][36];  // [tap][o][i]
   __shared__ __align__(16) float cff[36][12];
   const int tiles_o = p.Opad / 8;
@@ -204,7 +204,7 @@ wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const
       const size_t idx = (static_cast<size_t>(tp) * p.I + i) * p.O + o;
       float v = st[tp][ol][il];
       if (has_q) v = fmaf(gqv, __ldg(w + idx), v);
-      gw[idx] += v;
+      gw[idx] = accumulate ? gw[idx] + v : v;
     }
   }
 }
@@ -217,7 +217,7 @@ wfold_kernel(const float* __restrict__ gfwd, const float* __restrict__ gq, const
 __global__ void __launch_bounds__(256)
 wfold_adj_kernel(const float* __restrict__ gadj, const float* __restrict__ w, float* __restrict__ gw, int taps, int I,
                  int O, int Opad, float coef, const float* __restrict__ sv, const float* __restrict__ tv, int nb,
-                 int flip) {
+                 int flip, int accumulate) {
   const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= static_cast<long long>(I) * O) return;
   const int i = static_cast<int>(e / O), o = static_cast<int>(e % O);
@@ -234,7 +234,7 @@ wfold_adj_kernel(const float* __restrict__ gadj, const float* __restrict__ w, fl
     const int ta = flip ? taps - 1 - tp : tp;   // the matrix holds the spatially flipped kernel
     float v = coef * __ldg(gadj + (static_cast<size_t>(i) * taps + ta) * Opad + o);
     if (sv != nullptr) v = fmaf(gqv, __ldg(w + idx), v);
-    gw[idx] += v;
+    gw[idx] = accumulate ? gw[idx] + v : v;
   }
 }
 
@@ -243,13 +243,13 @@ wfold_adj_kernel(const float* __restrict__ gadj, const float* __restrict__ w, fl
 using namespace tbg;
 
 extern "C" int tbg_wfold_adj(const float* gadj, const float* w, float coef, int KH, int KW, int I, int O, int Opad,
-                             float* gw, const float* s, const float* t, int nb, int flip, void* stream_v) {
+                             float* gw, const float* s, const float* t, int nb, int flip, int accumulate, void* stream_v) {
   TBG_CHECK_ARG(gadj && gw, "tbg_wfold_adj: null pointer");
   TBG_CHECK_ARG(KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3 && I >= 1 && O >= 1 && Opad >= O, "tbg_wfold_adj: bad shape");
   TBG_CHECK_ARG((s == nullptr) == (t == nullptr) && (!s || (w && nb >= 1)), "tbg_wfold_adj: (s, t, nb) need the master weight");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const long long n = static_cast<long long>(I) * O;
-  wfold_adj_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(gadj, w, gw, KH * KW, I, O, Opad, coef, s, t, nb, flip);
+  wfold_adj_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(gadj, w, gw, KH * KW, I, O, Opad, coef, s, t, nb, flip, accumulate);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
@@ -303,7 +303,7 @@ extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH
 
 extern "C" int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH,
                          int KW, int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb,
-                         void* stream_v) {
+                         int accumulate, void* stream_v) {
   TBG_CHECK_ARG(gfwd && tables && gw, "tbg_wfold: null pointer");
   TBG_CHECK_ARG(!(gq || s) || w, "tbg_wfold: gq / (s, t) need the master weight");
   TBG_CHECK_ARG((s == nullptr) == (t == nullptr) && !(s && gq) && (!s || nb >= 1), "tbg_wfold: pass gq or (s, t, nb)");
@@ -314,7 +314,7 @@ extern "C" int tbg_wfold(const float* gfwd, const float* gq, const float* w, con
   TBG_CHECK_ARG(p.fy.P * p.fx.P * p.fy.T * p.fx.T <= 36, "tbg_wfold: too many (phase, tap) combinations");
   p.KH = KH; p.KW = KW; p.I = I; p.O = O; p.Ipad = Ipad; p.Opad = Opad; p.coef = coef;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  wfold_kernel<<<(Ipad / 32) * (Opad / 8), 256, 0, stream>>>(gfwd, gq, w, gw, p, s, t, nb);
+  wfold_kernel<<<(Ipad / 32) * (Opad / 8), 256, 0, stream>>>(gfwd, gq, w, gw, p, s, t, nb, accumulate);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -90,6 +90,12 @@ def conv2d_igemm(
     _require(w, torch.bfloat16, "w")
     if isinstance(up, bool):
         up = (int(up), int(up))
+    if (HALO > 0 and residual is None and relu_mask is None and not out_fp32 and tap_mask is None and act in (0, 1)
+            and x.shape[1] == Ho and x.shape[2] == Wo and halo_applicable(x, w, taps, pad, stride, up)):
+        flops = 2.0 * x.shape[0] * Ho * Wo * w.shape[0] * 9 * x.shape[3]
+        with _Timed("conv_igemm", flops):      # same profiling bucket: it computes the same convolution
+            return conv3x3_halo(x, w, col_scale=col_scale, bias=bias, noise=noise, noise_strength=noise_strength, act=act,
+                                act_gain=act_gain, out=out)
     B, H, W_, Cin = x.shape
     n_total = w.shape[0]
     cout = n_total // ((1 + up[0]) * (1 + up[1]))
@@ -321,15 +327,16 @@ def wfold(gfwd: torch.Tensor, spec, *, gq: Optional[torch.Tensor] = None, w_raw:
     """Accumulate the master-weight gradient from the fp32 gradient of the fwd GEMM matrix; the
     demodulation term comes from ``gq`` [I,O] or from (``s`` [B,I], ``t`` [B,O]) of demod_bwd."""
     _require(gfwd, torch.float32, "gfwd")
+    accumulate = out is not None
     if out is None:
-        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
+        out = torch.empty((spec.KH, spec.KW, spec.I, spec.O), device=gfwd.device, dtype=torch.float32)
     nb = 0
     if s is not None:
         _require(s, torch.float32, "s")
         _require(t, torch.float32, "t")
         nb = s.shape[0]
     st = _lib.load().tbg_wfold(_ptr(gfwd), _ptr(gq), _ptr(w_raw), spec.ctable, spec.coef, spec.KH, spec.KW, spec.I,
-                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _ptr(s), _ptr(t), nb, _stream())
+                               spec.O, spec.Ipad, spec.Opad, _ptr(out), _ptr(s), _ptr(t), nb, int(accumulate), _stream())
     _lib.check(st, "tbg_wfold")
     return out
 
@@ -396,6 +403,63 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     return gstyle, gws, gbs
 
 
+# Experimental halo-reuse 3x3 convolution (csrc/conv_halo.cu).  HALO = 0: off; 1 / 2: on with descriptor base_offset 0 /
+# (start >> 7) & 7 — whichever variant scripts/exp_halo_umma.cu validates on the device.
+HALO = int(__import__("os").environ.get("TBG_CONV_HALO", "0"))
+
+
+def halo_applicable(x: torch.Tensor, w: torch.Tensor, taps, pad, stride, up) -> bool:
+    B, H, W_, Cin = x.shape
+    return (HALO > 0 and tuple(taps) == (3, 3) and tuple(pad) == (1, 1) and tuple(stride) == (1, 1) and not any(up)
+            and H % 16 == 0 and W_ % 16 == 0 and Cin % 64 == 0 and w.shape[0] in (32, 64, 128))
+
+
+def conv3x3_halo(x: torch.Tensor, w: torch.Tensor, *, col_scale=None, bias=None, noise=None, noise_strength=None,
+                 act: int = 0, act_gain: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 SAME conv, bf16 NHWC in/out — see include/tbg.h (tbg_conv3x3_halo)."""
+    _require(x, torch.bfloat16, "x")
+    _require(w, torch.bfloat16, "w")
+    B, H, W_, Cin = x.shape
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W_, cout), device=x.device, dtype=torch.bfloat16)
+    col_scale, bias = _aligned(col_scale), _aligned(bias)
+    st = _lib.load().tbg_conv3x3_halo(_ptr(x), _ptr(w), _ptr(out), B, H, W_, Cin, cout, _ptr(col_scale), _ptr(bias),
+                                      _ptr(noise), _ptr(noise_strength), int(act), float(act_gain), int(HALO == 2),
+                                      _stream())
+    _lib.check(st, "tbg_conv3x3_halo")
+    return out
+
+
+def crop_resize_fwd(img: torch.Tensor, labels: torch.Tensor, blank: int, char_width, out_hw) -> torch.Tensor:
+    """convert_inputs forward — see include/tbg.h (tbg_crop_resize_fwd)."""
+    from fractions import Fraction
+
+    _require(img, torch.float32, "img")
+    _require(labels, torch.int32, "labels")
+    B, _, H, W_ = img.shape
+    cw = Fraction(char_width)
+    out = torch.empty((B, out_hw[0], out_hw[1], 3), device=img.device, dtype=torch.float32)
+    st = _lib.load().tbg_crop_resize_fwd(_ptr(img), _ptr(labels), _ptr(out), B, H, W_, out_hw[0], out_hw[1], labels.shape[1],
+                                         int(blank), cw.numerator, cw.denominator, _stream())
+    _lib.check(st, "tbg_crop_resize_fwd")
+    return out
+
+
+def crop_resize_bwd(g: torch.Tensor, labels: torch.Tensor, blank: int, char_width, img_hw) -> torch.Tensor:
+    from fractions import Fraction
+
+    _require(g, torch.float32, "g")
+    _require(labels, torch.int32, "labels")
+    B, oh, ow, _ = g.shape
+    cw = Fraction(char_width)
+    gimg = torch.zeros((B, 3, img_hw[0], img_hw[1]), device=g.device, dtype=torch.float32)
+    st = _lib.load().tbg_crop_resize_bwd(_ptr(g), _ptr(labels), _ptr(gimg), B, img_hw[0], img_hw[1], oh, ow, labels.shape[1],
+                                         int(blank), cw.numerator, cw.denominator, _stream())
+    _lib.check(st, "tbg_crop_resize_bwd")
+    return gimg
+
+
 def fromrgb_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coef: float, gain: float) -> torch.Tensor:
     """img fp32 NCHW [B,3,H,W], w fp32 [3,C], bias [C] -> lrelu(coef*img.w + bias)*gain, bf16 NHWC [B,H,W,C]."""
     _require(img, torch.float32, "img")
@@ -448,11 +512,12 @@ def wfold_adj(gadj: torch.Tensor, spec, *, w_raw: Optional[torch.Tensor] = None,
     """Master-weight gradient from a gradient in the adjoint-matrix layout [Ipad, taps*Opad] (identity tables,
     or the spatially flipped kernel when ``flip``)."""
     _require(gadj, torch.float32, "gadj")
+    accumulate = out is not None
     if out is None:
-        out = torch.zeros((spec.KH, spec.KW, spec.I, spec.O), device=gadj.device, dtype=torch.float32)
+        out = torch.empty((spec.KH, spec.KW, spec.I, spec.O), device=gadj.device, dtype=torch.float32)
     nb = s.shape[0] if s is not None else 0
     st = _lib.load().tbg_wfold_adj(_ptr(gadj), _ptr(w_raw), spec.coef, spec.KH, spec.KW, spec.I, spec.O, spec.Opad,
-                                   _ptr(out), _ptr(s), _ptr(t), nb, int(flip), _stream())
+                                   _ptr(out), _ptr(s), _ptr(t), nb, int(flip), int(accumulate), _stream())
     _lib.check(st, "tbg_wfold_adj")
     return out
 

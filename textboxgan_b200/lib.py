@@ -82,11 +82,14 @@ _SIGNATURES = [
     ("tbg_torgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
-    ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
+    ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
+    ("tbg_conv3x3_halo", c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 4 + [c_int, c_float, c_int, c_void_p]),
+    ("tbg_crop_resize_fwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
+    ("tbg_crop_resize_bwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fromrgb_bwd", c_int, [c_void_p] * 7 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fir4", c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] + [c_void_p] * 4 + [c_int, c_float, c_void_p]),
-    ("tbg_wfold_adj", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 5 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
+    ("tbg_wfold_adj", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 5 + [c_void_p] * 3 + [c_int, c_int, c_int, c_void_p]),
     ("tbg_style_dense_fwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     ("tbg_style_dense_bwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                     c_void_p]),
