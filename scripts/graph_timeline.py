@@ -16,7 +16,7 @@ nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = baseline_config(idx)
 dev = "cuda:0"
 G = Generator(cfg, device=dev, seed=0); D = Discriminator(cfg, device=dev, seed=1)
-aster = AsterInferer(cfg, device=dev)
+aster = AsterInferer(cfg, device=dev, synthetic_weights=True)
 go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
 mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
 ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), 8, 16, torch.zeros((), device=dev), cfg)

@@ -44,7 +44,7 @@ real, words, labels = OT.synthetic_batch(cfg, 4, g)
 with emulated_kernels():
     G = Generator(cfg, device="cpu", seed=0); G.load_state_dict(GP)
     D = Discriminator(cfg, device="cpu", seed=0); D.load_state_dict(DP)
-    aster = AsterInferer(cfg, device="cpu")
+    aster = AsterInferer(cfg, device="cpu", synthetic_weights=True)
     go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
     mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
     ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), 8, 16, torch.zeros(()), cfg)

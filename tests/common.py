@@ -13,6 +13,7 @@ def small_cfg(batch=4):
     cfg = baseline_config(0)
     cfg.batch_size_per_gpu = batch
     cfg.batch_size = batch
+    cfg.aster_synthetic_weights = True      # explicit opt-in: the reference's pretrained ASTER is not in its repository
     return cfg
 
 

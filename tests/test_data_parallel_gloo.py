@@ -89,3 +89,40 @@ def test_two_ranks_sum_gradients_of_their_shards():
     # identical replicas stay identical: rank 0's weights after the update are what a single process
     # applying the summed gradient would hold (checked through the Adam step bound)
     assert (r2["G"] - s0["G"]).abs().max().item() < 5e-3
+
+
+def _init_run(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from common import small_cfg
+    from emu import emulated_kernels
+    from textboxgan_b200.model_loader import ModelLoader
+    from textboxgan_b200.strategy import Strategy
+
+    torch.set_num_threads(2)
+    torch.manual_seed(1000 + rank)             # every rank has its own RNG stream, like independent processes do
+    cfg = small_cfg(2)
+    cfg.attach_strategy(Strategy(backend="gloo"))
+    with emulated_kernels():
+        D, G, g_clone = ModelLoader(cfg, device="cpu").initiate_models()
+    ret[rank] = {"G": G.flat.detach().clone(), "D": D.flat.detach().clone(), "C": g_clone.flat.detach().clone(),
+                 "w_avg": G.params["latent_encoder/w_avg"].detach().clone(),
+                 "next_rand": float(torch.rand(()))}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicas_start_from_identical_weights():
+    """ModelLoader.initiate_models on 2 ranks with different RNG states: rank 0's initialisation is broadcast, so the
+    generator, its clone and the discriminator are bit-identical across replicas (MirroredStrategy semantics); the
+    user's global RNG stream is consumed, not reseeded."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_init_run, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for k in ("G", "D", "C", "w_avg"):
+        assert torch.equal(ret[0][k], ret[1][k]), k
+    assert torch.equal(ret[0]["G"], ret[0]["C"])
+    assert float(ret[0]["G"].abs().sum()) > 0
+    assert ret[0]["next_rand"] != ret[1]["next_rand"]          # per-rank streams stay distinct (manual_seed respected)

@@ -567,7 +567,7 @@ def test_relu_mask_epilogue_and_fused_encoder_backward():
     assert rel_err(y, ref) < 2e-5 and float((y.cpu()[m <= 0]).abs().max()) == 0.0
 
     cfg = baseline_config(0)
-    aster = AI.AsterInferer(cfg, device=DEV)
+    aster = AI.AsterInferer(cfg, device=DEV, synthetic_weights=True)
     img = torch.randn(4, 64, 256, 3, generator=gen).to(DEV)
     gm = torch.randn(4, 64, 512, generator=gen).to(DEV)       # T = 256 / 4 feature columns
     outs = []
@@ -627,7 +627,7 @@ def _product(cfg, GP, DP, with_ocr=True):
     G.load_state_dict(GP)
     D = Discriminator(cfg, device=DEV, seed=0)
     D.load_state_dict(DP)
-    aster = AsterInferer(cfg, device=DEV) if with_ocr else None
+    aster = AsterInferer(cfg, device=DEV, synthetic_weights=True) if with_ocr else None
     go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
     mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
     ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), 8, 16, torch.zeros((), device=DEV), cfg)

@@ -68,7 +68,7 @@ def test_flat_adam_matches_per_variable_update_and_ignores_padding():
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the oracle port of the reference's CPU path, no GPU involved)."""
     env = dict(os.environ, OMP_NUM_THREADS="4")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "8",
                           "--warmup", "1", "--config", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
@@ -76,6 +76,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["unit"] == "images/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # the line states what actually ran: 8 iterations of the schedule (the 8th is a path-length step) at batch 4
+    assert line["steps"] == 8 and line["warmup"] == 1 and line["config"]["sample_batch"] == 4
+    assert "7 plain, 1 path-length, 0 path-length+R1" in line["cpu_baseline"]["sample"]
+    assert abs(line["ms_per_step"] * 1e-3 * line["value"] - 4.0) < 1e-6
 
 
 def test_bench_synthetic_inputs_follow_the_loader_contract():
@@ -102,13 +106,3 @@ def test_bench_synthetic_inputs_follow_the_loader_contract():
     src = open(os.path.join(ROOT, "bench.py")).read()
     body = src[src.index("def run_ours"):src.index("def main")]
     assert "from oracle" not in body and "import oracle" not in body        # only the cpu_baseline leg calls it
-
-
-def test_bench_mix16_child_failures_never_reach_the_headline_line():
-    """The 16-step schedule measurement runs in a child process; without a GPU the child fails and the parent-side
-    helper must return an error record instead of raising."""
-    sys.path.insert(0, ROOT)
-    import bench
-
-    rec = bench.mix16_subprocess(1, timeout_s=300)
-    assert set(rec) == {"error"} and "CUDA" in rec["error"]

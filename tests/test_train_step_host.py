@@ -23,7 +23,7 @@ def _build(cfg, GP, DP, with_ocr):
     G.load_state_dict(GP)
     D = Discriminator(cfg, device="cpu", seed=0)
     D.load_state_dict(DP)
-    aster = AsterInferer(cfg, device="cpu") if with_ocr else None
+    aster = AsterInferer(cfg, device="cpu", synthetic_weights=True) if with_ocr else None
     g_opt = update_optimizer_params(cfg.g_opt)
     d_opt = update_optimizer_params(cfg.d_opt)
     mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
@@ -133,7 +133,7 @@ def test_four_consecutive_steps_follow_the_oracle_loss_curve():
         clone.load_state_dict(GP)
         D = Discriminator(cfg, device="cpu", seed=0)
         D.load_state_dict(DP)
-        aster = AsterInferer(cfg, device="cpu")
+        aster = AsterInferer(cfg, device="cpu", synthetic_weights=True)
         g_opt, d_opt = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
         mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
         pl_mean = torch.zeros(())

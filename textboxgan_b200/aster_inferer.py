@@ -258,11 +258,44 @@ def _pack_decoder(P, device) -> dict:
                 wdT=wd.t().to(act).contiguous(), bd=m("dec/dense/b").contiguous())
 
 
+def load_aster_weights(path: str) -> Dict[str, torch.Tensor]:
+    """Weight dictionary for :class:`AsterInferer` from ``path``: a ``.npz`` / ``.pt`` file holding the names of
+    :func:`init_aster_params`, or a TensorFlow checkpoint prefix / SavedModel ``variables`` directory, read with the
+    TensorBundle reader of :mod:`textboxgan_b200.tf_checkpoint` and mapped by name (README.md:60-66)."""
+    import os
+
+    import numpy as np
+
+    if path.endswith(".npz"):
+        with np.load(path) as z:
+            P = {k: torch.from_numpy(np.asarray(z[k])).float() for k in z.files}
+    elif path.endswith(".pt") or path.endswith(".pth"):
+        P = {k: v.float() for k, v in torch.load(path, map_location="cpu").items()}
+    else:
+        from .tf_checkpoint import aster_weights_from_checkpoint
+
+        P = aster_weights_from_checkpoint(path)
+    want = init_aster_params(0)
+    missing = sorted(set(want) - set(P))
+    if missing:
+        raise KeyError(f"load_aster_weights({path!r}): missing {len(missing)} tensors, e.g. {missing[:4]}")
+    for k, v in want.items():
+        if tuple(P[k].shape) != tuple(v.shape):
+            raise ValueError(f"load_aster_weights: {k} has shape {tuple(P[k].shape)}, expected {tuple(v.shape)}")
+    return {k: P[k] for k in want}
+
+
 class AsterInferer:
     """Reads the word written in a text box (aster_inferer.py:7-37)."""
 
     def __init__(self, cfg: Config, device="cuda", combine_forward_and_backward: bool = False,
-                 weights: Optional[Dict[str, torch.Tensor]] = None, seed: int = 1234):
+                 weights: Optional[Dict[str, torch.Tensor]] = None, seed: int = 1234,
+                 synthetic_weights: Optional[bool] = None):
+        """``weights``: a weight dictionary (names of :func:`init_aster_params`); else ``cfg.aster_weights`` (path of a
+        converted weight file, see :func:`load_aster_weights`); else seeded synthetic weights — silently only when
+        ``synthetic_weights=True`` (tests, bench), with a warning when it is None, an error when it is False (the
+        product entry points Trainer / Infer pass ``cfg.aster_synthetic_weights``, default False: the reference
+        always loads the pretrained recogniser, aster_inferer.py:24-26)."""
         if combine_forward_and_backward:
             raise NotImplementedError("combine_forward_and_backward=True needs the backward predictor of the "
                                       "external ASTER SavedModel (aster_inferer.py:39-114); the reference default "
@@ -270,7 +303,20 @@ class AsterInferer:
         self.cfg = cfg
         self.device = torch.device(device)
         self.combine_forward_and_backward = combine_forward_and_backward
-        P = weights if weights is not None else init_aster_params(seed)
+        if weights is None and getattr(cfg, "aster_weights", None):
+            weights = load_aster_weights(cfg.aster_weights)
+        if weights is None:
+            if synthetic_weights is False:
+                raise RuntimeError("AsterInferer: no recogniser weights (cfg.aster_weights is None).  The OCR loss would be "
+                                   "computed against a random recogniser; set cfg.aster_weights to a converted weight file "
+                                   "or opt in explicitly with cfg.aster_synthetic_weights = True")
+            if synthetic_weights is None:
+                import warnings
+
+                warnings.warn("AsterInferer: cfg.aster_weights is None — using seeded SYNTHETIC recogniser weights; OCR "
+                              "losses are not comparable with the reference's pretrained ASTER", RuntimeWarning, stacklevel=2)
+            weights = init_aster_params(seed)
+        P = weights
         self.P = {k: v.to(self.device).float() for k, v in P.items()}
         self._build_encoder(P)
         self.lstm = {n: _LstmLayer(P, n, self.device) for n in ("rnn/l0", "rnn/l1")}

@@ -38,6 +38,9 @@ class Config:
     ocr_loss_type: str = "softmax_crossentropy"
     aster_image_dims: Tuple[int, int] = (64, 256)
     aster_weights: Optional[str] = None
+    # explicit opt-in to seeded synthetic recogniser weights when aster_weights is None (tests, benchmarks); the
+    # product entry points refuse to train against a random recogniser otherwise
+    aster_synthetic_weights: bool = False
     # Summaries / checkpoints (config/config.py:97-103)
     summary_steps_frequency: dict = field(default_factory=lambda: {"print_steps": [50, 500], "log_losses": [False, True]})
     image_summary_step_frequency: int = 500

@@ -16,7 +16,7 @@ import torch
 from . import conv as C
 from . import layers as L
 from .config import Config
-from .model_base import Model
+from .model_base import Model, fresh_seed
 
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
 
@@ -31,7 +31,7 @@ class Discriminator(Model):
         self._build(seed)
 
     def _build(self, seed: Optional[int]) -> None:
-        g = torch.Generator().manual_seed(seed if seed is not None else torch.seed() % (2 ** 31))
+        g = torch.Generator().manual_seed(seed if seed is not None else fresh_seed())
 
         def randn(*shape):
             return torch.randn(*shape, generator=g)

@@ -18,7 +18,7 @@ import torch
 from . import kernels as K
 from . import layers as L
 from .config import Config
-from .model_base import Model, Submodel
+from .model_base import Model, Submodel, fresh_seed
 
 MAIN_VOCAB_SIZE = 70  # len(cfg.char_tokenizer.main.word_index) (word_encoder.py:17): <OOV> + 69 chars
 
@@ -40,7 +40,7 @@ class Generator(Model):
     # ------------------------------------------------------------------------------------------
     def _build(self, seed: Optional[int]) -> None:
         cfg = self.cfg
-        g = torch.Generator().manual_seed(seed if seed is not None else torch.seed() % (2 ** 31))
+        g = torch.Generator().manual_seed(seed if seed is not None else fresh_seed())
         S = cfg.style_dim
 
         def randn(*shape, std=1.0):

@@ -30,7 +30,7 @@ class Infer:
         self.device = device
         self.generator = generator if generator is not None else ModelLoader(self.cfg, device=device).load_generator(
             is_g_clone=True, ckpt_dir=ckpt_dir)                                          # infer.py:30-32
-        self.aster_ocr = AsterInferer(self.cfg, device=device)
+        self.aster_ocr = AsterInferer(self.cfg, device=device, synthetic_weights=bool(self.cfg.aster_synthetic_weights))
         self.test_step = ValidationStep(self.generator, self.aster_ocr, self.cfg)
         self.strategy = self.cfg.strategy
         self._print = printer

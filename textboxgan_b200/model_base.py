@@ -9,6 +9,12 @@ from typing import Dict, Iterable, List, Sequence
 import torch
 
 
+def fresh_seed() -> int:
+    """Initialisation seed for a model built without an explicit one: drawn from torch's global CPU generator, so a
+    user's ``torch.manual_seed`` governs it and is not discarded (``torch.seed()`` would reseed the global RNG)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (), dtype=torch.int64))
+
+
 class Model:
     ALIGN = 64   # floats; start alignment of every variable inside the flat buffer
 
@@ -94,6 +100,19 @@ class Model:
             off += (n + A - 1) // A * A
         self.flat = flat
         return self
+
+    def broadcast_from(self, src: int = 0) -> None:
+        """Make every replica start from rank ``src``'s variables (trainable flat buffer + non-trainable state).  The
+        reference's MirroredStrategy mirrors identical variables on all replicas (config/config.py:140); with one
+        process per GPU each rank would otherwise initialise from its own RNG."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        with torch.no_grad():
+            dist.broadcast(self.flat, src)
+            for k in sorted(self._non_trainable):
+                dist.broadcast(self.params[k], src)
 
     def flat_range(self, names: Sequence[str]):
         """(start, end) of the flat buffer covered by ``names``; they must be contiguous."""

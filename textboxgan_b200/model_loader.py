@@ -94,6 +94,10 @@ class ModelLoader:
         discriminator = self._load_discriminator()
         generator = self.load_generator(is_g_clone=False, ckpt_dir=None)
         g_clone = self.load_generator(is_g_clone=True, ckpt_dir=None)
+        # one process per GPU: every replica starts from rank 0's initialisation (MirroredStrategy mirrors the
+        # variables, config/config.py:140); gradients are SUM-all-reduced afterwards, so the replicas stay identical
+        discriminator.broadcast_from(0)
+        generator.broadcast_from(0)
         g_clone.set_weights(generator.get_weights())          # set initial g_clone weights same as generator
         return discriminator, generator, g_clone
 

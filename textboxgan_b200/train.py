@@ -65,7 +65,7 @@ class Trainer:
         mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
         self.d_optimizer, self.g_optimizer, self.ocr_optimizer = mk(self.d_opt), mk(self.g_opt), mk(self.g_opt)
         self.ocr_loss_weight = cfg.ocr_loss_weight
-        self.aster_ocr = AsterInferer(cfg, device=device)
+        self.aster_ocr = AsterInferer(cfg, device=device, synthetic_weights=bool(cfg.aster_synthetic_weights))
         self.training_step = TrainingStep(self.generator, self.discriminator, self.aster_ocr, self.g_optimizer,
                                           self.ocr_optimizer, self.d_optimizer, self.g_opt["reg_interval"],
                                           self.d_opt["reg_interval"], self.pl_mean, cfg)           # train.py:80-90
