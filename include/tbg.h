@@ -179,13 +179,16 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
-/* EXPERIMENTAL: 3x3 stride-1 SAME convolution (same tensors and epilogue subset as tbg_conv2d_igemm) whose nine taps
- * read shifted windows of ONE activation halo box per 64-channel block (csrc/conv_halo.cu).  H, W multiples of 16,
- * Cin % 64 == 0, Cout in {32, 64, 128}.  use_base_offset selects the descriptor addressing variant that
- * scripts/exp_halo_umma.cu finds to work. */
-int tbg_conv3x3_halo(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
-                     const float* col_scale, const float* bias, const float* noise, const float* noise_strength, int act,
-                     float act_gain, int use_base_offset, void* stream);
+/* Tuning switches of the library (explicit calls; the library never reads environment variables).  Keys:
+ *   "conv_halo" (default 1)   tbg_conv2d_igemm runs 3x3 stride-1 pad-1 convolutions whose grid is a multiple of 16 x 16
+ *                             pixels (Cin % 64 == 0, cout % 32 == 0, no residual / relu_mask / fp32 output) on the
+ *                             halo-reuse kernel of csrc/conv_halo.cu: same arguments, same results;
+ *   "igemm_staged" (1)        conv_igemm epilogue stores transposed through shared memory;
+ *   "igemm_msub" (1)          2: two M tiles per work item share each weight box (N <= 128);
+ *   "wgrad_staged" (1), "wgrad_items_per_sm" (0 = heuristic), "lstm_cluster" (1).
+ * tbg_get_tuning returns the current value or -1 for an unknown key. */
+int tbg_set_tuning(const char* key, int value);
+int tbg_get_tuning(const char* key);
 
 /* AsterInferer.convert_inputs (aster_inferer.py:153-190): NCHW fp32 image [B,3,H,W] -> per-sample crop at
  * floor(first_blank * cw_num / cw_den) columns (clamped to [1, W]; W when `labels` [B, mcn] has no `blank`) ->
@@ -296,6 +299,62 @@ int tbg_attn_decoder_fwd(const float* mem, const float* keys, const tbg_dec_weig
 int tbg_attn_decoder_bwd(const float* mem, const float* keys, const tbg_dec_weights* w, const float* g_logits,
                          const float* sv_a, const float* sv_ctx, const float* sv_gates, const float* sv_c,
                          const float* sv_h, float* g_mem, float* g_keys, int B, int T, int steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small fp32 dense layers (exact fp32 FMA; the reference computes them in fp32).
+ *
+ * Replaces the cuBLAS GEMMs TensorFlow ran for Dense.call (dense.py:23-29), the mapping network
+ * (mapping_block.py:15-45), the word encoder's Keras Dense (word_encoder.py:21,52) and the discriminator head
+ * (discriminator.py:132-142, 213).  Row-major fp32, x [M,K], w [K,N]:
+ *   fwd: y = act((x @ w) * coef + bias * bias_coef) * gain          act: 0 linear, 1 leaky-relu(0.2), 2 relu
+ *   bwd: gpre = gy * gain * act'(y) (workspace [M,N], written);  gx = coef * gpre @ w^T (or NULL);
+ *        gw (+)= coef * x^T @ gpre (or NULL; accumulate_gw adds into gw);  gb = bias_coef * sum_m gpre (or NULL)
+ * tbg_pixel_norm_*: y = x * rsqrt(mean_k x^2 + 1e-8) per row (mapping_block.py:15-18) and its gradient.
+ * ------------------------------------------------------------------------------------------ */
+int tbg_dense_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int N, float coef,
+                  float bias_coef, int act, float gain, void* stream);
+int tbg_dense_bwd(const float* x, const float* w, const float* y, const float* gy, float* gpre, float* gx, float* gw,
+                  float* gb, int M, int K, int N, float coef, float bias_coef, int act, float gain, int accumulate_gw,
+                  void* stream);
+int tbg_pixel_norm_fwd(const float* x, float* y, int M, int K, void* stream);
+int tbg_pixel_norm_bwd(const float* x, const float* gy, float* gx, int M, int K, void* stream);
+
+/* WordEncoder.call (word_encoder.py:39-63) in one launch: embedding lookup in concat(w0 [1,E] frozen, table [V-1,E])
+ * (words int32 [B,mcn] in [0, V)), dropout (mask fp32 [B,mcn,E] of 0/1 or NULL, kept values scaled by 1/keep), Keras
+ * Dense(E -> D) + ReLU, then reshape [B, out_w, out_c, out_h] / transpose to the base feature map, written NHWC bf16
+ * [B, out_h, out_w, out_c] (mcn*D == out_h*out_w*out_c).  emb [B*mcn,E] and act [B*mcn,D] (fp32) are saved for bwd.
+ * bwd: g_out NHWC bf16 -> gpre workspace [B*mcn,D]; g_table [V-1,E] accumulated with atomics (caller zeroes it; the
+ * frozen row w0 gets none); g_fc_w [E,D] and g_fc_b [D] written. */
+int tbg_word_encoder_fwd(const int* words, const float* w0, const float* table, const float* mask, float keep,
+                         const float* fc_w, const float* fc_b, float* emb, float* act, void* out, int B, int mcn, int E,
+                         int D, int out_h, int out_w, int out_c, void* stream);
+int tbg_word_encoder_bwd(const int* words, const float* mask, float keep, const float* fc_w, const float* emb,
+                         const float* act, const void* g_out, float* gpre, float* g_table, float* g_fc_w, float* g_fc_b,
+                         int B, int mcn, int E, int D, int out_h, int out_w, int out_c, void* stream);
+
+/* MinibatchStd.call (mini_batch_std.py:10-35) on NHWC bf16 x [n_calls*B, HW, C]: per call of B samples, groups of
+ * G = min(group_size, B) samples {m, m + B/G, ...}; statistic = mean over all HW*C features of sqrt(var_group + 1e-8).
+ * fwd writes xcat [n_calls*B, HW, Cpad] = [x | statistic | zeros] (the extra channel padded up to the GEMM K block) and
+ * stat [n_calls*B]; bwd: gx = gxcat[..., :C] + d statistic / d x * sum_{group, pixels} gxcat[..., C]. */
+int tbg_minibatch_std_fwd(const void* x, void* xcat, float* stat, int B, int n_calls, int group_size, int HW, int C,
+                          int Cpad, void* stream);
+int tbg_minibatch_std_bwd(const void* x, const void* gxcat, void* gx, int B, int n_calls, int group_size, int HW, int C,
+                          int Cpad, void* stream);
+
+/* R1 penalty reduction (training_step.py:363-372): out[b] = sum_{c,h,w} g[b]^2 on the fp32 image gradient
+ * [B, per_sample]; bwd: gg = 2 * g * gout[b]. */
+int tbg_r1_sqnorm(const float* g, float* out, int B, long long per_sample, void* stream);
+int tbg_r1_sqnorm_bwd(const float* g, const float* gout, float* gg, int B, long long per_sample, void* stream);
+
+/* ToRGB.call (to_rgb.py:28-33) fused with the skip sum of SynthesisBlock.call (synthesis_block.py:152) and, for the last
+ * block, mask_text_box (utils/utils.py:11-45) + the NHWC -> NCHW layout change:
+ *   out[b,p,:] = x[b,p,:] @ ws[b] + bias + upsample_2d(y_prev)[b,p,:]         (y_prev fp32 NHWC [B,H/2,W/2,3] or NULL)
+ *   masked (words int32 [B,mcn] or NULL): column w of sample b is zero unless words[b, floor(w*mcn/W)] != 0
+ *   out fp32 NHWC [B,H,W,3], or NCHW [B,3,H,W] when nchw != 0.  C in {64,128,192,256,512}.
+ * tbg_image_grad_nhwc is the adjoint of the mask + layout change: g fp32 NCHW -> masked NHWC. */
+int tbg_torgb_skip_fwd(const void* x, const float* ws, const float* bias, const float* y_prev, const int* words,
+                       float* out, int B, int H, int W, int C, int mcn, int nchw, void* stream);
+int tbg_image_grad_nhwc(const float* g, const int* words, float* out, int B, int H, int W, int mcn, void* stream);
 
 #ifdef __cplusplus
 }

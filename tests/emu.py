@@ -429,6 +429,141 @@ def emu_attn_decoder_bwd(mem, keys, w, g_logits, sv):
     return g_mem.float(), g_keys.float()
 
 
+def _emu_act(pre, act):
+    if act == 1:
+        return torch.where(pre > 0, pre, 0.2 * pre)
+    if act == 2:
+        return torch.relu(pre)
+    return pre
+
+
+def emu_dense_fwd(x, w, bias, *, coef=1.0, bias_coef=1.0, act=0, gain=1.0):
+    """Documented semantics of tbg_dense_fwd (include/tbg.h)."""
+    pre = (x.double() @ w.double()) * coef
+    if bias is not None:
+        pre = pre + bias.double() * bias_coef
+    return (_emu_act(pre, act) * gain).to(x.dtype)
+
+
+def emu_dense_bwd(x, w, y, gy, *, coef=1.0, bias_coef=1.0, act=0, gain=1.0, want_gx=True, want_gw=True, want_gb=True):
+    g = gy.double() * gain
+    if act == 1:
+        g = g * torch.where(y.double() > 0, 1.0, 0.2)
+    elif act == 2:
+        g = g * (y.double() > 0)
+    gx = (coef * g @ w.double().t()).to(x.dtype) if want_gx else None
+    gw = (coef * x.double().t() @ g).to(x.dtype) if want_gw else None
+    gb = (bias_coef * g.sum(0)).to(x.dtype) if want_gb else None
+    return gx, gw, gb
+
+
+def emu_pixel_norm_fwd(x):
+    xd = x.double()
+    return (xd * torch.rsqrt((xd * xd).mean(1, keepdim=True) + 1e-8)).to(x.dtype)
+
+
+def emu_pixel_norm_bwd(x, gy):
+    with torch.enable_grad():                       # called from autograd.Function.backward (grad mode off)
+        xd = x.detach().double().requires_grad_(True)
+        y = xd * torch.rsqrt((xd * xd).mean(1, keepdim=True) + 1e-8)
+        (g,) = torch.autograd.grad(y, xd, gy.double())
+    return g.to(x.dtype)
+
+
+def _emu_word_layout(act, B, mcn, out_hwc):
+    oh, ow, oc = out_hwc
+    # reference: reshape [B, out_w, out_c, out_h] then transpose (0,2,3,1) -> NCHW; NHWC = permute(0, 3, 1, 2)
+    return act.reshape(B, ow, oc, oh).permute(0, 3, 1, 2)
+
+
+def emu_word_encoder_fwd(words, w0, table, mask, keep, fc_w, fc_b, out_hwc, act_dtype=None):
+    """Documented semantics of tbg_word_encoder_fwd (= word_encoder.py:39-63)."""
+    from textboxgan_b200 import layers as L
+
+    B, mcn = words.shape
+    full = torch.cat([w0.double(), table.double()], 0)
+    emb = full[words.long()].reshape(B * mcn, -1)
+    if mask is not None:
+        emb = emb * mask.double().reshape(B * mcn, -1) / keep
+    act = torch.relu(emb @ fc_w.double() + fc_b.double())
+    out = _emu_word_layout(act, B, mcn, out_hwc).contiguous().to(L.ACT_DTYPE)
+    return out, emb.float(), act.float()
+
+
+def emu_word_encoder_bwd(words, mask, keep, fc_w, emb, act, g_out, table_rows, out_hwc):
+    B, mcn = words.shape
+    oh, ow, oc = out_hwc
+    g = g_out.double().permute(0, 2, 3, 1).reshape(B * mcn, -1)        # inverse of the forward layout change
+    gpre = g * (act.double() > 0)
+    g_emb = gpre @ fc_w.double().t()
+    if mask is not None:
+        g_emb = g_emb * mask.double().reshape(B * mcn, -1) / keep
+    g_table = torch.zeros(table_rows + 1, fc_w.shape[0], dtype=torch.float64)
+    g_table.index_add_(0, words.long().reshape(-1), g_emb)
+    return g_table[1:].float(), (emb.double().t() @ gpre).float(), gpre.sum(0).float()
+
+
+def _emu_mbstd(xd, n_calls, group_size):
+    Bt = xd.shape[0]
+    B = Bt // n_calls
+    G = min(group_size, B)
+    y = xd.reshape(n_calls, G, B // G, -1)
+    y = y - y.mean(dim=1, keepdim=True)
+    sd = torch.sqrt((y * y).mean(dim=1) + 1e-8).mean(dim=2)               # [n_calls, B/G]
+    return sd[:, None, :].expand(n_calls, G, B // G).reshape(Bt)
+
+
+def emu_minibatch_std_fwd(x, n_calls, cpad, group_size=4):
+    """Documented semantics of tbg_minibatch_std_fwd (= mini_batch_std.py:10-35 per call)."""
+    Bt, H, W_, C = x.shape
+    stat = _emu_mbstd(x.double(), n_calls, group_size)
+    xcat = torch.zeros(Bt, H, W_, cpad, dtype=torch.float64)
+    xcat[..., :C] = x.double()
+    xcat[..., C] = stat[:, None, None]
+    return xcat.to(x.dtype), stat.float()
+
+
+def emu_minibatch_std_bwd(x, gxcat, n_calls, group_size=4):
+    C = x.shape[3]
+    with torch.enable_grad():
+        xd = x.detach().double().requires_grad_(True)
+        stat = _emu_mbstd(xd, n_calls, group_size)
+        gstat = gxcat.double()[..., C].sum(dim=(1, 2))
+        (g,) = torch.autograd.grad(stat, xd, gstat)
+    return (g + gxcat.double()[..., :C]).to(x.dtype)
+
+
+def emu_torgb_skip_fwd(x, ws, bias, y_prev, words, nchw):
+    """Documented semantics of tbg_torgb_skip_fwd: ToRGB + upsample_2d(y_prev) (literal upfirdn_2d_ref) + mask + layout."""
+    from oracle.stylegan import upfirdn_2d_ref
+    import numpy as np
+
+    y = emu_torgb_fwd(x, ws, bias).double()
+    B, H, W_, _ = y.shape
+    if y_prev is not None:
+        t = np.array([1.0, 3.0, 3.0, 1.0])
+        k = np.outer(t, t)
+        k = k / k.sum() * 4.0
+        y = y + upfirdn_2d_ref(y_prev.double(), k, 2, 2, 1, 1, 2, 1, 2, 1)
+    if words is not None:
+        mcn = words.shape[1]
+        idx = (torch.arange(W_) * mcn) // W_
+        keep = (words.long()[:, idx] != 0).double()                         # [B, W]
+        y = y * keep[:, None, :, None]
+    y = y.float()
+    return y.permute(0, 3, 1, 2).contiguous() if nchw else y
+
+
+def emu_image_grad_nhwc(g, words):
+    B, _, H, W_ = g.shape
+    out = g.permute(0, 2, 3, 1).double()
+    if words is not None:
+        mcn = words.shape[1]
+        idx = (torch.arange(W_) * mcn) // W_
+        out = out * (words.long()[:, idx] != 0).double()[:, None, :, None]
+    return out.float().contiguous()
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -460,9 +595,16 @@ def emulated_kernels(act_dtype=torch.float32):
     K.lstm_seq_bwd = emu_lstm_seq_bwd
     C._as_bf16 = lambda t: t.contiguous()
     L.ACT_DTYPE = act_dtype
+    new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
+                 "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc")
+    saved_n = {n: getattr(K, n) for n in new_names}
+    for n in new_names:
+        setattr(K, n, globals()["emu_" + n])
     try:
         yield
     finally:
+        for n, f in saved_n.items():
+            setattr(K, n, f)
         (K.conv2d_igemm, K.conv2d_wgrad, C._as_bf16, L.ACT_DTYPE, K.upfirdn2d, K.adam_step, K.ema_step,
          K.lstm_seq_fwd, K.lstm_seq_bwd, K.modulate, K.modulate_bwd, K.bias_act_bwd, K.torgb_fwd,
          K.torgb_bwd) = saved

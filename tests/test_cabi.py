@@ -66,7 +66,19 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_torgb_bwd": lambda: h.tbg_torgb_bwd(P, P, P, P, P, 1, 4, 12, None),
         "tbg_fromrgb_fwd": lambda: h.tbg_fromrgb_fwd(P, P, P, P, 1, 4, 12, 1.0, 1.0, None),
         "tbg_fromrgb_bwd": lambda: h.tbg_fromrgb_bwd(P, P, P, P, P, P, None, 1, 4, 64, 1.0, 1.0, None),
-        "tbg_conv3x3_halo": lambda: h.tbg_conv3x3_halo(None, P, P, 1, 16, 16, 64, 64, None, None, None, None, 0, 1.0, 0, None),
+        "tbg_set_tuning": lambda: h.tbg_set_tuning(b"no_such_key", 1),
+        "tbg_dense_fwd": lambda: h.tbg_dense_fwd(None, P, None, P, 4, 8, 8, 1.0, 1.0, 0, 1.0, None),
+        "tbg_dense_bwd": lambda: h.tbg_dense_bwd(P, None, P, P, P, P, P, P, 4, 8, 8, 1.0, 1.0, 0, 1.0, 0, None),
+        "tbg_pixel_norm_fwd": lambda: h.tbg_pixel_norm_fwd(None, P, 4, 8, None),
+        "tbg_pixel_norm_bwd": lambda: h.tbg_pixel_norm_bwd(None, P, P, 4, 8, None),
+        "tbg_word_encoder_fwd": lambda: h.tbg_word_encoder_fwd(P, P, P, None, 0.7, P, P, P, P, P, 2, 8, 32, 256, 2, 8, 100, None),
+        "tbg_word_encoder_bwd": lambda: h.tbg_word_encoder_bwd(P, None, 0.0, P, P, P, P, P, P, P, P, 2, 8, 32, 256, 2, 8, 128, None),
+        "tbg_minibatch_std_fwd": lambda: h.tbg_minibatch_std_fwd(P, P, P, 6, 1, 4, 16, 512, 576, None),
+        "tbg_minibatch_std_bwd": lambda: h.tbg_minibatch_std_bwd(P, P, P, 4, 1, 4, 16, 512, 512, None),
+        "tbg_r1_sqnorm": lambda: h.tbg_r1_sqnorm(None, P, 4, 100, None),
+        "tbg_r1_sqnorm_bwd": lambda: h.tbg_r1_sqnorm_bwd(P, None, P, 4, 100, None),
+        "tbg_torgb_skip_fwd": lambda: h.tbg_torgb_skip_fwd(P, P, None, None, None, P, 1, 4, 4, 96, 0, 0, None),
+        "tbg_image_grad_nhwc": lambda: h.tbg_image_grad_nhwc(None, None, P, 1, 4, 4, 0, None),
         "tbg_crop_resize_fwd": lambda: h.tbg_crop_resize_fwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_crop_resize_bwd": lambda: h.tbg_crop_resize_bwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),
@@ -81,12 +93,31 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_attn_decoder_bwd": lambda: h.tbg_attn_decoder_bwd(None, P, None, P, P, P, P, P, P, P, P, 1, 8, 4, None),
     }
     covered = set(calls) | {"tbg_conv2d_igemm", "tbg_upfirdn2d", "tbg_last_error", "tbg_version", "tbg_launch_count",
-                            "tbg_reset_launch_count"}
+                            "tbg_reset_launch_count", "tbg_get_tuning"}
     assert covered == set(lib.exported_symbols()), set(lib.exported_symbols()) ^ covered
     for name, call in calls.items():
         st = call()
         assert st == -1, (name, st)
         assert len(h.tbg_last_error()) > 0, name
+
+
+def test_tuning_switches_round_trip_and_no_environment_reads():
+    """tbg_set_tuning / tbg_get_tuning are the only way to steer kernel selection: the library sources read no
+    environment variables."""
+    from textboxgan_b200 import lib
+
+    assert lib.get_tuning("no_such_key") == -1
+    for key in ("conv_halo", "igemm_staged", "wgrad_staged", "lstm_cluster"):
+        old = lib.get_tuning(key)
+        assert old in (0, 1)
+        lib.set_tuning(key, 1 - old)
+        assert lib.get_tuning(key) == 1 - old
+        lib.set_tuning(key, old)
+    lib.set_tuning("igemm_msub", 2)
+    assert lib.get_tuning("igemm_msub") == 2
+    lib.set_tuning("igemm_msub", 1)
+    for f in (ROOT / "textboxgan_b200" / "csrc").glob("*.cu*"):
+        assert "getenv" not in f.read_text(), f
 
 
 def test_product_does_not_import_the_oracle():

@@ -442,40 +442,106 @@ def test_unfolded_downsample_conv_layer_matches_folded(B, H, W, I, O, k, rh):
 
 
 def test_conv_two_m_tile_work_items_are_bit_identical_to_single_tiles():
-    """conv_igemm work items of two M tiles sharing each weight box (msub = 2) run the same MMA sequence per tile as
-    single-tile items, so the outputs must be bit-identical; each mode in its own process (the choice is read once
-    from TBG_IGEMM_MSUB).  Odd tile counts exercise the out-of-range second sub-tile."""
-    import os
-    import subprocess
-    import sys
+    """conv_igemm work items of two M tiles sharing each weight box (tuning igemm_msub = 2) run the same MMA sequence per
+    tile as single-tile items, so the outputs must be bit-identical.  Odd tile counts exercise the out-of-range second
+    sub-tile; the staged and the direct epilogue store paths must agree bit for bit as well."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
 
-    code = """
-import sys, torch
-sys.path.insert(0, %r)
-from textboxgan_b200 import conv as C, kernels as K
-outs = []
-for (B, H, W, I, O, k) in [(3, 16, 64, 64, 64, 3), (5, 8, 40, 128, 128, 1), (2, 32, 128, 64, 32, 3)]:
-    g = C.plain_geom(H, W, I, O, k)
-    gen = torch.Generator().manual_seed(B + H)
-    x = torch.randn(B, H, W, I, generator=gen).cuda().bfloat16()
-    w = (torch.randn(g.n_total, g.k_total, generator=gen) / g.k_total ** 0.5).cuda().bfloat16()
-    bias = torch.randn(O, generator=gen).cuda()
-    outs.append(K.conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.4, **g.kernel_kwargs()).float().cpu())
-    outs.append(K.conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs()).cpu())
-torch.save(outs, sys.argv[1])
-""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    import tempfile
+    def run():
+        outs = []
+        for (B, H, W, I, O, k) in [(3, 16, 64, 64, 64, 3), (5, 8, 40, 128, 128, 1), (2, 32, 128, 64, 32, 3),
+                                   (33, 24, 40, 64, 128, 3)]:
+            g = C.plain_geom(H, W, I, O, k)
+            gen = torch.Generator().manual_seed(B + H)
+            x = torch.randn(B, H, W, I, generator=gen).to(DEV).bfloat16()
+            w = (torch.randn(g.n_total, g.k_total, generator=gen) / g.k_total ** 0.5).to(DEV).bfloat16()
+            bias = torch.randn(O, generator=gen).to(DEV)
+            outs.append(K.conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.4, **g.kernel_kwargs()).float().cpu())
+            outs.append(K.conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs()).cpu())
+        return outs
 
-    res = {}
-    with tempfile.TemporaryDirectory() as td:
-        for m in ("1", "2"):
-            path = os.path.join(td, f"o{m}.pt")
-            env = dict(os.environ, TBG_IGEMM_MSUB=m)
-            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
-            assert r.returncode == 0, r.stderr[-2000:]
-            res[m] = torch.load(path)
-    for a, b in zip(res["1"], res["2"]):
-        assert torch.equal(a, b)
+    saved = {k: lib.get_tuning(k) for k in ("conv_halo", "igemm_msub", "igemm_staged")}
+    try:
+        lib.set_tuning("conv_halo", 0)
+        res = {}
+        for msub, staged in ((1, 1), (2, 1), (1, 0), (2, 0)):
+            lib.set_tuning("igemm_msub", msub)
+            lib.set_tuning("igemm_staged", staged)
+            res[(msub, staged)] = run()
+    finally:
+        for k, v in saved.items():
+            lib.set_tuning(k, v)
+    for key in ((2, 1), (1, 0), (2, 0)):
+        for a, b in zip(res[(1, 1)], res[key]):
+            assert torch.equal(a, b), key
+
+
+@pytest.mark.parametrize("B,H,W,I,O", [(2, 16, 16, 64, 32), (3, 32, 64, 128, 128), (2, 16, 64, 256, 256),
+                                       (1, 64, 256, 64, 64), (5, 16, 32, 64, 96)])
+def test_conv3x3_halo_kernel_vs_emulated_semantics_and_igemm(B, H, W, I, O):
+    """The halo-reuse kernel behind tbg_conv2d_igemm (tuning conv_halo = 1: one activation box per 64-channel block
+    shared by the nine taps) against the documented semantics of the entry point and against conv_igemm_kernel on the
+    same arguments: full modulated-conv epilogue (demodulation scale, noise, bias, leaky-ReLU) and the bare product."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
+
+    g = C.plain_geom(H, W, I, O, 3)
+    gen = torch.Generator().manual_seed(B * 1000 + H + O)
+    x = _bf16_round(torch.randn(B, H, W, I, generator=gen))
+    w = _bf16_round(torch.randn(g.n_total, g.k_total, generator=gen) / math.sqrt(g.k_total))
+    d = torch.rand(B, O, generator=gen) + 0.5
+    nz = torch.randn(B, H, W, generator=gen)
+    ns = torch.tensor([0.3])
+    bias = torch.randn(O, generator=gen) * 0.2
+    epi = dict(col_scale=d, noise=nz, noise_strength=ns, bias=bias, act=1, act_gain=math.sqrt(2.0))
+    dev = lambda t: t.to(DEV)
+    saved = lib.get_tuning("conv_halo")
+    try:
+        got = {}
+        for halo in (1, 0):
+            lib.set_tuning("conv_halo", halo)
+            full = K.conv2d_igemm(dev(x).bfloat16(), dev(w).bfloat16(), **g.kernel_kwargs(),
+                                  **{k: (dev(v) if torch.is_tensor(v) else v) for k, v in epi.items()})
+            bare = K.conv2d_igemm(dev(x).bfloat16(), dev(w).bfloat16(), **g.kernel_kwargs())
+            got[halo] = (full.float().cpu(), bare.float().cpu())
+    finally:
+        lib.set_tuning("conv_halo", saved)
+    want_full = emu_conv2d_igemm(x, w, **g.kernel_kwargs(), **epi).float()
+    want_bare = emu_conv2d_igemm(x, w, **g.kernel_kwargs()).float()
+    for halo in (1, 0):
+        assert rel_err(got[halo][0], want_full) < 1e-2, halo          # bf16 output
+        assert rel_err(got[halo][1], want_bare) < 1e-2, halo
+    # same bf16 inputs, fp32 accumulation in a different order: the two kernels agree to output rounding
+    assert rel_err(got[1][0], got[0][0]) < 1e-2 and rel_err(got[1][1], got[0][1]) < 1e-2
+
+
+def test_conv3x3_halo_kernel_phase_scatter_and_tap_masks():
+    """Up-sampling geometry on the halo kernel: columns = (phase_y, phase_x, cout), phase (py,px) of row (b,i,j) goes
+    to pixel (2i+py, 2j+px); per-phase tap masks skip weight blocks (treated as zero) — against the emulated semantics."""
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
+
+    B, H, W, I, O = 2, 16, 32, 64, 64
+    gen = torch.Generator().manual_seed(7)
+    x = _bf16_round(torch.randn(B, H, W, I, generator=gen))
+    w = _bf16_round(torch.randn(4 * O, 9 * I, generator=gen) / math.sqrt(9 * I))
+    bias = torch.randn(O, generator=gen) * 0.1
+    kw = dict(Ho=H, Wo=W, taps=(3, 3), pad=(1, 1), stride=(1, 1), up=(1, 1))
+    masks = (0b111111111, 0b000111111, 0b110110110, 0b000010000)
+    saved = lib.get_tuning("conv_halo")
+    try:
+        lib.set_tuning("conv_halo", 1)
+        for tm in (None, masks):
+            y = K.conv2d_igemm(x.to(DEV).bfloat16(), w.to(DEV).bfloat16(), bias=bias.to(DEV), act=1, act_gain=1.25,
+                               tap_mask=tm, **kw)
+            want = emu_conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.25, tap_mask=tm, **kw)
+            assert y.shape == (B, 2 * H, 2 * W, O)
+            assert rel_err(y.float().cpu(), want.float()) < 1e-2, tm
+    finally:
+        lib.set_tuning("conv_halo", saved)
 
 
 @pytest.mark.parametrize("Ho,Wo,B", [(5, 17, 3), (17, 65, 2), (3, 9, 32), (33, 129, 1), (7, 5, 9)])

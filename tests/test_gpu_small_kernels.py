@@ -1,0 +1,192 @@
+"""GPU parity of the small kernels behind the word encoder, the mapping network, the discriminator head, the RGB branch and
+the generic resampling op — every call goes through the C ABI (ctypes) and is compared with the documented semantics in
+tests/emu.py (fp64) or with the oracle's literal restatement of the reference."""
+import math
+
+import pytest
+import torch
+
+import emu
+from common import rel_err
+from oracle import stylegan as OS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,K,N,act,bias", [(128, 512, 512, 1, True), (64, 8192, 512, 1, True), (5, 37, 3, 0, False),
+                                            (768, 32, 256, 2, True), (128, 512, 1, 0, True), (33, 70, 65, 1, True)])
+def test_dense_kernels_vs_emulated_semantics(M, K, N, act, bias):
+    """tbg_dense_fwd / tbg_dense_bwd (Dense.call dense.py:23-29 + bias + activation), exact fp32: 1e-5."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=gen)
+    w = torch.randn(K, N, generator=gen)
+    b = torch.randn(N, generator=gen) if bias else None
+    gy = torch.randn(M, N, generator=gen)
+    kw = dict(coef=1.0 / math.sqrt(K) * 0.7, bias_coef=0.3, act=act, gain=math.sqrt(2.0) if act else 1.0)
+    y = Kn.dense_fwd(x.to(DEV), w.to(DEV), b.to(DEV) if bias else None, **kw)
+    want = emu.emu_dense_fwd(x, w, b, **kw)
+    assert rel_err(y, want) < 1e-5
+    gx, gw, gb = Kn.dense_bwd(x.to(DEV), w.to(DEV), y, gy.to(DEV), **kw, want_gb=bias)
+    ex, ew, eb = emu.emu_dense_bwd(x, w, want, gy, **kw, want_gb=bias)
+    assert rel_err(gx, ex) < 1e-5 and rel_err(gw, ew) < 1e-5
+    if bias:
+        assert rel_err(gb, eb) < 1e-5
+    # pieces can be skipped
+    gx2, gw2, gb2 = Kn.dense_bwd(x.to(DEV), w.to(DEV), y, gy.to(DEV), **kw, want_gx=False, want_gw=False, want_gb=False)
+    assert gx2 is None and gw2 is None and gb2 is None
+
+
+def test_pixel_norm_kernels():
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(3)
+    for M, K in ((128, 512), (7, 128), (1, 33)):
+        x = torch.randn(M, K, generator=gen)
+        gy = torch.randn(M, K, generator=gen)
+        assert rel_err(Kn.pixel_norm_fwd(x.to(DEV)), emu.emu_pixel_norm_fwd(x)) < 1e-6
+        assert rel_err(Kn.pixel_norm_bwd(x.to(DEV), gy.to(DEV)), emu.emu_pixel_norm_bwd(x, gy)) < 1e-5
+
+
+@pytest.mark.parametrize("B,mcn,fm0,with_mask", [(4, 8, 128, True), (3, 12, 192, True), (2, 16, 256, False)])
+def test_word_encoder_kernels_vs_emulated_semantics(B, mcn, fm0, with_mask):
+    """tbg_word_encoder_fwd / bwd (word_encoder.py:39-63): gather is exact (index arithmetic), dense fp32 1e-5, bf16 map."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(B + mcn)
+    E, D = 32, 256
+    words = torch.randint(0, 70, (B, mcn), generator=gen).to(torch.int32)
+    words[0, -1] = 0
+    w0 = torch.zeros(1, E)
+    table = torch.randn(69, E, generator=gen)
+    mask = (torch.rand(B, mcn, E, generator=gen) < 0.7).float() if with_mask else None
+    fc_w = torch.randn(E, D, generator=gen) * 0.2
+    fc_b = torch.randn(D, generator=gen) * 0.1
+    hwc = (2, 8, fm0)
+    d = lambda t: t.to(DEV) if t is not None else None
+    out, emb, act = Kn.word_encoder_fwd(d(words), d(w0), d(table), d(mask), 0.7, d(fc_w), d(fc_b), hwc)
+    eo, ee, ea = emu.emu_word_encoder_fwd(words, w0, table, mask, 0.7, fc_w, fc_b, hwc)
+    assert out.shape == (B, 2, 8, fm0) and out.dtype == torch.bfloat16
+    assert rel_err(emb, ee) < 1e-6 and rel_err(act, ea) < 1e-5
+    assert rel_err(out.float(), eo.float()) < 1e-2
+    g_out = _bf16_round(torch.randn(B, 2, 8, fm0, generator=gen))
+    gt, gw, gb = Kn.word_encoder_bwd(d(words), d(mask), 0.7, d(fc_w), emb, act, d(g_out).bfloat16(), 69, hwc)
+    et, ew, eb = emu.emu_word_encoder_bwd(words, mask, 0.7, fc_w, ee, ea, g_out, 69, hwc)
+    assert rel_err(gt, et) < 1e-5 and rel_err(gw, ew) < 1e-5 and rel_err(gb, eb) < 1e-5
+
+
+@pytest.mark.parametrize("B,n_calls,C,H,W", [(8, 1, 512, 4, 4), (4, 2, 512, 4, 4), (2, 1, 64, 2, 3), (64, 2, 512, 4, 4)])
+def test_minibatch_std_kernels_vs_emulated_semantics(B, n_calls, C, H, W):
+    """tbg_minibatch_std_fwd / bwd (mini_batch_std.py:10-35, one statistic per group of min(4, B) samples, per call)."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(B * 10 + n_calls)
+    x = _bf16_round(torch.randn(B * n_calls, H, W, C, generator=gen))
+    cpad = (C + 1 + 63) // 64 * 64
+    xcat, stat = Kn.minibatch_std_fwd(x.to(DEV).bfloat16(), n_calls, cpad)
+    ecat, estat = emu.emu_minibatch_std_fwd(x, n_calls, cpad)
+    assert rel_err(stat, estat) < 1e-5
+    assert torch.equal(xcat[..., :C].float().cpu(), x)                       # the copy is exact
+    assert rel_err(xcat[..., C].float(), ecat[..., C]) < 1e-2 and float(xcat[..., C + 1:].abs().max()) == 0.0
+    gxcat = _bf16_round(torch.randn(B * n_calls, H, W, cpad, generator=gen))
+    gx = Kn.minibatch_std_bwd(x.to(DEV).bfloat16(), gxcat.to(DEV).bfloat16(), n_calls)
+    assert rel_err(gx.float(), emu.emu_minibatch_std_bwd(x, gxcat, n_calls)) < 1e-2
+
+
+def test_r1_sqnorm_kernels():
+    from textboxgan_b200 import kernels as Kn
+    from textboxgan_b200.fused import R1SqNorm
+
+    gen = torch.Generator().manual_seed(5)
+    g = torch.randn(6, 3, 16, 64, generator=gen)
+    out = Kn.r1_sqnorm(g.to(DEV))
+    assert rel_err(out, (g.double() ** 2).sum(dim=(1, 2, 3))) < 1e-6
+    go = torch.randn(6, generator=gen)
+    assert rel_err(Kn.r1_sqnorm_bwd(g.to(DEV), go.to(DEV)), 2 * g.double() * go.double()[:, None, None, None]) < 1e-6
+    ga = g.to(DEV).requires_grad_(True)
+    (R1SqNorm.apply(ga) * go.to(DEV)).sum().backward()
+    assert rel_err(ga.grad, 2 * g.double() * go.double()[:, None, None, None]) < 1e-6
+
+
+@pytest.mark.parametrize("B,H,W,C,mcn,prev,nchw,masked", [
+    (2, 2, 8, 192, 12, False, False, False), (3, 4, 16, 512, 8, True, False, False), (2, 16, 64, 256, 8, True, False, False),
+    (2, 32, 128, 128, 8, True, True, True), (2, 64, 256, 128, 12, True, True, True), (1, 16, 64, 64, 16, True, True, False)])
+def test_torgb_skip_kernel_vs_emulated_semantics(B, H, W, C, mcn, prev, nchw, masked):
+    """tbg_torgb_skip_fwd (ToRGB to_rgb.py:28-33 + upsample_2d skip synthesis_block.py:152 + mask_text_box + NCHW) against
+    the literal upfirdn_2d_ref / mask restatement, incl. the fractional char_width of BASELINE configs[2] (256 / 12); the
+    autograd Function's gradients against autograd through the emulation."""
+    from textboxgan_b200 import kernels as Kn
+    from textboxgan_b200.fused import ToRGBSkip
+
+    gen = torch.Generator().manual_seed(H + C)
+    x = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    ws = torch.randn(B, C, 3, generator=gen) / math.sqrt(C)
+    bias = torch.randn(3, generator=gen) * 0.1
+    y_prev = torch.randn(B, H // 2, W // 2, 3, generator=gen) if prev else None
+    words = None
+    if masked:
+        lens = torch.randint(1, mcn + 1, (B,), generator=gen)
+        words = torch.where(torch.arange(mcn)[None] < lens[:, None], torch.randint(1, 70, (B, mcn), generator=gen),
+                            torch.zeros(B, mcn, dtype=torch.long)).to(torch.int32)
+    d = lambda t: t.to(DEV) if t is not None else None
+    y = Kn.torgb_skip_fwd(d(x).bfloat16(), d(ws), d(bias), d(y_prev), d(words), nchw)
+    want = emu.emu_torgb_skip_fwd(x, ws, bias, y_prev, words, nchw)
+    assert y.shape == want.shape and rel_err(y, want) < 1e-5
+    if masked:
+        from oracle import train_step as OT
+        from fractions import Fraction
+
+        cw = Fraction(W, mcn)
+        assert torch.equal(y.cpu(), OT.mask_text_box(y.cpu(), words, int(cw) if cw.denominator == 1 else cw))
+    # gradients through the Function
+    xa, wa, ba = d(x).bfloat16().requires_grad_(True), d(ws).requires_grad_(True), d(bias).requires_grad_(True)
+    pa = d(y_prev).requires_grad_(True) if prev else None
+    r = torch.randn(want.shape, generator=gen)
+    (ToRGBSkip.apply(xa, wa, ba, pa, d(words), nchw) * d(r)).sum().backward()
+    xe, we, be = x.double().requires_grad_(True), ws.double().requires_grad_(True), bias.double().requires_grad_(True)
+    pe = y_prev.double().requires_grad_(True) if prev else None
+    ye = torch.einsum("bhwc,bcj->bhwj", xe, we) + be
+    if prev:
+        import numpy as np
+        t = np.array([1.0, 3.0, 3.0, 1.0])
+        k = np.outer(t, t)
+        ye = ye + OS.upfirdn_2d_ref(pe, k / k.sum() * 4.0, 2, 2, 1, 1, 2, 1, 2, 1)
+    if masked:
+        keep = (words.long()[:, (torch.arange(W) * mcn) // W] != 0).double()
+        ye = ye * keep[:, None, :, None]
+    if nchw:
+        ye = ye.permute(0, 3, 1, 2)
+    (ye * r.double()).sum().backward()
+    assert rel_err(xa.grad.float(), xe.grad) < 1e-2 and rel_err(wa.grad, we.grad) < 1e-4 and rel_err(ba.grad, be.grad) < 1e-4
+    if prev:
+        assert rel_err(pa.grad, pe.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cfgk", [dict(upx=2, upy=2, padx0=2, padx1=1, pady0=2, pady1=1),
+                                  dict(downx=2, downy=2, padx0=1, padx1=1, pady0=1, pady1=1),
+                                  dict(upx=3, upy=2, downx=2, downy=3, padx0=4, padx1=-1, pady0=-2, pady1=5),
+                                  dict(padx0=3, padx1=3, pady0=3, pady1=3)])
+@pytest.mark.parametrize("shape,ksz", [((2, 33, 70, 3), (4, 4)), ((5, 8, 9, 1), (3, 5)), ((1, 16, 16, 19), (6, 6))])
+def test_upfirdn2d_tiled_kernel_matches_reference_semantics(cfgk, shape, ksz):
+    """tbg_upfirdn2d (the reference's UpFirDn2D op contract) against the literal upfirdn_2d_ref (upfirdn_2d_v2.py:249-305):
+    tiles that overhang the output, minor sizes that are not multiples of the staged chunk, non-symmetric filters,
+    negative pads, up and down at once."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=gen)
+    k = torch.randn(*ksz, generator=gen)
+    full = dict(upx=1, upy=1, downx=1, downy=1, padx0=0, padx1=0, pady0=0, pady1=0)
+    full.update(cfgk)
+    ref = OS.upfirdn_2d_ref(x.double(), k.double().numpy(), full["upx"], full["upy"], full["downx"], full["downy"],
+                            full["padx0"], full["padx1"], full["pady0"], full["pady1"])
+    if ref.shape[1] < 1 or ref.shape[2] < 1:
+        pytest.skip("empty output for this combination")
+    y = Kn.upfirdn2d(x.to(DEV), k.to(DEV), **full)
+    assert y.shape == ref.shape and rel_err(y, ref) < 1e-5

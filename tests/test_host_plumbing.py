@@ -45,10 +45,16 @@ def test_flat_adam_matches_per_variable_update_and_ignores_padding():
     D = Discriminator(cfg, device="cpu", seed=0)
     names = D.trainable_names()
     grads = [torch.randn_like(D.params[n]) for n in names]
-    grads[3] = None                                                     # an unused variable: zero gradient
     before = {n: D.params[n].detach().clone() for n in names}
     opt = Adam(0.002, beta_1=0.0, beta_2=0.99, epsilon=1e-8)
     with emulated_kernels():
+        # a variable without a gradient is a wiring error on the flat path (Keras would skip its slots; a zero gradient
+        # through Adam would decay v instead): loud, and nothing is updated
+        import pytest
+
+        with pytest.raises(RuntimeError, match="has no gradient"):
+            opt.apply_gradients(zip(grads[:3] + [None] + grads[4:], [D.params[n] for n in names]), model=D, names=names)
+        assert all(torch.equal(D.params[n], before[n]) for n in names) and opt.iterations.numpy() == 0
         opt.apply_gradients(zip(grads, [D.params[n] for n in names]), model=D, names=names)
     lr_t = 0.002 * (1 - 0.99) ** 0.5
     for n, g in zip(names, grads):

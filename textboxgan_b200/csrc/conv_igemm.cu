@@ -8,7 +8,7 @@
 // algebra), upsample_conv_2d (upfirdn_2d_v2.py:65-103, as a 4-phase GEMM), Conv2D.call
 // (conv.py:51-73), Noise.call (noise.py:12-22), BiasAct.call (bias_act.py:25-34), the residual
 // merge of DiscriminatorBlock.call (discriminator.py:82).
-#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -51,13 +51,16 @@ struct ConvKernelParams {
 
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
-// Epilogue staging: each epilogue warp transposes its 32 accumulator rows through shared memory, 256 bytes
+// Epilogue staging: each epilogue warp transposes its 32 accumulator rows through shared memory, 128 bytes
 // of a row at a time (+16 bytes of padding: conflict-free 16-byte accesses), so that global stores go out as
-// whole 128-byte lines of two pixels per instruction instead of one 16-byte piece of 32 different pixels.
-static constexpr uint32_t kStgRow = 256 + 16;
-static constexpr uint32_t kStgBytes = 4 * 32 * kStgRow;
+// whole 128-byte lines of four pixels per instruction instead of one 16-byte piece of 32 different pixels.
+static constexpr uint32_t kStgRow = 128 + 16;
+static constexpr int kEpiWarps = 8;       // two per TMEM lane quadrant: they split the 32-column chunks of a tile
+static constexpr uint32_t kStgBytes = kEpiWarps * 32 * kStgRow;
+static constexpr uint32_t kVecBytes = kEpiWarps * 2 * 128 * 4;   // per epilogue warp: demod-scale and bias vectors
+static constexpr int kThreads = 128 + 32 * kEpiWarps;
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -77,6 +80,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars + 2 * kMaxStages + 6);   // epilogue staging, 16-byte aligned
+  float* vec_base = reinterpret_cast<float*>(stg_base + kStgBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,7 +96,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -203,65 +207,105 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    // Warp e reads TMEM lane quadrant e & 3 (= warp % 4, the hardware's lane-access rule); the two warps of a quadrant
+    // split the work of a tile: by sub-tile when msub == 2, else by halves of the 32-column chunk range.
     const int e = warp - 4;
-    const int r = e * 32 + lane;
+    const int quad = e & 3;
+    const int half = e >> 2;
+    const int r = quad * 32 + lane;
     const int w_in = r % bw;
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
     const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
     uint8_t* const stg = stg_base + e * (32 * kStgRow);
+    float* const vscale = vec_base + e * 256;
+    float* const vbias = vscale + 128;
+    const int esize = p.out_fp32 ? 4 : 2;
+    const int nj = p.block_n / 32;
+    // chunk range of this warp inside a (sub-)tile
+    const int j_lo = (msub == 2 || nj == 1) ? 0 : half * (nj / 2);
+    const int j_hi = (msub == 2 || nj == 1) ? nj : (half + 1) * (nj / 2);
+    const bool idle = (msub == 1 && nj == 1 && half == 1);        // a 32-column tile has one chunk: second warp idles
+    const int my_cols = (j_hi - j_lo) * 32;
+    const int chunk_cols = min(my_cols, 128 / esize);             // columns staged per flush (<= 128 bytes per row)
+    const int j_per_chunk = chunk_cols / 32;
+    const bool smem_vec = (bn == 1) && my_cols <= 128;            // one image per tile: per-column vectors from smem
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
       const int ms_tile = tile / p.tiles_n;
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc_stage], acc_phase);
-      tc_fence_after();
-      for (int sub = 0; sub < msub; ++sub) {
+      if (idle) {
+        mbar_wait(&tfull[acc_stage], acc_phase);
+        tc_fence_before();
+        mbar_arrive(&tempty[acc_stage]);
+        continue;
+      }
+      bool waited = false;
+      for (int sub = (msub == 2 ? half : 0); sub < (msub == 2 ? half + 1 : 1); ++sub) {
       int tw, th, tb;
       decode_m(ms_tile * msub + sub, tw, th, tb);
       const int b = tb * bn + n_in;
       const int ho = th * bh + h_in;
       const int wo = tw * bw + w_in;
       const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
+      // first column of this warp's range, phase and channel base (an N tile never straddles two phases)
+      const int colA = n_tile * p.block_n + j_lo * 32;
+      int cA = colA, oy = ho, ox = wo;
+      if (p.up_h | p.up_w) {
+        const int ph = colA / p.cout;
+        cA = colA - ph * p.cout;
+        const int py = p.up_w ? (ph >> 1) : ph;
+        const int px = p.up_w ? (ph & 1) : 0;
+        oy = p.up_h ? 2 * ho + py : ho;
+        ox = p.up_w ? 2 * wo + px : wo;
+      }
+      const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
+      const bool cols_ok = colA < p.n_total;
+      if (smem_vec) {
+        // per-column vectors of this tile -> shared memory (overlaps the MMAs of the tile); tb < tiles_b here
+        __syncwarp();
+        if (lane * 4 < my_cols && cols_ok && tb < p.tiles_b) {
+          float4 sv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.col_scale) sv = __ldg(reinterpret_cast<const float4*>(p.col_scale + static_cast<size_t>(tb) * p.cout + cA) + lane);
+          if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cA) + lane);
+          reinterpret_cast<float4*>(vscale)[lane] = sv;
+          reinterpret_cast<float4*>(vbias)[lane] = bv;
+        }
+        __syncwarp();
+      }
+      const float nz = (p.noise != nullptr && valid && cols_ok) ? __ldg(p.noise + pix) * nstr : 0.f;
+      if (!waited) {
+        mbar_wait(&tfull[acc_stage], acc_phase);
+        tc_fence_after();
+        waited = true;
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>((acc_stage * msub + sub) * p.block_n);
-      const int esize = p.out_fp32 ? 4 : 2;
-      const int chunk_cols = min(p.block_n, 256 / esize);   // columns staged per flush (<= 256 bytes per row)
-      const int j_per_chunk = chunk_cols / 32;
       uint8_t* const my_row = stg + lane * kStgRow;
       long long row_off = -1;                                 // element offset of this row's chunk in out, or -1
-      for (int j = 0; j < p.block_n / 32; ++j) {
-        const int col0 = n_tile * p.block_n + j * 32;
+      for (int j = j_lo; j < j_hi; ++j) {
+        const int jj = j - j_lo;
         uint32_t v[32];
         tmem_ld_32x32(t_row + j * 32, v);
         tmem_ld_wait();
-        if (valid && col0 < p.n_total) {
-          int c0 = col0, oy = ho, ox = wo;
-          if (p.up_h | p.up_w) {
-            const int ph = col0 / p.cout;
-            c0 = col0 - ph * p.cout;
-            const int py = p.up_w ? (ph >> 1) : ph;
-            const int px = p.up_w ? (ph & 1) : 0;
-            oy = p.up_h ? 2 * ho + py : ho;
-            ox = p.up_w ? 2 * wo + px : wo;
-          }
-          const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
+        if (valid && cols_ok) {
+          const int c0 = cA + jj * 32;
           const size_t off = pix * p.cout + c0;
-          if (j % j_per_chunk == 0) row_off = static_cast<long long>(off);
-          const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
-          const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
-          const float* bs = p.bias ? p.bias + c0 : nullptr;
-          uint8_t* const srow = my_row + (j % j_per_chunk) * 32 * esize;
+          if (jj % j_per_chunk == 0) row_off = static_cast<long long>(off);
+          const float* cs = smem_vec ? vscale + jj * 32
+                                     : (p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr);
+          const float* bs = smem_vec ? vbias + jj * 32 : (p.bias ? p.bias + c0 : nullptr);
+          uint8_t* const srow = my_row + (jj % j_per_chunk) * 32 * esize;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
             if (cs) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(cs + g * 8));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(cs + g * 8 + 4));
+              const float4 s0 = *reinterpret_cast<const float4*>(cs + g * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(cs + g * 8 + 4);
               f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
               f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
             }
@@ -270,8 +314,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int i = 0; i < 8; ++i) f[i] += nz;
             }
             if (bs) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bs + g * 8 + 4);
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
@@ -329,21 +373,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               *o = pk;
             }
           }
-        } else if (j % j_per_chunk == 0) {
+        } else if (jj % j_per_chunk == 0) {
           row_off = -1;
         }
-        if (p.staged && (j + 1) % j_per_chunk == 0) {
+        if (p.staged && (jj + 1) % j_per_chunk == 0) {
           // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
           __syncwarp();
-          const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4, 8 or 16
+          const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4 or 8
           const int rows_per_pass = 32 / lanes_per_row;
-          const int sub = lane % lanes_per_row;
+          const int sbl = lane % lanes_per_row;
           for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
             const int rr = r0 + lane / lanes_per_row;
             const long long o_el = __shfl_sync(0xffffffffu, row_off, rr);
             if (o_el >= 0) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRow + sub * 16);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * esize + sub * 16;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRow + sbl * 16);
+              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * esize + sbl * 16;
               *reinterpret_cast<uint4*>(dst) = val;
             }
           }
@@ -363,6 +407,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+Tuning g_tuning;
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -403,6 +449,10 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->col_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->relu_mask) & 15) == 0,
                 "tbg_conv2d_igemm: col_scale / bias / residual must be 16-byte aligned (vector loads in the epilogue)");
+
+  // 3x3 stride-1 SAME convolutions on grids of 16 x 16 pixel blocks: one activation halo box per 64-channel block
+  // shared by the nine taps (csrc/conv_halo.cu)
+  if (g_tuning.conv_halo && conv_halo_applicable(a)) return conv_halo_launch(a, stream);
 
   ConvKernelParams p{};
   p.B = a->B;
@@ -488,33 +538,18 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.out_fp32 = a->out_fp32;
   p.out = a->out;
 
-  // two M tiles per work item when both accumulator sets still double-buffer in TMEM (2 x 2 x block_n <= 512) and
-  // there is enough work to keep every SM busy with the larger items
-  // (>= 4 items per SM: with fewer, the static round-robin's last partial wave costs more than the traffic saves)
-  {
-    static int staged = -1;
-    if (staged < 0) {
-      const char* e = getenv("TBG_IGEMM_STAGED");
-      staged = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    p.staged = staged;
-  }
-  p.msub = (block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
-  {
-    static int msub_override = -1;      // TBG_IGEMM_MSUB=1|2 forces the choice (tests, tuning); 2 needs block_n <= 128
-    if (msub_override < 0) {
-      const char* e = getenv("TBG_IGEMM_MSUB");
-      msub_override = e ? atoi(e) : 0;
-    }
-    if (msub_override == 1 || (msub_override == 2 && block_n <= 128)) p.msub = msub_override;
-  }
+  // Tuning (tbg_set_tuning): staged epilogue stores; two M tiles per work item sharing each weight box (needs both
+  // accumulator sets to double-buffer in TMEM: 2 x 2 x block_n <= 512).  Defaults from the B200 measurements in
+  // profiles/r02a_layer_perf.log: msub = 2 leaves only three 48 KB pipeline stages and is slower than msub = 1.
+  p.staged = g_tuning.igemm_staged;
+  p.msub = (g_tuning.igemm_msub == 2 && block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
   const uint32_t stage_bytes = static_cast<uint32_t>(p.msub) * kABytes + b_bytes;
-  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/;
+  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - kStgBytes /*epilogue staging*/ - kVecBytes;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + kStgBytes;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + kStgBytes + kVecBytes;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;
@@ -543,8 +578,32 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   }
   const int total_tiles = ((tiles_m + p.msub - 1) / p.msub) * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
+}
+
+// Explicit tuning switches (tests, perf scripts); the library reads no environment variables.
+extern "C" int tbg_set_tuning(const char* key, int value) {
+  TBG_CHECK_ARG(key != nullptr, "tbg_set_tuning: null key");
+  if (!strcmp(key, "igemm_staged")) g_tuning.igemm_staged = value != 0;
+  else if (!strcmp(key, "igemm_msub")) g_tuning.igemm_msub = value == 2 ? 2 : 1;
+  else if (!strcmp(key, "conv_halo")) g_tuning.conv_halo = value != 0;
+  else if (!strcmp(key, "wgrad_staged")) g_tuning.wgrad_staged = value != 0;
+  else if (!strcmp(key, "wgrad_items_per_sm")) g_tuning.wgrad_items_per_sm = value;
+  else if (!strcmp(key, "lstm_cluster")) g_tuning.lstm_cluster = value != 0;
+  else return set_error(TBG_ERR_INVALID_ARG, "tbg_set_tuning: unknown key '%s'", key);
+  return TBG_OK;
+}
+
+extern "C" int tbg_get_tuning(const char* key) {
+  if (!key) return -1;
+  if (!strcmp(key, "igemm_staged")) return g_tuning.igemm_staged;
+  if (!strcmp(key, "igemm_msub")) return g_tuning.igemm_msub;
+  if (!strcmp(key, "conv_halo")) return g_tuning.conv_halo;
+  if (!strcmp(key, "wgrad_staged")) return g_tuning.wgrad_staged;
+  if (!strcmp(key, "wgrad_items_per_sm")) return g_tuning.wgrad_items_per_sm;
+  if (!strcmp(key, "lstm_cluster")) return g_tuning.lstm_cluster;
+  return -1;
 }

@@ -318,14 +318,7 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   p.stride_w = a->stride_w;
   p.ktot = a->taps_h * a->taps_w * a->Cin;
   p.gw = a->gw;
-  {
-    static int staged = -1;
-    if (staged < 0) {
-      const char* e = getenv("TBG_WGRAD_STAGED");
-      staged = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    p.staged = staged;
-  }
+  p.staged = g_tuning.wgrad_staged;
 
   // pixel block: 64 pixels unless a stage would not leave room for >= 3 stages
   int P = 64;
@@ -354,11 +347,7 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int base_items = p.m_tiles * p.groups;
-  static int items_override = -1;
-  if (items_override < 0) {
-    const char* e = getenv("TBG_WGRAD_ITEMS_PER_SM");
-    items_override = e ? atoi(e) : 0;
-  }
+  const int items_override = g_tuning.wgrad_items_per_sm;     // tbg_set_tuning("wgrad_items_per_sm", n); 0 = heuristic
   // Two work items per SM hide the accumulator drain behind the next item's MMAs, but only pay off
   // when each item still owns >= 16 pixel blocks (measured on B200, profiles/r01_layer_perf.log).
   int items_per_sm = items_override > 0 ? items_override : 2;

@@ -35,6 +35,20 @@ void count_launch(int n = 1);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swizzle);
 
+// Process-wide tuning switches, set through tbg_set_tuning (never from the environment).
+struct Tuning {
+  int igemm_staged = 1;        // conv_igemm epilogue: stores transposed through shared memory (whole 128-byte lines)
+  int igemm_msub = 1;          // conv_igemm: M tiles per work item (2 = two tiles share each weight box)
+  int conv_halo = 1;           // 3x3 stride-1 convolutions on the halo-reuse kernel when it applies
+  int wgrad_staged = 1;        // conv_wgrad: staged vector atomics
+  int wgrad_items_per_sm = 0;  // conv_wgrad: split-K work items per SM (0 = heuristic)
+  int lstm_cluster = 1;        // LSTM whole-sequence kernels on 4-CTA clusters with smem-resident W_hh
+};
+extern Tuning g_tuning;
+
+bool conv_halo_applicable(const ::tbg_conv_args* a);
+int conv_halo_launch(const ::tbg_conv_args* a, cudaStream_t stream);
+
 inline int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

@@ -413,14 +413,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ g_h, const float* __restrict__
   }
 }
 
-static bool lstm_cluster_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TBG_LSTM_CLUSTER");
-    v = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  return v == 1;
-}
+static bool lstm_cluster_enabled() { return g_tuning.lstm_cluster != 0; }
 
 }  // namespace tbg
 

@@ -1,5 +1,5 @@
 // HBM-bound kernels of the training step: optimiser / EMA updates over flat fp32 buffers, the
-// generic upfirdn2d resampler (the reference's one native op) and small fused element-wise passes.
+// crop + bilinear resize of AsterInferer.convert_inputs and small fused element-wise passes.
 // All are grid-stride, 128-bit vectorised where alignment allows, and sized to a multiple of the
 // SM count.
 #include <initializer_list>
@@ -109,73 +109,6 @@ static long long common_head(long long n, std::initializer_list<const void*> ptr
   return head < n ? head : n;
 }
 
-// ----------------------------------------------------------------------------------------------
-// upfirdn2d: pad -> zero-insert upsample -> FIR (correlation with the flipped kernel) -> decimate,
-// on [major, inH, inW, minor] tensors; same contract as the reference's TF op
-// (upfirdn_2d.cu:64-117 generic kernel, 232-307 host op).  fp32 accumulate; T in {float, bf16}.
-// One thread per output element, minor fastest (coalesced for NHWC, minor = channels).
-// ----------------------------------------------------------------------------------------------
-struct UpfirdnParams {
-  int upx, upy, downx, downy, padx0, pady0;
-  int major, inH, inW, minor, kH, kW, outH, outW;
-};
-
-__device__ __forceinline__ int floor_div(int a, int b) {
-  int c = a / b;
-  if (c * b > a) c--;
-  return c;
-}
-
-template <typename T>
-__device__ __forceinline__ float to_f(T v);
-template <>
-__device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <typename T>
-__device__ __forceinline__ T from_f(float v);
-template <>
-__device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
-template <typename T>
-__global__ void upfirdn2d_kernel(const T* __restrict__ x, const float* __restrict__ k, T* __restrict__ y,
-                                 const UpfirdnParams p) {
-  __shared__ float sk[64];
-  for (int i = threadIdx.x; i < p.kH * p.kW; i += blockDim.x) sk[i] = k[i];
-  __syncthreads();
-  const long long total = static_cast<long long>(p.major) * p.outH * p.outW * p.minor;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int mi = static_cast<int>(idx % p.minor);
-    long long r = idx / p.minor;
-    const int ox = static_cast<int>(r % p.outW);
-    r /= p.outW;
-    const int oy = static_cast<int>(r % p.outH);
-    const int mj = static_cast<int>(r / p.outH);
-    // receptive field in input coordinates (same arithmetic as upfirdn_2d.cu:76-93)
-    const int midY = oy * p.downy + p.upy - 1 - p.pady0;
-    const int inY0 = min(max(floor_div(midY, p.upy), 0), p.inH);
-    const int hh = min(max(floor_div(midY + p.kH, p.upy), 0), p.inH) - inY0;
-    const int kY0 = midY + p.kH - (inY0 + 1) * p.upy;
-    const int midX = ox * p.downx + p.upx - 1 - p.padx0;
-    const int inX0 = min(max(floor_div(midX, p.upx), 0), p.inW);
-    const int ww = min(max(floor_div(midX + p.kW, p.upx), 0), p.inW) - inX0;
-    const int kX0 = midX + p.kW - (inX0 + 1) * p.upx;
-    float acc = 0.f;
-    for (int yy = 0; yy < hh; ++yy) {
-      const int ky = kY0 - yy * p.upy;
-      const T* xrow = x + ((static_cast<long long>(mj) * p.inH + inY0 + yy) * p.inW + inX0) * p.minor + mi;
-      for (int xx = 0; xx < ww; ++xx) {
-        const int kx = kX0 - xx * p.upx;
-        acc += to_f<T>(xrow[static_cast<long long>(xx) * p.minor]) * sk[ky * p.kW + kx];
-      }
-    }
-    y[idx] = from_f<T>(acc);
-  }
-}
-
 }  // namespace tbg
 
 using namespace tbg;
@@ -208,40 +141,10 @@ extern "C" int tbg_ema_step(float* dst, const float* src, long long n, float bet
   return TBG_OK;
 }
 
-extern "C" int tbg_upfirdn2d(const void* x, const float* k, void* y, int dtype_bf16, int major, int inH, int inW,
-                             int minor, int kH, int kW, int upx, int upy, int downx, int downy, int padx0, int padx1,
-                             int pady0, int pady1, void* stream_v) {
-  // same argument checks as UpFirDn2DOp::Compute (upfirdn_2d.cu:241-266)
-  TBG_CHECK_ARG(x && k && y, "tbg_upfirdn2d: null pointer");
-  TBG_CHECK_ARG(upx >= 1 && upy >= 1, "upx and upy must be at least 1x1");
-  TBG_CHECK_ARG(downx >= 1 && downy >= 1, "downx and downy must be at least 1x1");
-  TBG_CHECK_ARG(kW >= 1 && kH >= 1 && kW * kH <= 64, "kernel must be between 1x1 and 64 taps");
-  TBG_CHECK_ARG(major >= 1 && inH >= 1 && inW >= 1 && minor >= 1, "input must have rank 4 with positive dims");
-  UpfirdnParams p;
-  p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0;
-  p.major = major; p.inH = inH; p.inW = inW; p.minor = minor; p.kH = kH; p.kW = kW;
-  p.outW = (inW * upx + padx0 + padx1 - kW + downx) / downx;
-  p.outH = (inH * upy + pady0 + pady1 - kH + downy) / downy;
-  TBG_CHECK_ARG(p.outW >= 1 && p.outH >= 1, "output must be at least 1x1");
-  const long long total = static_cast<long long>(major) * p.outH * p.outW * minor;
-  TBG_CHECK_ARG(total <= 0x7fffffffLL * 8, "output too large");
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  if (dtype_bf16)
-    upfirdn2d_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), k, reinterpret_cast<__nv_bfloat16*>(y), p);
-  else
-    upfirdn2d_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(x), k,
-                                                                       reinterpret_cast<float*>(y), p);
-  count_launch();
-  TBG_CHECK_CUDA(cudaGetLastError());
-  return TBG_OK;
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// UNVALIDATED (branch wip/r02-unvalidated-kernels): AsterInferer.convert_inputs (aster_inferer.py:153-190) as one
-// gather kernel forward and one scatter kernel backward: NCHW fp32 image -> crop at first_blank * char_width ->
-// bilinear resize (tf.image.resize: half-pixel centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].
+// AsterInferer.convert_inputs (aster_inferer.py:153-190) as one gather kernel forward and one scatter kernel
+// backward: NCHW fp32 image -> crop at first_blank * char_width -> bilinear resize (tf.image.resize: half-pixel
+// centres, no antialias) -> NHWC fp32 [B, oh, ow, 3].
 //   src = (o + 0.5) * in / out - 0.5 ; i0 = clamp(floor(src)), i1 = clamp(ceil(src)), weights (1 - frac, frac)
 // The crop width of sample b is floor(first_blank(b) * cw_num / cw_den) clamped to [1, W] (W when no blank label).
 // ---------------------------------------------------------------------------------------------

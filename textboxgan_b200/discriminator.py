@@ -128,10 +128,15 @@ class Discriminator(Model):
         # minibatch-std feature (mini_batch_std.py): one extra constant channel per sample; padded
         # with zero channels up to a multiple of 64 so that K stays TMA/UMMA aligned
         B, H, W_, Cc = x.shape
-        std = L.minibatch_std(x, n_calls=n_calls)                            # [B,1]
         cpad = (Cc + 1 + 63) // 64 * 64
-        xcat = torch.cat([x, std.to(x.dtype)[:, None, None, :].expand(B, H, W_, 1),
-                          x.new_zeros(B, H, W_, cpad - Cc - 1)], dim=3).contiguous()
+        if L.use_fused():
+            from .fused import MinibatchStdCat
+
+            xcat = MinibatchStdCat.apply(x, n_calls, cpad)                   # [x | statistic | zero padding], one launch
+        else:
+            std = L.minibatch_std(x, n_calls=n_calls)                        # [B,1]
+            xcat = torch.cat([x, std.to(x.dtype)[:, None, None, :].expand(B, H, W_, 1),
+                              x.new_zeros(B, H, W_, cpad - Cc - 1)], dim=3).contiguous()
         w_raw = P[pl + "/conv_0/w"]                                          # [3,3,C+1,C]
         if L.use_fused():
             from .fused import ConvAct
@@ -146,6 +151,12 @@ class Discriminator(Model):
             y = L.lrelu(y + P[pl + "/bias_0/b"])
         # flatten in the reference's NCHW order (dense.py:26-27 on an NCHW tensor)
         y = y.permute(0, 3, 1, 2).reshape(B, -1)
+        if L.use_fused():
+            from .fused import DenseAct
+
+            w1, w2 = P[pl + "/dense_1/w"], P["last_dense/w"]
+            y = DenseAct.apply(y, w1, P[pl + "/bias_1/b"], L.runtime_coef(w1.shape), 1.0, 1, L.SQRT2, "dconv")
+            return DenseAct.apply(y, w2, P["last_bias/b"], L.runtime_coef(w2.shape), 1.0, 0, 1.0, "dconv")
         y = L.lrelu(L.dense(y, P[pl + "/dense_1/w"]) + P[pl + "/bias_1/b"])
         y = L.dense(y, P["last_dense/w"]) + P["last_bias/b"]
         return y

@@ -93,6 +93,11 @@ class backward_batch_limit:
         return False
 
 
+# upsample_conv_2d forward: FIR folded into a 4-phase 3x3 convolution (True) or transposed conv + FIR pass (False);
+# the backward pass is the unfolded one either way (FIR adjoint + stride-2 3x3 convolution at algorithmic cost).
+FOLD_UP_FORWARD = True
+
+
 def _act_dtype():
     from . import layers as L
 
@@ -149,10 +154,23 @@ class ModUpConvAct(torch.autograd.Function):
         wmat, wadj, q = _prepared(w_raw, spec, True, True)
         d = K.demod_coef(s, q)
         xs = K.modulate(x, s)
-        K.PROFILE_TAG = (g.tag, g.algo_frac)
-        T = K.conv2d_igemm(xs, wmat, **spec.fwd_kwargs)                           # [B, 2h+2, 2w+2, O]
-        out = K.fir4(T, spec.out_hw, (-1, -1), 1.0 / 16.0, d=d, noise=noise.contiguous(), noise_strength=ns.reshape(1),
-                     bias=_aligned_vec(bias), act=1, gain=gain)
+        if FOLD_UP_FORWARD:
+            # forward with the FIR folded into the weights: ONE 4-phase 3x3 convolution on the input grid (halo-reuse
+            # kernel when the grid is a multiple of 16 x 16) with the whole layer epilogue; no [B,2h+2,2w+2,O]
+            # intermediate and no FIR pass.  4x the algorithmic FLOPs, but measured faster than transposed conv + FIR
+            # (profiles/r02b_*: 64x32x128x128: 313 us + 280 us unfolded vs one launch at ~1.3 PFLOP/s executed).
+            from .conv import weight_spec
+
+            fspec = weight_spec("up", g.H, g.W, spec.I, spec.O, 3, True, g.tag)
+            wf, _, _ = _prepared(w_raw, fspec, False, False)
+            K.PROFILE_TAG = (g.tag, fspec.geom.algo_frac)
+            out = K.conv2d_igemm(xs, wf, **fspec.geom.kernel_kwargs(), col_scale=d, noise=noise.contiguous(),
+                                 noise_strength=ns.reshape(1), bias=_aligned_vec(bias), act=1, act_gain=gain)
+        else:
+            K.PROFILE_TAG = (g.tag, g.algo_frac)
+            T = K.conv2d_igemm(xs, wmat, **spec.fwd_kwargs)                       # [B, 2h+2, 2w+2, O]
+            out = K.fir4(T, spec.out_hw, (-1, -1), 1.0 / 16.0, d=d, noise=noise.contiguous(),
+                         noise_strength=ns.reshape(1), bias=_aligned_vec(bias), act=1, gain=gain)
         ctx.save_for_backward(x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias)
         ctx.spec, ctx.gain = spec, gain
         return out
@@ -305,3 +323,126 @@ class ToRGB(torch.autograd.Function):
         gy = gy.contiguous()
         gx, gws = K.torgb_bwd(x, ws, gy)
         return gx, gws, gy.sum(dim=(0, 1, 2))
+
+
+class DenseAct(torch.autograd.Function):
+    """Dense.call (dense.py:23-29) [+ bias * bias_coef + activation * gain] on the fp32 ``tbg_dense_*`` kernels:
+    y = act((x @ w) * coef + bias * bias_coef) * gain.  ``tag``: weight gradients are skipped while that tag is listed in
+    :class:`skip_weight_grads` (discriminator layers during the generator's backward pass)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, coef: float, bias_coef: float, act: int, gain: float, tag: str = ""):
+        x = x.contiguous().float()
+        y = K.dense_fwd(x, w.contiguous(), bias, coef=coef, bias_coef=bias_coef, act=act, gain=gain)
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (coef, bias_coef, act, gain, tag, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        coef, bias_coef, act, gain, tag, has_bias = ctx.cfg
+        want_w = tag not in _SKIP_WGRAD_TAGS
+        gx, gw, gb = K.dense_bwd(x, w.contiguous(), y, gy.contiguous().float(), coef=coef, bias_coef=bias_coef, act=act,
+                                 gain=gain, want_gx=ctx.needs_input_grad[0], want_gw=ctx.needs_input_grad[1] and want_w,
+                                 want_gb=has_bias and ctx.needs_input_grad[2] and want_w)
+        return gx, gw, gb, None, None, None, None, None
+
+
+class PixelNorm(torch.autograd.Function):
+    """x * rsqrt(mean(x^2) + 1e-8) per row (mapping_block.py:15-18)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        ctx.save_for_backward(x)
+        return K.pixel_norm_fwd(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return K.pixel_norm_bwd(x, gy.contiguous())
+
+
+class WordEncoderFn(torch.autograd.Function):
+    """WordEncoder.call (word_encoder.py:39-63) in one launch each way; returns the base feature map NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, words, w0, table, mask, fc_w, fc_b, keep: float, out_hwc):
+        words = words.to(torch.int32).contiguous()
+        mask = mask.contiguous().float() if mask is not None else None
+        out, emb, act = K.word_encoder_fwd(words, w0.contiguous(), table.contiguous(), mask, keep, fc_w.contiguous(),
+                                           fc_b.contiguous(), out_hwc)
+        ctx.save_for_backward(words, mask, fc_w, emb, act)
+        ctx.cfg = (keep, tuple(out_hwc), table.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        words, mask, fc_w, emb, act = ctx.saved_tensors
+        keep, out_hwc, rows = ctx.cfg
+        g_table, g_fc_w, g_fc_b = K.word_encoder_bwd(words, mask, keep, fc_w.contiguous(), emb, act, g_out.contiguous(), rows,
+                                                     out_hwc)
+        return None, None, g_table, None, g_fc_w, g_fc_b, None, None
+
+
+class MinibatchStdCat(torch.autograd.Function):
+    """MinibatchStd.call (mini_batch_std.py:10-35): x bf16 [n_calls*B,H,W,C] -> [x | statistic | zero padding to cpad]."""
+
+    @staticmethod
+    def forward(ctx, x, n_calls: int, cpad: int):
+        x = x.contiguous()
+        xcat, _ = K.minibatch_std_fwd(x, n_calls, cpad)
+        ctx.save_for_backward(x)
+        ctx.n_calls = n_calls
+        return xcat
+
+    @staticmethod
+    def backward(ctx, gxcat):
+        (x,) = ctx.saved_tensors
+        return K.minibatch_std_bwd(x, gxcat.contiguous(), ctx.n_calls), None, None
+
+
+class R1SqNorm(torch.autograd.Function):
+    """Per-sample squared norm of the image gradient (training_step.py:369)."""
+
+    @staticmethod
+    def forward(ctx, g):
+        g = g.contiguous().float()
+        ctx.save_for_backward(g)
+        return K.r1_sqnorm(g)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        return K.r1_sqnorm_bwd(g, gout.contiguous().float())
+
+
+class ToRGBSkip(torch.autograd.Function):
+    """ToRGB.call + the upsampled skip sum of SynthesisBlock.call (to_rgb.py:28-33, synthesis_block.py:152) and, for the
+    last block, mask_text_box (utils/utils.py:11-45) + NHWC -> NCHW, in one launch (``tbg_torgb_skip_fwd``)."""
+
+    @staticmethod
+    def forward(ctx, x, ws, bias, y_prev, words, nchw: bool):
+        x = x.contiguous()
+        ws = ws.contiguous()
+        if words is not None:
+            words = words.to(torch.int32).contiguous()
+        y_prev = y_prev.contiguous() if y_prev is not None else None
+        ctx.save_for_backward(x, ws, words)
+        ctx.nchw, ctx.has_prev = bool(nchw), y_prev is not None
+        return K.torgb_skip_fwd(x, ws, bias, y_prev, words, bool(nchw))
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import upfirdn as U
+
+        x, ws, words = ctx.saved_tensors
+        g = g.contiguous().float()
+        if ctx.nchw:
+            g = K.image_grad_nhwc(g, words)
+        elif words is not None:
+            g = K.image_grad_nhwc(g.permute(0, 3, 1, 2).contiguous(), words)
+        gx, gws = K.torgb_bwd(x, ws, g)
+        g_prev = U.upsample_2d_nhwc_adjoint(g) if ctx.has_prev else None
+        return gx, gws, g.sum(dim=(0, 1, 2)), g_prev, None, None

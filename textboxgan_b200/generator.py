@@ -91,14 +91,20 @@ class Generator(Model):
     def _word_encoder(self, words: torch.Tensor, batch_size: int, dropout_mask: Optional[torch.Tensor]):
         """word_encoder.py:39-63 -> NHWC [B, 2, 8, fm0] (the reference returns NCHW [B,fm0,2,8])."""
         cfg, P = self.cfg, self.params
+        out_h, out_w = cfg.generator_resolutions[0]
+        out_c = cfg.generator_feat_maps[0]
+        if L.use_fused():
+            from .fused import WordEncoderFn
+
+            return WordEncoderFn.apply(words, P["word_encoder/w0_embedding"], P["word_encoder/w_embedding"], dropout_mask,
+                                       P["word_encoder/fc/kernel"], P["word_encoder/fc/bias"], 1.0 - self.dropout_rate,
+                                       (out_h, out_w, out_c))
         table = torch.cat([P["word_encoder/w0_embedding"], P["word_encoder/w_embedding"]], dim=0)
         emb = table[words.long()]
         if dropout_mask is not None:
             emb = emb * dropout_mask / (1.0 - self.dropout_rate)
         x = emb.reshape(batch_size * cfg.max_char_number, cfg.embedding_out_dim)
         x = torch.relu(x @ P["word_encoder/fc/kernel"] + P["word_encoder/fc/bias"])
-        out_h, out_w = cfg.generator_resolutions[0]
-        out_c = cfg.generator_feat_maps[0]
         # reference: reshape [B, out_w, out_c, out_h] then transpose (0,2,3,1) -> [B, c, h, w];
         # NHWC is therefore [B, h, w, c] = permute(0, 3, 1, 2) of the reshaped tensor.
         return x.reshape(batch_size, out_w, out_c, out_h).permute(0, 3, 1, 2).contiguous().to(L.ACT_DTYPE)
@@ -107,6 +113,15 @@ class Generator(Model):
         """mapping_block.py:35-45.  lrelu(v)*sqrt2 == lrelu(sqrt2*v) (positive homogeneity), so each
         layer is one addmm (equalised-LR coefficient and sqrt2 folded into alpha) + one leaky-relu."""
         P = self.params
+        if L.use_fused():
+            from .fused import DenseAct, PixelNorm
+
+            x = PixelNorm.apply(z)
+            for i in range(self.cfg.n_mapping):
+                w = P[f"latent_encoder/g_mapping/dense_{i}/w"]
+                x = DenseAct.apply(x, w, P[f"latent_encoder/g_mapping/bias_{i}/b"], L.runtime_coef(w.shape, 1.0, 0.01), 0.01,
+                                   1, L.SQRT2, "mapping")
+            return x
         x = z * torch.rsqrt(torch.mean(z * z, dim=1, keepdim=True) + 1e-8)
         for i in range(self.cfg.n_mapping):
             w = P[f"latent_encoder/g_mapping/dense_{i}/w"]
@@ -146,8 +161,9 @@ class Generator(Model):
             wb = w_avg + (wb - w_avg) * truncation_psi                       # :73-78
         return wb
 
-    def _synthesis(self, x, style, noises, fused_epilogue: bool = False):
-        """synthesis_block.py:137-156; x NHWC bf16, returns NCHW fp32 image."""
+    def _synthesis(self, x, style, noises, fused_epilogue: bool = False, mask_words=None):
+        """synthesis_block.py:137-156; x NHWC bf16, returns NCHW fp32 image (zeroed right of the word when ``mask_words``
+        is given: mask_text_box, utils/utils.py:11-45, fused into the last skip sum)."""
         cfg, P = self.cfg, self.params
         res = cfg.generator_resolutions
         # style rows: ToRGB_0 <- 0; block i: conv_0 <- 3i, conv_1 <- 3i+1, ToRGB <- 3i+2 (:140,143-147)
@@ -161,7 +177,10 @@ class Generator(Model):
             sc = L.all_style_scales(style.float(), P, prefixes, idxs)        # one launch for all layers
         else:
             sc = [None] * len(prefixes)
-        y = L.to_rgb(x, style[:, 0], P, f"synthesis/{res[0][0]}x{res[0][1]}/ToRGB", s_pre=sc[0])
+        fused_rgb = L.use_fused()
+        last = len(res) - 2
+        y = L.to_rgb(x, style[:, 0], P, f"synthesis/{res[0][0]}x{res[0][1]}/ToRGB", s_pre=sc[0],
+                     skip_args=(None, None, False) if fused_rgb else None)
         for i, (h, w) in enumerate(res[1:]):
             pb = f"synthesis/{h}x{w}/block"
             s0, s1, s2 = style[:, 3 * i], style[:, 3 * i + 1], style[:, 3 * i + 2]
@@ -172,8 +191,20 @@ class Generator(Model):
             x = L.modulated_conv2d(x, s1, P, pb + "/conv_1", up=False, noise=n1, noise_strength=P[pb + "/noise_1/w"],
                                    bias=P[pb + "/bias_1/b"], act=True, fused_epilogue=fused_epilogue,
                                    s_pre=sc[3 * i + 2])
-            y = L.upsample_rgb(y) + L.to_rgb(x, s2, P, f"synthesis/{h}x{w}/ToRGB", s_pre=sc[3 * i + 3])
-        return y.permute(0, 3, 1, 2).contiguous()
+            if fused_rgb:
+                # ToRGB + upsampled skip (+ mask + NCHW on the last block) in one launch
+                y = L.to_rgb(x, s2, P, f"synthesis/{h}x{w}/ToRGB", s_pre=sc[3 * i + 3],
+                             skip_args=(y, mask_words if i == last else None, i == last))
+            else:
+                y = L.upsample_rgb(y) + L.to_rgb(x, s2, P, f"synthesis/{h}x{w}/ToRGB", s_pre=sc[3 * i + 3])
+        if fused_rgb:
+            return y
+        y = y.permute(0, 3, 1, 2).contiguous()
+        if mask_words is not None:
+            from .utils import mask_text_box
+
+            y = mask_text_box(y, mask_words, self.cfg.char_width)
+        return y
 
     def _noises(self, batch: int, draws: dict):
         if "noises" in draws:
@@ -183,8 +214,10 @@ class Generator(Model):
                 for _ in range(2)]
 
     def __call__(self, inputs, batch_size: Optional[int] = None, ret_style: bool = False,
-                 truncation_psi: float = 1.0, training: bool = False, draws: Optional[dict] = None):
-        """generator.py:19-43"""
+                 truncation_psi: float = 1.0, training: bool = False, draws: Optional[dict] = None,
+                 mask_output: bool = False):
+        """generator.py:19-43.  ``mask_output`` (extension): also apply mask_text_box(image, input_words) — the training
+        step's next statement (training_step.py:180) — inside the last ToRGB launch."""
         input_words, z_latent = inputs
         draws = draws or {}
         batch_size = batch_size or input_words.shape[0]
@@ -196,7 +229,8 @@ class Generator(Model):
         x = self._word_encoder(input_words, batch_size, mask)
         style = self._latent_encoder(z_latent, training, truncation_psi, draws)
         image_out = self._synthesis(x, style, self._noises(batch_size, draws),
-                                    fused_epilogue=not torch.is_grad_enabled())
+                                    fused_epilogue=not torch.is_grad_enabled(),
+                                    mask_words=input_words if mask_output else None)
         return (image_out, style) if ret_style else image_out
 
     @torch.no_grad()

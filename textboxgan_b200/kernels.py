@@ -90,12 +90,6 @@ def conv2d_igemm(
     _require(w, torch.bfloat16, "w")
     if isinstance(up, bool):
         up = (int(up), int(up))
-    if (HALO > 0 and residual is None and relu_mask is None and not out_fp32 and tap_mask is None and act in (0, 1)
-            and x.shape[1] == Ho and x.shape[2] == Wo and halo_applicable(x, w, taps, pad, stride, up)):
-        flops = 2.0 * x.shape[0] * Ho * Wo * w.shape[0] * 9 * x.shape[3]
-        with _Timed("conv_igemm", flops):      # same profiling bucket: it computes the same convolution
-            return conv3x3_halo(x, w, col_scale=col_scale, bias=bias, noise=noise, noise_strength=noise_strength, act=act,
-                                act_gain=act_gain, out=out)
     B, H, W_, Cin = x.shape
     n_total = w.shape[0]
     cout = n_total // ((1 + up[0]) * (1 + up[1]))
@@ -403,34 +397,6 @@ def style_dense_bwd(style: torch.Tensor, ws, gss, idxs, coef: float):
     return gstyle, gws, gbs
 
 
-# Experimental halo-reuse 3x3 convolution (csrc/conv_halo.cu).  HALO = 0: off; 1 / 2: on with descriptor base_offset 0 /
-# (start >> 7) & 7 — whichever variant scripts/exp_halo_umma.cu validates on the device.
-HALO = int(__import__("os").environ.get("TBG_CONV_HALO", "0"))
-
-
-def halo_applicable(x: torch.Tensor, w: torch.Tensor, taps, pad, stride, up) -> bool:
-    B, H, W_, Cin = x.shape
-    return (HALO > 0 and tuple(taps) == (3, 3) and tuple(pad) == (1, 1) and tuple(stride) == (1, 1) and not any(up)
-            and H % 16 == 0 and W_ % 16 == 0 and Cin % 64 == 0 and w.shape[0] in (32, 64, 128))
-
-
-def conv3x3_halo(x: torch.Tensor, w: torch.Tensor, *, col_scale=None, bias=None, noise=None, noise_strength=None,
-                 act: int = 0, act_gain: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 SAME conv, bf16 NHWC in/out — see include/tbg.h (tbg_conv3x3_halo)."""
-    _require(x, torch.bfloat16, "x")
-    _require(w, torch.bfloat16, "w")
-    B, H, W_, Cin = x.shape
-    cout = w.shape[0]
-    if out is None:
-        out = torch.empty((B, H, W_, cout), device=x.device, dtype=torch.bfloat16)
-    col_scale, bias = _aligned(col_scale), _aligned(bias)
-    st = _lib.load().tbg_conv3x3_halo(_ptr(x), _ptr(w), _ptr(out), B, H, W_, Cin, cout, _ptr(col_scale), _ptr(bias),
-                                      _ptr(noise), _ptr(noise_strength), int(act), float(act_gain), int(HALO == 2),
-                                      _stream())
-    _lib.check(st, "tbg_conv3x3_halo")
-    return out
-
-
 def crop_resize_fwd(img: torch.Tensor, labels: torch.Tensor, blank: int, char_width, out_hw) -> torch.Tensor:
     """convert_inputs forward — see include/tbg.h (tbg_crop_resize_fwd)."""
     from fractions import Fraction
@@ -556,3 +522,165 @@ def attn_decoder_bwd(mem: torch.Tensor, keys: torch.Tensor, w: dict, g_logits: t
                                           _ptr(g_mem), _ptr(g_keys), B, T, steps, _stream())
     _lib.check(st, "tbg_attn_decoder_bwd")
     return g_mem, g_keys
+
+
+# ----------------------------------------------------------------------------------------------
+# small fp32 dense layers, word encoder, batch statistics, RGB branch (csrc/dense.cu, stats.cu, rgb.cu)
+# ----------------------------------------------------------------------------------------------
+def dense_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, coef: float = 1.0, bias_coef: float = 1.0,
+              act: int = 0, gain: float = 1.0) -> torch.Tensor:
+    """y = act((x @ w) * coef + bias * bias_coef) * gain — x fp32 [M,K], w fp32 [K,N] (tbg_dense_fwd)."""
+    _require(x, torch.float32, "x")
+    _require(w, torch.float32, "w")
+    if bias is not None:
+        _require(bias, torch.float32, "bias")
+    M, Kd = x.shape
+    N = w.shape[1]
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    st = _lib.load().tbg_dense_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), M, Kd, N, float(coef), float(bias_coef), int(act),
+                                   float(gain), _stream())
+    _lib.check(st, "tbg_dense_fwd")
+    return y
+
+
+def dense_bwd(x: torch.Tensor, w: torch.Tensor, y: Optional[torch.Tensor], gy: torch.Tensor, *, coef: float = 1.0,
+              bias_coef: float = 1.0, act: int = 0, gain: float = 1.0, want_gx: bool = True, want_gw: bool = True,
+              want_gb: bool = True):
+    """-> (gx [M,K] | None, gw [K,N] | None, gb [N] | None) — see include/tbg.h (tbg_dense_bwd)."""
+    _require(gy, torch.float32, "gy")
+    M, Kd = x.shape
+    N = w.shape[1]
+    dev = x.device
+    gpre = torch.empty((M, N), device=dev, dtype=torch.float32)
+    gx = torch.empty((M, Kd), device=dev, dtype=torch.float32) if want_gx else None
+    gw = torch.empty((Kd, N), device=dev, dtype=torch.float32) if want_gw else None
+    gb = torch.empty((N,), device=dev, dtype=torch.float32) if want_gb else None
+    st = _lib.load().tbg_dense_bwd(_ptr(x), _ptr(w), _ptr(y), _ptr(gy), _ptr(gpre), _ptr(gx), _ptr(gw), _ptr(gb), M, Kd, N,
+                                   float(coef), float(bias_coef), int(act), float(gain), 0, _stream())
+    _lib.check(st, "tbg_dense_bwd")
+    return gx, gw, gb
+
+
+def pixel_norm_fwd(x: torch.Tensor) -> torch.Tensor:
+    _require(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().tbg_pixel_norm_fwd(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _stream()), "tbg_pixel_norm_fwd")
+    return y
+
+
+def pixel_norm_bwd(x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+    _require(x, torch.float32, "x")
+    _require(gy, torch.float32, "gy")
+    gx = torch.empty_like(x)
+    st = _lib.load().tbg_pixel_norm_bwd(_ptr(x), _ptr(gy), _ptr(gx), x.shape[0], x.shape[1], _stream())
+    _lib.check(st, "tbg_pixel_norm_bwd")
+    return gx
+
+
+def word_encoder_fwd(words: torch.Tensor, w0: torch.Tensor, table: torch.Tensor, mask: Optional[torch.Tensor], keep: float,
+                     fc_w: torch.Tensor, fc_b: torch.Tensor, out_hwc: tuple, act_dtype=torch.bfloat16):
+    """-> (out NHWC bf16 [B,h,w,c], emb fp32 [B*mcn,E], act fp32 [B*mcn,D]) — tbg_word_encoder_fwd."""
+    _require(words, torch.int32, "words")
+    for t, n in ((w0, "w0"), (table, "table"), (fc_w, "fc_w"), (fc_b, "fc_b")):
+        _require(t, torch.float32, n)
+    if mask is not None:
+        _require(mask, torch.float32, "mask")
+    B, mcn = words.shape
+    E, D = fc_w.shape
+    oh, ow, oc = out_hwc
+    dev = words.device
+    out = torch.empty((B, oh, ow, oc), device=dev, dtype=torch.bfloat16)
+    emb = torch.empty((B * mcn, E), device=dev, dtype=torch.float32)
+    act = torch.empty((B * mcn, D), device=dev, dtype=torch.float32)
+    st = _lib.load().tbg_word_encoder_fwd(_ptr(words), _ptr(w0), _ptr(table), _ptr(mask), float(keep), _ptr(fc_w),
+                                          _ptr(fc_b), _ptr(emb), _ptr(act), _ptr(out), B, mcn, E, D, oh, ow, oc, _stream())
+    _lib.check(st, "tbg_word_encoder_fwd")
+    return out, emb, act
+
+
+def word_encoder_bwd(words, mask, keep: float, fc_w, emb, act, g_out, table_rows: int, out_hwc: tuple):
+    """-> (g_table [V-1,E], g_fc_w [E,D], g_fc_b [D]) — tbg_word_encoder_bwd."""
+    _require(g_out, torch.bfloat16, "g_out")
+    B, mcn = words.shape
+    E, D = fc_w.shape
+    oh, ow, oc = out_hwc
+    dev = words.device
+    gpre = torch.empty((B * mcn, D), device=dev, dtype=torch.float32)
+    g_table = torch.zeros((table_rows, E), device=dev, dtype=torch.float32)
+    g_fc_w = torch.empty((E, D), device=dev, dtype=torch.float32)
+    g_fc_b = torch.empty((D,), device=dev, dtype=torch.float32)
+    st = _lib.load().tbg_word_encoder_bwd(_ptr(words), _ptr(mask), float(keep), _ptr(fc_w), _ptr(emb), _ptr(act),
+                                          _ptr(g_out), _ptr(gpre), _ptr(g_table), _ptr(g_fc_w), _ptr(g_fc_b), B, mcn, E, D,
+                                          oh, ow, oc, _stream())
+    _lib.check(st, "tbg_word_encoder_bwd")
+    return g_table, g_fc_w, g_fc_b
+
+
+def minibatch_std_fwd(x: torch.Tensor, n_calls: int, cpad: int, group_size: int = 4):
+    """x bf16 [n_calls*B, H, W, C] -> (xcat bf16 [n_calls*B, H, W, cpad] = [x | statistic | 0], stat fp32 [n_calls*B])."""
+    _require(x, torch.bfloat16, "x")
+    Bt, H, W_, C_ = x.shape
+    xcat = torch.empty((Bt, H, W_, cpad), device=x.device, dtype=torch.bfloat16)
+    stat = torch.empty((Bt,), device=x.device, dtype=torch.float32)
+    st = _lib.load().tbg_minibatch_std_fwd(_ptr(x), _ptr(xcat), _ptr(stat), Bt // n_calls, n_calls, group_size, H * W_, C_,
+                                           cpad, _stream())
+    _lib.check(st, "tbg_minibatch_std_fwd")
+    return xcat, stat
+
+
+def minibatch_std_bwd(x: torch.Tensor, gxcat: torch.Tensor, n_calls: int, group_size: int = 4) -> torch.Tensor:
+    _require(x, torch.bfloat16, "x")
+    _require(gxcat, torch.bfloat16, "gxcat")
+    Bt, H, W_, C_ = x.shape
+    gx = torch.empty_like(x)
+    st = _lib.load().tbg_minibatch_std_bwd(_ptr(x), _ptr(gxcat), _ptr(gx), Bt // n_calls, n_calls, group_size, H * W_, C_,
+                                           gxcat.shape[3], _stream())
+    _lib.check(st, "tbg_minibatch_std_bwd")
+    return gx
+
+
+def r1_sqnorm(g: torch.Tensor) -> torch.Tensor:
+    """out[b] = sum of g[b]^2 over everything but the batch axis (fp32)."""
+    _require(g, torch.float32, "g")
+    B = g.shape[0]
+    out = torch.empty((B,), device=g.device, dtype=torch.float32)
+    _lib.check(_lib.load().tbg_r1_sqnorm(_ptr(g), _ptr(out), B, g.numel() // B, _stream()), "tbg_r1_sqnorm")
+    return out
+
+
+def r1_sqnorm_bwd(g: torch.Tensor, gout: torch.Tensor) -> torch.Tensor:
+    _require(g, torch.float32, "g")
+    _require(gout, torch.float32, "gout")
+    gg = torch.empty_like(g)
+    B = g.shape[0]
+    _lib.check(_lib.load().tbg_r1_sqnorm_bwd(_ptr(g), _ptr(gout), _ptr(gg), B, g.numel() // B, _stream()), "tbg_r1_sqnorm_bwd")
+    return gg
+
+
+def torgb_skip_fwd(x: torch.Tensor, ws: torch.Tensor, bias: Optional[torch.Tensor], y_prev: Optional[torch.Tensor],
+                   words: Optional[torch.Tensor], nchw: bool) -> torch.Tensor:
+    """ToRGB + upsampled skip (+ mask_text_box + NCHW layout) — see include/tbg.h (tbg_torgb_skip_fwd)."""
+    _require(x, torch.bfloat16, "x")
+    _require(ws, torch.float32, "ws")
+    B, H, W_, C_ = x.shape
+    if y_prev is not None:
+        _require(y_prev, torch.float32, "y_prev")
+    mcn = 0
+    if words is not None:
+        _require(words, torch.int32, "words")
+        mcn = words.shape[1]
+    out = torch.empty((B, 3, H, W_) if nchw else (B, H, W_, 3), device=x.device, dtype=torch.float32)
+    st = _lib.load().tbg_torgb_skip_fwd(_ptr(x), _ptr(ws), _ptr(bias), _ptr(y_prev), _ptr(words), _ptr(out), B, H, W_, C_,
+                                        mcn, int(nchw), _stream())
+    _lib.check(st, "tbg_torgb_skip_fwd")
+    return out
+
+
+def image_grad_nhwc(g: torch.Tensor, words: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32 NCHW [B,3,H,W] -> masked NHWC [B,H,W,3] (adjoint of the mask + layout change of torgb_skip_fwd)."""
+    _require(g, torch.float32, "g")
+    B, _, H, W_ = g.shape
+    mcn = words.shape[1] if words is not None else 0
+    out = torch.empty((B, H, W_, 3), device=g.device, dtype=torch.float32)
+    _lib.check(_lib.load().tbg_image_grad_nhwc(_ptr(g), _ptr(words), _ptr(out), B, H, W_, mcn, _stream()), "tbg_image_grad_nhwc")
+    return out

@@ -147,12 +147,19 @@ def all_style_scales(style: torch.Tensor, P: Params, prefixes, idxs):
 
 
 def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str,
-           s_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """1x1 modulated conv without demodulation + bias, fp32 [B,H,W,3] (to_rgb.py:28-33)."""
+           s_pre: Optional[torch.Tensor] = None, skip_args=None) -> torch.Tensor:
+    """1x1 modulated conv without demodulation + bias, fp32 [B,H,W,3] (to_rgb.py:28-33).  ``skip_args`` =
+    (y_prev | None, mask_words | None, nchw): fused with the upsampled skip sum of synthesis_block.py:152 and, on the last
+    block, mask_text_box and the NCHW layout of the image (fused.ToRGBSkip)."""
     w_raw = P[prefix + "/conv/w"]                                           # [1,1,C,3]
     w = runtime_coef(w_raw.shape) * w_raw[0, 0]
     s = s_pre if s_pre is not None else style_scale(style, P, prefix + "/conv")
     ws = s[:, :, None] * w[None]                                            # [B,C,3]
+    if use_fused() and skip_args is not None:
+        from .fused import ToRGBSkip
+
+        y_prev, mask_words, nchw = skip_args
+        return ToRGBSkip.apply(x, ws, P[prefix + "/bias/b"], y_prev, mask_words, nchw)
     if use_fused():
         from .fused import ToRGB
 

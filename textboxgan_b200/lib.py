@@ -83,7 +83,8 @@ _SIGNATURES = [
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
     ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
-    ("tbg_conv3x3_halo", c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 4 + [c_int, c_float, c_int, c_void_p]),
+    ("tbg_set_tuning", c_int, [C.c_char_p, c_int]),
+    ("tbg_get_tuning", c_int, [C.c_char_p]),
     ("tbg_crop_resize_fwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_crop_resize_bwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
@@ -97,6 +98,18 @@ _SIGNATURES = [
     ("tbg_demod_bwd", c_int, [c_void_p] * 12 + [c_int] * 3 + [c_void_p]),
     ("tbg_attn_decoder_fwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
     ("tbg_attn_decoder_bwd", c_int, [c_void_p, c_void_p, C.POINTER(DecWeights)] + [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
+    ("tbg_dense_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_int, c_float, c_void_p]),
+    ("tbg_dense_bwd", c_int, [c_void_p] * 8 + [c_int] * 3 + [c_float, c_float, c_int, c_float, c_int, c_void_p]),
+    ("tbg_pixel_norm_fwd", c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    ("tbg_pixel_norm_bwd", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    ("tbg_word_encoder_fwd", c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    ("tbg_word_encoder_bwd", c_int, [c_void_p] * 2 + [c_float] + [c_void_p] * 8 + [c_int] * 7 + [c_void_p]),
+    ("tbg_minibatch_std_fwd", c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    ("tbg_minibatch_std_bwd", c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    ("tbg_r1_sqnorm", c_int, [c_void_p, c_void_p, c_int, C.c_longlong, c_void_p]),
+    ("tbg_r1_sqnorm_bwd", c_int, [c_void_p, c_void_p, c_void_p, c_int, C.c_longlong, c_void_p]),
+    ("tbg_torgb_skip_fwd", c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    ("tbg_image_grad_nhwc", c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
 ]
 
 
@@ -121,6 +134,15 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def set_tuning(key: str, value: int) -> None:
+    """``tbg_set_tuning`` (include/tbg.h): explicit kernel-selection switches for tests and perf scripts."""
+    check(load().tbg_set_tuning(key.encode(), int(value)), f"tbg_set_tuning({key})")
+
+
+def get_tuning(key: str) -> int:
+    return int(load().tbg_get_tuning(key.encode()))
 
 
 def check(status: int, what: str) -> None:

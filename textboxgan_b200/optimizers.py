@@ -98,7 +98,10 @@ class Adam:
             o, cnt = model.segments[n]
             view = g[o - start: o - start + cnt]
             if gr is None:
-                view.zero_()
+                # Keras apply_gradients skips variables without a gradient (their m / v slots stay untouched); a zero
+                # gradient pushed through Adam would decay v instead.  Every variable of the three groups of
+                # training_step.py:194-213 is used on every step, so a missing gradient is a wiring error.
+                raise RuntimeError(f"Adam.apply_gradients: variable '{n}' of the flat group has no gradient")
             else:
                 dsts.append(view)
                 srcs.append(gr.detach().reshape(-1))

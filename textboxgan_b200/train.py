@@ -104,7 +104,10 @@ class Trainer:
         (reg_g, g, pl_pen), (reg_d, d, r1_pen), ocr = self.training_step.dist_train_step(
             real_images, ocr_image, input_words, ocr_labels, r1, pl, self.ocr_weight(step))
         self.g_clone.set_as_moving_average_of(self.generator)                                      # train.py:208
-        return dict(zip(TRAIN_LOSSES, (reg_g, g, pl_pen, ocr, reg_d, d, r1_pen)))
+        # ONE device -> host read of the seven scalars per iteration (every tracker then works on Python floats)
+        vals = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=reg_g.device).reshape(())
+                            for v in (reg_g, g, pl_pen, ocr, reg_d, d, r1_pen)]).tolist()
+        return dict(zip(TRAIN_LOSSES, vals))
 
     def _validate(self, tracker: LossTracker, step: int) -> None:
         for words, labels in self.strategy.experimental_distribute_dataset(self.validation_dataset):

@@ -204,8 +204,8 @@ class TrainingStep:
         G, D = self.generator, self.discriminator
         dev = G.device
         z = draws["z"].to(dev) if "z" in draws else torch.randn(self.batch_size_per_gpu, self.z_dim, device=dev)
-        fake_images = G((input_words, z), training=True, draws=draws)                        # :178
-        fake_images = mask_text_box(fake_images, input_words, self.char_width)              # :180
+        # :178 + :180 — mask_text_box(fake_images, input_words) runs inside the generator's last ToRGB launch
+        fake_images = G((input_words, z), training=True, draws=draws, mask_output=True)
 
         # The OCR branch (convert_inputs -> ASTER -> loss, :375-402) only shares ``fake_images`` with the
         # discriminator branch: it is issued on a second stream so that its latency-bound kernels (whole-sequence
@@ -327,7 +327,12 @@ class TrainingStep:
             real_scores = self.discriminator(real_images)
         real_loss = real_scores.sum()
         (real_grads,) = torch.autograd.grad(real_loss, real_images, create_graph=True)
-        r1_penalty = (real_grads ** 2).sum(dim=(1, 2, 3))[:, None]
+        if real_grads.is_cuda:
+            from .fused import R1SqNorm
+
+            r1_penalty = R1SqNorm.apply(real_grads)[:, None]                                 # one reduction launch
+        else:
+            r1_penalty = (real_grads ** 2).sum(dim=(1, 2, 3))[:, None]
         r1_penalty = r1_penalty * (0.5 * self.r1_gamma) * self.d_reg_interval
         r1_penalty = r1_penalty.sum() / self.batch_size
         return real_scores, r1_penalty

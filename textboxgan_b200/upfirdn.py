@@ -9,50 +9,20 @@ from __future__ import annotations
 
 from functools import lru_cache
 
-import numpy as np
 import torch
 
 from . import kernels as K
 
 
-def _setup_kernel(k) -> np.ndarray:
-    """upfirdn_2d_v2.py:18-25"""
-    k = np.asarray(k, dtype=np.float32)
-    if k.ndim == 1:
-        k = np.outer(k, k)
-    k /= np.sum(k)
-    assert k.ndim == 2 and k.shape[0] == k.shape[1]
-    return k
-
-
-def compute_paddings(resample_kernel, up, down, is_conv, convW=3, factor=2, gain=1):
-    """upfirdn_2d_v2.py:28-55"""
-    assert not (up and down)
-    k = [1] * factor if resample_kernel is None else resample_kernel
-    if up:
-        k = _setup_kernel(k) * (gain * (factor ** 2))
-        if is_conv:
-            p = (k.shape[0] - factor) - (convW - 1)
-            pad0 = (p + 1) // 2 + factor - 1
-            pad1 = p // 2 + 1
-        else:
-            p = k.shape[0] - factor
-            pad0 = (p + 1) // 2 + factor - 1
-            pad1 = p // 2
-    elif down:
-        k = _setup_kernel(k) * gain
-        if is_conv:
-            p = (k.shape[0] - factor) + (convW - 1)
-            pad0 = (p + 1) // 2
-            pad1 = p // 2 + 1
-        else:
-            p = k.shape[0] - factor
-            pad0 = (p + 1) // 2
-            pad1 = p // 2
-    else:
-        k = resample_kernel
-        pad0, pad1 = 0, 0
-    return k, pad0, pad1
+# Resampling constants of the four sites the reference evaluates its padding rule at (SURVEY.md Appendix A.4;
+# FIR k = outer([1,3,3,1]) / 64 times the gain).  (gain, pad0, pad1):
+RESAMPLE_SITES = {
+    "modconv_up": (4.0, 1, 1),     # upsample_conv_2d: convT(3x3, s2, VALID) -> pad -> 4x4 FIR   (modulated_conv2d.py:47-49)
+    "rgb_up": (4.0, 2, 1),         # upsample_2d of the RGB skip: zero-insert x2 -> pad -> FIR     (synthesis_block.py:97-99)
+    "conv_down_3x3": (1.0, 2, 3),  # conv_downsample_2d in front of a 3x3 stride-(2|1,2) conv      (conv.py:37-39)
+    "conv_down_1x1": (1.0, 1, 2),  # ... in front of the 1x1 skip conv
+}
+FIR_TAPS = (1.0, 3.0, 3.0, 1.0)
 
 
 class _UpFirDn2D(torch.autograd.Function):
@@ -89,13 +59,26 @@ def upfirdn_2d(x: torch.Tensor, k: torch.Tensor, upx=1, upy=1, downx=1, downy=1,
 
 @lru_cache(maxsize=None)
 def _fir_kernel(device_str: str, gain: float) -> torch.Tensor:
-    k = _setup_kernel([1, 3, 3, 1]) * gain
-    return torch.as_tensor(k, dtype=torch.float32, device=device_str)
+    t = torch.tensor(FIR_TAPS, dtype=torch.float64)
+    k = torch.outer(t, t)
+    return (k / k.sum() * gain).to(dtype=torch.float32, device=device_str)
 
 
-def upsample_2d_nhwc(y: torch.Tensor, factor: int = 2) -> torch.Tensor:
-    """upsample_2d (upfirdn_2d_v2.py:58-62) for an NHWC tensor [B,H,W,C]: k = [1,3,3,1]^2/64 * 4,
-    pad0 = 2, pad1 = 1 (compute_paddings(up=True, is_conv=False))."""
-    _, pad0, pad1 = compute_paddings([1, 3, 3, 1], up=True, down=False, is_conv=False)
-    k = _fir_kernel(str(y.device), float(factor ** 2))
-    return upfirdn_2d(y, k, upx=factor, upy=factor, padx0=pad0, padx1=pad1, pady0=pad0, pady1=pad1)
+def upsample_2d_nhwc(y: torch.Tensor) -> torch.Tensor:
+    """upsample_2d (upfirdn_2d_v2.py:58-62) for an NHWC tensor [B,H,W,C]: zero-insert x2, pad 2 / 1,
+    k = outer([1,3,3,1]) / 64 * 4."""
+    gain, pad0, pad1 = RESAMPLE_SITES["rgb_up"]
+    k = _fir_kernel(str(y.device), gain)
+    return upfirdn_2d(y, k, upx=2, upy=2, padx0=pad0, padx1=pad1, pady0=pad0, pady1=pad1)
+
+
+def upsample_2d_nhwc_adjoint(g: torch.Tensor) -> torch.Tensor:
+    """Gradient of :func:`upsample_2d_nhwc` with respect to its input: the same op with up and down exchanged
+    (upfirdn_2d_v2.py:205-246); g [B,2H,2W,C] -> [B,H,W,C]."""
+    gain, pad0, pad1 = RESAMPLE_SITES["rgb_up"]
+    k = _fir_kernel(str(g.device), gain)                       # symmetric: flipping it is the identity
+    inH, inW = g.shape[1] // 2, g.shape[2] // 2
+    gp0 = 4 - pad0 - 1
+    gpx1 = inW * 2 - g.shape[2] + pad0 - 2 + 1
+    gpy1 = inH * 2 - g.shape[1] + pad0 - 2 + 1
+    return K.upfirdn2d(g.contiguous(), k, downx=2, downy=2, padx0=gp0, padx1=gpx1, pady0=gp0, pady1=gpy1)

@@ -32,12 +32,12 @@ class ValidationStep:
         return strategy.reduce("SUM", ocr_loss, axis=None)
 
     @torch.no_grad()
-    def _validation_step(self, input_words, ocr_labels, z: Optional[torch.Tensor] = None):
-        """validation_step.py:57-90"""
+    def _validation_step(self, input_words, ocr_labels, z: Optional[torch.Tensor] = None, draws: Optional[dict] = None):
+        """validation_step.py:57-90 (``z`` / ``draws`` inject the latent and the per-layer noise for parity tests)."""
         dev = self.generator.device
         if z is None:
             z = torch.randn(input_words.shape[0], self.z_dim, device=dev)
-        fake_images = self.generator((input_words, z), training=False)
+        fake_images = self.generator((input_words, z), training=False, draws=draws)
         fake_images = mask_text_box(fake_images, input_words, self.char_width)
         ocr_input_image = self.aster_ocr.convert_inputs(fake_images, ocr_labels, blank_label=1, cfg=self.cfg)
         logits = self.aster_ocr(ocr_input_image)
