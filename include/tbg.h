@@ -36,6 +36,9 @@ int tbg_version(void);
  * gpu_launches counter). tbg_reset_launch_count() zeroes it. */
 long long tbg_launch_count(void);
 void tbg_reset_launch_count(void);
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the tensor checksum of TensorFlow
+ * checkpoints (tf.train.Checkpoint files of train.py:94-108, read by textboxgan_b200/tf_checkpoint.py).  No device work. */
+unsigned int tbg_crc32c(const void* data, unsigned long long n, unsigned int crc);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
@@ -183,9 +186,12 @@ int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, i
  *   "conv_halo" (default 1)   tbg_conv2d_igemm runs 3x3 stride-1 pad-1 convolutions whose grid is a multiple of 16 x 16
  *                             pixels (Cin % 64 == 0, cout % 32 == 0, no residual / relu_mask / fp32 output) on the
  *                             halo-reuse kernel of csrc/conv_halo.cu: same arguments, same results;
- *   "igemm_staged" (1)        conv_igemm epilogue stores transposed through shared memory;
+ *   "igemm_staged" (0)        conv_igemm epilogue stores transposed through shared memory;
  *   "igemm_msub" (1)          2: two M tiles per work item share each weight box (N <= 128);
- *   "wgrad_staged" (1), "wgrad_items_per_sm" (0 = heuristic), "lstm_cluster" (1).
+ *   "wgrad_staged" (0), "wgrad_items_per_sm" (0 = heuristic), "lstm_cluster" (1);
+ *   "wgrad_halo" (1)          tbg_conv2d_wgrad runs 3x3 stride-1 pad-1 weight gradients on large grids on the halo-reuse
+ *                             kernel of csrc/conv_wgrad_halo.cu;
+ *   "halo_a_stages" (2..3), "halo_b_stages" (2..8), "halo_staged" (0|1): pipeline depth / store path of conv_halo.
  * tbg_get_tuning returns the current value or -1 for an unknown key. */
 int tbg_set_tuning(const char* key, int value);
 int tbg_get_tuning(const char* key);

@@ -93,7 +93,7 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_attn_decoder_bwd": lambda: h.tbg_attn_decoder_bwd(None, P, None, P, P, P, P, P, P, P, P, 1, 8, 4, None),
     }
     covered = set(calls) | {"tbg_conv2d_igemm", "tbg_upfirdn2d", "tbg_last_error", "tbg_version", "tbg_launch_count",
-                            "tbg_reset_launch_count", "tbg_get_tuning"}
+                            "tbg_reset_launch_count", "tbg_get_tuning", "tbg_crc32c"}
     assert covered == set(lib.exported_symbols()), set(lib.exported_symbols()) ^ covered
     for name, call in calls.items():
         st = call()

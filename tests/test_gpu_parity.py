@@ -781,3 +781,34 @@ def test_launches_are_counted_and_library_is_loaded():
     assert h.tbg_launch_count() >= 6
     maps = open("/proc/self/maps").read()
     assert "libtbg.so" in maps
+
+
+@pytest.mark.parametrize("B,H,W,I,O", [(8, 32, 64, 128, 128), (4, 16, 64, 256, 256), (16, 32, 32, 64, 64),
+                                       (6, 16, 128, 192, 96)])
+def test_wgrad_halo_kernel_vs_emulated_semantics_and_wgrad(B, H, W, I, O):
+    """The halo-reuse weight-gradient kernel behind tbg_conv2d_wgrad (tuning wgrad_halo = 1: one x halo box per 64-channel
+    block shared by the taps of a work item, MN-major shifted windows) against the documented semantics of the entry
+    point and against conv_wgrad_kernel on the same arguments; accumulation into a non-zero gw."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
+
+    g = C.plain_geom(H, W, I, O, 3)
+    gen = torch.Generator().manual_seed(B * 100 + H + I)
+    x = _bf16_round(torch.randn(B, H, W, I, generator=gen))
+    gy = _bf16_round(torch.randn(B, H, W, O, generator=gen))
+    init = torch.randn(O, 9 * I, generator=gen)
+    want = emu_conv2d_wgrad(x, gy, **g.kernel_kwargs()).double() + init.double()
+    saved = lib.get_tuning("wgrad_halo")
+    try:
+        got = {}
+        for halo in (1, 0):
+            lib.set_tuning("wgrad_halo", halo)
+            gw = init.clone().to(DEV)
+            K.conv2d_wgrad(x.to(DEV).bfloat16(), gy.to(DEV).bfloat16(), gw=gw, **g.kernel_kwargs())
+            got[halo] = gw.cpu()
+    finally:
+        lib.set_tuning("wgrad_halo", saved)
+    for halo in (1, 0):
+        assert rel_err(got[halo], want) < 2e-5, halo            # fp32 accumulation of exact bf16 products
+    assert rel_err(got[1], got[0]) < 2e-5

@@ -42,11 +42,13 @@ struct HaloParams {
   int act;
   float act_gain;
   void* out;                     // bf16 [B, out_H, out_W, cout]
+  int a_stages, b_stages;        // halo boxes / weight boxes in flight (the kernel is bound by TMA bytes in flight)
+  int staged;                    // epilogue stores through the shared-memory transpose (else 16-byte pieces per thread)
 };
 
 static constexpr int kHaloPitch = 24, kHaloRows = 18;
 static constexpr uint32_t kHaloBytes = kHaloPitch * kHaloRows * 128;   // 55296 = 54 * 1024
-static constexpr int kHaloAStages = 2, kHaloBStages = 4;
+static constexpr int kHaloMaxA = 3, kHaloMaxB = 8;
 static constexpr int kHaloEpiWarps = 8;
 static constexpr uint32_t kHStgRow = 128 + 16;                          // 64 bf16 columns of a row + padding
 static constexpr uint32_t kHStgWarp = 32 * kHStgRow;                    // 4608 B per epilogue warp
@@ -59,18 +61,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int N = p.block_n;
   const uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
-  uint8_t* smA = smem;                                         // kHaloAStages x 54 KB (each 1024-aligned)
-  uint8_t* smB = smem + kHaloAStages * kHaloBytes;             // kHaloBStages x N*128 B
+  const int kHaloAStages = p.a_stages, kHaloBStages = p.b_stages;
+  uint8_t* smA = smem;                                         // a_stages x 54 KB (each 1024-aligned)
+  uint8_t* smB = smem + kHaloAStages * kHaloBytes;             // b_stages x N*128 B
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kHaloBStages * b_bytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + kHaloAStages;
-  uint64_t* b_full = bars + 2 * kHaloAStages;
-  uint64_t* b_empty = b_full + kHaloBStages;
-  uint64_t* tfull = b_empty + kHaloBStages;
+  uint64_t* a_empty = bars + kHaloMaxA;
+  uint64_t* b_full = bars + 2 * kHaloMaxA;
+  uint64_t* b_empty = b_full + kHaloMaxB;
+  uint64_t* tfull = b_empty + kHaloMaxB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* stg_base = reinterpret_cast<uint8_t*>(tempty + 4);                  // 16-byte aligned
-  float* vec_base = reinterpret_cast<float*>(stg_base + kHaloEpiWarps * kHStgWarp);
+  float* vec_base = reinterpret_cast<float*>(tempty + 4);                      // 16-byte aligned
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(vec_base) + kHaloEpiWarps * kHVecWarp;   // staged path only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && elect_one()) {
@@ -254,9 +257,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           pk.y = pack_bf16x2(f[2], f[3]);
           pk.z = pack_bf16x2(f[4], f[5]);
           pk.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(srow + g * 16) = pk;
+          if (p.staged)
+            *reinterpret_cast<uint4*>(srow + g * 16) = pk;
+          else
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_el + j * 32 + g * 8) = pk;
         }
-        if ((j + 1) % j_per_chunk == 0) {
+        if (p.staged && (j + 1) % j_per_chunk == 0) {
           // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
           __syncwarp();
           const long long chunk_el = static_cast<long long>((j / j_per_chunk) * chunk_cols);
@@ -325,8 +331,16 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
     int rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  const size_t smem_bytes = kHaloAStages * kHaloBytes + kHaloBStages * (size_t)block_n * 128 + 256 +
-                            kHaloEpiWarps * (kHStgWarp + kHVecWarp) + 1024;
+  p.staged = g_tuning.halo_staged;
+  p.a_stages = g_tuning.halo_a_stages;
+  p.b_stages = g_tuning.halo_b_stages;
+  const size_t epi_bytes = kHaloEpiWarps * (kHVecWarp + (p.staged ? kHStgWarp : 0u));
+  auto smem_need = [&]() {
+    return (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * block_n * 128 + 512 + epi_bytes + 1024;
+  };
+  while (smem_need() > 227 * 1024 && p.b_stages > 2) --p.b_stages;
+  while (smem_need() > 227 * 1024 && p.a_stages > 2) --p.a_stages;
+  const size_t smem_bytes = smem_need();
   static bool attr_set = false;
   if (!attr_set) {
     TBG_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

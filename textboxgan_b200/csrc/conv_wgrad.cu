@@ -294,6 +294,9 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
                 "tbg_conv2d_wgrad: strides must be 1 or 2");
   TBG_CHECK_ARG((a->up_h | a->up_w) == 0 || a->cout % 64 == 0, "tbg_conv2d_wgrad: up needs cout %% 64 == 0");
 
+  // 3x3 stride-1 SAME convolutions on large grids: one x halo box per 64-channel block shared by up to four taps
+  if (g_tuning.wgrad_halo && wgrad_halo_applicable(a)) return wgrad_halo_launch(a, stream);
+
   WgradParams p{};
   p.B = a->B;
   p.n_total = a->n_total;
@@ -324,7 +327,7 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   int P = 64;
   {
     const uint32_t stage64 = 2u * 64 * 128 + (uint32_t)p.G * (p.block_c / 64) * 64 * 128;
-    if (stage64 * 3 > 225u * 1024u - kWgStgBytes) P = 32;
+    if (stage64 * 3 > 225u * 1024u - (p.staged ? kWgStgBytes : 0u)) P = 32;
   }
   const int npix = a->Ho * a->Wo;
   while (P > 1 && (int64_t)P > (int64_t)npix * a->B) P >>= 1;  // tiny problems
@@ -367,12 +370,13 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
 
   const uint32_t chunk_bytes = (uint32_t)P * 128u;
   const uint32_t stage_bytes = 2u * chunk_bytes + (uint32_t)p.G * (p.block_c / 64) * chunk_bytes;
-  const uint32_t budget = 227u * 1024u - 1024u - 256u - kWgStgBytes;
+  const uint32_t stg_bytes = p.staged ? kWgStgBytes : 0u;
+  const uint32_t budget = 227u * 1024u - 1024u - 256u - stg_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   TBG_CHECK_ARG(stages >= 2, "tbg_conv2d_wgrad: stage too large (%u bytes)", stage_bytes);
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + kWgStgBytes;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + stg_bytes;
 
   CUtensorMap tmGY, tmX;
   {

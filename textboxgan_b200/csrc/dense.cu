@@ -3,7 +3,8 @@
 // (word_encoder.py:39-63: embedding lookup, dropout, Keras Dense(256) + ReLU, reshape/transpose to the base feature map)
 // and the discriminator head (discriminator.py:132-142, 213).  All are parameter-sized GEMMs (M = batch or batch*chars,
 // K, N <= 8192): exact fp32 FMA on the CUDA cores (the reference computes them in fp32; a TF32 library GEMM would be
-// narrower), 32 x 32 output tile per CTA, K streamed through shared memory in 32-deep slabs.
+// narrower), 64 x 64 output tile per CTA (4 x 4 per thread), K streamed through shared memory in 16-deep slabs, split-K
+// over CTAs (fp32 atomics + a finishing pass) when a long reduction meets few output tiles.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -24,57 +25,95 @@ struct DenseEpilogue {
   int accumulate;      // 1: C += result (no bias / activation)
 };
 
-static constexpr int kDT = 32;   // tile edge (M, N and K)
+static constexpr int kDM = 64, kDN = 64, kDK = 16;   // CTA tile (4 x 4 outputs per thread, 256 threads)
 
+__device__ __forceinline__ float dense_epilogue(float r, int j, const DenseEpilogue& ep) {
+  if (ep.bias) r = fmaf(__ldg(ep.bias + j), ep.bias_coef, r);
+  if (ep.act == 1) r = r > 0.f ? r : 0.2f * r;
+  else if (ep.act == 2) r = fmaxf(r, 0.f);
+  return r * ep.gain;
+}
+
+// blockIdx.z = K split: split s handles k in [s*k_per_split, (s+1)*k_per_split).  With one split the epilogue is applied
+// here; with several the partial products (times alpha) are added atomically into C, which the host entry zeroed, and
+// dense_finish_kernel applies the epilogue afterwards.
 __global__ void __launch_bounds__(256)
-dense_gemm_kernel(GemmOperand A, GemmOperand Bm, float* __restrict__ C, long long ldc, int M, int N, int K, float alpha,
-                  DenseEpilogue ep) {
-  __shared__ float As[kDT][kDT + 1];   // [k][i]
-  __shared__ float Bs[kDT][kDT + 1];   // [k][j]
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16 threads, 2 x 2 outputs each
-  const int i0 = blockIdx.y * kDT, j0 = blockIdx.x * kDT;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+dense_gemm_kernel(GemmOperand A, GemmOperand Bm, float* __restrict__ C, long long ldc, int M, int N, int K, int k_per_split,
+                  float alpha, DenseEpilogue ep) {
+  __shared__ __align__(16) float As[kDK][kDM + 4];   // [k][i]
+  __shared__ __align__(16) float Bs[kDK][kDN + 4];   // [k][j]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16 threads
+  const int i0 = blockIdx.y * kDM, j0 = blockIdx.x * kDN;
+  const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
   // loader mapping: consecutive threads along whichever index is contiguous in memory
   const bool a_kfast = (A.s_k == 1), b_kfast = (Bm.s_k == 1);
-  for (int k0 = 0; k0 < K; k0 += kDT) {
+  int a_i[4], a_k[4], b_j[4], b_k[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = threadIdx.x + 256 * r;            // 1024 elements per operand tile
+    a_i[r] = a_kfast ? (e >> 4) : (e & 63);
+    a_k[r] = a_kfast ? (e & 15) : (e >> 6);
+    b_j[r] = b_kfast ? (e >> 4) : (e & 63);
+    b_k[r] = b_kfast ? (e & 15) : (e >> 6);
+  }
+  float ra[4], rb[4];                                // next slab, prefetched into registers during the FMAs
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int e = threadIdx.x + 256 * r;
-      const int a_i = a_kfast ? (e >> 5) : (e & 31), a_k = a_kfast ? (e & 31) : (e >> 5);
-      const int b_j = b_kfast ? (e >> 5) : (e & 31), b_k = b_kfast ? (e & 31) : (e >> 5);
-      const int gi = i0 + a_i, gka = k0 + a_k, gj = j0 + b_j, gkb = k0 + b_k;
-      As[a_k][a_i] = (gi < M && gka < K) ? __ldg(A.p + gi * A.s_outer + gka * A.s_k) : 0.f;
-      Bs[b_k][b_j] = (gj < N && gkb < K) ? __ldg(Bm.p + gj * Bm.s_outer + gkb * Bm.s_k) : 0.f;
+      const int gi = i0 + a_i[r], gka = k0 + a_k[r], gj = j0 + b_j[r], gkb = k0 + b_k[r];
+      ra[r] = (gi < M && gka < k_end) ? __ldg(A.p + gi * A.s_outer + gka * A.s_k) : 0.f;
+      rb[r] = (gj < N && gkb < k_end) ? __ldg(Bm.p + gj * Bm.s_outer + gkb * Bm.s_k) : 0.f;
+    }
+  };
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += kDK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      As[a_k[r]][a_i[r]] = ra[r];
+      Bs[b_k[r]][b_j[r]] = rb[r];
     }
     __syncthreads();
+    if (k0 + kDK < k_end) fetch(k0 + kDK);
 #pragma unroll
-    for (int k = 0; k < kDT; ++k) {
-      const float a0 = As[k][ty], a1 = As[k][ty + 16];
-      const float b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]);
-      acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]);
-      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    for (int k = 0; k < kDK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
     }
     __syncthreads();
   }
+  const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < 4; ++u) {
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int i = i0 + ty + 16 * u, j = j0 + tx + 16 * v;
+    for (int v = 0; v < 4; ++v) {
+      const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
       if (i >= M || j >= N) continue;
-      float r = acc[u][v] * alpha;
+      const float r = acc[u][v] * alpha;
       float* dst = C + i * ldc + j;
-      if (ep.accumulate) {
-        *dst += r;
-        continue;
-      }
-      if (ep.bias) r = fmaf(__ldg(ep.bias + j), ep.bias_coef, r);
-      if (ep.act == 1) r = r > 0.f ? r : 0.2f * r;
-      else if (ep.act == 2) r = fmaxf(r, 0.f);
-      *dst = r * ep.gain;
+      if (split) atomicAdd(dst, r);
+      else if (ep.accumulate) *dst += r;
+      else *dst = dense_epilogue(r, j, ep);
     }
+  }
+}
+
+__global__ void dense_finish_kernel(float* __restrict__ C, long long ldc, int M, int N, DenseEpilogue ep) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e / N), j = static_cast<int>(e - static_cast<long long>(i) * N);
+    float* dst = C + i * ldc + j;
+    *dst = dense_epilogue(*dst, j, ep);
   }
 }
 
@@ -197,10 +236,33 @@ __global__ void word_encoder_bwd_kernel(const int* __restrict__ words, const flo
 
 static int launch_gemm(GemmOperand A, GemmOperand Bm, float* C, long long ldc, int M, int N, int K, float alpha,
                        DenseEpilogue ep, cudaStream_t stream) {
-  dim3 grid((N + kDT - 1) / kDT, (M + kDT - 1) / kDT);
-  dense_gemm_kernel<<<grid, 256, 0, stream>>>(A, Bm, C, ldc, M, N, K, alpha, ep);
+  dim3 grid((N + kDN - 1) / kDN, (M + kDM - 1) / kDM, 1);
+  // long reductions over few output tiles (the 8192 -> 512 discriminator dense layer at batch 64-128): split K so that
+  // about two CTAs per SM are busy, each split at least 128 deep
+  int splits = 1;
+  const int tiles = grid.x * grid.y;
+  if (tiles < 148 && K >= 512) {
+    splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > K / 128) splits = K / 128;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ((K + splits - 1) / splits + kDK - 1) / kDK * kDK;
+  splits = (K + k_per_split - 1) / k_per_split;
+  grid.z = splits;
+  if (splits > 1 && !ep.accumulate) {
+    // partial products are added atomically: start from zero (dense rows: ldc == N for every caller of this path)
+    if (ldc != N) return set_error(TBG_ERR_INVALID_ARG, "dense split-K needs a dense output (ldc == N)");
+    TBG_CHECK_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
+  }
+  dense_gemm_kernel<<<grid, 256, 0, stream>>>(A, Bm, C, ldc, M, N, K, k_per_split, alpha, ep);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
+  if (splits > 1 && !ep.accumulate && (ep.bias || ep.act || ep.gain != 1.f)) {
+    const long long total = static_cast<long long>(M) * N;
+    dense_finish_kernel<<<static_cast<int>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream>>>(C, ldc, M, N, ep);
+    count_launch();
+    TBG_CHECK_CUDA(cudaGetLastError());
+  }
   return TBG_OK;
 }
 

@@ -1,5 +1,7 @@
 #include "host_util.h"
 
+#include <string.h>
+
 #include <mutex>
 
 namespace tbg {
@@ -67,7 +69,39 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 }  // namespace tbg
 
+// CRC-32C (Castagnoli) of a host buffer, slicing-by-8 — the checksum of TensorFlow tensor bundles (checkpoint import,
+// textboxgan_b200/tf_checkpoint.py).  Host-only helper: no device work.
+static uint32_t g_crc_table[8][256];
+static bool g_crc_ready = false;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
+    g_crc_table[0][i] = c;
+  }
+  for (int t = 1; t < 8; ++t)
+    for (uint32_t i = 0; i < 256; ++i) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xFF];
+  g_crc_ready = true;
+}
+
 extern "C" {
+unsigned int tbg_crc32c(const void* data, unsigned long long n, unsigned int crc) {
+  if (!g_crc_ready) crc_init();
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = g_crc_table[7][w & 0xFF] ^ g_crc_table[6][(w >> 8) & 0xFF] ^ g_crc_table[5][(w >> 16) & 0xFF] ^
+        g_crc_table[4][(w >> 24) & 0xFF] ^ g_crc_table[3][(w >> 32) & 0xFF] ^ g_crc_table[2][(w >> 40) & 0xFF] ^
+        g_crc_table[1][(w >> 48) & 0xFF] ^ g_crc_table[0][(w >> 56) & 0xFF];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = g_crc_table[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
 const char* tbg_last_error(void) { return tbg::last_error_buf(); }
 int tbg_version(void) { return 1; }
 long long tbg_launch_count(void) { return tbg::g_launches.load(); }

@@ -37,15 +37,21 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 // Process-wide tuning switches, set through tbg_set_tuning (never from the environment).
 struct Tuning {
-  int igemm_staged = 1;        // conv_igemm epilogue: stores transposed through shared memory (whole 128-byte lines)
+  int igemm_staged = 0;        // conv_igemm epilogue: stores transposed through shared memory (costs two pipeline stages: off)
   int igemm_msub = 1;          // conv_igemm: M tiles per work item (2 = two tiles share each weight box)
   int conv_halo = 1;           // 3x3 stride-1 convolutions on the halo-reuse kernel when it applies
-  int wgrad_staged = 1;        // conv_wgrad: staged vector atomics
+  int wgrad_staged = 0;        // conv_wgrad: staged vector atomics (measured slower on B200, profiles/r02b_layer_perf.log: off)
   int wgrad_items_per_sm = 0;  // conv_wgrad: split-K work items per SM (0 = heuristic)
+  int halo_a_stages = 2;       // conv3x3_halo: activation halo boxes in flight (54 KB each)
+  int halo_b_stages = 4;       // conv3x3_halo: weight boxes in flight (N x 128 B each)
+  int halo_staged = 1;         // conv3x3_halo epilogue: stores transposed through shared memory
+  int wgrad_halo = 1;          // 3x3 stride-1 weight gradients on the halo-reuse kernel when it applies
   int lstm_cluster = 1;        // LSTM whole-sequence kernels on 4-CTA clusters with smem-resident W_hh
 };
 extern Tuning g_tuning;
 
+bool wgrad_halo_applicable(const ::tbg_wgrad_args* a);
+int wgrad_halo_launch(const ::tbg_wgrad_args* a, cudaStream_t stream);
 bool conv_halo_applicable(const ::tbg_conv_args* a);
 int conv_halo_launch(const ::tbg_conv_args* a, cudaStream_t stream);
 

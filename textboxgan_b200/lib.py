@@ -68,6 +68,7 @@ _SIGNATURES = [
     ("tbg_version", c_int, []),
     ("tbg_launch_count", C.c_longlong, []),
     ("tbg_reset_launch_count", None, []),
+    ("tbg_crc32c", C.c_uint, [c_void_p, C.c_ulonglong, C.c_uint]),
     ("tbg_conv2d_igemm", c_int, [C.POINTER(ConvArgs), c_void_p]),
     ("tbg_conv2d_wgrad", c_int, [C.POINTER(WgradArgs), c_void_p]),
     ("tbg_upfirdn2d", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),

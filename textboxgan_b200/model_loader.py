@@ -122,4 +122,33 @@ class ModelLoader:
             else manager.latest_checkpoint
         if manager.restore(resume_checkpoint, expect_partial):
             print("{} restored from {}".format(model_description, resume_checkpoint))
+        elif self._restore_tf_checkpoint(ckpt_kwargs, ckpt_dir, resume_step):
+            print("{} restored from the TensorFlow checkpoint in {}".format(model_description, ckpt_dir))
         return manager
+
+    @staticmethod
+    def _restore_tf_checkpoint(ckpt_kwargs: dict, ckpt_dir: str, resume_step: int) -> bool:
+        """A directory written by the reference itself (tf.train.Checkpoint: ``ckpt-N.index`` + data shards, e.g. the
+        authors' "trained model", README.md:60-66): models are restored through the TensorBundle reader of
+        :mod:`textboxgan_b200.tf_checkpoint`; optimiser slots of a TensorFlow checkpoint are not imported."""
+        if not os.path.isdir(ckpt_dir):
+            return False
+        if resume_step != -1:
+            path = os.path.join(ckpt_dir, f"ckpt-{resume_step}")
+            if not os.path.exists(path + ".index"):
+                return False
+        elif any(f.endswith(".index") for f in os.listdir(ckpt_dir)):
+            path = ckpt_dir
+        else:
+            return False
+        from . import tf_checkpoint as T
+
+        done = False
+        for name, obj in ckpt_kwargs.items():
+            if isinstance(obj, Generator) and name in ("generator", "g_clone"):
+                T.load_generator_from_tf_checkpoint(obj, path, is_g_clone=(name == "g_clone"))
+                done = True
+            elif isinstance(obj, Discriminator) and name == "discriminator":
+                T.load_discriminator_from_tf_checkpoint(obj, path)
+                done = True
+        return done
