@@ -9,6 +9,11 @@ old.tbg_conv2d_igemm_r01.restype = C.c_int
 old.tbg_conv2d_igemm_r01.argtypes = [C.POINTER(lib.ConvArgs), C.c_void_p]
 new = lib.load()
 lib.set_tuning("conv_halo", 0)
+epi4 = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libepi4.so"))
+epi4.tbg_conv2d_igemm.restype = C.c_int
+epi4.tbg_conv2d_igemm.argtypes = [C.POINTER(lib.ConvArgs), C.c_void_p]
+epi4.tbg_set_tuning.argtypes = [C.c_char_p, C.c_int]
+epi4.tbg_set_tuning(b"conv_halo", 0)
 
 
 def bench(fn, n=30):
@@ -48,6 +53,11 @@ def run(name, B, g):
     for staged in (1, 0):
         lib.set_tuning("igemm_staged", staged)
         res.append(f"now(staged={staged}) {bench(f_new):6.1f} us")
+    def f_epi4():
+        a = args(out2); assert epi4.tbg_conv2d_igemm(C.byref(a), st) == 0
+    for staged in (1, 0):
+        epi4.tbg_set_tuning(b"igemm_staged", staged)
+        res.append(f"4-warp(staged={staged}) {bench(f_epi4):6.1f} us")
     i[0] = 0; f_old(); i[0] = 0; f_new(); torch.cuda.synchronize()
     res.append("bit-identical" if torch.equal(out, out2) else f"max diff {(out.float() - out2.float()).abs().max():.3g}")
     print(f"{name:26s} B={B} | " + " | ".join(res), flush=True)

@@ -1,5 +1,6 @@
 """Kernel timeline of CUDA-graph replays of the training step (torch.profiler, CUDA activity only):
-per-kernel-name busy time inside the graph, idle gaps, concurrency.  Usage: python scripts/graph_timeline.py [cfg] [steps]"""
+per-kernel-name busy time inside the graph, idle gaps, concurrency.
+Usage: python scripts/graph_timeline.py [cfg] [steps] [plain|pl|r1pl]"""
 import collections, os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,7 +26,9 @@ g = torch.Generator().manual_seed(4444)
 real, words, labels = OT.synthetic_batch(cfg, cfg.batch_size_per_gpu, g)
 real, words, labels = real.to(dev), words.to(dev), labels.to(dev)
 zero = torch.zeros((), device=dev)
-step = lambda: ts.dist_train_step(real, zero, words, labels, False, False, 1e-4)
+variant = sys.argv[3] if len(sys.argv) > 3 else "plain"
+do_r1, do_pl = {"plain": (False, False), "pl": (False, True), "r1pl": (True, True)}[variant]
+step = lambda: ts.dist_train_step(real, zero, words, labels, do_r1, do_pl, 1e-4)
 for _ in range(5): step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
@@ -53,7 +56,7 @@ for s, e, n in evs:
 tot = sum(v[1] for v in agg.values())
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/graph_timeline.txt", "w") as f:
-    f.write(f"config {idx}: {nsteps} graph replays, span {(t1 - t0) / nsteps / 1e3:.3f} ms/step, GPU busy (union) {busy / nsteps / 1e3:.3f} ms/step, "
+    f.write(f"config {idx} [{variant}]: {nsteps} graph replays, span {(t1 - t0) / nsteps / 1e3:.3f} ms/step, GPU busy (union) {busy / nsteps / 1e3:.3f} ms/step, "
             f"sum of kernel durations {tot / nsteps / 1e3:.3f} ms/step, {len(evs) / nsteps:.0f} kernels/step\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
         f.write(f"{v[1] / tot * 100:6.2f}% {v[0] / nsteps:7.1f}/step {v[1] / v[0]:8.1f}us avg {v[1] / nsteps / 1e3:7.3f} ms/step  {k}\n")

@@ -55,7 +55,12 @@ static constexpr int kMaxStages = 8;
 // of a row at a time (+16 bytes of padding: conflict-free 16-byte accesses), so that global stores go out as
 // whole 128-byte lines of four pixels per instruction instead of one 16-byte piece of 32 different pixels.
 static constexpr uint32_t kStgRow = 128 + 16;
-static constexpr int kEpiWarps = 8;       // two per TMEM lane quadrant: they split the 32-column chunks of a tile
+#ifndef TBG_IGEMM_EPI_WARPS
+#define TBG_IGEMM_EPI_WARPS 8
+#endif
+static constexpr int kEpiWarps = TBG_IGEMM_EPI_WARPS;   // 8: two per TMEM lane quadrant, splitting a tile's 32-column chunks
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
+static constexpr int kEpiSplit = kEpiWarps / 4;
 static constexpr uint32_t kStgBytes = kEpiWarps * 32 * kStgRow;
 static constexpr uint32_t kVecBytes = kEpiWarps * 2 * 128 * 4;   // per epilogue warp: demod-scale and bias vectors
 static constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -224,9 +229,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int esize = p.out_fp32 ? 4 : 2;
     const int nj = p.block_n / 32;
     // chunk range of this warp inside a (sub-)tile
-    const int j_lo = (msub == 2 || nj == 1) ? 0 : half * (nj / 2);
-    const int j_hi = (msub == 2 || nj == 1) ? nj : (half + 1) * (nj / 2);
-    const bool idle = (msub == 1 && nj == 1 && half == 1);        // a 32-column tile has one chunk: second warp idles
+    const bool split_cols = (kEpiSplit == 2) && msub == 1 && nj > 1;   // two warps per quadrant share a tile's columns
+    const bool split_subs = (kEpiSplit == 2) && msub == 2;              // ... or take one sub-tile each
+    const int j_lo = split_cols ? half * (nj / 2) : 0;
+    const int j_hi = split_cols ? (half + 1) * (nj / 2) : nj;
+    const bool idle = (kEpiSplit == 2) && msub == 1 && nj == 1 && half == 1;   // a 32-column tile: the second warp idles
     const int my_cols = (j_hi - j_lo) * 32;
     const int chunk_cols = min(my_cols, 128 / esize);             // columns staged per flush (<= 128 bytes per row)
     const int j_per_chunk = chunk_cols / 32;
@@ -244,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         continue;
       }
       bool waited = false;
-      for (int sub = (msub == 2 ? half : 0); sub < (msub == 2 ? half + 1 : 1); ++sub) {
+      for (int sub = (split_subs ? half : 0); sub < (split_subs ? half + 1 : msub); ++sub) {
       int tw, th, tb;
       decode_m(ms_tile * msub + sub, tw, th, tb);
       const int b = tb * bn + n_in;

@@ -39,6 +39,7 @@ class Adam:
         self.epsilon = float(epsilon)
         self.iterations = _Iterations()
         self._lr_dev: Optional[torch.Tensor] = None   # device copy of lr_t (CUDA-graph replay)
+        self._pending = None                           # (p, g, m, v, work) between begin_apply and finish_apply
         self.defer_iteration = False                   # True while a captured graph owns the update
         self._slots: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
 
@@ -74,7 +75,9 @@ class Adam:
         (the three groups of training_step.py:194-213 all do); per-variable path otherwise."""
         grads_and_vars = [(g, v) for g, v in grads_and_vars]
         if model is not None and names is not None:
-            self._apply_flat(model, list(names), [g for g, _ in grads_and_vars])
+            self.begin_apply(model, list(names), [g for g, _ in grads_and_vars])
+            self.finish_apply()
+            return
         else:
             for g, v in grads_and_vars:
                 if g is None:
@@ -83,7 +86,13 @@ class Adam:
         if not self.defer_iteration:
             self.iterations.value += 1
 
-    def _apply_flat(self, model, names: List[str], grads: List[Optional[torch.Tensor]]) -> None:
+    # -- split form of apply_gradients: gather + cross-replica SUM first, Adam later ---------------------------------
+    def begin_apply(self, model, names: List[str], grads: List[Optional[torch.Tensor]]) -> None:
+        """Gather the group's gradients into its flat buffer and START the cross-replica SUM (asynchronous all-reduce on
+        the communication stream).  The caller keeps computing — the training step issues the discriminator group's
+        reduce before the two generator backward passes, so the 62 MB exchange overlaps them — and calls
+        :meth:`finish_apply` where the reference calls ``apply_gradients`` (training_step.py:233-235)."""
+        assert getattr(self, "_pending", None) is None, "begin_apply called twice without finish_apply"
         start, end = model.flat_range(names)
         p = model.flat[start:end]
         key = (id(model), start, end)
@@ -91,8 +100,6 @@ class Adam:
             phase = start % 4
             self._slots[key] = tuple(self._aligned_like(end - start, phase, p.device) for _ in range(3))
         g, m, v = self._slots[key]
-        # gather the per-variable gradients into the flat buffer with one multi-tensor copy (padding between
-        # variables stays zero)
         dsts, srcs = [], []
         for n, gr in zip(names, grads):
             o, cnt = model.segments[n]
@@ -102,14 +109,24 @@ class Adam:
                 # gradient pushed through Adam would decay v instead.  Every variable of the three groups of
                 # training_step.py:194-213 is used on every step, so a missing gradient is a wiring error.
                 raise RuntimeError(f"Adam.apply_gradients: variable '{n}' of the flat group has no gradient")
-            else:
-                dsts.append(view)
-                srcs.append(gr.detach().reshape(-1))
+            dsts.append(view)
+            srcs.append(gr.detach().reshape(-1))
         if dsts:
             torch._foreach_copy_(dsts, srcs)
+        work = None
         if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)      # SUM: every loss already carries 1/global_batch
+            # SUM: every loss already carries 1/global_batch
+            work = dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+        self._pending = (p, g, m, v, work)
+
+    def finish_apply(self) -> None:
+        p, g, m, v, work = self._pending
+        self._pending = None
+        if work is not None:
+            work.wait()                      # the compute stream waits for the reduce; the host does not block
         K.adam_step(p, g, m, v, self._lr_arg(), self.beta_1, self.beta_2, self.epsilon)
+        if not self.defer_iteration:
+            self.iterations.value += 1
 
     def _apply_flat_range(self, p: torch.Tensor, g: torch.Tensor, key_id: int) -> None:
         key = (key_id, 0, p.numel())

@@ -242,6 +242,13 @@ class TrainingStep:
         o_vars = [G.params[n] for n in self._ocr_names]
         d_vars = [D.params[n] for n in self._d_names]
         # three tape.gradient calls on one persistent tape (:194-213): all at pre-update weights
+        # The discriminator group first: its gradient all-reduce (the largest of the three, ~62 MB) is started right away
+        # and overlaps the two generator backward passes below (all three are taken at the pre-update weights, so the
+        # order of the tape.gradient calls is free).
+        updates = not draws.get("skip_updates")
+        d_grads = torch.autograd.grad(reg_d_loss, d_vars, retain_graph=True, allow_unused=True)
+        if updates:
+            self.d_optimizer.begin_apply(D, self._d_names, list(d_grads))
         g_fake_ocr = None
         if side is not None:
             # first half of the OCR pass (chain rule split at fake_images): back through the frozen recogniser on
@@ -252,22 +259,23 @@ class TrainingStep:
                 _fused.backward_batch_limit("dconv", fake_images.shape[0] if self._batched_d else 1 << 30):
             # only generator variables are wanted from this pass
             g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
+        if updates:
+            self.g_optimizer.begin_apply(G, self._g_names, list(g_grads))
         if g_fake_ocr is not None:
             main.wait_stream(side)
             g_fake_ocr.record_stream(main)
-            o_grads = torch.autograd.grad(fake_images, o_vars, grad_outputs=g_fake_ocr, retain_graph=True,
-                                          allow_unused=True)
+            o_grads = torch.autograd.grad(fake_images, o_vars, grad_outputs=g_fake_ocr, allow_unused=True)
         else:
-            o_grads = torch.autograd.grad(ocr_loss, o_vars, retain_graph=True, allow_unused=True) \
-                if ocr_loss is not None else None
-        d_grads = torch.autograd.grad(reg_d_loss, d_vars, allow_unused=True)
+            o_grads = torch.autograd.grad(ocr_loss, o_vars, allow_unused=True) if ocr_loss is not None else None
         self.last_grads = (g_grads, o_grads, d_grads) if draws.get("keep_grads") else None
 
-        if not draws.get("skip_updates"):
-            self.g_optimizer.apply_gradients(zip(g_grads, g_vars), model=G, names=self._g_names)
+        if updates:
+            # reference order of the three updates (:194-213): generator group, OCR group (synthesis is updated twice), D
+            self.g_optimizer.finish_apply()
             if o_grads is not None:
-                self.ocr_optimizer.apply_gradients(zip(o_grads, o_vars), model=G, names=self._ocr_names)
-            self.d_optimizer.apply_gradients(zip(d_grads, d_vars), model=D, names=self._d_names)
+                self.ocr_optimizer.begin_apply(G, self._ocr_names, list(o_grads))
+                self.ocr_optimizer.finish_apply()
+            self.d_optimizer.finish_apply()
 
         _fused.clear_step_cache()
         gen_losses = (reg_g_loss.detach(), g_loss.detach(), pl_penalty.detach())
