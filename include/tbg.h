@@ -186,8 +186,6 @@ int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, i
  *   "conv_halo" (default 1)   tbg_conv2d_igemm runs 3x3 stride-1 pad-1 convolutions whose grid is a multiple of 16 x 16
  *                             pixels (Cin % 64 == 0, cout % 32 == 0, no residual / relu_mask / fp32 output) on the
  *                             halo-reuse kernel of csrc/conv_halo.cu: same arguments, same results;
- *   "igemm_staged" (0)        conv_igemm epilogue stores transposed through shared memory;
- *   "igemm_msub" (1)          2: two M tiles per work item share each weight box (N <= 128);
  *   "wgrad_staged" (0), "wgrad_items_per_sm" (0 = heuristic), "lstm_cluster" (1);
  *   "wgrad_halo" (1)          tbg_conv2d_wgrad runs 3x3 stride-1 pad-1 weight gradients on large grids on the halo-reuse
  *                             kernel of csrc/conv_wgrad_halo.cu;

@@ -28,14 +28,14 @@ def run(B, H, W, I, O):
                noise_strength=torch.ones(1, device=dev), bias=torch.randn(O, device=dev), act=1, act_gain=1.4)
     fl = 2.0 * B * H * W * 9 * I * O
     cols = []
-    for name, tune in (("igemm staged", dict(conv_halo=0, igemm_staged=1)), ("igemm direct", dict(conv_halo=0, igemm_staged=0)),
+    for name, tune in (("igemm", dict(conv_halo=0)),
                        ("halo", dict(conv_halo=1))):
         for k, v in tune.items():
             lib.set_tuning(k, v)
         tb = bench(lambda i: K.conv2d_igemm(xs[i], w, out=out, **g.kernel_kwargs()), n_rot)
         tf = bench(lambda i: K.conv2d_igemm(xs[i], w, out=out, **g.kernel_kwargs(), **epi), n_rot)
         cols.append(f"{name}: bare {tb:6.1f} us {fl / tb / 1e6:6.0f} TF/s, full-epilogue {tf:6.1f} us {fl / tf / 1e6:6.0f} TF/s")
-    lib.set_tuning("conv_halo", 1); lib.set_tuning("igemm_staged", 1)
+    lib.set_tuning("conv_halo", 1)
     print(f"{H}x{W} {I}->{O} B={B} | " + " | ".join(cols), flush=True)
 
 

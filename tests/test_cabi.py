@@ -107,15 +107,15 @@ def test_tuning_switches_round_trip_and_no_environment_reads():
     from textboxgan_b200 import lib
 
     assert lib.get_tuning("no_such_key") == -1
-    for key in ("conv_halo", "igemm_staged", "wgrad_staged", "lstm_cluster"):
+    for key in ("conv_halo", "wgrad_halo", "halo_staged", "wgrad_staged", "lstm_cluster"):
         old = lib.get_tuning(key)
         assert old in (0, 1)
         lib.set_tuning(key, 1 - old)
         assert lib.get_tuning(key) == 1 - old
         lib.set_tuning(key, old)
-    lib.set_tuning("igemm_msub", 2)
-    assert lib.get_tuning("igemm_msub") == 2
-    lib.set_tuning("igemm_msub", 1)
+    lib.set_tuning("halo_b_stages", 6)
+    assert lib.get_tuning("halo_b_stages") == 6
+    lib.set_tuning("halo_b_stages", 4)
     for f in (ROOT / "textboxgan_b200" / "csrc").glob("*.cu*"):
         assert "getenv" not in f.read_text(), f
 

@@ -441,40 +441,40 @@ def test_unfolded_downsample_conv_layer_matches_folded(B, H, W, I, O, k, rh):
         assert _rel_l2(a, b) < 5e-2          # see test_unfolded_upsample_conv_kernels_vs_emulated_semantics
 
 
-def test_conv_two_m_tile_work_items_are_bit_identical_to_single_tiles():
-    """conv_igemm work items of two M tiles sharing each weight box (tuning igemm_msub = 2) run the same MMA sequence per
-    tile as single-tile items, so the outputs must be bit-identical.  Odd tile counts exercise the out-of-range second
-    sub-tile; the staged and the direct epilogue store paths must agree bit for bit as well."""
+def test_halo_kernel_store_paths_and_pipeline_depths_are_bit_identical():
+    """The halo kernel's tuning switches (staged / direct epilogue stores, number of halo and weight boxes in flight) change
+    the schedule, never the arithmetic: every configuration produces bit-identical outputs."""
     from textboxgan_b200 import conv as C
     from textboxgan_b200 import kernels as K
     from textboxgan_b200 import lib
 
     def run():
         outs = []
-        for (B, H, W, I, O, k) in [(3, 16, 64, 64, 64, 3), (5, 8, 40, 128, 128, 1), (2, 32, 128, 64, 32, 3),
-                                   (33, 24, 40, 64, 128, 3)]:
-            g = C.plain_geom(H, W, I, O, k)
+        for (B, H, W, I, O) in [(3, 16, 64, 64, 64), (2, 32, 128, 128, 128), (5, 16, 32, 256, 96)]:
+            g = C.plain_geom(H, W, I, O, 3)
             gen = torch.Generator().manual_seed(B + H)
             x = torch.randn(B, H, W, I, generator=gen).to(DEV).bfloat16()
             w = (torch.randn(g.n_total, g.k_total, generator=gen) / g.k_total ** 0.5).to(DEV).bfloat16()
             bias = torch.randn(O, generator=gen).to(DEV)
             outs.append(K.conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.4, **g.kernel_kwargs()).float().cpu())
-            outs.append(K.conv2d_igemm(x, w, out_fp32=True, **g.kernel_kwargs()).cpu())
         return outs
 
-    saved = {k: lib.get_tuning(k) for k in ("conv_halo", "igemm_msub", "igemm_staged")}
+    keys = ("conv_halo", "halo_staged", "halo_a_stages", "halo_b_stages")
+    saved = {k: lib.get_tuning(k) for k in keys}
     try:
-        lib.set_tuning("conv_halo", 0)
+        lib.set_tuning("conv_halo", 1)
         res = {}
-        for msub, staged in ((1, 1), (2, 1), (1, 0), (2, 0)):
-            lib.set_tuning("igemm_msub", msub)
-            lib.set_tuning("igemm_staged", staged)
-            res[(msub, staged)] = run()
+        for staged, a_st, b_st in ((1, 2, 4), (0, 2, 4), (0, 3, 3), (1, 2, 2), (0, 2, 8)):
+            lib.set_tuning("halo_staged", staged)
+            lib.set_tuning("halo_a_stages", a_st)
+            lib.set_tuning("halo_b_stages", b_st)
+            res[(staged, a_st, b_st)] = run()
     finally:
         for k, v in saved.items():
             lib.set_tuning(k, v)
-    for key in ((2, 1), (1, 0), (2, 0)):
-        for a, b in zip(res[(1, 1)], res[key]):
+    ref = res[(1, 2, 4)]
+    for key, outs in res.items():
+        for a, b in zip(ref, outs):
             assert torch.equal(a, b), key
 
 

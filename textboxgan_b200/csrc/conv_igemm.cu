@@ -32,8 +32,6 @@ struct ConvKernelParams {
   int cout;
   int out_H, out_W;
   int stages;
-  int staged;  // 1: epilogue stores go through the shared-memory transpose (TBG_IGEMM_STAGED=0 restores direct stores)
-  int msub;  // M sub-tiles per work item (1 or 2): two 128-pixel tiles share every weight box (halves weight traffic)
   // epilogue
   const float* col_scale;
   const float* bias;
@@ -51,21 +49,8 @@ struct ConvKernelParams {
 
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
-// Epilogue staging: each epilogue warp transposes its 32 accumulator rows through shared memory, 128 bytes
-// of a row at a time (+16 bytes of padding: conflict-free 16-byte accesses), so that global stores go out as
-// whole 128-byte lines of four pixels per instruction instead of one 16-byte piece of 32 different pixels.
-static constexpr uint32_t kStgRow = 128 + 16;
-#ifndef TBG_IGEMM_EPI_WARPS
-#define TBG_IGEMM_EPI_WARPS 8
-#endif
-static constexpr int kEpiWarps = TBG_IGEMM_EPI_WARPS;   // 8: two per TMEM lane quadrant, splitting a tile's 32-column chunks
-static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
-static constexpr int kEpiSplit = kEpiWarps / 4;
-static constexpr uint32_t kStgBytes = kEpiWarps * 32 * kStgRow;
-static constexpr uint32_t kVecBytes = kEpiWarps * 2 * 128 * 4;   // per epilogue warp: demod-scale and bias vectors
-static constexpr int kThreads = 128 + 32 * kEpiWarps;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,19 +59,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int stages = p.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
-  const int msub = p.msub;
-  const uint32_t a_stage = static_cast<uint32_t>(msub) * kABytes;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + stages * a_stage;
+  uint8_t* smB = smem + stages * kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + stages * b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  // epilogue scratch (16-byte aligned): per-warp column vectors, then (staged store path only) the transpose buffers
-  float* vec_base = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);
-  uint8_t* stg_base = reinterpret_cast<uint8_t*>(vec_base) + kVecBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,7 +82,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 32 * kEpiWarps);
+      mbar_init(&tempty[i], 128);
     }
     fence_barrier_init();
   }
@@ -116,20 +96,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int tiles_ms = (tiles_m + msub - 1) / msub;       // work items along M (each = msub adjacent M tiles)
-  const int total_tiles = tiles_ms * p.tiles_n;
+  const int total_tiles = tiles_m * p.tiles_n;
   const int bw = p.bw, bh = p.bh, bn = p.bn;
-  // M tile -> (tw, th, tb); a tile index past the end maps to tb = tiles_b, i.e. fully out of bounds (TMA zero fill,
-  // epilogue rows invalid)
-  auto decode_m = [&](int m_tile, int& tw, int& th, int& tb) {
-    if (m_tile >= tiles_m) {
-      tw = 0; th = 0; tb = p.tiles_b;
-    } else {
-      tw = m_tile % p.tiles_w;
-      th = (m_tile / p.tiles_w) % p.tiles_h;
-      tb = m_tile / (p.tiles_w * p.tiles_h);
-    }
-  };
   const uint32_t a_bytes = static_cast<uint32_t>(bw * bh * bn) * 128u;  // bytes one activation box delivers
   // output phase of an N tile (up-sampling geometries put the phases side by side along N)
   auto tile_mask = [&](int n_tile) -> uint64_t {
@@ -144,15 +112,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.tiles_n;
-        const int ms_tile = tile / p.tiles_n;
-        int w_base[2], h_base[2], n_base[2];
-        for (int sub = 0; sub < msub; ++sub) {
-          int tw, th, tb;
-          decode_m(ms_tile * msub + sub, tw, th, tb);
-          w_base[sub] = tw * bw * p.stride_w + p.in_off_w;
-          h_base[sub] = th * bh * p.stride_h + p.in_off_h;
-          n_base[sub] = tb * bn;
-        }
+        const int m_tile = tile / p.tiles_n;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tb = m_tile / (p.tiles_w * p.tiles_h);
+        const int w_base = tw * bw * p.stride_w + p.in_off_w;
+        const int h_base = th * bh * p.stride_h + p.in_off_h;
+        const int n_base = tb * bn;
         const uint64_t mask = tile_mask(n_tile);
         for (int ty = 0; ty < p.taps_h; ++ty) {
           for (int tx = 0; tx < p.taps_w; ++tx) {
@@ -160,10 +126,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int kcol = (ty * p.taps_w + tx) * p.cin;
             for (int ch = 0; ch < p.cin_chunks; ++ch, kcol += 64) {
               mbar_wait(&empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full[stage], msub * a_bytes + b_bytes);
-              for (int sub = 0; sub < msub; ++sub)
-                tma_load_4d(smA + stage * a_stage + sub * kABytes, &tmA, &full[stage], ch * 64, w_base[sub] + tx,
-                            h_base[sub] + ty, n_base[sub]);
+              mbar_arrive_expect_tx(&full[stage], a_bytes + b_bytes);
+              tma_load_4d(smA + stage * kABytes, &tmA, &full[stage], ch * 64, w_base + tx, h_base + ty, n_base);
               tma_load_2d(smB + stage * b_bytes, &tmB, &full[stage], kcol, n_tile * p.block_n);
               if (++stage == stages) {
                 stage = 0;
@@ -186,21 +150,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc_stage], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * msub * p.block_n);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
         const uint64_t mask = tile_mask(tile % p.tiles_n);
         const int k_blocks = __popcll(mask) * p.cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * a_stage);
+          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
           const uint32_t b_addr = smem_u32(smB + stage * b_bytes);
-          for (int sub = 0; sub < msub; ++sub) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = umma_smem_desc_sw128(a_addr + sub * kABytes + k * 32, 0, 1024);
-              const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-              umma_bf16(d_tmem + static_cast<uint32_t>(sub * p.block_n), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (kb == k_blocks - 1) umma_commit(&tfull[acc_stage]);
@@ -213,107 +175,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    // Warp e reads TMEM lane quadrant e & 3 (= warp % 4, the hardware's lane-access rule); the two warps of a quadrant
-    // split the work of a tile: by sub-tile when msub == 2, else by halves of the 32-column chunk range.
     const int e = warp - 4;
-    const int quad = e & 3;
-    const int half = e >> 2;
-    const int r = quad * 32 + lane;
+    const int r = e * 32 + lane;
     const int w_in = r % bw;
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
     const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
-    uint8_t* const stg = stg_base + e * (32 * kStgRow);
-    float* const vscale = vec_base + e * 256;
-    float* const vbias = vscale + 128;
-    const int esize = p.out_fp32 ? 4 : 2;
-    const int nj = p.block_n / 32;
-    // chunk range of this warp inside a (sub-)tile
-    const bool split_cols = (kEpiSplit == 2) && msub == 1 && nj > 1;   // two warps per quadrant share a tile's columns
-    const bool split_subs = (kEpiSplit == 2) && msub == 2;              // ... or take one sub-tile each
-    const int j_lo = split_cols ? half * (nj / 2) : 0;
-    const int j_hi = split_cols ? (half + 1) * (nj / 2) : nj;
-    const bool idle = (kEpiSplit == 2) && msub == 1 && nj == 1 && half == 1;   // a 32-column tile: the second warp idles
-    const int my_cols = (j_hi - j_lo) * 32;
-    const int chunk_cols = min(my_cols, 128 / esize);             // columns staged per flush (<= 128 bytes per row)
-    const int j_per_chunk = chunk_cols / 32;
-    const bool smem_vec = (bn == 1) && my_cols <= 128;            // one image per tile: per-column vectors from smem
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
-      const int ms_tile = tile / p.tiles_n;
-      const int acc_stage = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (idle) {
-        mbar_wait(&tfull[acc_stage], acc_phase);
-        tc_fence_before();
-        mbar_arrive(&tempty[acc_stage]);
-        continue;
-      }
-      bool waited = false;
-      for (int sub = (split_subs ? half : 0); sub < (split_subs ? half + 1 : msub); ++sub) {
-      int tw, th, tb;
-      decode_m(ms_tile * msub + sub, tw, th, tb);
+      const int m_tile = tile / p.tiles_n;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tb = m_tile / (p.tiles_w * p.tiles_h);
       const int b = tb * bn + n_in;
       const int ho = th * bh + h_in;
       const int wo = tw * bw + w_in;
       const bool valid = (n_in < bn) && (b < p.B) && (ho < p.Ho) && (wo < p.Wo);
-      // first column of this warp's range, phase and channel base (an N tile never straddles two phases)
-      const int colA = n_tile * p.block_n + j_lo * 32;
-      int cA = colA, oy = ho, ox = wo;
-      if (p.up_h | p.up_w) {
-        const int ph = colA / p.cout;
-        cA = colA - ph * p.cout;
-        const int py = p.up_w ? (ph >> 1) : ph;
-        const int px = p.up_w ? (ph & 1) : 0;
-        oy = p.up_h ? 2 * ho + py : ho;
-        ox = p.up_w ? 2 * wo + px : wo;
-      }
-      const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
-      const bool cols_ok = colA < p.n_total;
-      if (smem_vec) {
-        // per-column vectors of this tile -> shared memory (overlaps the MMAs of the tile); tb < tiles_b here
-        __syncwarp();
-        if (lane * 4 < my_cols && cols_ok && tb < p.tiles_b) {
-          float4 sv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.col_scale) sv = __ldg(reinterpret_cast<const float4*>(p.col_scale + static_cast<size_t>(tb) * p.cout + cA) + lane);
-          if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cA) + lane);
-          reinterpret_cast<float4*>(vscale)[lane] = sv;
-          reinterpret_cast<float4*>(vbias)[lane] = bv;
-        }
-        __syncwarp();
-      }
-      const float nz = (p.noise != nullptr && valid && cols_ok) ? __ldg(p.noise + pix) * nstr : 0.f;
-      if (!waited) {
-        mbar_wait(&tfull[acc_stage], acc_phase);
-        tc_fence_after();
-        waited = true;
-      }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>((acc_stage * msub + sub) * p.block_n);
-      uint8_t* const my_row = stg + lane * kStgRow;
-      long long row_off = -1;                                 // element offset of this row's chunk in out, or -1
-      for (int j = j_lo; j < j_hi; ++j) {
-        const int jj = j - j_lo;
+      const int acc_stage = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc_stage], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
+                             static_cast<uint32_t>(acc_stage * p.block_n);
+      for (int j = 0; j < p.block_n / 32; ++j) {
+        const int col0 = n_tile * p.block_n + j * 32;
         uint32_t v[32];
         tmem_ld_32x32(t_row + j * 32, v);
         tmem_ld_wait();
-        if (valid && cols_ok) {
-          const int c0 = cA + jj * 32;
+        if (valid && col0 < p.n_total) {
+          int c0 = col0, oy = ho, ox = wo;
+          if (p.up_h | p.up_w) {
+            const int ph = col0 / p.cout;
+            c0 = col0 - ph * p.cout;
+            const int py = p.up_w ? (ph >> 1) : ph;
+            const int px = p.up_w ? (ph & 1) : 0;
+            oy = p.up_h ? 2 * ho + py : ho;
+            ox = p.up_w ? 2 * wo + px : wo;
+          }
+          const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
           const size_t off = pix * p.cout + c0;
-          if (jj % j_per_chunk == 0) row_off = static_cast<long long>(off);
-          const float* cs = smem_vec ? vscale + jj * 32
-                                     : (p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr);
-          const float* bs = smem_vec ? vbias + jj * 32 : (p.bias ? p.bias + c0 : nullptr);
-          uint8_t* const srow = my_row + (jj % j_per_chunk) * 32 * esize;
+          const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
+          const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
+          const float* bs = p.bias ? p.bias + c0 : nullptr;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
             if (cs) {
-              const float4 s0 = *reinterpret_cast<const float4*>(cs + g * 8);
-              const float4 s1 = *reinterpret_cast<const float4*>(cs + g * 8 + 4);
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(cs + g * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(cs + g * 8 + 4));
               f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
               f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
             }
@@ -322,8 +234,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int i = 0; i < 8; ++i) f[i] += nz;
             }
             if (bs) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bs + g * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bs + g * 8 + 4);
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
@@ -366,43 +278,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.out_fp32) {
-              float4* o = p.staged ? reinterpret_cast<float4*>(srow + g * 32)
-                                   : reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + g * 8);
-              o[0] = make_float4(f[0], f[1], f[2], f[3]);
-              o[1] = make_float4(f[4], f[5], f[6], f[7]);
+              float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
               uint4 pk;
               pk.x = pack_bf16x2(f[0], f[1]);
               pk.y = pack_bf16x2(f[2], f[3]);
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
-              uint4* o = p.staged ? reinterpret_cast<uint4*>(srow + g * 16)
-                                  : reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8);
-              *o = pk;
+              *reinterpret_cast<uint4*>(o) = pk;
             }
           }
-        } else if (jj % j_per_chunk == 0) {
-          row_off = -1;
-        }
-        if (p.staged && (jj + 1) % j_per_chunk == 0) {
-          // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
-          __syncwarp();
-          const int lanes_per_row = (chunk_cols * esize) >> 4;          // 4 or 8
-          const int rows_per_pass = 32 / lanes_per_row;
-          const int sbl = lane % lanes_per_row;
-          for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
-            const int rr = r0 + lane / lanes_per_row;
-            const long long o_el = __shfl_sync(0xffffffffu, row_off, rr);
-            if (o_el >= 0) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRow + sbl * 16);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * esize + sbl * 16;
-              *reinterpret_cast<uint4*>(dst) = val;
-            }
-          }
-          __syncwarp();
         }
       }
-      }  // sub
       tc_fence_before();
       mbar_arrive(&tempty[acc_stage]);
     }
@@ -546,21 +436,13 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   p.out_fp32 = a->out_fp32;
   p.out = a->out;
 
-  // Tuning (tbg_set_tuning): staged epilogue stores; two M tiles per work item sharing each weight box (needs both
-  // accumulator sets to double-buffer in TMEM: 2 x 2 x block_n <= 512).  Defaults from the B200 measurements in
-  // profiles/r02a_layer_perf.log: msub = 2 leaves only three 48 KB pipeline stages and is slower than msub = 1.
-  p.staged = g_tuning.igemm_staged;
-  p.msub = (g_tuning.igemm_msub == 2 && block_n <= 128 && tiles_m * p.tiles_n >= 8 * num_sms()) ? 2 : 1;
   const uint32_t b_bytes = static_cast<uint32_t>(block_n) * 128u;
-  const uint32_t stage_bytes = static_cast<uint32_t>(p.msub) * kABytes + b_bytes;
-  // Shared memory not needed by the epilogue goes to pipeline stages: the kernel is bound by TMA bytes in flight
-  // (measured on B200, profiles/r02d_igemm_ab.log: 7 stages vs 5 = 1.3-1.45x on every layer shape).
-  const uint32_t epi_bytes = kVecBytes + (p.staged ? kStgBytes : 0u);
-  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/ - epi_bytes;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t budget = 227u * 1024u - 1024u /*align slack*/ - 256u /*barriers*/;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + epi_bytes;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;
@@ -587,9 +469,9 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
     TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = ((tiles_m + p.msub - 1) / p.msub) * p.tiles_n;
+  const int total_tiles = tiles_m * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
@@ -598,9 +480,7 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 // Explicit tuning switches (tests, perf scripts); the library reads no environment variables.
 extern "C" int tbg_set_tuning(const char* key, int value) {
   TBG_CHECK_ARG(key != nullptr, "tbg_set_tuning: null key");
-  if (!strcmp(key, "igemm_staged")) g_tuning.igemm_staged = value != 0;
-  else if (!strcmp(key, "igemm_msub")) g_tuning.igemm_msub = value == 2 ? 2 : 1;
-  else if (!strcmp(key, "conv_halo")) g_tuning.conv_halo = value != 0;
+  if (!strcmp(key, "conv_halo")) g_tuning.conv_halo = value != 0;
   else if (!strcmp(key, "wgrad_staged")) g_tuning.wgrad_staged = value != 0;
   else if (!strcmp(key, "wgrad_items_per_sm")) g_tuning.wgrad_items_per_sm = value;
   else if (!strcmp(key, "lstm_cluster")) g_tuning.lstm_cluster = value != 0;
@@ -614,8 +494,6 @@ extern "C" int tbg_set_tuning(const char* key, int value) {
 
 extern "C" int tbg_get_tuning(const char* key) {
   if (!key) return -1;
-  if (!strcmp(key, "igemm_staged")) return g_tuning.igemm_staged;
-  if (!strcmp(key, "igemm_msub")) return g_tuning.igemm_msub;
   if (!strcmp(key, "conv_halo")) return g_tuning.conv_halo;
   if (!strcmp(key, "wgrad_staged")) return g_tuning.wgrad_staged;
   if (!strcmp(key, "wgrad_items_per_sm")) return g_tuning.wgrad_items_per_sm;

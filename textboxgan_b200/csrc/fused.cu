@@ -122,12 +122,17 @@ __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* 
 //   slope = act ? (out - res > 0 ? 1 : 0.2) : 1 ;  g_pre = g_out*gain*slope ;  gy0 = g_pre*d
 //   S1[b,c] += g_pre ; Spre[b,c] += g_pre*pre ; Snz[b,c] += g_pre*nz      (pre = (out-res)/(gain*slope))
 // ---------------------------------------------------------------------------------------------
-__global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ out,
-                                    const uint4* __restrict__ res, const float* __restrict__ noise,
-                                    const float* __restrict__ d, uint4* __restrict__ gy0, float* __restrict__ S1,
-                                    float* __restrict__ Spre, float* __restrict__ Snz, int hw, int c8,
-                                    int pix_per_cta, int act, float gain, int want_sums, int s1_over_batch) {
-  extern __shared__ float red[];  // [rows][c8*8][3]
+// MODE 0: gy0 only; 1: + S1 (bias gradient); 2: + S1, Spre, Snz (demodulation / noise-strength gradients).
+// Written multiply-only (the slope and its inverse are selected, not divided): the kernel is bandwidth-bound
+// (3 activation passes) only when the per-element arithmetic stays below ~10 instructions.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ out,
+                    const uint4* __restrict__ res, const float* __restrict__ noise,
+                    const float* __restrict__ d, uint4* __restrict__ gy0, float* __restrict__ S1,
+                    float* __restrict__ Spre, float* __restrict__ Snz, int hw, int c8,
+                    int pix_per_cta, int act, float gain, int s1_over_batch) {
+  extern __shared__ float red[];  // [rows][c8*8][MODE == 2 ? 3 : 1]
   const int b = blockIdx.y;
   const int rows = blockDim.x / c8;
   const int cv = threadIdx.x % c8;
@@ -145,9 +150,13 @@ __global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) a1[i] = a2[i] = a3[i] = 0.f;
+  // slope of the negative side and the factor that recovers the pre-activation from the output there
+  const float neg_slope = act == 0 ? 1.f : (act == 2 ? 0.f : 0.2f);
+  const float g_pos = gain, g_neg = gain * neg_slope;                     // g_pre = g_out * (out > 0 ? g_pos : g_neg)
   const float inv_gain = 1.f / gain;
+  const float r_pos = inv_gain, r_neg = (act == 1) ? inv_gain * 5.f : (act == 0 ? inv_gain : 0.f);   // pre = out * r_*
   if (r < rows) {
-#pragma unroll 2
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += rows) {
       const long long pix = static_cast<long long>(b) * hw + p;
       const long long idx = pix * c8 + cv;
@@ -160,44 +169,52 @@ __global__ void bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] -= rv[i];
       }
-      const float nz = (noise != nullptr) ? __ldg(noise + pix) : 0.f;
+      float nz = 0.f;
+      if (MODE == 2 && noise != nullptr) nz = __ldg(noise + pix);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float neg_slope = (act == 2) ? 0.f : 0.2f;       // 1: leaky-relu(0.2), 2: relu
-        const float slope = (act && !(o[i] > 0.f)) ? neg_slope : 1.f;
-        const float gp = g[i] * gain * slope;
-        const float pre = (slope > 0.f) ? o[i] * inv_gain / slope : 0.f;
-        a1[i] += gp;
-        a2[i] = fmaf(gp, pre, a2[i]);
-        a3[i] = fmaf(gp, nz, a3[i]);
+        const bool pos = o[i] > 0.f;
+        const float gp = g[i] * (pos ? g_pos : g_neg);
+        if (MODE >= 1) a1[i] += gp;
+        if (MODE == 2) {
+          a2[i] = fmaf(gp, o[i] * (pos ? r_pos : r_neg), a2[i]);
+          a3[i] = fmaf(gp, nz, a3[i]);
+        }
         g[i] = gp * dv[i];
       }
       gy0[idx] = pack8(g);
     }
   }
-  if (!want_sums) return;
+  if (MODE == 0) return;
+  constexpr int NS = MODE == 2 ? 3 : 1;
   const int cw = c8 * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    red[(r * cw + cv * 8 + i) * 3 + 0] = a1[i];
-    red[(r * cw + cv * 8 + i) * 3 + 1] = a2[i];
-    red[(r * cw + cv * 8 + i) * 3 + 2] = a3[i];
+    red[(r * cw + cv * 8 + i) * NS + 0] = a1[i];
+    if (MODE == 2) {
+      red[(r * cw + cv * 8 + i) * NS + 1] = a2[i];
+      red[(r * cw + cv * 8 + i) * NS + 2] = a3[i];
+    }
   }
   __syncthreads();
   if (r == 0) {
     for (int rr = 1; rr < rows; ++rr)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        a1[i] += red[(rr * cw + cv * 8 + i) * 3 + 0];
-        a2[i] += red[(rr * cw + cv * 8 + i) * 3 + 1];
-        a3[i] += red[(rr * cw + cv * 8 + i) * 3 + 2];
+        a1[i] += red[(rr * cw + cv * 8 + i) * NS + 0];
+        if (MODE == 2) {
+          a2[i] += red[(rr * cw + cv * 8 + i) * NS + 1];
+          a3[i] += red[(rr * cw + cv * 8 + i) * NS + 2];
+        }
       }
     const long long o0 = (static_cast<long long>(s1_over_batch ? 0 : b) * c8 + cv) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       atomicAdd(S1 + o0 + i, a1[i]);
-      if (Spre != nullptr) atomicAdd(Spre + o0 + i, a2[i]);
-      if (noise != nullptr) atomicAdd(Snz + o0 + i, a3[i]);
+      if (MODE == 2) {
+        if (Spre != nullptr) atomicAdd(Spre + o0 + i, a2[i]);
+        if (noise != nullptr) atomicAdd(Snz + o0 + i, a3[i]);
+      }
     }
   }
 }
@@ -304,75 +321,93 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
 //   out[b,y,x,c] = scale * sum_{m,n<4} k[m] k[n] in[b, y+m+offy, x+n+offx, c]     (in = 0 out of bounds)
 // optionally followed by the layer epilogue  v = act(v*d[b,c] + noise[b,y,x]*ns + bias[c]) * gain.
 // The kernel is symmetric, so the adjoint is the same call with off' = -3 - off and in/out swapped.
-// One thread per (pixel, 8 channels); neighbouring pixels are re-read from L1/L2.
 // ---------------------------------------------------------------------------------------------
-// One CTA per (8 rows x 32 columns x 64 channels) output tile: the (8+3) x (32+3) input patch is staged in
-// shared memory with fully independent coalesced 16-byte loads (each input element leaves L2 once per
-// tile), then every thread slides a 4-row window of horizontally filtered values down its column.
-static constexpr int kFirRows = 8, kFirCols = 32;
+static constexpr int kFirCols = 32, kFirStrip = 32;   // CTA: 32 output columns x 8 channel vectors, a strip of 32 rows
 
+// 4 x 4 FIR [1,3,3,1] x [1,3,3,1] * scale on NHWC bf16 with the optional layer epilogue.  No shared memory: thread
+// (x, 8-channel vector) walks down a strip of output rows keeping the last four horizontally filtered rows in registers;
+// the four horizontal taps of a row are four fully coalesced 16-byte loads (neighbouring threads re-read the same
+// pixels: L1 hits), so HBM sees each input element once per 32-column tile (+3 halo columns, +3 halo rows per strip).
+// EPI = false: bare filter (the FIR adjoint of the up layers' backward pass, the blur in front of the strided
+// discriminator convolutions) with a smaller register footprint.
+template <bool EPI>
 __global__ void __launch_bounds__(256)
 fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int IW, int OH, int OW, int c8, int offy,
             int offx, float scale, const float* __restrict__ d, const float* __restrict__ noise,
             const float* __restrict__ ns, const float* __restrict__ bias, int act, float gain, int cgroups) {
-  extern __shared__ uint4 tile[];  // [kFirRows+3][kFirCols+3][8]
-  constexpr int TR = kFirRows + 3, TC = kFirCols + 3;
-  const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirRows;
+  const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirStrip;
   const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
-  const int nv = min(8, c8 - cg * 8);  // 8-channel vectors of this channel group
-  for (int e = threadIdx.x; e < TR * TC * 8; e += 256) {
-    const int v = e & 7, c = (e >> 3) % TC, r = (e >> 3) / TC;
-    const int iy = y0 + offy + r, ix = x0 + offx + c;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (v < nv && iy >= 0 && iy < IH && ix >= 0 && ix < IW)
-      val = __ldg(in + ((static_cast<long long>(b) * IH + iy) * IW + ix) * c8 + cg * 8 + v);
-    tile[e] = val;
-  }
-  __syncthreads();
   const int v = threadIdx.x & 7, xl = threadIdx.x >> 3;
   const int x = x0 + xl, cv = cg * 8 + v;
-  if (x >= OW || v >= nv) return;
-  const float nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
-  float dv[8], bv[8];
+  if (x >= OW || cv >= c8) return;
+  const uint4* src = in + static_cast<long long>(b) * IH * IW * c8 + cv;
+  const int ix0 = x + offx;
+  // horizontally filtered input row iy (zero outside the tensor)
+  auto hrow = [&](int iy, float (&h)[8]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) * scale : scale;
-    bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+    for (int i = 0; i < 8; ++i) h[i] = 0.f;
+    if (iy < 0 || iy >= IH) return;
+    const uint4* row = src + static_cast<long long>(iy) * IW * c8;
+    uint4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ix = ix0 + k;
+      t[k] = (ix >= 0 && ix < IW) ? __ldg(row + static_cast<long long>(ix) * c8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(t[k], f);
+      const float wk = (k == 0 || k == 3) ? 1.f : 3.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = fmaf(f[i], wk, h[i]);
+    }
+  };
+  float dv[8], bv[8];
+  float nsv = 0.f;
+  if (EPI) {
+    nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) * scale : scale;
+      bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+    }
   }
   float win[4][8];
-  auto hrow = [&](int r, float (&h)[8]) {
-    float v0[8], v1[8], v2[8], v3[8];
-    unpack8(tile[(r * TC + xl) * 8 + v], v0);
-    unpack8(tile[(r * TC + xl + 1) * 8 + v], v1);
-    unpack8(tile[(r * TC + xl + 2) * 8 + v], v2);
-    unpack8(tile[(r * TC + xl + 3) * 8 + v], v3);
+  hrow(y0 + offy + 0, win[0]);
+  hrow(y0 + offy + 1, win[1]);
+  hrow(y0 + offy + 2, win[2]);
+  const int y_end = min(y0 + kFirStrip, OH);
+  for (int yb = y0; yb < y_end; yb += 4) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = v0[i] + v3[i] + 3.f * (v1[i] + v2[i]);
-  };
-  hrow(0, win[0]);
-  hrow(1, win[1]);
-  hrow(2, win[2]);
-#pragma unroll
-  for (int yy = 0; yy < kFirRows; ++yy) {
-    const int y = y0 + yy;
-    if (y >= OH) break;
-    hrow(yy + 3, win[(yy + 3) & 3]);
+    for (int q = 0; q < 4; ++q) {          // q is a compile-time constant: the ring indices below stay in registers
+    const int y = yb + q;
+    if (y >= y_end) return;
+    hrow(y + offy + 3, win[(q + 3) & 3]);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      acc[i] = (win[yy & 3][i] + win[(yy + 3) & 3][i] + 3.f * (win[(yy + 1) & 3][i] + win[(yy + 2) & 3][i])) * dv[i];
-    if (noise != nullptr) {
-      const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
+      acc[i] = win[q & 3][i] + win[(q + 3) & 3][i] + 3.f * (win[(q + 1) & 3][i] + win[(q + 2) & 3][i]);
+    if (EPI) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += nz;
-    }
+      for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
+      if (noise != nullptr) {
+        const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float o = acc[i] + bv[i];
-      if (act == 1) o = o > 0.f ? o : 0.2f * o;
-      acc[i] = o * gain;
+        for (int i = 0; i < 8; ++i) acc[i] += nz;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float o = acc[i] + bv[i];
+        if (act == 1) o = o > 0.f ? o : 0.2f * o;
+        acc[i] = o * gain;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= scale;
     }
     out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
+    }
   }
 }
 
@@ -559,17 +594,24 @@ extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* 
                 "tbg_bias_act_bwd: 16-byte alignment required");
   TBG_CHECK_ARG(gain > 0.f, "tbg_bias_act_bwd: gain must be positive");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, C / 8, 3);
+  const int mode = S1 == nullptr ? 0 : ((Spre != nullptr || noise != nullptr) ? 2 : 1);
+  const RedGeom g = red_geom(B, HW, C / 8, mode == 2 ? 3 : 1);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(bias_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(bias_act_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(bias_act_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
-  bias_act_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
-      reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), reinterpret_cast<const uint4*>(residual),
-      noise, d, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, HW, C / 8, g.pix_per_cta, act, gain, S1 != nullptr,
-      s1_over_batch);
+  const dim3 grid(g.chunks, B);
+#define TBG_BAB(M, SMEM)                                                                                                  \
+  bias_act_bwd_kernel<M><<<grid, g.threads, SMEM, stream>>>(                                                              \
+      reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), reinterpret_cast<const uint4*>(residual), \
+      noise, d, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, HW, C / 8, g.pix_per_cta, act, gain, s1_over_batch)
+  if (mode == 0) TBG_BAB(0, 0);
+  else if (mode == 1) TBG_BAB(1, g.smem);
+  else TBG_BAB(2, g.smem);
+#undef TBG_BAB
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
@@ -622,16 +664,16 @@ extern "C" int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH
   TBG_CHECK_ARG(TBG_ALIGNED16(in) && TBG_ALIGNED16(out) && TBG_ALIGNED16(d), "tbg_fir4: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int cgroups = (C / 8 + 7) / 8;
-  const size_t smem = static_cast<size_t>(kFirRows + 3) * (kFirCols + 3) * 8 * sizeof(uint4);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(fir4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    attr = true;
-  }
   TBG_CHECK_ARG(static_cast<long long>(B) * cgroups <= 65535, "tbg_fir4: B * channel groups exceeds the grid limit");
-  const dim3 grid((OW + kFirCols - 1) / kFirCols, (OH + kFirRows - 1) / kFirRows, B * cgroups);
-  fir4_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW, OH, OW,
-                                           C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain, cgroups);
+  const dim3 grid((OW + kFirCols - 1) / kFirCols, (OH + kFirStrip - 1) / kFirStrip, B * cgroups);
+  const bool epi = d != nullptr || noise != nullptr || bias != nullptr || act != 0 || gain != 1.f;
+  if (epi)
+    fir4_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW, OH,
+                                                OW, C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain, cgroups);
+  else
+    fir4_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW,
+                                                 OH, OW, C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain,
+                                                 cgroups);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

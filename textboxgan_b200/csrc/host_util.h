@@ -37,8 +37,6 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 // Process-wide tuning switches, set through tbg_set_tuning (never from the environment).
 struct Tuning {
-  int igemm_staged = 0;        // conv_igemm epilogue: stores transposed through shared memory (costs two pipeline stages: off)
-  int igemm_msub = 1;          // conv_igemm: M tiles per work item (2 = two tiles share each weight box)
   int conv_halo = 1;           // 3x3 stride-1 convolutions on the halo-reuse kernel when it applies
   int wgrad_staged = 0;        // conv_wgrad: staged vector atomics (measured slower on B200, profiles/r02b_layer_perf.log: off)
   int wgrad_items_per_sm = 0;  // conv_wgrad: split-K work items per SM (0 = heuristic)

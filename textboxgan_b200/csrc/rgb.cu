@@ -122,66 +122,79 @@ torgb_skip_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws,
   }
   const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f, b2 = bias ? __ldg(bias + 2) : 0.f;
   const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, hw);
-  for (int pb = p0; pb < p1; pb += ngrp) {          // uniform trip count per CTA: the shuffles below need every lane
-    const int p = pb + grp;
-    const bool in_range = p < p1;
-    const size_t pix = static_cast<size_t>(b) * hw + (in_range ? p : p0);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  // epilogue of one pixel (lane 0 of its group): bias, upsampled skip, mask, store
+  auto finish = [&](int p, float a0, float a1, float a2) {
+    const size_t pix = static_cast<size_t>(b) * hw + p;
+    const int py = p / W, px = p - py * W;
+    float r0 = a0 + b0, r1 = a1 + b1, r2 = a2 + b2;
+    if (y_prev) {
+      const int h2 = H >> 1, w2 = W >> 1;
+      const int qy = py >> 1, qx = px >> 1;
+      // rows / columns and weights of the two contributing low-resolution samples per axis
+      const int ya = (py & 1) ? qy : qy - 1, yb = (py & 1) ? qy + 1 : qy;
+      const int xa = (px & 1) ? qx : qx - 1, xb = (px & 1) ? qx + 1 : qx;
+      const float wya = (py & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
+      const float wxa = (px & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
+      const float* yp = y_prev + static_cast<size_t>(b) * h2 * w2 * 3;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      auto tap = [&](int yy, int xx, float wt) {
+        if (yy >= 0 && yy < h2 && xx >= 0 && xx < w2) {
+          const float* q = yp + (static_cast<size_t>(yy) * w2 + xx) * 3;
+          s0 = fmaf(__ldg(q), wt, s0);
+          s1 = fmaf(__ldg(q + 1), wt, s1);
+          s2 = fmaf(__ldg(q + 2), wt, s2);
+        }
+      };
+      tap(ya, xa, wya * wxa);
+      tap(ya, xb, wya * wxb);
+      tap(yb, xa, wyb * wxa);
+      tap(yb, xb, wyb * wxb);
+      r0 += s0; r1 += s1; r2 += s2;
+    }
+    if (words) {
+      const int ch = static_cast<int>((static_cast<long long>(px) * mcn) / W);
+      if (__ldg(words + b * mcn + ch) == 0) { r0 = 0.f; r1 = 0.f; r2 = 0.f; }
+    }
+    if (nchw) {
+      float* o = out + static_cast<size_t>(b) * 3 * hw + p;
+      o[0] = r0; o[hw] = r1; o[2 * static_cast<size_t>(hw)] = r2;
+    } else {
+      float* o = out + pix * 3;
+      o[0] = r0; o[1] = r1; o[2] = r2;
+    }
+  };
+  constexpr int U = (CV == 1) ? 4 : 2;                // pixels per group and iteration: U independent 16-byte loads in flight
+  for (int pb = p0; pb < p1; pb += ngrp * U) {        // uniform trip count per CTA: the shuffles below need every lane
+    uint4 xv[U][CV];
+    int pp[U];
 #pragma unroll
-    for (int v = 0; v < CV; ++v) {
-      float f[8];
-      unpack8_bf16(__ldg(x + pix * c8 + v * LPP + sub), f);
+    for (int u = 0; u < U; ++u) {
+      pp[u] = pb + u * ngrp + grp;
+      const size_t pix = static_cast<size_t>(b) * hw + (pp[u] < p1 ? pp[u] : p0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a0 = fmaf(f[i], w[v][i][0], a0);
-        a1 = fmaf(f[i], w[v][i][1], a1);
-        a2 = fmaf(f[i], w[v][i][2], a2);
-      }
+      for (int v = 0; v < CV; ++v) xv[u][v] = __ldg(x + pix * c8 + v * LPP + sub);
     }
 #pragma unroll
-    for (int o = LPP / 2; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (sub == 0 && in_range) {
-      const int py = p / W, px = p - py * W;
-      float r0 = a0 + b0, r1 = a1 + b1, r2 = a2 + b2;
-      if (y_prev) {
-        const int h2 = H >> 1, w2 = W >> 1;
-        const int qy = py >> 1, qx = px >> 1;
-        // rows / columns and weights of the two contributing low-resolution samples per axis
-        const int ya = (py & 1) ? qy : qy - 1, yb = (py & 1) ? qy + 1 : qy;
-        const int xa = (px & 1) ? qx : qx - 1, xb = (px & 1) ? qx + 1 : qx;
-        const float wya = (py & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
-        const float wxa = (px & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
-        const float* yp = y_prev + static_cast<size_t>(b) * h2 * w2 * 3;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        auto tap = [&](int yy, int xx, float wt) {
-          if (yy >= 0 && yy < h2 && xx >= 0 && xx < w2) {
-            const float* q = yp + (static_cast<size_t>(yy) * w2 + xx) * 3;
-            s0 = fmaf(__ldg(q), wt, s0);
-            s1 = fmaf(__ldg(q + 1), wt, s1);
-            s2 = fmaf(__ldg(q + 2), wt, s2);
-          }
-        };
-        tap(ya, xa, wya * wxa);
-        tap(ya, xb, wya * wxb);
-        tap(yb, xa, wyb * wxa);
-        tap(yb, xb, wyb * wxb);
-        r0 += s0; r1 += s1; r2 += s2;
+    for (int u = 0; u < U; ++u) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < CV; ++v) {
+        float f[8];
+        unpack8_bf16(xv[u][v], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a0 = fmaf(f[i], w[v][i][0], a0);
+          a1 = fmaf(f[i], w[v][i][1], a1);
+          a2 = fmaf(f[i], w[v][i][2], a2);
+        }
       }
-      if (words) {
-        const int ch = static_cast<int>((static_cast<long long>(px) * mcn) / W);
-        if (__ldg(words + b * mcn + ch) == 0) { r0 = 0.f; r1 = 0.f; r2 = 0.f; }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
-      if (nchw) {
-        float* o = out + static_cast<size_t>(b) * 3 * hw + p;
-        o[0] = r0; o[hw] = r1; o[2 * static_cast<size_t>(hw)] = r2;
-      } else {
-        float* o = out + pix * 3;
-        o[0] = r0; o[1] = r1; o[2] = r2;
-      }
+      if (sub == 0 && pp[u] < p1) finish(pp[u], a0, a1, a2);
     }
   }
 }
