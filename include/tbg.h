@@ -211,6 +211,13 @@ int tbg_fromrgb_fwd(const float* img, const float* w, const float* bias, void* o
                     float gain, void* stream);
 int tbg_fromrgb_bwd(const float* img, const float* w, const void* g_out, const void* out, float* gimg, float* gw, float* gb,
                     int B, int HW, int C, float coef, float gain, void* stream);
+/* Stand-alone nodes of the twice-differentiable path (path-length / R1 regularisers, training_step.py:300-373):
+ *   tbg_bias_act_fwd: out = act(t + noise[b,p]*noise_strength + bias[c]) * gain      (noise.py:21, bias_act.py:25-34)
+ *   tbg_rowdot:       out[b,c] += sum_p a[b,p,c] * b[b,p,c]   (fp32 [B,C], zeroed by the caller; the adjoint of the
+ *                     style modulation x * s[b,c], modulated_conv2d.py:96) */
+int tbg_bias_act_fwd(const void* t, const float* noise, const float* noise_strength, const float* bias, void* out, int B,
+                     int HW, int C, int act, float gain, void* stream);
+int tbg_rowdot(const void* a, const void* b, float* out, int B, int HW, int C, void* stream);
 int tbg_torgb_fwd(const void* x, const float* ws, const float* bias, float* y, int B, int HW, int C, void* stream);
 int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, float* gws, int B, int HW, int C,
                   void* stream);

@@ -429,6 +429,20 @@ def emu_attn_decoder_bwd(mem, keys, w, g_logits, sv):
     return g_mem.float(), g_keys.float()
 
 
+def emu_bias_act_fwd(t, *, noise=None, noise_strength=None, bias=None, act=1, gain=1.0):
+    """Documented semantics of tbg_bias_act_fwd (include/tbg.h)."""
+    v = t.double()
+    if noise is not None:
+        v = v + noise.double()[..., None] * noise_strength.double().reshape(())
+    if bias is not None:
+        v = v + bias.double()
+    return (_emu_act(v, act) * gain).to(t.dtype)
+
+
+def emu_rowdot(a, b):
+    return (a.double() * b.double()).reshape(a.shape[0], -1, a.shape[-1]).sum(1).float()
+
+
 def _emu_act(pre, act):
     if act == 1:
         return torch.where(pre > 0, pre, 0.2 * pre)
@@ -596,7 +610,7 @@ def emulated_kernels(act_dtype=torch.float32):
     C._as_bf16 = lambda t: t.contiguous()
     L.ACT_DTYPE = act_dtype
     new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
-                 "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc")
+                 "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot")
     saved_n = {n: getattr(K, n) for n in new_names}
     for n in new_names:
         setattr(K, n, globals()["emu_" + n])

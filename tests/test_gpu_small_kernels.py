@@ -190,3 +190,65 @@ def test_upfirdn2d_tiled_kernel_matches_reference_semantics(cfgk, shape, ksz):
         pytest.skip("empty output for this combination")
     y = Kn.upfirdn2d(x.to(DEV), k.to(DEV), **full)
     assert y.shape == ref.shape and rel_err(y, ref) < 1e-5
+
+
+def test_bias_act_fwd_and_rowdot_kernels():
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(11)
+    for B, H, W, C in ((3, 8, 16, 64), (2, 16, 64, 256), (5, 3, 7, 128)):
+        t = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+        u = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+        nz = torch.randn(B, H, W, generator=gen)
+        ns = torch.tensor([0.4])
+        bias = torch.randn(C, generator=gen) * 0.3
+        for act, gain in ((1, math.sqrt(2.0)), (0, 1.0), (2, 1.0)):
+            got = Kn.bias_act_fwd(t.to(DEV).bfloat16(), noise=nz.to(DEV), noise_strength=ns.to(DEV), bias=bias.to(DEV), act=act, gain=gain)
+            assert rel_err(got.float(), emu.emu_bias_act_fwd(t, noise=nz, noise_strength=ns, bias=bias, act=act, gain=gain).float()) < 1e-2
+        got = Kn.bias_act_fwd(t.to(DEV).bfloat16(), bias=bias.to(DEV), act=1, gain=1.0)
+        assert rel_err(got.float(), emu.emu_bias_act_fwd(t, bias=bias, act=1, gain=1.0).float()) < 1e-2
+        assert rel_err(Kn.rowdot(t.to(DEV).bfloat16(), u.to(DEV).bfloat16()), emu.emu_rowdot(t, u)) < 1e-5
+
+
+def test_second_order_primitives_match_autograd_of_plain_torch():
+    """The closed primitive set of second_order.py (modulate, rowdot, bias_act, mask_mul, to_rgb and its adjoints): first
+    and SECOND derivatives of a path-length-like scalar against fp64 autograd through the same composite written with
+    plain torch ops: J = d(sum(img * n)) / ds with create_graph, then d(sum(J^2)) / d(x, s, ws, d)."""
+    from textboxgan_b200 import second_order as SO
+
+    gen = torch.Generator().manual_seed(5)
+    B, H, W, C = 3, 8, 16, 64
+    x0 = _bf16_round(torch.randn(B, H, W, C, generator=gen))
+    s0 = torch.rand(B, C, generator=gen) + 0.5
+    d0 = torch.rand(B, C, generator=gen) + 0.5
+    nz = torch.randn(B, H, W, generator=gen)
+    ns0 = torch.tensor(0.3)
+    b0 = torch.randn(C, generator=gen) * 0.2
+    ws0 = torch.randn(B, C, 3, generator=gen) / math.sqrt(C)
+    n_img = torch.randn(B, H, W, 3, generator=gen)
+    g2 = math.sqrt(2.0)
+
+    def run(device, dtype, prim):
+        x = x0.to(device, dtype).requires_grad_(True)
+        s, d, ws = (t.to(device).double().requires_grad_(True) if not prim else t.to(device).requires_grad_(True)
+                    for t in (s0, d0, ws0))
+        nzd, nsd, bd, nd = nz.to(device), ns0.to(device), b0.to(device), n_img.to(device)
+        if prim:
+            t = SO.modulate(SO.modulate(x, s), d)
+            y = SO.bias_act(t, nzd, nsd, bd, 1, g2)
+            img = SO.to_rgb(y, ws)
+        else:
+            t = x.double() * s[:, None, None, :] * d[:, None, None, :]
+            pre = t + nzd.double()[..., None] * nsd.double() + bd.double()
+            y = torch.nn.functional.leaky_relu(pre, 0.2) * g2
+            img = torch.einsum("bhwc,bcj->bhwj", y, ws)
+        (J,) = torch.autograd.grad((img * nd.to(img.dtype)).sum(), s, create_graph=True)
+        pen = (J ** 2).sum()
+        grads = torch.autograd.grad(pen, [x, s, ws, d])
+        return J.detach().double().cpu(), [g.detach().double().cpu() for g in grads]
+
+    J_ref, g_ref = run("cpu", torch.float64, False)
+    J_got, g_got = run(DEV, torch.bfloat16, True)
+    assert rel_err(J_got, J_ref) < 3e-2
+    for name, a, b in zip(("x", "s", "ws", "d"), g_got, g_ref):
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 6e-2, name

@@ -72,6 +72,40 @@ __global__ void modulate_kernel(const uint4* __restrict__ x, const float* __rest
 // gx = gxs * s ; gs[b,c] += sum_{pixels of the CTA's chunk} gxs * x
 // grid = (chunks, B); block = c8 * rows threads: thread (r, cv) walks pixels r, r+rows, ...
 // ---------------------------------------------------------------------------------------------
+// out = act(t + noise[b,p]*ns + bias[c]) * gain — the element-wise tail of a layer (noise.py:21, bias_act.py:25-34) as a
+// stand-alone pass; the plain training step applies it in the convolution epilogue, the twice-differentiable path of the
+// regularisers (path length / R1) needs it as a separate differentiable node.
+__global__ void bias_act_fwd_kernel(const uint4* __restrict__ t, const float* __restrict__ noise,
+                                    const float* __restrict__ ns, const float* __restrict__ bias, uint4* __restrict__ out,
+                                    long long n_vec, int hw, int c8, int act, float gain) {
+  const float nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const int cv = static_cast<int>(i % c8);
+    const long long pix = i / c8;
+    float f[8];
+    unpack8(__ldg(t + i), f);
+    const float nz = (noise != nullptr) ? __ldg(noise + pix) * nsv : 0.f;
+    float bv[8];
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8 + 4));
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bv[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = f[k] + nz + bv[k];
+      if (act == 1) v = v > 0.f ? v : 0.2f * v;
+      else if (act == 2) v = fmaxf(v, 0.f);
+      f[k] = v * gain;
+    }
+    out[i] = pack8(f);
+  }
+}
+
 __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* __restrict__ x,
                                     const float* __restrict__ s, uint4* __restrict__ gx, float* __restrict__ gs,
                                     int hw, int c8, int pix_per_cta) {
@@ -83,7 +117,7 @@ __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* 
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
   float sv[8], acc[8];
-  {
+  if (gx != nullptr) {
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8));
     const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (static_cast<long long>(b) * c8 + cv) * 8 + 4));
     sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
@@ -91,18 +125,19 @@ __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (r < rows) {
-#pragma unroll 2
+#pragma unroll 4
     for (int p = p0 + r; p < p1; p += rows) {
       const long long idx = (static_cast<long long>(b) * hw + p) * c8 + cv;
       float g[8], xv[8];
       unpack8(__ldg(gxs + idx), g);
       unpack8(__ldg(x + idx), xv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] = fmaf(g[i], xv[i], acc[i]);
-        g[i] *= sv[i];
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(g[i], xv[i], acc[i]);
+      if (gx != nullptr) {              // gx == nullptr: reduction only (tbg_rowdot)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= sv[i];
+        gx[idx] = pack8(g);
       }
-      gx[idx] = pack8(g);
     }
   }
 #pragma unroll
@@ -577,6 +612,39 @@ extern "C" int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, 
   modulate_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
       reinterpret_cast<const uint4*>(gxs), reinterpret_cast<const uint4*>(x), s, reinterpret_cast<uint4*>(gx), gs, HW,
       C / 8, g.pix_per_cta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_rowdot(const void* a, const void* b, float* out, int B, int HW, int C, void* stream_v) {
+  TBG_CHECK_ARG(a && b && out, "tbg_rowdot: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_rowdot: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(TBG_ALIGNED16(a) && TBG_ALIGNED16(b), "tbg_rowdot: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, C / 8, 1);
+  modulate_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), nullptr, nullptr, out, HW, C / 8, g.pix_per_cta);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_bias_act_fwd(const void* t, const float* noise, const float* noise_strength, const float* bias, void* out,
+                                int B, int HW, int C, int act, float gain, void* stream_v) {
+  TBG_CHECK_ARG(t && out, "tbg_bias_act_fwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && HW >= 1, "tbg_bias_act_fwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(!noise || noise_strength, "tbg_bias_act_fwd: noise without noise_strength");
+  TBG_CHECK_ARG(act >= 0 && act <= 2, "tbg_bias_act_fwd: act must be 0, 1 or 2");
+  TBG_CHECK_ARG(TBG_ALIGNED16(t) && TBG_ALIGNED16(out) && TBG_ALIGNED16(bias), "tbg_bias_act_fwd: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long n_vec = static_cast<long long>(B) * HW * (C / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = static_cast<long long>(sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  bias_act_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(t), noise, noise_strength,
+                                                                    bias, reinterpret_cast<uint4*>(out), n_vec, HW, C / 8, act,
+                                                                    gain);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

@@ -90,14 +90,13 @@ class Discriminator(Model):
                        res_scale=INV_SQRT2 if residual is not None else 1.0)
             return C.conv(x, wmat, geom, epi)
         y = C.conv(x, wmat, geom)
-        if bias is None and residual is None:
-            return y
-        y = y.float()
         if bias is not None:
-            y = L.lrelu(y + P[bias])
+            from . import second_order as SO
+
+            y = SO.bias_act(y, None, None, P[bias], 1, L.SQRT2)            # twice differentiable (R1, training_step.py:363-368)
         if residual is not None:
-            y = (y + residual.float()) * INV_SQRT2
-        return y.to(L.ACT_DTYPE)
+            y = (y + residual) * INV_SQRT2
+        return y
 
     def __call__(self, images: torch.Tensor, n_calls: int = 1) -> torch.Tensor:
         """discriminator.py:202-214: [B,3,H,W] fp32 -> [B,1] fp32.  ``n_calls`` > 1 evaluates that many

@@ -684,3 +684,26 @@ def image_grad_nhwc(g: torch.Tensor, words: Optional[torch.Tensor]) -> torch.Ten
     out = torch.empty((B, H, W_, 3), device=g.device, dtype=torch.float32)
     _lib.check(_lib.load().tbg_image_grad_nhwc(_ptr(g), _ptr(words), _ptr(out), B, H, W_, mcn, _stream()), "tbg_image_grad_nhwc")
     return out
+
+
+def bias_act_fwd(t: torch.Tensor, *, noise: Optional[torch.Tensor] = None, noise_strength: Optional[torch.Tensor] = None,
+                 bias: Optional[torch.Tensor] = None, act: int = 1, gain: float = 1.0) -> torch.Tensor:
+    """out = act(t + noise*noise_strength + bias) * gain — t bf16 [B,...,C] (tbg_bias_act_fwd)."""
+    _require(t, torch.bfloat16, "t")
+    B, HW, C_ = _bhwc(t)
+    out = torch.empty_like(t)
+    bias = _aligned(bias)
+    st = _lib.load().tbg_bias_act_fwd(_ptr(t), _ptr(noise), _ptr(noise_strength), _ptr(bias), _ptr(out), B, HW, C_, int(act),
+                                      float(gain), _stream())
+    _lib.check(st, "tbg_bias_act_fwd")
+    return out
+
+
+def rowdot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out[b,c] = sum over pixels of a*b — a, b bf16 [B,...,C] -> fp32 [B,C] (tbg_rowdot)."""
+    _require(a, torch.bfloat16, "a")
+    _require(b, torch.bfloat16, "b")
+    B, HW, C_ = _bhwc(a)
+    out = torch.zeros((B, C_), device=a.device, dtype=torch.float32)
+    _lib.check(_lib.load().tbg_rowdot(_ptr(a), _ptr(b), _ptr(out), B, HW, C_, _stream()), "tbg_rowdot")
+    return out

@@ -121,17 +121,18 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
                    act=1 if act else 0, act_gain=SQRT2 if act else 1.0)
         with torch.no_grad():
             return C.conv(xs, wmat, geom, epi)
-    xs = (x.float() * s[:, None, None, :]).to(ACT_DTYPE)                    # :96
-    y = C.conv(xs, wmat, geom).float()
+    # twice-differentiable path (path-length regulariser): every node is a member of the closed primitive set of
+    # second_order.py, so the first AND the second backward pass stay on the kernels
+    from . import second_order as SO
+
+    xs = SO.modulate(x.to(ACT_DTYPE), s)                                    # :96
+    y = C.conv(xs, wmat, geom)
     if d is not None:
-        y = y * d[:, None, None, :]                                         # :121
-    if noise is not None:
-        y = y + noise[..., None] * noise_strength                           # noise.py:21
-    if bias is not None:
-        y = y + bias                                                        # bias_act.py:25-31
-    if act:
-        y = lrelu(y)
-    return y.to(ACT_DTYPE)
+        y = SO.modulate(y, d)                                               # :121
+    if noise is None and bias is None and not act:
+        return y
+    return SO.bias_act(y, noise, noise_strength if noise is not None else None, bias, 1 if act else 0,
+                       SQRT2 if act else 1.0)                               # noise.py:21, bias_act.py:25-34
 
 
 def all_style_scales(style: torch.Tensor, P: Params, prefixes, idxs):
@@ -164,9 +165,9 @@ def to_rgb(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: str,
         from .fused import ToRGB
 
         return ToRGB.apply(x, ws, P[prefix + "/bias/b"])
-    B, H, W_, Cc = x.shape
-    y = torch.bmm(x.reshape(B, H * W_, Cc).float(), ws).reshape(B, H, W_, 3)
-    return y + P[prefix + "/bias/b"]
+    from . import second_order as SO
+
+    return SO.to_rgb(x.to(ACT_DTYPE), ws) + P[prefix + "/bias/b"]
 
 
 def upsample_rgb(y: torch.Tensor) -> torch.Tensor:
