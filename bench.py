@@ -424,6 +424,9 @@ def run_ours(args) -> None:
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured graphs hold NCCL kernel nodes and communicator references: release them before the process group
+        ts._graphs.clear()
+        del ts
         _teardown(dist)
 
 

@@ -238,9 +238,12 @@ def test_second_order_primitives_match_autograd_of_plain_torch():
             y = SO.bias_act(t, nzd, nsd, bd, 1, g2)
             img = SO.to_rgb(y, ws)
         else:
-            t = x.double() * s[:, None, None, :] * d[:, None, None, :]
+            # same bf16 rounding points as the kernels (values rounded, gradients passed straight through), so that the
+            # leaky-ReLU masks of near-zero pre-activations agree
+            r = lambda v: v + (v.to(torch.bfloat16).double() - v).detach()
+            t = r(r(x.double() * s[:, None, None, :]) * d[:, None, None, :])
             pre = t + nzd.double()[..., None] * nsd.double() + bd.double()
-            y = torch.nn.functional.leaky_relu(pre, 0.2) * g2
+            y = r(torch.nn.functional.leaky_relu(pre, 0.2) * g2)
             img = torch.einsum("bhwc,bcj->bhwj", y, ws)
         (J,) = torch.autograd.grad((img * nd.to(img.dtype)).sum(), s, create_graph=True)
         pen = (J ** 2).sum()
@@ -249,6 +252,9 @@ def test_second_order_primitives_match_autograd_of_plain_torch():
 
     J_ref, g_ref = run("cpu", torch.float64, False)
     J_got, g_got = run(DEV, torch.bfloat16, True)
-    assert rel_err(J_got, J_ref) < 3e-2
+    rl2 = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    print("second-order primitives: rel-L2 of J", rl2(J_got, J_ref), "of d(sum J^2)/d(x, s, ws, d)",
+          [rl2(a, b) for a, b in zip(g_got, g_ref)])
+    assert rl2(J_got, J_ref) < 2e-2                    # gradients travel as bf16 tensors between the kernels
     for name, a, b in zip(("x", "s", "ws", "d"), g_got, g_ref):
-        assert float((a - b).norm() / (b.norm() + 1e-30)) < 6e-2, name
+        assert rl2(a, b) < 5e-2, name

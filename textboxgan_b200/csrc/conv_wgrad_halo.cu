@@ -79,14 +79,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmGY, const __grid_co
   const int k_tiles = p.tiles_w * p.tiles_h * p.B;
   const int base_items = p.m_tiles * p.c_tiles * p.groups;
   const int total_items = base_items * p.splits;
-  // item -> (m_tile, c_tile, tap group, K range); split fastest: neighbouring CTAs reduce into the same gw tile
+  // item -> (tap group, c_tile, m_tile, K range); the (group, c_tile, m_tile) index runs fastest, so the CTAs that read the
+  // SAME pixel range of gy and x for different taps / channel tiles run side by side and share those lines in L2
+  // (ncu, profiles/r02h_ncu_conv_summary.txt: with the K range fastest each tap group re-read both tensors from DRAM,
+  // 1.29 GB for 0.54 GB of activations)
   auto decode = [&](int item, int& m_tile, int& c_tile, int& t0, int& t1, int& kt0, int& kt1) {
-    const int split = item % p.splits;
-    int rest = item / p.splits;
+    int rest = item;
     const int group = rest % p.groups;
     rest /= p.groups;
     c_tile = rest % p.c_tiles;
-    m_tile = rest / p.c_tiles;
+    rest /= p.c_tiles;
+    m_tile = rest % p.m_tiles;
+    const int split = rest / p.m_tiles;
     t0 = group * p.taps_per_group;
     t1 = min(9, t0 + p.taps_per_group);
     const int per = (k_tiles + p.splits - 1) / p.splits;
