@@ -382,6 +382,17 @@ def run_ours(args) -> None:
 
     # ---- roofline pass: CUDA events around every tensor-core launch of two instrumented plain steps ----
     roof = None
+    if args.no_roofline:
+        if rank == 0:
+            gb = B * world
+            print(json.dumps({"metric": METRIC, "value": gb / (ms_eff * 1e-3), "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "ms_per_step": ms_eff, "per_gpu_batch": B,
+                              "plain_step": {"value": gb / (ms_plain * 1e-3), "ms_per_step": ms_plain},
+                              "config": _config_dict(c, cfg, world)["workload"]}), flush=True)
+        if world > 1:
+            ts._graphs.clear()
+            _teardown(dist)
+        return
     # every rank runs the two instrumented eager steps (they contain collectives); rank 0 records
     K.PROFILE = [] if rank == 0 else None
     ts.use_cuda_graph = False                     # events around every launch need eager launches
@@ -404,6 +415,11 @@ def run_ours(args) -> None:
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"1 timed plain training iteration (after 1 warm-up) at batch 4 of the configs[{c}] shape, "
                              f"oracle restatement of the reference cpu_only path, fp32, {threads} host threads"}
+        # single-GPU rate at the per-GPU batch of the multi-GPU workload (configs[3]: 32 images per GPU), so that weak
+        # scaling can be read against the same per-GPU work; measured by a child process after this one is done
+        base = None
+        if world == 1 and c == 2 and not args.no_scaling_base:
+            base = _scaling_base_subprocess()
         gb = B * world
         n_pl = sum(1 for i in range(args.steps) if not plain_only and _schedule(i, cfg)[1])
         n_r1 = sum(1 for i in range(args.steps) if not plain_only and _schedule(i, cfg)[0])
@@ -419,6 +435,7 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "plain_step": {"value": gb / (ms_plain * 1e-3), "unit": UNIT, "ms_per_step": ms_plain, "steps": n_plain},
             "mix16": mix16,
+            "weak_scaling_base": base,
             "roofline": roof,
             "cpu_baseline": cpu,
         }
@@ -428,6 +445,24 @@ def run_ours(args) -> None:
         ts._graphs.clear()
         del ts
         _teardown(dist)
+
+
+def _scaling_base_subprocess(timeout_s: int = 240) -> dict:
+    """`bench.py --config 3 --gpus 1` (the multi-GPU workload's per-GPU batch on one GPU) in a child process."""
+    import subprocess
+
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "3", "--steps", "32", "--warmup", "3",
+                            "--no-roofline", "--no-cpu-baseline"], capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+        d = json.loads(lines[-1])
+        return {"value": d["value"], "unit": UNIT, "ms_per_step": d["ms_per_step"], "per_gpu_batch": d["per_gpu_batch"],
+                "plain_step": d["plain_step"], "workload": d["config"],
+                "note": "one GPU at the per-GPU batch of BASELINE configs[3] (256 / 8): the base of the weak-scaling runs"}
+    except Exception as ex:   # timeout, JSON error, ...
+        return {"error": repr(ex)[:300]}
 
 
 def _teardown(dist) -> None:
@@ -568,6 +603,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--plain-only", action="store_true", help="time non-regularised iterations only")
+    ap.add_argument("--no-roofline", action="store_true", help="short line: skip the roofline / cpu_baseline passes")
+    ap.add_argument("--no-scaling-base", action="store_true", help="skip the configs[3]-per-GPU-batch child measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

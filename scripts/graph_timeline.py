@@ -1,6 +1,6 @@
 """Kernel timeline of CUDA-graph replays of the training step (torch.profiler, CUDA activity only):
 per-kernel-name busy time inside the graph, idle gaps, concurrency.
-Usage: python scripts/graph_timeline.py [cfg] [steps] [plain|pl|r1pl]"""
+Usage: python scripts/graph_timeline.py [cfg] [steps] [plain|pl|r1pl] [per-GPU batch]"""
 import collections, os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,6 +15,8 @@ from oracle import train_step as OT
 idx = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = baseline_config(idx)
+if len(sys.argv) > 4:
+    cfg.batch_size_per_gpu = cfg.batch_size = int(sys.argv[4])
 dev = "cuda:0"
 G = Generator(cfg, device=dev, seed=0); D = Discriminator(cfg, device=dev, seed=1)
 aster = AsterInferer(cfg, device=dev, synthetic_weights=True)

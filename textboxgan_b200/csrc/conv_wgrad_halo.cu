@@ -11,9 +11,10 @@
 //         box + ((ty + 2k) * 10 + tx) * 128 B for tap (ty,tx) and 16-pixel K step k, SBO = 10 * 128 B, LBO = distance
 //         between the channel blocks).  tcgen05 applies the 128B swizzle to absolute shared-memory address bits, so the
 //         shifted window reads back what TMA wrote (scripts/experiments/exp_halo_umma.cu part 2, measured on B200).
-// A work item = (128 output channels, up to 128 input channels, a group of up to 4 taps, a range of K blocks): the four
-// accumulators fill the 512 TMEM columns, every x box feeds all taps of the group.  L2 traffic per K block: 32 KB (gy)
-// + 2 x 23 KB (x halo) for 4 x 8 x 64 = 2048 tensor clocks = 38 B/clk/SM.  The accumulators are reduced into fp32 gw with
+// A work item = (128 output channels, up to 128 input channels, a group of 3 taps (5 / 4 for 64-channel items), a range of
+// K blocks): the accumulators sit in TMEM (<= 512 columns), every x box feeds all taps of the group.  L2 traffic per K
+// block: 32 KB (gy) + 2 x 23 KB (x halo) for 3 x 8 x 64 = 1536 tensor clocks = 51 B/clk/SM, most of it L2 hits because the
+// items of one pixel range run side by side.  The accumulators are reduced into fp32 gw with
 // vector atomics (split-K over CTAs), like conv_wgrad_kernel.
 #include "common.cuh"
 #include "host_util.h"
@@ -210,9 +211,12 @@ int wgrad_halo_launch(const tbg_wgrad_args* a, cudaStream_t stream) {
   p.block_c = (a->Cin % 128 == 0) ? 128 : 64;
   p.c_tiles = a->Cin / p.block_c;
   p.m_tiles = (a->cout + 127) / 128;
-  p.taps_per_group = 512 / p.block_c;
-  if (p.taps_per_group > 9) p.taps_per_group = 9;
-  p.groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
+  // tap groups of equal size (3 x 3 taps for 128-channel items, 5 + 4 for 64-channel items): with the static round-robin
+  // over CTAs unequal groups (4 + 4 + 1) left the CTAs holding the short items idle (profiles/r02j_wgrad.log)
+  int max_taps = 512 / p.block_c;
+  if (max_taps > 9) max_taps = 9;
+  p.groups = (9 + max_taps - 1) / max_taps;
+  p.taps_per_group = (9 + p.groups - 1) / p.groups;
   p.tiles_w = a->W / 8; p.tiles_h = a->H / 16;
   p.ktot = 9 * a->Cin;
   p.gw = a->gw;
