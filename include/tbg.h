@@ -203,6 +203,12 @@ int tbg_crop_resize_fwd(const float* img, const int* labels, float* out, int B, 
 int tbg_crop_resize_bwd(const float* g, const int* labels, float* gimg, int B, int H, int W, int oh, int ow, int mcn,
                         int blank, int cw_num, int cw_den, void* stream);
 
+/* Loader transform of a whole batch on the device (dataset_utils/training_data_loader.py:64-86): sample b = BGR uint8 image
+ * src + offsets[b], src_h[b] x src_w[b] x 3 (HWC) -> cv2.resize(INTER_LINEAR) to dst_w[b] x H, rounded to the uint8 grid,
+ * / 127.5 - 1, zero-padded on the right to W, written CHW into out fp32 [B,3,H,W].  All arrays are DEVICE pointers. */
+int tbg_batch_resize_normalize(const unsigned char* src, const long long* offsets, const int* src_h, const int* src_w,
+                               const int* dst_w, float* out, int B, int H, int W, void* stream);
+
 /* FromRGB (from_rgb.py:26-29): 1x1 conv 3 -> C of the NCHW fp32 image + bias + leaky-ReLU(0.2)*gain -> NHWC bf16:
  *   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] w[j,c] + bias[c]) * gain,   w fp32 [3, C]
  * bwd: gpre = g_out*gain*slope(out); gimg[b,j,p] = coef sum_c gpre w[j,c] (NCHW fp32, may be NULL);

@@ -443,6 +443,38 @@ def emu_rowdot(a, b):
     return (a.double() * b.double()).reshape(a.shape[0], -1, a.shape[-1]).sum(1).float()
 
 
+def emu_batch_resize_normalize(packed, offsets, src_h, src_w, dst_w, H, W):
+    """Documented semantics of tbg_batch_resize_normalize (float bilinear at pixel centres, rounded to the uint8 grid)."""
+    import numpy as np
+
+    B = offsets.shape[0]
+    out = np.zeros((B, 3, H, W), dtype=np.float32)
+    buf = packed.cpu().numpy()
+    for b in range(B):
+        sh, sw, dw = int(src_h[b]), int(src_w[b]), int(dst_w[b])
+        img = buf[int(offsets[b]): int(offsets[b]) + sh * sw * 3].reshape(sh, sw, 3).astype(np.float32)
+        if sw == 2 * dw and sh == 2 * H:
+            i = img.astype(np.int64)
+            r = ((i[0::2, 0::2] + i[0::2, 1::2] + i[1::2, 0::2] + i[1::2, 1::2] + 2) >> 2).astype(np.float32)
+        else:
+            def axis(n_dst, n_src):
+                f = (np.arange(n_dst, dtype=np.float32) + np.float32(0.5)) * (np.float32(n_src) / np.float32(n_dst)) - np.float32(0.5)
+                i0 = np.floor(f).astype(np.int64)
+                f = (f - i0).astype(np.float32)
+                lo, hi = i0 < 0, i0 >= n_src - 1
+                f[lo | hi] = 0
+                i0[lo] = 0
+                i0[hi] = n_src - 1
+                return i0, np.minimum(i0 + 1, n_src - 1), f
+            x0, x1, fx = axis(dw, sw)
+            y0, y1, fy = axis(H, sh)
+            top = img[y0][:, x0] + (img[y0][:, x1] - img[y0][:, x0]) * fx[None, :, None]
+            bot = img[y1][:, x0] + (img[y1][:, x1] - img[y1][:, x0]) * fx[None, :, None]
+            r = np.rint(top + (bot - top) * fy[:, None, None])
+        out[b, :, :, :dw] = (r / np.float32(127.5) - np.float32(1.0)).transpose(2, 0, 1)
+    return torch.from_numpy(out)
+
+
 def _emu_act(pre, act):
     if act == 1:
         return torch.where(pre > 0, pre, 0.2 * pre)
@@ -610,7 +642,8 @@ def emulated_kernels(act_dtype=torch.float32):
     C._as_bf16 = lambda t: t.contiguous()
     L.ACT_DTYPE = act_dtype
     new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
-                 "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot")
+                 "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot",
+                 "batch_resize_normalize")
     saved_n = {n: getattr(K, n) for n in new_names}
     for n in new_names:
         setattr(K, n, globals()["emu_" + n])

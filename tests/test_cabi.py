@@ -69,6 +69,7 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_set_tuning": lambda: h.tbg_set_tuning(b"no_such_key", 1),
         "tbg_bias_act_fwd": lambda: h.tbg_bias_act_fwd(None, None, None, None, P, 1, 4, 64, 1, 1.0, None),
         "tbg_rowdot": lambda: h.tbg_rowdot(P, P, None, 1, 4, 64, None),
+        "tbg_batch_resize_normalize": lambda: h.tbg_batch_resize_normalize(P, P, P, None, P, P, 2, 16, 64, None),
         "tbg_dense_fwd": lambda: h.tbg_dense_fwd(None, P, None, P, 4, 8, 8, 1.0, 1.0, 0, 1.0, None),
         "tbg_dense_bwd": lambda: h.tbg_dense_bwd(P, None, P, P, P, P, P, P, 4, 8, 8, 1.0, 1.0, 0, 1.0, 0, None),
         "tbg_pixel_norm_fwd": lambda: h.tbg_pixel_norm_fwd(None, P, 4, 8, None),

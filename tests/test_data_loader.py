@@ -71,3 +71,42 @@ def test_stream_batches_shuffle_and_corpus_swap(tmp_path):
     v = ValidationDataLoader(cfg, corpus, "validation_corpus.txt")
     vb = list(v.load_dataset(batch_size=2))
     assert len(vb) == 1 and vb[0][0].shape == (2, cfg.max_char_number) and int(vb[0][1][0, 5]) == 1
+
+
+def test_device_transform_matches_host_transform(tmp_path):
+    """The batched transform (tbg_batch_resize_normalize semantics, emulated on the CPU here) against the host path
+    ``cv2.resize(...)/127.5 - 1`` + right pad + HWC->CHW (training_data_loader.py:63-82).  cv2's fixed-point bilinear
+    and the kernel's float bilinear may round a value to the neighbouring uint8 level: tolerance 1 LSB = 1/127.5."""
+    from emu import emulated_kernels
+
+    cfg = small_cfg(2)
+    words = ["Hi", "a,b", "World!", "x"]
+    boxes, corpus = _make_dataset(tmp_path, words)
+    # one image at exactly 2x the target size: cv2 switches INTER_LINEAR to the 2x2 area mean there
+    w2 = int(cfg.char_width * 2)
+    rng = np.random.RandomState(5)
+    cv2.imwrite(os.path.join(boxes, "4.png"), rng.randint(0, 256, size=(2 * cfg.char_height, 2 * w2, 3), dtype=np.uint8))
+    with open(os.path.join(boxes, "annotations_filtered.txt"), "a") as f:
+        f.write("4.png,ab\n")
+    host = TrainingDataLoader(cfg, boxes, None, seed=7)
+    devl = TrainingDataLoader(cfg, boxes, None, seed=7, device_transform=True)
+    with emulated_kernels():
+        got = list(devl.load_dataset(batch_size=5, repeat=False))
+    ref = list(host.load_dataset(batch_size=5, repeat=False))
+    assert len(got) == len(ref) == 1
+    for a, b in zip(got[0][1:], ref[0][1:]):
+        assert torch.equal(a, b)
+    g, r = got[0][0], ref[0][0]
+    assert g.shape == r.shape and g.dtype == torch.float32
+    diff = (g - r).abs()
+    assert float(diff.max()) <= 1.0 / 127.5 + 1e-6
+    assert float((diff > 1e-6).float().mean()) < 0.35            # the two roundings agree on most pixels
+    assert torch.equal(g == 0, r == 0) or float(g[r == 0].abs().max()) <= 1.0 / 127.5 + 1e-6
+    # the 2:1 sample and the zero pad are exact
+    lens = (ref[0][2] > 0).sum(1)
+    exact = 0
+    for i in range(5):
+        wpx = int(cfg.char_width * int(lens[i]))
+        assert float(g[i, :, :, wpx:].abs().max()) == 0.0
+        exact += int(torch.equal(g[i], r[i]))
+    assert exact >= 1                                            # at least the 2:1 sample

@@ -161,7 +161,7 @@ __global__ void modulate_bwd_kernel(const uint4* __restrict__ gxs, const uint4* 
 // Written multiply-only (the slope and its inverse are selected, not divided): the kernel is bandwidth-bound
 // (3 activation passes) only when the per-element arithmetic stays below ~10 instructions.
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ out,
                     const uint4* __restrict__ res, const float* __restrict__ noise,
                     const float* __restrict__ d, uint4* __restrict__ gy0, float* __restrict__ S1,
@@ -189,7 +189,7 @@ bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ o
   const float neg_slope = act == 0 ? 1.f : (act == 2 ? 0.f : 0.2f);
   const float g_pos = gain, g_neg = gain * neg_slope;                     // g_pre = g_out * (out > 0 ? g_pos : g_neg)
   const float inv_gain = 1.f / gain;
-  const float r_pos = inv_gain, r_neg = (act == 1) ? inv_gain * 5.f : (act == 0 ? inv_gain : 0.f);   // pre = out * r_*
+  const float r_pos = inv_gain;                                           // pre = out / gain on the positive side
   if (r < rows) {
 #pragma unroll 4
     for (int p = p0 + r; p < p1; p += rows) {
@@ -212,7 +212,8 @@ bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ o
         const float gp = g[i] * (pos ? g_pos : g_neg);
         if (MODE >= 1) a1[i] += gp;
         if (MODE == 2) {
-          a2[i] = fmaf(gp, o[i] * (pos ? r_pos : r_neg), a2[i]);
+          // g_pre * pre: the slope and its inverse cancel (linear / leaky-ReLU), so no second select is needed
+          a2[i] = fmaf(act == 2 ? gp * r_pos : g[i], o[i], a2[i]);
           a3[i] = fmaf(gp, nz, a3[i]);
         }
         g[i] = gp * dv[i];

@@ -251,3 +251,78 @@ extern "C" int tbg_crop_resize_bwd(const float* g, const int* labels, float* gim
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Batched loader transform (dataset_utils/training_data_loader.py:64-86) on the device.  For sample b the BGR uint8 image
+// src + offsets[b] (src_h[b] x src_w[b] x 3, HWC) is resized bilinearly to dst_w[b] x H (cv2.resize INTER_LINEAR: pixel
+// centres, edge clamp, no antialias; the exact 2:1 decimation uses the 2 x 2 mean as cv2 does), rounded to the uint8 grid,
+// scaled to [-1, 1] (v / 127.5 - 1), zero-padded on the right up to W (cv2.copyMakeBorder) and written CHW: out fp32
+// [B,3,H,W].  One thread per output pixel; the host ships all images of a batch in ONE pinned buffer.
+// ---------------------------------------------------------------------------------------------
+namespace tbg {
+
+__global__ void __launch_bounds__(256)
+batch_resize_normalize_kernel(const unsigned char* __restrict__ src, const long long* __restrict__ offsets,
+                              const int* __restrict__ src_h, const int* __restrict__ src_w, const int* __restrict__ dst_w,
+                              float* __restrict__ out, int B, int H, int W) {
+  const long long total = static_cast<long long>(B) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(W) * H));
+    float v[3] = {0.f, 0.f, 0.f};
+    const int dw = dst_w[b];
+    if (x < dw) {
+      const int sh = src_h[b], sw = src_w[b];
+      const unsigned char* img = src + offsets[b];
+      float r[3];
+      if (sw == 2 * dw && sh == 2 * H) {
+        for (int c = 0; c < 3; ++c) {
+          const int s = img[((2 * y) * sw + 2 * x) * 3 + c] + img[((2 * y) * sw + 2 * x + 1) * 3 + c] +
+                        img[((2 * y + 1) * sw + 2 * x) * 3 + c] + img[((2 * y + 1) * sw + 2 * x + 1) * 3 + c];
+          r[c] = static_cast<float>((s + 2) >> 2);
+        }
+      } else {
+        float fx = (x + 0.5f) * (static_cast<float>(sw) / dw) - 0.5f;
+        float fy = (y + 0.5f) * (static_cast<float>(sh) / H) - 0.5f;
+        int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
+        fx -= x0;
+        fy -= y0;
+        if (x0 < 0) { x0 = 0; fx = 0.f; }
+        if (x0 >= sw - 1) { x0 = sw - 1; fx = 0.f; }
+        if (y0 < 0) { y0 = 0; fy = 0.f; }
+        if (y0 >= sh - 1) { y0 = sh - 1; fy = 0.f; }
+        const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+        for (int c = 0; c < 3; ++c) {
+          const float p00 = img[(y0 * sw + x0) * 3 + c], p01 = img[(y0 * sw + x1) * 3 + c];
+          const float p10 = img[(y1 * sw + x0) * 3 + c], p11 = img[(y1 * sw + x1) * 3 + c];
+          const float top = p00 + (p01 - p00) * fx, bot = p10 + (p11 - p10) * fx;
+          r[c] = rintf(top + (bot - top) * fy);
+        }
+      }
+      for (int c = 0; c < 3; ++c) v[c] = r[c] / 127.5f - 1.f;
+    }
+    const size_t plane = static_cast<size_t>(H) * W;
+    float* o = out + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * W + x;
+    o[0] = v[0];
+    o[plane] = v[1];
+    o[2 * plane] = v[2];
+  }
+}
+
+}  // namespace tbg
+
+extern "C" int tbg_batch_resize_normalize(const unsigned char* src, const long long* offsets, const int* src_h,
+                                          const int* src_w, const int* dst_w, float* out, int B, int H, int W,
+                                          void* stream_v) {
+  TBG_CHECK_ARG(src && offsets && src_h && src_w && dst_w && out, "tbg_batch_resize_normalize: null pointer");
+  TBG_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "tbg_batch_resize_normalize: bad shape B=%d H=%d W=%d", B, H, W);
+  const long long total = static_cast<long long>(B) * H * W;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  tbg::batch_resize_normalize_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(src, offsets, src_h, src_w,
+                                                                                                dst_w, out, B, H, W);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}

@@ -31,10 +31,14 @@ class TrainingDataLoader:
     """Loads the dataset which is used for training."""
 
     def __init__(self, cfg: Config, text_boxes_dir: str, text_corpus_dir: Optional[str] = None, device="cpu",
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None, device_transform: bool = False):
+        """``device_transform``: decode on the host, then resize / normalise / pad / transpose the WHOLE batch in one
+        kernel launch on ``device`` (``tbg_batch_resize_normalize``) instead of per-sample cv2 calls — at 10-20 K images/s
+        the per-sample host transform cannot feed the training step."""
         self.cfg = cfg
         self.text_boxes_dir = text_boxes_dir
         self.device = device
+        self.device_transform = bool(device_transform)
         self.return_ocr_image = cfg.ocr_loss_type == "mse"                         # :17
         self.use_corpus_word = cfg.ocr_loss_type == "softmax_crossentropy"         # :18
         self.corpus_words: List[str] = []
@@ -58,17 +62,24 @@ class TrainingDataLoader:
         image = cv2.imread(os.path.join(self.text_boxes_dir, image_name))
         if image is None:
             raise FileNotFoundError(os.path.join(self.text_boxes_dir, image_name))
-        main_image = cv2.resize(image, (self._word_width(len(word)), cfg.char_height))
-        main_image = main_image.astype(np.float32) / 127.5 - 1.0
+        raw_image, raw_width = image, self._word_width(len(word))
+        if self.device_transform:
+            main_image = None                      # resized on the device, batch at a time (_collate)
+        else:
+            main_image = cv2.resize(image, (raw_width, cfg.char_height))
+            main_image = main_image.astype(np.float32) / 127.5 - 1.0
         if self.return_ocr_image:
             ocr_image = cv2.resize(image, (cfg.aster_image_dims[1], cfg.aster_image_dims[0]))
             ocr_image = ocr_image.astype(np.float32) / 127.5 - 1.0
         else:
             ocr_image = np.float32(0.0)
-        padding_length = cfg.image_width - main_image.shape[1]     # == (max_char_number - len(word)) * char_width
-        padded_image = cv2.copyMakeBorder(src=main_image, top=0, bottom=0, left=0, right=padding_length,
-                                          borderType=cv2.BORDER_CONSTANT)
-        padded_image = np.transpose(padded_image, (2, 0, 1))       # H,W,C to C,H,W
+        if self.device_transform:
+            padded_image = (np.ascontiguousarray(raw_image), raw_width)
+        else:
+            padding_length = cfg.image_width - main_image.shape[1]     # == (max_char_number - len(word)) * char_width
+            padded_image = cv2.copyMakeBorder(src=main_image, top=0, bottom=0, left=0, right=padding_length,
+                                              borderType=cv2.BORDER_CONSTANT)
+            padded_image = np.transpose(padded_image, (2, 0, 1))       # H,W,C to C,H,W
         if self.use_corpus_word and self.corpus_words and self._rng.random() > 1 - self.corpus_word_ratio:
             word = next(self.corpus_words_generator, None)
             if word is None:
@@ -112,9 +123,32 @@ class TrainingDataLoader:
                 yield self._collate(batch)
                 batch = []
 
+    def _device_images(self, items: List[tuple]) -> torch.Tensor:
+        """[(uint8 HWC BGR image, target width)] -> fp32 [B,3,H,W] on the device: one packed host buffer, one
+        host-to-device copy, one kernel launch."""
+        from . import kernels as K
+
+        cfg, dev = self.cfg, self.device
+        sizes = [im.size for im, _ in items]
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        packed = torch.empty(int(sum(sizes)), dtype=torch.uint8)
+        if torch.device(dev).type == "cuda":
+            packed = packed.pin_memory()
+        flat = packed.numpy()
+        for (im, _), off, n in zip(items, offsets, sizes):
+            flat[off: off + n] = im.reshape(-1)
+        meta = lambda v, dt: torch.as_tensor(np.asarray(v), dtype=dt).to(dev, non_blocking=True)
+        return K.batch_resize_normalize(packed.to(dev, non_blocking=True), meta(offsets, torch.int64),
+                                        meta([im.shape[0] for im, _ in items], torch.int32),
+                                        meta([im.shape[1] for im, _ in items], torch.int32),
+                                        meta([w for _, w in items], torch.int32), cfg.char_height, cfg.image_width)
+
     def _collate(self, batch: List[tuple]) -> tuple:
         dev = self.device
-        real = torch.from_numpy(np.stack([b[0] for b in batch])).to(dev)
+        if self.device_transform:
+            real = self._device_images([b[0] for b in batch])
+        else:
+            real = torch.from_numpy(np.stack([b[0] for b in batch])).to(dev)
         ocr = torch.from_numpy(np.stack([b[1] for b in batch])).to(dev) if self.return_ocr_image \
             else torch.zeros((), device=dev)
         words = torch.from_numpy(np.stack([b[2] for b in batch]).astype(np.int32)).to(dev)

@@ -707,3 +707,19 @@ def rowdot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros((B, C_), device=a.device, dtype=torch.float32)
     _lib.check(_lib.load().tbg_rowdot(_ptr(a), _ptr(b), _ptr(out), B, HW, C_, _stream()), "tbg_rowdot")
     return out
+
+
+def batch_resize_normalize(packed: torch.Tensor, offsets: torch.Tensor, src_h: torch.Tensor, src_w: torch.Tensor,
+                           dst_w: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Loader transform of a batch on the device — see include/tbg.h (tbg_batch_resize_normalize).  ``packed`` uint8 device
+    buffer holding every HWC BGR image back to back; offsets int64 [B]; src_h / src_w / dst_w int32 [B]."""
+    _require(packed, torch.uint8, "packed")
+    _require(offsets, torch.int64, "offsets")
+    for t, n in ((src_h, "src_h"), (src_w, "src_w"), (dst_w, "dst_w")):
+        _require(t, torch.int32, n)
+    B = offsets.shape[0]
+    out = torch.empty((B, 3, H, W), device=packed.device, dtype=torch.float32)
+    st = _lib.load().tbg_batch_resize_normalize(_ptr(packed), _ptr(offsets), _ptr(src_h), _ptr(src_w), _ptr(dst_w), _ptr(out),
+                                                B, int(H), int(W), _stream())
+    _lib.check(st, "tbg_batch_resize_normalize")
+    return out

@@ -90,6 +90,7 @@ _SIGNATURES = [
     ("tbg_get_tuning", c_int, [C.c_char_p]),
     ("tbg_crop_resize_fwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
     ("tbg_crop_resize_bwd", c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p]),
+    ("tbg_batch_resize_normalize", c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
     ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fromrgb_bwd", c_int, [c_void_p] * 7 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fir4", c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] + [c_void_p] * 4 + [c_int, c_float, c_void_p]),
