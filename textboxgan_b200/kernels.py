@@ -160,6 +160,8 @@ def conv2d_wgrad(
     )
     with _Timed("conv_wgrad", 2.0 * B * Ho * Wo * n_total * taps[0] * taps[1] * Cin):
         _lib.check(_lib.load().tbg_conv2d_wgrad(C.byref(a), _stream()), "tbg_conv2d_wgrad")
+    if PROFILE is not None:
+        PROFILE[-1] = PROFILE[-1] + (dict(x_shape=tuple(x.shape), w_shape=tuple(gy.shape), stride=stride, up=up),)
     return gw
 
 
