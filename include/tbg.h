@@ -182,6 +182,17 @@ int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, c
 int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int offy, int offx, float scale,
              const float* d, const float* noise, const float* noise_strength, const float* bias, int act, float gain,
              void* stream);
+/* The skip branch of a residual block (discriminator.py:126-131: conv_downsample_2d with a 1x1 kernel,
+ * upfirdn_2d_v2.py:106-113) needs the filtered tensor only at the pixels its stride-(sy, 2) convolution reads:
+ *   out[b,p,q,c] = scale * sum_{m,n<4} k[m] k[n] in[b, sy*p+m+offy, 2*q+n+offx, c]      (in = 0 out of bounds; sy = 1 | 2)
+ * in [B,IH,IW,C] bf16 -> out [B,OH,OW,C] bf16.  tbg_fir4_down_adjoint is its transpose, optionally added to the
+ * gradient that arrives through the main branch (add may be NULL):
+ *   out[b,y,x,c] = add[b,y,x,c] + scale * sum k[m] k[n] g[b,p,q,c]  over sy*p+m+offy = y, 2*q+n+offx = x
+ * g [B,OH,OW,C], add / out [B,IH,IW,C]. */
+int tbg_fir4_down(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int sy, int offy, int offx,
+                  float scale, void* stream);
+int tbg_fir4_down_adjoint(const void* g, const void* add, void* out, int B, int IH, int IW, int OH, int OW, int C, int sy,
+                          int offy, int offx, float scale, void* stream);
 /* Tuning switches of the library (explicit calls; the library never reads environment variables).  Keys:
  *   "conv_halo" (default 1)   tbg_conv2d_igemm runs 3x3 stride-1 pad-1 convolutions whose grid is a multiple of 16 x 16
  *                             pixels (Cin % 64 == 0, cout % 32 == 0, no residual / relu_mask / fp32 output) on the

@@ -249,6 +249,41 @@ def emu_fir4(x, out_hw, off, scale, *, d=None, noise=None, noise_strength=None, 
     return (acc * gain).to(x.dtype)
 
 
+def _fir4_down_f64(x, out_hw, sy, off, scale):
+    B, IH, IW, C = x.shape
+    OH, OW = out_hw
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    lo_y, lo_x = max(0, -off[0]), max(0, -off[1])
+    hi_y, hi_x = max(0, sy * (OH - 1) + 4 + off[0] - IH), max(0, 2 * (OW - 1) + 4 + off[1] - IW)
+    xp = torch.nn.functional.pad(x.double(), (0, 0, lo_x, hi_x, lo_y, hi_y))
+    acc = torch.zeros(B, OH, OW, C, dtype=torch.float64)
+    for m in range(4):
+        for n in range(4):
+            y0, x0 = m + off[0] + lo_y, n + off[1] + lo_x
+            acc = acc + k[m] * k[n] * xp[:, y0: y0 + sy * (OH - 1) + 1: sy, x0: x0 + 2 * (OW - 1) + 1: 2]
+    return acc * scale
+
+
+def emu_fir4_down(x, out_hw, sy, off, scale):
+    """Documented semantics of tbg_fir4_down (include/tbg.h)."""
+    return _fir4_down_f64(x, out_hw, sy, off, scale).to(x.dtype)
+
+
+def emu_fir4_down_adjoint(g, in_hw, sy, off, scale, add=None, out=None):
+    """Documented semantics of tbg_fir4_down_adjoint: the exact transpose of emu_fir4_down (by autograd) + add."""
+    B, OH, OW, C = g.shape
+    with torch.enable_grad():
+        x = torch.zeros(B, in_hw[0], in_hw[1], C, dtype=torch.float64, requires_grad=True)
+        y = _fir4_down_f64(x, (OH, OW), sy, off, scale)
+        (gx,) = torch.autograd.grad(y, x, g.double())
+    if add is not None:
+        gx = gx + add.double()
+    if out is not None:
+        out.copy_(gx.to(out.dtype))
+        return out
+    return gx.to(g.dtype)
+
+
 def emu_wfold_adj(gadj, spec, *, w_raw=None, s=None, t=None, out=None, flip=False):
     taps = spec.KH * spec.KW
     g = gadj.double().reshape(spec.Ipad, taps, spec.Opad)[: spec.I, :, : spec.O]
@@ -643,7 +678,7 @@ def emulated_kernels(act_dtype=torch.float32):
     L.ACT_DTYPE = act_dtype
     new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
                  "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot",
-                 "batch_resize_normalize")
+                 "batch_resize_normalize", "fir4_down", "fir4_down_adjoint")
     saved_n = {n: getattr(K, n) for n in new_names}
     for n in new_names:
         setattr(K, n, globals()["emu_" + n])

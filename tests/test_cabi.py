@@ -85,6 +85,8 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_crop_resize_fwd": lambda: h.tbg_crop_resize_fwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_crop_resize_bwd": lambda: h.tbg_crop_resize_bwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),
+        "tbg_fir4_down": lambda: h.tbg_fir4_down(P, P, 1, 4, 4, 2, 2, 8, 3, -1, -1, 1.0, None),
+        "tbg_fir4_down_adjoint": lambda: h.tbg_fir4_down_adjoint(P, None, P, 1, 4, 4, 2, 2, 12, 2, -1, -1, 1.0, None),
         "tbg_wprep": lambda: h.tbg_wprep(P, None, 1.0, 3, 3, 64, 64, 64, 64, P, P, None, None),
         "tbg_wfold": lambda: h.tbg_wfold(P, None, None, None, 1.0, 3, 3, 64, 64, 64, 64, P, None, None, 0, 0, None),
         "tbg_wfold_adj": lambda: h.tbg_wfold_adj(None, None, 1.0, 3, 3, 64, 64, 64, P, None, None, 0, 0, 0, None),

@@ -540,6 +540,21 @@ def test_conv3x3_halo_kernel_phase_scatter_and_tap_masks():
             want = emu_conv2d_igemm(x, w, bias=bias, act=1, act_gain=1.25, tap_mask=tm, **kw)
             assert y.shape == (B, 2 * H, 2 * W, O)
             assert rel_err(y.float().cpu(), want.float()) < 1e-2, tm
+        # 64 channels per phase: one 128-column tile holds two phases when their tap masks agree (pairs (0,1), (2,3)),
+        # with per-sample column scales and per-output-pixel noise; also the width-only up-sampling geometry
+        for up in ((1, 1), (0, 1)):
+            nph = (1 + up[0]) * (1 + up[1])
+            kw2 = dict(kw, up=up)
+            w2 = _bf16_round(torch.randn(nph * O, 9 * I, generator=gen) / math.sqrt(9 * I))
+            scale = torch.rand(B, O, generator=gen) + 0.5
+            noise = torch.randn(B, H * (1 + up[0]), W * (1 + up[1]), generator=gen)
+            ns = torch.tensor([0.3])
+            for tm in (None, (0b101111101, 0b101111101, 0b000111111, 0b000111111)[:nph] + (0,) * (4 - nph)):
+                y = K.conv2d_igemm(x.to(DEV).bfloat16(), w2.to(DEV).bfloat16(), bias=bias.to(DEV), col_scale=scale.to(DEV),
+                                   noise=noise.to(DEV), noise_strength=ns.to(DEV), act=1, act_gain=1.25, tap_mask=tm, **kw2)
+                want = emu_conv2d_igemm(x, w2, bias=bias, col_scale=scale, noise=noise, noise_strength=ns, act=1,
+                                        act_gain=1.25, tap_mask=tm, **kw2)
+                assert rel_err(y.float().cpu(), want.float()) < 1e-2, (up, tm)
     finally:
         lib.set_tuning("conv_halo", saved)
 

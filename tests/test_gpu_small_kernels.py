@@ -291,3 +291,31 @@ def test_batch_resize_normalize_kernel_vs_emulation_and_cv2():
         if w_ < W:
             assert float(got[b, :, :, w_:].abs().max()) == 0.0
     assert torch.equal(got[1], want[1]) and torch.equal(got[5], want[5])      # 2:1 area mean and identity are exact
+
+
+@pytest.mark.parametrize("sy", [1, 2])
+@pytest.mark.parametrize("B,H,W,C", [(3, 16, 64, 64), (2, 8, 34, 128), (1, 66, 70, 8), (2, 4, 4, 256)])
+def test_fir4_down_and_adjoint_kernels(sy, B, H, W, C):
+    """tbg_fir4_down / tbg_fir4_down_adjoint (skip branch of a residual block: upfirdn_2d_v2.py:106-113 with a 1x1 kernel):
+    the decimated filter equals the full-resolution tbg_fir4 semantics sub-sampled, the adjoint is the exact transpose
+    (+ add); one bf16 rounding of the result."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(H * 7 + W + sy)
+    x = torch.randn(B, H, W, C, generator=gen).bfloat16()
+    OH, OW = H // sy, W // 2
+    got = Kn.fir4_down(x.to(DEV), (OH, OW), sy, (-1, -1), 1.0 / 64.0).cpu()
+    want = emu.emu_fir4_down(x, (OH, OW), sy, (-1, -1), 1.0 / 64.0)
+    full = emu.emu_fir4(x, (H, W), (-1, -1), 1.0 / 64.0)[:, ::sy, ::2][:, :OH, :OW]
+    assert torch.equal(want, full)
+    assert rel_err(got, want) < 4e-3 and float((got.float() - want.float()).abs().max()) <= 2.0 ** -7 * float(want.abs().max())
+    g = torch.randn(B, OH, OW, C, generator=gen).bfloat16()
+    add = torch.randn(B, H, W, C, generator=gen).bfloat16()
+    for a in (None, add):
+        gx = Kn.fir4_down_adjoint(g.to(DEV), (H, W), sy, (-1, -1), 1.0 / 64.0, add=a.to(DEV) if a is not None else None).cpu()
+        ex = emu.emu_fir4_down_adjoint(g, (H, W), sy, (-1, -1), 1.0 / 64.0, add=a)
+        assert rel_err(gx, ex) < 4e-3, (sy, a is not None, rel_err(gx, ex))
+    # <fir_down(x), g> == <x, adjoint(g)> within bf16 rounding of the two results
+    lhs = float((got.double() * g.double()).sum())
+    rhs = float((x.double() * Kn.fir4_down_adjoint(g.to(DEV), (H, W), sy, (-1, -1), 1.0 / 64.0).cpu().double()).sum())
+    assert abs(lhs - rhs) <= 2e-2 * (got.double() * g.double()).abs().sum() ** 0.5 + 1e-3 * abs(lhs)

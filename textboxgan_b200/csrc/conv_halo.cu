@@ -198,32 +198,40 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_tile = item / tiles_px, px_item = item - n_tile * tiles_px;
       const int tw = px_item % p.tiles_w, th = (px_item / p.tiles_w) % p.tiles_h, b = px_item / (p.tiles_w * p.tiles_h);
       const int acc_stage = it & 1;
-      // per-column vectors of this item -> shared memory (broadcast reads below); overlaps the MMAs of the item
-      int c_base = n_tile * N, py = 0, px = 0;
-      if (has_up) {
-        const int ph = c_base / p.cout;
-        c_base -= ph * p.cout;
-        py = p.up_w ? (ph >> 1) : ph;
-        px = p.up_w ? (ph & 1) : 0;
-      }
+      // per-column vectors of this item -> shared memory (broadcast reads below); overlaps the MMAs of the item.
+      // With up-sampling an N tile may hold several output phases (cout < N): column -> (phase, channel).
+      const int col0 = n_tile * N;
       __syncwarp();
       if (lane * 4 < N) {
+        const int c = has_up ? (col0 + lane * 4) % p.cout : col0 + lane * 4;
         float4 sv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.col_scale) sv = __ldg(reinterpret_cast<const float4*>(p.col_scale + static_cast<size_t>(b) * p.cout + c_base) + lane);
-        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c_base) + lane);
+        if (p.col_scale) sv = __ldg(reinterpret_cast<const float4*>(p.col_scale + static_cast<size_t>(b) * p.cout + c));
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
         reinterpret_cast<float4*>(vscale)[lane] = sv;
         reinterpret_cast<float4*>(vbias)[lane] = bv;
       }
       __syncwarp();
       const int iy = th * 16 + y_in, ix = tw * 16 + 8 * sub + x_in;
-      const int oy = p.up_h ? 2 * iy + py : iy, ox = p.up_w ? 2 * ix + px : ix;
-      const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
-      const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
-      const long long row_el = static_cast<long long>(pix * p.cout + c_base);
+      float nz = 0.f;
+      long long row_el = 0;                                    // first element of this row's current column chunk
       mbar_wait(&tfull[acc_stage], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((acc_stage * 2 + sub) * N);
       for (int j = 0; j < N / 32; ++j) {
+        if (j % j_per_chunk == 0) {
+          // a chunk (<= 64 columns, cout % chunk == 0) lies inside one output phase
+          int c_base = col0 + j * 32, py = 0, px = 0;
+          if (has_up) {
+            const int ph = c_base / p.cout;
+            c_base -= ph * p.cout;
+            py = p.up_w ? (ph >> 1) : ph;
+            px = p.up_w ? (ph & 1) : 0;
+          }
+          const int oy = p.up_h ? 2 * iy + py : iy, ox = p.up_w ? 2 * ix + px : ix;
+          const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
+          nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
+          row_el = static_cast<long long>(pix * p.cout + c_base);
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_row + j * 32, v);
         tmem_ld_wait();
@@ -260,15 +268,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.staged)
             *reinterpret_cast<uint4*>(srow + g * 16) = pk;
           else
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_el + j * 32 + g * 8) = pk;
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_el + (j % j_per_chunk) * 32 + g * 8) = pk;
         }
         if (p.staged && (j + 1) % j_per_chunk == 0) {
           // flush the staged chunk: lanes_per_row consecutive lanes write one row's contiguous bytes
           __syncwarp();
-          const long long chunk_el = static_cast<long long>((j / j_per_chunk) * chunk_cols);
           for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
             const int rr = r0 + lane / lanes_per_row;
-            const long long o_el = __shfl_sync(0xffffffffu, row_el, rr) + chunk_el;
+            const long long o_el = __shfl_sync(0xffffffffu, row_el, rr);
             const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kHStgRow + sbl * 16);
             *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(o_el) * 2 + sbl * 16) = val;
           }
@@ -302,8 +309,6 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
   p.cin = a->Cin; p.cin_chunks = a->Cin / 64; p.cout = a->cout;
   int block_n = 128;
   while (block_n > 32 && (a->cout % block_n) != 0) block_n >>= 1;
-  p.block_n = block_n;
-  p.tiles_n = a->n_total / block_n;
   p.tiles_w = a->W / 16; p.tiles_h = a->H / 16;
   p.up_h = a->up_h; p.up_w = a->up_w;
   p.out_H = a->up_h ? 2 * a->H : a->H;
@@ -313,6 +318,11 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
     p.tap_mask[i] = static_cast<uint32_t>((a->tap_mask[i] ? a->tap_mask[i] : 0x1FFull) & 0x1FFull);
     if (i < nph) TBG_CHECK_ARG(p.tap_mask[i] != 0, "tbg_conv2d_igemm(halo): phase %d has no taps", i);
   }
+  // 64 output channels per phase: one 128-column tile holds two neighbouring phases (N = 64 MMAs are shared-memory
+  // bound at half the tensor rate) when both compute the same taps
+  if (nph > 1 && a->cout == 64 && p.tap_mask[0] == p.tap_mask[1] && (nph == 2 || p.tap_mask[2] == p.tap_mask[3])) block_n = 128;
+  p.block_n = block_n;
+  p.tiles_n = a->n_total / block_n;
   p.col_scale = a->col_scale; p.bias = a->bias; p.noise = a->noise; p.noise_strength = a->noise_strength;
   p.act = a->act; p.act_gain = a->act_gain; p.out = a->out;
   CUtensorMap tmA, tmB;

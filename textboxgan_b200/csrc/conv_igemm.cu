@@ -449,7 +449,8 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
     const uint64_t strides[4] = {0, (uint64_t)a->Cin * 2, (uint64_t)a->W * a->Cin * 2, (uint64_t)a->H * a->W * a->Cin * 2};
-    // with element stride s the box spans b*s source elements and delivers b of them
+    // with element stride s the box spans b*s source elements and delivers b of them.  (A parity-split 5-D view of x
+    // that turns every tap into a dense box measured the same, profiles/r02p_perf_shapes.log, and was dropped.)
     const uint32_t box[4] = {64, (uint32_t)(bw * a->stride_w), (uint32_t)(bh * a->stride_h), (uint32_t)bn};
     const uint32_t estr[4] = {1, (uint32_t)a->stride_w, (uint32_t)a->stride_h, 1};
     int rc = encode_tmap_bf16(&tmA, a->x, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);

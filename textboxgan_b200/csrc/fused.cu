@@ -448,6 +448,142 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same 4x4 FIR evaluated only at the pixels a stride-(SY, 2) 1x1 convolution reads (the skip branch of a residual
+// block, discriminator.py:126-131 -> conv_downsample_2d with a 1x1 kernel, upfirdn_2d_v2.py:106-113):
+//   out[b,p,q,c] = scale * sum_{m,n<4} k[m] k[n] in[b, SY*p+m+offy, 2*q+n+offx, c]        (in = 0 out of bounds)
+// Same thread layout as fir4_kernel; with SY = 2 two new horizontally filtered rows enter the window per output row.
+// ---------------------------------------------------------------------------------------------
+template <int SY>
+__global__ void __launch_bounds__(256)
+fir4_down_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int IW, int OH, int OW, int c8, int offy,
+                 int offx, float scale, int cgroups) {
+  const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirStrip;
+  const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
+  const int v = threadIdx.x & 7, xl = threadIdx.x >> 3;
+  const int x = x0 + xl, cv = cg * 8 + v;
+  if (x >= OW || cv >= c8) return;
+  const uint4* src = in + static_cast<long long>(b) * IH * IW * c8 + cv;
+  const int ix0 = 2 * x + offx;
+  auto hrow = [&](int iy, float (&h)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = 0.f;
+    if (iy < 0 || iy >= IH) return;
+    const uint4* row = src + static_cast<long long>(iy) * IW * c8;
+    uint4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ix = ix0 + k;
+      t[k] = (ix >= 0 && ix < IW) ? __ldg(row + static_cast<long long>(ix) * c8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(t[k], f);
+      const float wk = (k == 0 || k == 3) ? 1.f : 3.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = fmaf(f[i], wk, h[i]);
+    }
+  };
+  const int y_end = min(y0 + kFirStrip, OH);
+  uint4* dst = out + (static_cast<long long>(b) * OH * OW + x) * c8 + cv;
+  float win[4][8];
+  if (SY == 1) {
+    hrow(y0 + offy + 0, win[0]);
+    hrow(y0 + offy + 1, win[1]);
+    hrow(y0 + offy + 2, win[2]);
+    for (int yb = y0; yb < y_end; yb += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int y = yb + q;
+        if (y >= y_end) return;
+        hrow(y + offy + 3, win[(q + 3) & 3]);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          acc[i] = (win[q & 3][i] + win[(q + 3) & 3][i] + 3.f * (win[(q + 1) & 3][i] + win[(q + 2) & 3][i])) * scale;
+        dst[static_cast<long long>(y) * OW * c8] = pack8(acc);
+      }
+    }
+  } else {
+    hrow(2 * y0 + offy + 0, win[0]);
+    hrow(2 * y0 + offy + 1, win[1]);
+    for (int yb = y0; yb < y_end; yb += 2) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {          // q compile-time: the window halves swap roles without register moves
+        const int y = yb + q;
+        if (y >= y_end) return;
+        const int lo = 2 * q, hi = 2 * (q ^ 1);
+        hrow(2 * y + offy + 2, win[hi]);
+        hrow(2 * y + offy + 3, win[hi + 1]);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          acc[i] = (win[lo][i] + win[hi + 1][i] + 3.f * (win[lo + 1][i] + win[hi][i])) * scale;
+        dst[static_cast<long long>(y) * OW * c8] = pack8(acc);
+      }
+    }
+  }
+}
+
+// Adjoint of fir4_down (the input gradient of the skip branch), added to the gradient arriving through the main branch:
+//   gx[b,y,x,c] = add[b,y,x,c] + scale * sum k[m] k[n] g[b,p,q,c]   over (m,p): SY*p+m+offy = y and (n,q): 2*q+n+offx = x
+// One thread per (x, 8-channel vector) walking down a strip of rows; the (4/SY) x 2 contributing elements of the
+// (SY*2 times smaller) gradient tile are re-read through L1.
+template <int SY>
+__global__ void __launch_bounds__(256)
+fir4_down_adjoint_kernel(const uint4* __restrict__ g, const uint4* __restrict__ add, uint4* __restrict__ out, int IH, int IW,
+                         int OH, int OW, int c8, int offy, int offx, float scale, int cgroups) {
+  const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirStrip;
+  const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
+  const int v = threadIdx.x & 7, xl = threadIdx.x >> 3;
+  const int x = x0 + xl, cv = cg * 8 + v;
+  if (x >= IW || cv >= c8) return;
+  const uint4* src = g + static_cast<long long>(b) * OH * OW * c8 + cv;
+  // the two horizontal taps: n = n0, n0 + 2 with q = (x - offx - n) / 2
+  const int n0 = (x - offx) & 1;
+  const int q0 = (x - offx - n0) >> 1, q1 = q0 - 1;           // taps n0 and n0 + 2
+  const float wq0 = n0 == 0 ? 1.f : 3.f, wq1 = n0 == 0 ? 3.f : 1.f;
+  const bool ok0 = q0 >= 0 && q0 < OW, ok1 = q1 >= 0 && q1 < OW;
+  const int y_end = min(y0 + kFirStrip, IH);
+  for (int y = y0; y < y_end; ++y) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int t = y - offy - m;
+      if (SY == 2 && (t & 1)) continue;
+      const int p = SY == 2 ? (t >> 1) : t;
+      if (t < 0 || p >= OH) continue;
+      const float wm = (m == 0 || m == 3) ? 1.f : 3.f;
+      const uint4* row = src + static_cast<long long>(p) * OW * c8;
+      float f[8];
+      if (ok0) {
+        unpack8(__ldg(row + static_cast<long long>(q0) * c8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(f[i], wm * wq0, acc[i]);
+      }
+      if (ok1) {
+        unpack8(__ldg(row + static_cast<long long>(q1) * c8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(f[i], wm * wq1, acc[i]);
+      }
+    }
+    const long long o = ((static_cast<long long>(b) * IH + y) * IW + x) * c8 + cv;
+    if (add != nullptr) {
+      float f[8];
+      unpack8(__ldg(add + o), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], scale, f[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= scale;
+    }
+    out[o] = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FromRGB (from_rgb.py:26-29): 1x1 convolution 3 -> C on the NCHW fp32 image + bias + leaky-ReLU*gain,
 // written as NHWC bf16.  K = 3 makes it bandwidth-bound: one thread per (pixel, 8 channels).
 //   out[b,p,c] = lrelu(coef * sum_j img[b,j,p] * w[j,c] + bias[c]) * gain
@@ -743,6 +879,52 @@ extern "C" int tbg_fir4(const void* in, void* out, int B, int IH, int IW, int OH
     fir4_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW,
                                                  OH, OW, C / 8, offy, offx, scale, d, noise, noise_strength, bias, act, gain,
                                                  cgroups);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_fir4_down(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int sy, int offy,
+                             int offx, float scale, void* stream_v) {
+  TBG_CHECK_ARG(in && out, "tbg_fir4_down: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && IH >= 1 && IW >= 1 && OH >= 1 && OW >= 1,
+                "tbg_fir4_down: bad shape B=%d in=%dx%d out=%dx%d C=%d", B, IH, IW, OH, OW, C);
+  TBG_CHECK_ARG(sy == 1 || sy == 2, "tbg_fir4_down: sy must be 1 or 2 (the width stride is always 2)");
+  TBG_CHECK_ARG(TBG_ALIGNED16(in) && TBG_ALIGNED16(out), "tbg_fir4_down: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int cgroups = (C / 8 + 7) / 8;
+  TBG_CHECK_ARG(static_cast<long long>(B) * cgroups <= 65535, "tbg_fir4_down: B * channel groups exceeds the grid limit");
+  const dim3 grid((OW + kFirCols - 1) / kFirCols, (OH + kFirStrip - 1) / kFirStrip, B * cgroups);
+  if (sy == 1)
+    fir4_down_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW,
+                                                  OH, OW, C / 8, offy, offx, scale, cgroups);
+  else
+    fir4_down_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), IH, IW,
+                                                  OH, OW, C / 8, offy, offx, scale, cgroups);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_fir4_down_adjoint(const void* g, const void* add, void* out, int B, int IH, int IW, int OH, int OW, int C,
+                                     int sy, int offy, int offx, float scale, void* stream_v) {
+  TBG_CHECK_ARG(g && out, "tbg_fir4_down_adjoint: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && B >= 1 && IH >= 1 && IW >= 1 && OH >= 1 && OW >= 1,
+                "tbg_fir4_down_adjoint: bad shape B=%d in=%dx%d out=%dx%d C=%d", B, IH, IW, OH, OW, C);
+  TBG_CHECK_ARG(sy == 1 || sy == 2, "tbg_fir4_down_adjoint: sy must be 1 or 2 (the width stride is always 2)");
+  TBG_CHECK_ARG(TBG_ALIGNED16(g) && TBG_ALIGNED16(add) && TBG_ALIGNED16(out), "tbg_fir4_down_adjoint: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int cgroups = (C / 8 + 7) / 8;
+  TBG_CHECK_ARG(static_cast<long long>(B) * cgroups <= 65535, "tbg_fir4_down_adjoint: B * channel groups exceeds the grid limit");
+  const dim3 grid((IW + kFirCols - 1) / kFirCols, (IH + kFirStrip - 1) / kFirStrip, B * cgroups);
+  if (sy == 1)
+    fir4_down_adjoint_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(add),
+                                                          reinterpret_cast<uint4*>(out), IH, IW, OH, OW, C / 8, offy, offx,
+                                                          scale, cgroups);
+  else
+    fir4_down_adjoint_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(add),
+                                                          reinterpret_cast<uint4*>(out), IH, IW, OH, OW, C / 8, offy, offx,
+                                                          scale, cgroups);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

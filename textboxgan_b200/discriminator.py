@@ -118,8 +118,15 @@ class Discriminator(Model):
         for (h, w), (nh, nw) in zip(res[:-1], res[1:]):
             pb = f"{h}x{w}"
             rh = h != nh
-            skip = self._conv(x, pb + "/skip/w", bias=None, down=True, reduce_height=rh,
-                              scale=INV_SQRT2 if L.use_fused() else 1.0)
+            if L.use_fused() and L.SKIP_SPLIT and h % (2 if rh else 1) == 0 and w % 2 == 0:
+                from .fused import SkipSplit
+
+                # FIR evaluated at the strided pixels only, then a plain 1x1 convolution on the small grid
+                x, xd = SkipSplit.apply(x, 2 if rh else 1)
+                skip = self._conv(xd, pb + "/skip/w", bias=None, down=False, scale=INV_SQRT2)
+            else:
+                skip = self._conv(x, pb + "/skip/w", bias=None, down=True, reduce_height=rh,
+                                  scale=INV_SQRT2 if L.use_fused() else 1.0)
             x = self._conv(x, pb + "/conv_0/w", bias=pb + "/bias_0/b", down=False)
             x = self._conv(x, pb + "/conv_1/w", bias=pb + "/bias_1/b", down=True, reduce_height=rh, residual=skip)
         rf = res[-1]

@@ -253,6 +253,38 @@ class ConvAct(torch.autograd.Function):
         return gx, gw_raw, gbias, (g_out if ctx.has_res else None), None, None
 
 
+class SkipSplit(torch.autograd.Function):
+    """Entry of a discriminator residual block (discriminator.py:126-131): returns the block input for the main branch
+    and, for the skip branch, the 4x4 FIR of conv_downsample_2d (upfirdn_2d_v2.py:106-113) evaluated only at the pixels
+    the stride-(sy, 2) 1x1 convolution reads — xd[p,q] = sum k[m] k[n] x[sy*p+m-1, 2*q+n-1] / 64 — so that the 1x1
+    convolution, its input gradient and its weight gradient are plain GEMMs on the small grid.  backward adds the
+    transposed filter of the skip gradient to the main-branch gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, sy: int):
+        x = x.contiguous()
+        B, H, W_, _ = x.shape
+        ctx.sy, ctx.hw = sy, (H, W_)
+        xd = K.fir4_down(x, (H // sy, W_ // 2), sy, (-1, -1), 1.0 / 64.0)
+        return x.view_as(x), xd
+
+    @staticmethod
+    def backward(ctx, g_main, g_xd):
+        if g_xd is None:
+            return g_main, None
+        g_xd = g_xd.contiguous()
+        add = g_main.contiguous() if g_main is not None else None
+        nb = g_xd.shape[0]
+        lim = _BATCH_LIMIT.get("dconv")
+        if lim is not None and nb > lim and "dconv" in _SKIP_WGRAD_TAGS:
+            # generator pass through a concatenated (fake, real) evaluation: the cotangent is zero beyond ``lim`` samples
+            gx = torch.zeros((nb,) + tuple(ctx.hw) + (g_xd.shape[3],), device=g_xd.device, dtype=g_xd.dtype)
+            K.fir4_down_adjoint(g_xd[:lim], ctx.hw, ctx.sy, (-1, -1), 1.0 / 64.0, add=add[:lim] if add is not None else None,
+                                out=gx[:lim])
+            return gx, None
+        return K.fir4_down_adjoint(g_xd, ctx.hw, ctx.sy, (-1, -1), 1.0 / 64.0, add=add), None
+
+
 class FromRGB(torch.autograd.Function):
     """FromRGB.call (from_rgb.py:26-29) + BiasAct on the NCHW fp32 image -> NHWC bf16, one launch each way."""
 

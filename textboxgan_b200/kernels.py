@@ -475,6 +475,36 @@ def fir4(x: torch.Tensor, out_hw: tuple[int, int], off: tuple[int, int], scale: 
     return out
 
 
+def fir4_down(x: torch.Tensor, out_hw: tuple[int, int], sy: int, off: tuple[int, int], scale: float) -> torch.Tensor:
+    """The 4x4 FIR at the pixels a stride-(sy, 2) 1x1 convolution reads — see include/tbg.h (tbg_fir4_down)."""
+    _require(x, torch.bfloat16, "x")
+    B, IH, IW, C_ = x.shape
+    out = torch.empty((B, out_hw[0], out_hw[1], C_), device=x.device, dtype=torch.bfloat16)
+    st = _lib.load().tbg_fir4_down(_ptr(x), _ptr(out), B, IH, IW, out_hw[0], out_hw[1], C_, int(sy), int(off[0]),
+                                   int(off[1]), float(scale), _stream())
+    _lib.check(st, "tbg_fir4_down")
+    return out
+
+
+def fir4_down_adjoint(g: torch.Tensor, in_hw: tuple[int, int], sy: int, off: tuple[int, int], scale: float,
+                      add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Transpose of :func:`fir4_down` (+ ``add``) — see include/tbg.h (tbg_fir4_down_adjoint)."""
+    _require(g, torch.bfloat16, "g")
+    B, OH, OW, C_ = g.shape
+    if out is None:
+        out = torch.empty((B, in_hw[0], in_hw[1], C_), device=g.device, dtype=torch.bfloat16)
+    else:
+        _require(out, torch.bfloat16, "out")
+    if add is not None:
+        _require(add, torch.bfloat16, "add")
+        if tuple(add.shape) != tuple(out.shape):
+            raise _lib.TbgError(f"add: expected shape {tuple(out.shape)}, got {tuple(add.shape)}")
+    st = _lib.load().tbg_fir4_down_adjoint(_ptr(g), _ptr(add), _ptr(out), B, in_hw[0], in_hw[1], OH, OW, C_, int(sy),
+                                           int(off[0]), int(off[1]), float(scale), _stream())
+    _lib.check(st, "tbg_fir4_down_adjoint")
+    return out
+
+
 def wfold_adj(gadj: torch.Tensor, spec, *, w_raw: Optional[torch.Tensor] = None, s: Optional[torch.Tensor] = None,
               t: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, flip: bool = False) -> torch.Tensor:
     """Master-weight gradient from a gradient in the adjoint-matrix layout [Ipad, taps*Opad] (identity tables,

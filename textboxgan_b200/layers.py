@@ -36,6 +36,7 @@ UNFOLD_UP = True
 # conv_downsample_2d: FIR pre-pass + k x k strided conv (forward, weight gradient) instead of the folded
 # (k+3) x (k+3) convolution; the input gradient stays folded
 UNFOLD_DOWN = True
+SKIP_SPLIT = True          # residual skip branch: FIR at the strided pixels only + plain 1x1 GEMM (fused.SkipSplit)
 _DOUBLE_BACKWARD = False
 
 

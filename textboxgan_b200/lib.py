@@ -94,6 +94,8 @@ _SIGNATURES = [
     ("tbg_fromrgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fromrgb_bwd", c_int, [c_void_p] * 7 + [c_int] * 3 + [c_float, c_float, c_void_p]),
     ("tbg_fir4", c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] + [c_void_p] * 4 + [c_int, c_float, c_void_p]),
+    ("tbg_fir4_down", c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_float, c_void_p]),
+    ("tbg_fir4_down_adjoint", c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_float, c_void_p]),
     ("tbg_wfold_adj", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 5 + [c_void_p] * 3 + [c_int, c_int, c_int, c_void_p]),
     ("tbg_style_dense_fwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     ("tbg_style_dense_bwd", c_int, [C.POINTER(StyleLayer), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
