@@ -44,13 +44,13 @@ def run(xshape, wshape, taps, pad, stride, tunes, wgrad_gy=None):
             lib.set_tuning(key, v)
             t = bench(fn, n_rot)
             cols.append(f"{key}={v}: {t:7.1f} us {fl / t / 1e6:7.1f} TF/s {byt / t / 1e3:6.0f} GB/s")
-        lib.set_tuning(key, 1 if key != "conv_s2view" else 0)
+        lib.set_tuning(key, 1)
     kind = "wgrad" if wgrad_gy is not None else "conv "
     print(f"{kind} x{xshape} w{wshape if wgrad_gy is None else (O,)} t{taps} p{pad} s{stride} | " + " | ".join(cols), flush=True)
 
 
-S2 = [("conv_s2view", (0, 1))]
-ST = [("igemm_staged", (0, 1))]
+S2 = [("conv_halo", (1,))]
+ST = [("conv_halo", (1,))]
 run((128, 66, 258, 64), (128, 576), (3, 3), (0, 0), (2, 2), S2)
 run((64, 66, 258, 128), (128, 1152), (3, 3), (0, 0), (2, 2), S2)
 run((128, 34, 130, 128), (128, 1152), (3, 3), (0, 0), (2, 2), S2)

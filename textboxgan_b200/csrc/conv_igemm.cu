@@ -50,7 +50,8 @@ struct ConvKernelParams {
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
 
-__global__ void __launch_bounds__(256, 1)
+template <int EPI>
+__global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +83,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_barrier_init();
   }
@@ -175,12 +176,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    // Eight warps: warp e may read TMEM lanes 32*(e%4).. (its quadrant = 32 tile rows); the two warps of a quadrant take
+    // alternate 32-column groups.  One warp per scheduler runs this code latency-bound (ncu: ~400 dependent instructions
+    // per 32 x 32 block with every feature tested at run time, profiles/r02q_igemm_epilogue.txt), so the feature set is a
+    // template parameter: EPI 0 = bare bf16 store, 1 = column scale / noise / bias / activation, 2 = everything.
     const int e = warp - 4;
-    const int r = e * 32 + lane;
+    const int quad = e & 3, grp = e >> 2;
+    const int r = quad * 32 + lane;
     const int w_in = r % bw;
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
-    const float nstr = (p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    const float nstr = (EPI >= 1 && p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    const bool has_up = (p.up_h | p.up_w) != 0;
+    const int nj = p.block_n / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.tiles_n;
@@ -196,100 +204,110 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(e * 32) << 16) +
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc_stage * p.block_n);
-      for (int j = 0; j < p.block_n / 32; ++j) {
+      for (int j = grp; j < nj; j += 2) {
         const int col0 = n_tile * p.block_n + j * 32;
         uint32_t v[32];
         tmem_ld_32x32(t_row + j * 32, v);
         tmem_ld_wait();
-        if (valid && col0 < p.n_total) {
-          int c0 = col0, oy = ho, ox = wo;
-          if (p.up_h | p.up_w) {
-            const int ph = col0 / p.cout;
-            c0 = col0 - ph * p.cout;
-            const int py = p.up_w ? (ph >> 1) : ph;
-            const int px = p.up_w ? (ph & 1) : 0;
-            oy = p.up_h ? 2 * ho + py : ho;
-            ox = p.up_w ? 2 * wo + px : wo;
-          }
-          const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
-          const size_t off = pix * p.cout + c0;
-          const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
-          const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
-          const float* bs = p.bias ? p.bias + c0 : nullptr;
+        if (!valid || col0 >= p.n_total) continue;
+        int c0 = col0, oy = ho, ox = wo;
+        if (has_up) {
+          const int ph = col0 / p.cout;
+          c0 = col0 - ph * p.cout;
+          const int py = p.up_w ? (ph >> 1) : ph;
+          const int px = p.up_w ? (ph & 1) : 0;
+          oy = p.up_h ? 2 * ho + py : ho;
+          ox = p.up_w ? 2 * wo + px : wo;
+        }
+        const size_t pix = (static_cast<size_t>(b) * p.out_H + oy) * p.out_W + ox;
+        const size_t off = pix * p.cout + c0;
+        if (EPI == 0) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float f[8];
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            o[g] = pk;
+          }
+          continue;
+        }
+        const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
+        const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
+        const float* bs = p.bias ? p.bias + c0 : nullptr;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-            if (cs) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(cs + g * 8));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(cs + g * 8 + 4));
-              f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-              f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+          if (cs) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(cs + g * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(cs + g * 8 + 4));
+            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += nz;
+          if (bs) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          float rres[8];
+          if (EPI == 2 && p.residual) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + off + g * 8));
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 rf = __bfloat1622float2(rh[i]);
+              rres[2 * i] = rf.x;
+              rres[2 * i + 1] = rf.y;
             }
-            if (p.noise) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] += nz;
-            }
-            if (bs) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            float rres[8];
-            if (p.residual) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + off + g * 8));
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 rf = __bfloat1622float2(rh[i]);
-                rres[2 * i] = rf.x;
-                rres[2 * i + 1] = rf.y;
-              }
-              if (p.res_first) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
-              }
-            }
-            if (p.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
-            } else if (p.act == 2) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
-            if (p.residual && !p.res_first) {
+            if (p.res_first) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
             }
-            if (p.relu_mask) {   // gradient of a ReLU whose output is relu_mask (fused ReLU backward)
-              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + off + g * 8));
-              const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
+          }
+          if (p.act == 1) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 mf = __bfloat1622float2(mh[i]);
-                if (!(mf.x > 0.f)) f[2 * i] = 0.f;
-                if (!(mf.y > 0.f)) f[2 * i + 1] = 0.f;
-              }
+            for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
+          if (EPI == 2 && p.residual && !p.res_first) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
+          }
+          if (EPI == 2 && p.relu_mask) {   // gradient of a ReLU whose output is relu_mask (fused ReLU backward)
+            const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + off + g * 8));
+            const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 mf = __bfloat1622float2(mh[i]);
+              if (!(mf.x > 0.f)) f[2 * i] = 0.f;
+              if (!(mf.y > 0.f)) f[2 * i + 1] = 0.f;
             }
-            if (p.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
-              uint4 pk;
-              pk.x = pack_bf16x2(f[0], f[1]);
-              pk.y = pack_bf16x2(f[2], f[3]);
-              pk.z = pack_bf16x2(f[4], f[5]);
-              pk.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(o) = pk;
-            }
+          }
+          if (EPI == 2 && p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
+            *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + g * 8;
+            uint4 pk;
+            pk.x = pack_bf16x2(f[0], f[1]);
+            pk.y = pack_bf16x2(f[2], f[3]);
+            pk.z = pack_bf16x2(f[4], f[5]);
+            pk.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(o) = pk;
           }
         }
       }
@@ -467,12 +485,21 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int total_tiles = tiles_m * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+  const bool general = a->residual || a->relu_mask || a->out_fp32;
+  const bool bare = !general && !a->col_scale && !a->noise && !a->bias && a->act == 0 && a->act_gain == 1.f;
+  if (bare)
+    conv_igemm_kernel<0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+  else if (!general)
+    conv_igemm_kernel<1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+  else
+    conv_igemm_kernel<2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
