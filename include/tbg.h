@@ -254,6 +254,15 @@ int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, void* gx, flo
  * ------------------------------------------------------------------------------------------ */
 int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad, int Opad,
               void* fwd, void* adj, float* q, void* stream);
+/* Every weight of an iteration in one launch (the per-weight launches are latency-bound): tbg_wprep_make_job writes the
+ * description of ONE tbg_wprep call (same arguments, device pointers) into a HOST buffer of tbg_wprep_job_bytes() bytes and
+ * returns the number of CTAs it needs (> 0) or a negative status; block_begin is the sum of the counts of the jobs before
+ * it.  The caller copies the packed jobs to device memory (16-byte aligned) once and replays
+ * tbg_wprep_group(jobs_dev, n_jobs, total_blocks) every iteration; results equal n_jobs tbg_wprep calls. */
+int tbg_wprep_job_bytes(void);
+int tbg_wprep_make_job(void* job_host, int block_begin, const float* w, const float* tables, float coef, int KH, int KW,
+                       int I, int O, int Ipad, int Opad, void* fwd, void* adj, float* q);
+int tbg_wprep_group(const void* jobs_dev, int n_jobs, int total_blocks, void* stream);
 int tbg_wfold(const float* gfwd, const float* gq, const float* w, const float* tables, float coef, int KH, int KW,
               int I, int O, int Ipad, int Opad, float* gw, const float* s, const float* t, int nb, int accumulate,
               void* stream);

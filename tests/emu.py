@@ -645,6 +645,22 @@ def emu_image_grad_nhwc(g, words):
     return out.float().contiguous()
 
 
+class emu_WPrepPlan:
+    """K.WPrepPlan on the CPU: the same outputs as one emu_wprep call per entry, in persistent buffers."""
+
+    def __init__(self, entries):
+        self.entries = list(entries)
+        self.outputs = [tuple(None if t is None else torch.empty_like(t) for t in emu_wprep(w, spec, want_adj=a, want_q=q))
+                        for w, spec, a, q in self.entries]
+
+    def run(self):
+        for (w, spec, a, q), outs in zip(self.entries, self.outputs):
+            for dst, src in zip(outs, emu_wprep(w, spec, want_adj=a, want_q=q)):
+                if dst is not None:
+                    dst.copy_(src)
+        return self.outputs
+
+
 @contextlib.contextmanager
 def emulated_kernels(act_dtype=torch.float32):
     """Route textboxgan_b200.kernels through the CPU emulation (tests only)."""
@@ -679,6 +695,7 @@ def emulated_kernels(act_dtype=torch.float32):
     new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
                  "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot",
                  "batch_resize_normalize", "fir4_down", "fir4_down_adjoint")
+    new_names = new_names + ("WPrepPlan",)
     saved_n = {n: getattr(K, n) for n in new_names}
     for n in new_names:
         setattr(K, n, globals()["emu_" + n])

@@ -88,6 +88,8 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_fir4_down": lambda: h.tbg_fir4_down(P, P, 1, 4, 4, 2, 2, 8, 3, -1, -1, 1.0, None),
         "tbg_fir4_down_adjoint": lambda: h.tbg_fir4_down_adjoint(P, None, P, 1, 4, 4, 2, 2, 12, 2, -1, -1, 1.0, None),
         "tbg_wprep": lambda: h.tbg_wprep(P, None, 1.0, 3, 3, 64, 64, 64, 64, P, P, None, None),
+        "tbg_wprep_make_job": lambda: h.tbg_wprep_make_job(None, 0, P, None, 1.0, 3, 3, 64, 64, 64, 64, P, P, None),
+        "tbg_wprep_group": lambda: h.tbg_wprep_group(None, 1, 1, None),
         "tbg_wfold": lambda: h.tbg_wfold(P, None, None, None, 1.0, 3, 3, 64, 64, 64, 64, P, None, None, 0, 0, None),
         "tbg_wfold_adj": lambda: h.tbg_wfold_adj(None, None, 1.0, 3, 3, 64, 64, 64, P, None, None, 0, 0, 0, None),
         "tbg_demod_coef": lambda: h.tbg_demod_coef(None, P, P, 1, 64, 64, 1e-8, None),
@@ -98,7 +100,7 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_attn_decoder_bwd": lambda: h.tbg_attn_decoder_bwd(None, P, None, P, P, P, P, P, P, P, P, 1, 8, 4, None),
     }
     covered = set(calls) | {"tbg_conv2d_igemm", "tbg_upfirdn2d", "tbg_last_error", "tbg_version", "tbg_launch_count",
-                            "tbg_reset_launch_count", "tbg_get_tuning", "tbg_crc32c"}
+                            "tbg_reset_launch_count", "tbg_get_tuning", "tbg_crc32c", "tbg_wprep_job_bytes"}
     assert covered == set(lib.exported_symbols()), set(lib.exported_symbols()) ^ covered
     for name, call in calls.items():
         st = call()

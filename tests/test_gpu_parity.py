@@ -271,6 +271,35 @@ def test_weight_prep_and_fold_vs_emulated_semantics(kind, k, rh, I, O):
     assert abs(lhs - rhs) < 1e-4 * (abs(lhs) + 1)
 
 
+def test_grouped_weight_preparation_equals_single_launches():
+    """tbg_wprep_group (every weight of an iteration in one launch, K.WPrepPlan) writes bit-identical matrices to one
+    tbg_wprep call per weight, for every geometry kind, with and without the adjoint / q outputs, and on a re-run after
+    the weights changed in place (as the optimiser does)."""
+    from textboxgan_b200 import conv as C
+    from textboxgan_b200 import kernels as K
+
+    kinds = [("plain", 3, True, 128, 256), ("plain", 1, True, 64, 128), ("up", 3, True, 128, 64), ("down", 3, True, 64, 128),
+             ("down", 1, True, 128, 128), ("down", 3, False, 256, 256), ("plain", 3, True, 513, 512), ("upT", 3, True, 128, 128),
+             ("downU", 3, True, 64, 128)]
+    gen = torch.Generator().manual_seed(5)
+    entries = []
+    for n, (kind, k, rh, I, O) in enumerate(kinds):
+        spec = C.weight_spec(kind, 8, 16, I, O, k, rh, "t%d" % n)
+        w = torch.randn(k, k, I, O, generator=gen).to(DEV)
+        entries.append((w, spec, n % 3 != 1, n % 2 == 0))
+    plan = K.WPrepPlan(entries)
+    for rerun in range(2):
+        outs = plan.run()
+        for (w, spec, want_adj, want_q), got in zip(entries, outs):
+            ref = K.wprep(w, spec, want_adj=want_adj, want_q=want_q)
+            for a, b in zip(got, ref):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert torch.equal(a, b), (spec.geom.tag, rerun)
+        for w, _, _, _ in entries:
+            w.mul_(1.5).add_(0.01)
+
+
 @pytest.mark.parametrize("B,I,O", [(4, 512, 512), (32, 128, 64), (3, 192, 512), (5, 64, 3)])
 def test_demodulation_kernels_vs_emulated_semantics(B, I, O):
     """tbg_demod_coef / tbg_demod_bwd / tbg_wfold(s, t) / tbg_modulate_bwd(gs_init) / bias-gradient mode of

@@ -157,3 +157,5 @@ def test_four_consecutive_steps_follow_the_oracle_loss_curve():
             assert float((p.detach() - st.D[n]).abs().max()) <= bound, n
         assert abs(float(pl_mean) - float(st.pl_mean)) < 1e-4 * max(1.0, abs(float(st.pl_mean)))
         assert ts.g_optimizer.iterations.numpy() == 4 and ts.ocr_optimizer.iterations.numpy() == 4
+        # steps 2-4 prepared their weights through the grouped plan recorded by step 1 (fused.StepWeights)
+        assert ts._step_weights.plan is not None and len(ts._step_weights.keys) >= 10

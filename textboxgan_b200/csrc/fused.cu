@@ -256,6 +256,105 @@ bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------
+// bias_act_bwd of a modulated layer whose output also feeds a ToRGB (synthesis_block.py:143-152): the gradient that
+// reaches `out` is g_out (from the next block, absent on the last one) + g_rgb (x) ws — a rank-3 term that is formed here
+// from the [B,HW,3] image gradient instead of being materialised, added and re-read — and the ToRGB weight gradient
+// gws[b,c,j] = sum_p out[b,p,c] * g_rgb[b,p,j] needs the same pass over `out`:
+//   g = (g_out + sum_j g_rgb[p,j] ws[b,c,j]);  then exactly MODE 2 of bias_act_bwd_kernel (S1, Spre, Snz, gy0 = g_pre*d).
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_G>
+__global__ void __launch_bounds__(256, 2)
+bias_act_rgb_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ out, const float* __restrict__ noise,
+                        const float* __restrict__ d, const float* __restrict__ g_rgb, const float* __restrict__ ws,
+                        uint4* __restrict__ gy0, float* __restrict__ S1, float* __restrict__ Spre,
+                        float* __restrict__ Snz, float* __restrict__ gws, int hw, int c8, int pix_per_cta, int act,
+                        float gain) {
+  extern __shared__ float red[];  // [rows][c8*8][6]
+  const int b = blockIdx.y;
+  const int rows = blockDim.x / c8;
+  const int cv = threadIdx.x % c8;
+  const int r = threadIdx.x / c8;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
+  float dv[8], w[8][3], a1[8], a2[8], a3[8], aw[8][3];
+  {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(d + (static_cast<long long>(b) * c8 + cv) * 8));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(d + (static_cast<long long>(b) * c8 + cv) * 8 + 4));
+    dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+    const float* wp = ws + (static_cast<long long>(b) * c8 + cv) * 24;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a1[i] = a2[i] = a3[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        w[i][j] = __ldg(wp + i * 3 + j);
+        aw[i][j] = 0.f;
+      }
+    }
+  }
+  const float neg_slope = act == 0 ? 1.f : (act == 2 ? 0.f : 0.2f);
+  const float g_pos = gain, g_neg = gain * neg_slope;
+  const float r_pos = 1.f / gain;
+  if (r < rows) {
+#pragma unroll 2
+    for (int p = p0 + r; p < p1; p += rows) {
+      const long long pix = static_cast<long long>(b) * hw + p;
+      const long long idx = pix * c8 + cv;
+      const float r0 = __ldg(g_rgb + pix * 3 + 0), r1 = __ldg(g_rgb + pix * 3 + 1), r2 = __ldg(g_rgb + pix * 3 + 2);
+      float g[8], o[8];
+      if (HAS_G) {
+        unpack8(__ldg(g_out + idx), g);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = 0.f;
+      }
+      unpack8(__ldg(out + idx), o);
+      const float nz = (noise != nullptr) ? __ldg(noise + pix) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        aw[i][0] = fmaf(o[i], r0, aw[i][0]);
+        aw[i][1] = fmaf(o[i], r1, aw[i][1]);
+        aw[i][2] = fmaf(o[i], r2, aw[i][2]);
+        const float gt = g[i] + (r0 * w[i][0] + r1 * w[i][1] + r2 * w[i][2]);
+        const bool pos = o[i] > 0.f;
+        const float gp = gt * (pos ? g_pos : g_neg);
+        a1[i] += gp;
+        a2[i] = fmaf(act == 2 ? gp * r_pos : gt, o[i], a2[i]);
+        a3[i] = fmaf(gp, nz, a3[i]);
+        g[i] = gp * dv[i];
+      }
+      gy0[idx] = pack8(g);
+    }
+  }
+  const int cw = c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* rp = red + (r * cw + cv * 8 + i) * 6;
+    rp[0] = a1[i]; rp[1] = a2[i]; rp[2] = a3[i];
+    rp[3] = aw[i][0]; rp[4] = aw[i][1]; rp[5] = aw[i][2];
+  }
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float* rp = red + (rr * cw + cv * 8 + i) * 6;
+        a1[i] += rp[0]; a2[i] += rp[1]; a3[i] += rp[2];
+        aw[i][0] += rp[3]; aw[i][1] += rp[4]; aw[i][2] += rp[5];
+      }
+    const long long o0 = (static_cast<long long>(b) * c8 + cv) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(S1 + o0 + i, a1[i]);
+      atomicAdd(Spre + o0 + i, a2[i]);
+      if (noise != nullptr) atomicAdd(Snz + o0 + i, a3[i]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) atomicAdd(gws + (o0 + i) * 3 + j, aw[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // ToRGB: y[p, j] = sum_c x[p,c] * ws[b,c,j] (+ bias[j]); one warp per pixel, lanes over channels.
 // ---------------------------------------------------------------------------------------------
 __global__ void torgb_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws, const float* __restrict__ bias,
@@ -817,6 +916,38 @@ extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* 
   else if (mode == 1) TBG_BAB(1, g.smem);
   else TBG_BAB(2, g.smem);
 #undef TBG_BAB
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_bias_act_rgb_bwd(const void* g_out, const void* out, const float* noise, const float* d,
+                                    const float* g_rgb, const float* ws, void* gy0, float* S1, float* Spre, float* Snz,
+                                    float* gws, int B, int HW, int C, int act, float gain, void* stream_v) {
+  TBG_CHECK_ARG(out && d && g_rgb && ws && gy0 && S1 && Spre && gws, "tbg_bias_act_rgb_bwd: null pointer");
+  TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_bias_act_rgb_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TBG_CHECK_ARG(!noise || Snz, "tbg_bias_act_rgb_bwd: noise without Snz");
+  TBG_CHECK_ARG(act >= 0 && act <= 2 && gain > 0.f, "tbg_bias_act_rgb_bwd: bad activation / gain");
+  TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out) && TBG_ALIGNED16(d) && TBG_ALIGNED16(gy0),
+                "tbg_bias_act_rgb_bwd: 16-byte alignment required");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const RedGeom g = red_geom(B, HW, C / 8, 6);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bias_act_rgb_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(bias_act_rgb_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  TBG_CHECK_ARG(g.smem <= 96 * 1024, "tbg_bias_act_rgb_bwd: C=%d needs too much shared memory", C);
+  const dim3 grid(g.chunks, B);
+  if (g_out != nullptr)
+    bias_act_rgb_bwd_kernel<true><<<grid, g.threads, g.smem, stream>>>(
+        reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), noise, d, g_rgb, ws,
+        reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, gws, HW, C / 8, g.pix_per_cta, act, gain);
+  else
+    bias_act_rgb_bwd_kernel<false><<<grid, g.threads, g.smem, stream>>>(
+        nullptr, reinterpret_cast<const uint4*>(out), noise, d, g_rgb, ws, reinterpret_cast<uint4*>(gy0), S1, Spre, Snz, gws,
+        HW, C / 8, g.pix_per_cta, act, gain);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

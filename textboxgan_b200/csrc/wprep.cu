@@ -16,6 +16,8 @@
 //
 // Tiling: one CTA per 32(i) x 32(o) tile of the master weight, staged in shared memory so that both
 // the o-contiguous reads/writes and the i-contiguous ones are coalesced.
+#include <cstring>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -58,17 +60,17 @@ __device__ __forceinline__ void build_cf(const AxisTable& ty, const AxisTable& t
 // SMs; the tile is re-read by each chunk (L2 hits).  A thread owns two neighbouring elements along the
 // contiguous axis of the output matrix, keeps their nine taps in registers and emits one packed
 // bf16x2 store per combination; per-combination offsets and coefficients come from shared memory.
-__global__ void __launch_bounds__(256)
-wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ adj,
-             float* __restrict__ q, const WPrepParams p, const int chunk, const int fwd_chunks) {
+__device__ __forceinline__ void wprep_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                           __nv_bfloat16* __restrict__ adj, float* __restrict__ q, const WPrepParams& p,
+                                           const int chunk, const int fwd_chunks, const int bx, const int by) {
   __shared__ float sw[9][32][33];  // [kh*KW+kw][i][o]
   __shared__ __align__(16) float cf[36][12];
   __shared__ unsigned coff[36];    // element offset of combination c inside the output matrix
   const int tiles_o = p.Opad / 32;
-  const int i0 = (blockIdx.x / tiles_o) * 32, o0 = (blockIdx.x % tiles_o) * 32;
+  const int i0 = (bx / tiles_o) * 32, o0 = (bx % tiles_o) * 32;
   const int taps = p.KH * p.KW;
-  const bool is_adj = static_cast<int>(blockIdx.y) >= fwd_chunks;
-  const int chunk_id = is_adj ? blockIdx.y - fwd_chunks : blockIdx.y;
+  const bool is_adj = by >= fwd_chunks;
+  const int chunk_id = is_adj ? by - fwd_chunks : by;
   const AxisTable& ay = is_adj ? p.ay : p.fy;
   const AxisTable& ax = is_adj ? p.ax : p.fx;
   const int TT = ay.T * ax.T, ncomb = ay.P * ax.P * TT;
@@ -120,7 +122,7 @@ wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_
       a0 = fmaf(c2, v0[8], a0);   a1 = fmaf(c2, v1[8], a1);
       *reinterpret_cast<uint32_t*>(dst + coff[c]) = pack_bf16x2(a0, a1);
     }
-    if (q != nullptr && blockIdx.y == 0) {   // chunk 0 of the forward matrix also emits q[i, o]
+    if (q != nullptr && by == 0) {   // chunk 0 of the forward matrix also emits q[i, o]
       const int i = i0 + r, o = o0 + 2 * tx;
       float q0 = 0.f, q1 = 0.f;
 #pragma unroll
@@ -132,6 +134,41 @@ wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_
       if (i < p.I && o + 1 < p.O) q[static_cast<size_t>(i) * p.O + o + 1] = q1;
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ adj,
+             float* __restrict__ q, const WPrepParams p, const int chunk, const int fwd_chunks) {
+  wprep_tile(w, fwd, adj, q, p, chunk, fwd_chunks, blockIdx.x, blockIdx.y);
+}
+
+// Every weight of a training iteration in ONE launch: the per-layer launches are latency-bound (~25 us each for a few
+// hundred KB, 34 of them per iteration = 0.85 ms of a 19 ms step, profiles/r02n_graph_timeline_config2.txt).  A job is the
+// argument set of one tbg_wprep call; CTA b works on job j with block_begin[j] <= b < block_begin[j+1].
+struct WPrepJob {
+  const float* w;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* adj;
+  float* q;
+  WPrepParams p;
+  int chunk, fwd_chunks, tiles, blocks, block_begin, reserved;
+};
+
+__global__ void __launch_bounds__(256)
+wprep_group_kernel(const WPrepJob* __restrict__ jobs, const int n_jobs) {
+  __shared__ int sj;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_jobs - 1;                       // last job whose block_begin <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    sj = lo;
+  }
+  __syncthreads();
+  const WPrepJob& jb = jobs[sj];
+  const int local = static_cast<int>(blockIdx.x) - jb.block_begin;
+  wprep_tile(jb.w, jb.fwd, jb.adj, jb.q, jb.p, jb.chunk, jb.fwd_chunks, local % jb.tiles, local / jb.tiles);
 }
 
 // gw[tap,i,o] += coef * sum_c cf[c][tap] * gfwd_c[o,i]  (+ 2*coef^2*w*gq[i,o]).  One CTA per 32(i) x 8(o)
@@ -271,31 +308,72 @@ static int load_tables(const float* tables, WPrepParams& p) {
   return 0;
 }
 
-extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad,
-                         int Opad, void* fwd, void* adj, float* q, void* stream_v) {
-  TBG_CHECK_ARG(w && tables && fwd, "tbg_wprep: null pointer");
-  TBG_CHECK_ARG(KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3, "tbg_wprep: master kernel must be at most 3x3");
+// Validates one tbg_wprep argument set and fills the launch description shared by the single and the grouped entry.
+static int make_wprep_job(WPrepJob& jb, const char* who, const float* w, const float* tables, float coef, int KH, int KW,
+                          int I, int O, int Ipad, int Opad, void* fwd, void* adj, float* q, bool grouped) {
+  TBG_CHECK_ARG(w && tables && fwd, "%s: null pointer", who);
+  TBG_CHECK_ARG(KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3, "%s: master kernel must be at most 3x3", who);
   TBG_CHECK_ARG(Ipad % 32 == 0 && Opad % 32 == 0 && Ipad >= I && Opad >= O && I >= 1 && O >= 1,
-                "tbg_wprep: bad channel counts I=%d O=%d Ipad=%d Opad=%d", I, O, Ipad, Opad);
-  WPrepParams p;
-  TBG_CHECK_ARG(load_tables(tables, p) == 0, "tbg_wprep: malformed tables");
-  TBG_CHECK_ARG(p.fy.K == KH && p.fx.K == KW, "tbg_wprep: tables do not match the kernel size");
+                "%s: bad channel counts I=%d O=%d Ipad=%d Opad=%d", who, I, O, Ipad, Opad);
+  WPrepParams& p = jb.p;
+  TBG_CHECK_ARG(load_tables(tables, p) == 0, "%s: malformed tables", who);
+  TBG_CHECK_ARG(p.fy.K == KH && p.fx.K == KW, "%s: tables do not match the kernel size", who);
   p.KH = KH; p.KW = KW; p.I = I; p.O = O; p.Ipad = Ipad; p.Opad = Opad; p.coef = coef;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int ncf = p.fy.P * p.fx.P * p.fy.T * p.fx.T;
   const int nca = (p.ay.P > 0) ? p.ay.P * p.ax.P * p.ay.T * p.ax.T : 0;
-  TBG_CHECK_ARG(ncf <= 36 && nca <= 36, "tbg_wprep: too many (phase, tap) combinations");
-  TBG_CHECK_ARG(nca == 0 || adj, "tbg_wprep: adjoint tables without an adjoint output");
+  TBG_CHECK_ARG(ncf <= 36 && nca <= 36, "%s: too many (phase, tap) combinations", who);
+  TBG_CHECK_ARG(nca == 0 || adj, "%s: adjoint tables without an adjoint output", who);
   // split the (phase, tap) combinations into equal chunks of at most 9 (one CTA each): every CTA then does the
-  // same amount of work, so partial waves cost little, and even a 128 x 128 weight fills the SMs
+  // same amount of work, so partial waves cost little, and even a 128 x 128 weight fills the SMs (a grouped launch is
+  // filled by the other jobs: it keeps the larger chunks)
   const int tiles = (Ipad / 32) * (Opad / 32);
   const int nmax = ncf > nca ? ncf : nca;
   int chunk = nmax < 9 ? nmax : 9;
-  if (tiles * ((ncf + chunk - 1) / chunk + (nca + chunk - 1) / chunk) < 296 && chunk > 3) chunk = 3;
-  const int fwd_chunks = (ncf + chunk - 1) / chunk;
-  const int adj_chunks = (nca + chunk - 1) / chunk;
-  wprep_kernel<<<dim3(tiles, fwd_chunks + adj_chunks), 256, 0, stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(fwd), reinterpret_cast<__nv_bfloat16*>(adj), q, p, chunk, fwd_chunks);
+  if (!grouped && tiles * ((ncf + chunk - 1) / chunk + (nca + chunk - 1) / chunk) < 296 && chunk > 3) chunk = 3;
+  jb.w = w;
+  jb.fwd = reinterpret_cast<__nv_bfloat16*>(fwd);
+  jb.adj = reinterpret_cast<__nv_bfloat16*>(adj);
+  jb.q = q;
+  jb.chunk = chunk;
+  jb.fwd_chunks = (ncf + chunk - 1) / chunk;
+  jb.tiles = tiles;
+  jb.blocks = tiles * (jb.fwd_chunks + (nca + chunk - 1) / chunk);
+  jb.block_begin = 0;
+  jb.reserved = 0;
+  return TBG_OK;
+}
+
+extern "C" int tbg_wprep(const float* w, const float* tables, float coef, int KH, int KW, int I, int O, int Ipad,
+                         int Opad, void* fwd, void* adj, float* q, void* stream_v) {
+  WPrepJob jb;
+  const int rc = make_wprep_job(jb, "tbg_wprep", w, tables, coef, KH, KW, I, O, Ipad, Opad, fwd, adj, q, false);
+  if (rc != TBG_OK) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  wprep_kernel<<<dim3(jb.tiles, jb.blocks / jb.tiles), 256, 0, stream>>>(jb.w, jb.fwd, jb.adj, jb.q, jb.p, jb.chunk,
+                                                                          jb.fwd_chunks);
+  count_launch();
+  TBG_CHECK_CUDA(cudaGetLastError());
+  return TBG_OK;
+}
+
+extern "C" int tbg_wprep_job_bytes(void) { return static_cast<int>(sizeof(WPrepJob)); }
+
+extern "C" int tbg_wprep_make_job(void* job_host, int block_begin, const float* w, const float* tables, float coef, int KH,
+                                  int KW, int I, int O, int Ipad, int Opad, void* fwd, void* adj, float* q) {
+  TBG_CHECK_ARG(job_host != nullptr && block_begin >= 0, "tbg_wprep_make_job: bad job buffer / block offset");
+  WPrepJob jb;
+  const int rc = make_wprep_job(jb, "tbg_wprep_make_job", w, tables, coef, KH, KW, I, O, Ipad, Opad, fwd, adj, q, true);
+  if (rc != TBG_OK) return rc;
+  jb.block_begin = block_begin;
+  memcpy(job_host, &jb, sizeof(jb));
+  return jb.blocks;                                   // > 0: CTAs of this job
+}
+
+extern "C" int tbg_wprep_group(const void* jobs_dev, int n_jobs, int total_blocks, void* stream_v) {
+  TBG_CHECK_ARG(jobs_dev != nullptr && n_jobs >= 1 && total_blocks >= n_jobs, "tbg_wprep_group: bad job table");
+  TBG_CHECK_ARG((reinterpret_cast<uintptr_t>(jobs_dev) & 15) == 0, "tbg_wprep_group: job table must be 16-byte aligned");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  wprep_group_kernel<<<total_blocks, 256, 0, stream>>>(reinterpret_cast<const WPrepJob*>(jobs_dev), n_jobs);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

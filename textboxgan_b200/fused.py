@@ -28,14 +28,56 @@ from .conv import ConvGeom, relayout_for_adjoint
 # step (the discriminator runs twice per step, on fake and on real images, training_step.py:260,288;
 # weights only change in the optimiser updates at the end of the step).
 _STEP_CACHE: dict = {}
+# Requests of the running training iteration: key -> [w_raw, spec, want_adj, want_q] (None outside begin_step/end_step).
+_STEP_LOG: Optional[dict] = None
+GROUP_WPREP = True
 
 
 def clear_step_cache() -> None:
     _STEP_CACHE.clear()
 
 
+class StepWeights:
+    """Weight preparation of a training iteration as ONE grouped launch (K.WPrepPlan) instead of one latency-bound launch
+    per weight.  The first eager iteration records which (weight, geometry) pairs the step asks for; :meth:`end_step`
+    builds the plan from that record (never while a CUDA graph is being captured), and from then on :meth:`begin_step`
+    fills the step cache with one launch.  A request that is not in the plan (weights re-bound to new storage, a step
+    variant with more layers) falls back to its own launch and makes the next eager iteration rebuild the plan."""
+
+    def __init__(self):
+        self.plan = None
+        self.keys: dict = {}
+
+    def begin_step(self) -> None:
+        global _STEP_LOG
+        _STEP_CACHE.clear()
+        _STEP_LOG = {}
+        if self.plan is not None and GROUP_WPREP:
+            outs = self.plan.run()
+            for key, out in zip(self.keys, outs):
+                _STEP_CACHE[key] = out
+
+    def end_step(self) -> None:
+        global _STEP_LOG
+        log, _STEP_LOG = _STEP_LOG, None
+        _STEP_CACHE.clear()
+        if not GROUP_WPREP or not log:
+            return
+        covered = all(k in self.keys and self.keys[k][0] >= v[2] and self.keys[k][1] >= v[3] for k, v in log.items())
+        if covered or (log[next(iter(log))][0].is_cuda and torch.cuda.is_current_stream_capturing()):
+            return
+        self.keys = {k: (v[2], v[3]) for k, v in log.items()}
+        self.plan = K.WPrepPlan([tuple(v) for v in log.values()])
+
+
 def _prepared(w_raw, spec, want_adj: bool, want_q: bool):
     key = (w_raw.data_ptr(), id(spec))
+    if _STEP_LOG is not None:
+        rec = _STEP_LOG.get(key)
+        if rec is None:
+            _STEP_LOG[key] = [w_raw, spec, bool(want_adj), bool(want_q)]
+        else:
+            rec[2], rec[3] = rec[2] or bool(want_adj), rec[3] or bool(want_q)
     hit = _STEP_CACHE.get(key)
     if hit is not None and (hit[1] is not None or not want_adj) and (hit[2] is not None or not want_q):
         return hit

@@ -317,6 +317,40 @@ def wprep(w_raw: torch.Tensor, spec, *, want_adj: bool = True, want_q: bool = Fa
     return fwd, adj, q
 
 
+class WPrepPlan:
+    """All weight preparations of an iteration as one launch (tbg_wprep_group).  ``entries``: [(w_raw, spec, want_adj,
+    want_q)].  Output matrices are allocated once and overwritten by every :meth:`run`; the packed job table lives in
+    device memory, so a run is a single kernel launch (CUDA-graph capturable)."""
+
+    def __init__(self, entries):
+        h = _lib.load()
+        self.entries = list(entries)
+        nbytes = h.tbg_wprep_job_bytes()
+        host = (C.c_uint8 * (nbytes * len(self.entries)))()
+        self.outputs = []
+        begin = 0
+        for n, (w_raw, spec, want_adj, want_q) in enumerate(self.entries):
+            _require(w_raw, torch.float32, "w_raw")
+            dev = w_raw.device
+            fwd = torch.empty((spec.fwd_rows, spec.fwd_cols), device=dev, dtype=torch.bfloat16)
+            adj = torch.empty((spec.adj_rows, spec.adj_cols), device=dev, dtype=torch.bfloat16) if want_adj else None
+            q = torch.empty((spec.I, spec.O), device=dev, dtype=torch.float32) if want_q else None
+            tables = spec.ctable if want_adj else spec.ctable_noadj
+            blocks = h.tbg_wprep_make_job(C.byref(host, n * nbytes), begin, _ptr(w_raw), tables, spec.coef, spec.KH,
+                                          spec.KW, spec.I, spec.O, spec.Ipad, spec.Opad, _ptr(fwd), _ptr(adj), _ptr(q))
+            if blocks <= 0:
+                _lib.check(blocks if blocks < 0 else -1, "tbg_wprep_make_job")
+            begin += blocks
+            self.outputs.append((fwd, adj, q))
+        self.total_blocks = begin
+        self.jobs = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(self.entries[0][0].device)
+
+    def run(self):
+        st = _lib.load().tbg_wprep_group(_ptr(self.jobs), len(self.entries), self.total_blocks, _stream())
+        _lib.check(st, "tbg_wprep_group")
+        return self.outputs
+
+
 def wfold(gfwd: torch.Tensor, spec, *, gq: Optional[torch.Tensor] = None, w_raw: Optional[torch.Tensor] = None,
           out: Optional[torch.Tensor] = None, s: Optional[torch.Tensor] = None,
           t: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -85,6 +85,9 @@ _SIGNATURES = [
     ("tbg_torgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     ("tbg_torgb_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_wprep", c_int, [c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 4),
+    ("tbg_wprep_job_bytes", c_int, []),
+    ("tbg_wprep_make_job", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3),
+    ("tbg_wprep_group", c_int, [c_void_p, c_int, c_int, c_void_p]),
     ("tbg_wfold", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     ("tbg_set_tuning", c_int, [C.c_char_p, c_int]),
     ("tbg_get_tuning", c_int, [C.c_char_p]),

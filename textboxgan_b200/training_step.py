@@ -83,6 +83,7 @@ class TrainingStep:
         self._side = None
         self._graphs = {}
         self._static = None
+        self._step_weights = None          # fused.StepWeights: grouped weight preparation plan
 
     # ------------------------------------------------------------------------------------------
     def dist_train_step(self, real_images, ocr_images, input_words, ocr_labels, do_r1_reg: bool, do_pl_reg: bool,
@@ -200,7 +201,9 @@ class TrainingStep:
         from . import fused as _fused
 
         draws = draws or {}
-        _fused.clear_step_cache()
+        if self._step_weights is None:
+            self._step_weights = _fused.StepWeights()
+        self._step_weights.begin_step()                # all weight preparations of the iteration: one grouped launch
         G, D = self.generator, self.discriminator
         dev = G.device
         z = draws["z"].to(dev) if "z" in draws else torch.randn(self.batch_size_per_gpu, self.z_dim, device=dev)
@@ -277,7 +280,7 @@ class TrainingStep:
                 self.ocr_optimizer.finish_apply()
             self.d_optimizer.finish_apply()
 
-        _fused.clear_step_cache()
+        self._step_weights.end_step()
         gen_losses = (reg_g_loss.detach(), g_loss.detach(), pl_penalty.detach())
         disc_losses = (reg_d_loss.detach(), d_loss.detach(), r1_penalty.detach())
         ocr_out = (ocr_loss / ocr_loss_weight).detach() if ocr_loss is not None else torch.zeros((), device=dev)
