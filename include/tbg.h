@@ -172,6 +172,13 @@ int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, void* gx, f
 int tbg_bias_act_bwd(const void* g_out, const void* out, const void* residual, const float* noise, const float* d,
                      void* gy0, float* S1, float* Spre, float* Snz, int B, int HW, int C, int act, float gain,
                      int s1_over_batch, void* stream);
+/* tbg_bias_act_bwd (all three sums) for a modulated layer whose output also feeds a ToRGB (synthesis_block.py:143-152):
+ * the gradient reaching `out` is g_out (NULL on the last block) + g_rgb (x) ws, formed here from the image gradient
+ * g_rgb fp32 [B,HW,3] and ws fp32 [B,C,3] instead of being materialised; the same pass yields the ToRGB weight gradient
+ *   gws[b,c,j] += sum_p out[b,p,c] * g_rgb[b,p,j]        (gws, S1, Spre, Snz zeroed by the caller; d is required). */
+int tbg_bias_act_rgb_bwd(const void* g_out, const void* out, const float* noise, const float* d, const float* g_rgb,
+                         const float* ws, void* gy0, float* S1, float* Spre, float* Snz, float* gws, int B, int HW, int C,
+                         int act, float gain, void* stream);
 /* 4x4 separable FIR k = [1,3,3,1] (x) [1,3,3,1] on NHWC bf16 — the resample kernel upfirdn_2d applies after
  * the transposed convolution of upsample_conv_2d and before the strided convolution of
  * conv_downsample_2d (upfirdn_2d_v2.py:65-113):

@@ -43,6 +43,10 @@ for (H, W, C) in [(64, 256, 128), (32, 128, 128), (16, 64, 256), (64, 256, 64)]:
     report(f"bias_act_bwd {B}x{H}x{W}x{C} (modconv: sums)", t, 3 * n * 2)
     t = bench(lambda i: K.bias_act_bwd(g[i], o[i], act=True, gain=1.4, want_sums=False, bias_grad_only=True), n_rot)
     report(f"bias_act_bwd {B}x{H}x{W}x{C} (dconv: bias grad)", t, 3 * n * 2)
+    grgb = torch.randn(B, H, W, 3, device=dev)
+    wsr = torch.randn(B, C, 3, device=dev)
+    t = bench(lambda i: K.bias_act_rgb_bwd(g[i], o[i], grgb, wsr, noise=nz, d=d, act=1, gain=1.4), n_rot)
+    report(f"bias_act_rgb_bwd {B}x{H}x{W}x{C} (+ ToRGB gradient)", t, 3 * n * 2)
     t = bench(lambda i: K.modulate_bwd(g[i], o[i], s), n_rot)
     report(f"modulate_bwd {B}x{H}x{W}x{C}", t, 3 * n * 2)
     t = bench(lambda i: K.modulate(g[i], s), n_rot)

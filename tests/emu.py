@@ -351,6 +351,16 @@ def emu_bias_act_bwd(g_out, out, *, residual=None, noise=None, d=None, act=True,
     return gy0, S1, Spre, Snz
 
 
+def emu_bias_act_rgb_bwd(g_out, out, g_rgb, ws, *, noise, d, act=1, gain=1.0):
+    """Documented semantics of tbg_bias_act_rgb_bwd: bias_act_bwd on g_out + g_rgb (x) ws, plus the ToRGB weight gradient."""
+    B = out.shape[0]
+    gx_rgb = torch.bmm(g_rgb.double().reshape(B, -1, 3), ws.double().transpose(1, 2)).reshape(out.shape)
+    g = gx_rgb if g_out is None else g_out.double() + gx_rgb
+    gy0, S1, Spre, Snz = emu_bias_act_bwd(g, out, noise=noise, d=d, act=act, gain=gain)
+    gws = torch.bmm(out.double().reshape(B, -1, out.shape[-1]).transpose(1, 2), g_rgb.double().reshape(B, -1, 3)).float()
+    return gy0, S1, Spre, Snz, gws
+
+
 def emu_torgb_fwd(x, ws, bias):
     B = x.shape[0]
     y = torch.bmm(x.double().reshape(B, -1, x.shape[-1]), ws.double()).reshape(*x.shape[:-1], 3)
@@ -694,7 +704,7 @@ def emulated_kernels(act_dtype=torch.float32):
     L.ACT_DTYPE = act_dtype
     new_names = ("dense_fwd", "dense_bwd", "pixel_norm_fwd", "pixel_norm_bwd", "word_encoder_fwd", "word_encoder_bwd",
                  "minibatch_std_fwd", "minibatch_std_bwd", "torgb_skip_fwd", "image_grad_nhwc", "bias_act_fwd", "rowdot",
-                 "batch_resize_normalize", "fir4_down", "fir4_down_adjoint")
+                 "batch_resize_normalize", "fir4_down", "fir4_down_adjoint", "bias_act_rgb_bwd")
     new_names = new_names + ("WPrepPlan",)
     saved_n = {n: getattr(K, n) for n in new_names}
     for n in new_names:

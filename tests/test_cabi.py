@@ -84,6 +84,7 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_gpu():
         "tbg_image_grad_nhwc": lambda: h.tbg_image_grad_nhwc(None, None, P, 1, 4, 4, 0, None),
         "tbg_crop_resize_fwd": lambda: h.tbg_crop_resize_fwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
         "tbg_crop_resize_bwd": lambda: h.tbg_crop_resize_bwd(None, P, P, 1, 4, 4, 8, 8, 8, 1, 1, 1, None),
+        "tbg_bias_act_rgb_bwd": lambda: h.tbg_bias_act_rgb_bwd(None, P, None, P, P, P, P, P, P, None, P, 1, 4, 12, 1, 1.0, None),
         "tbg_fir4": lambda: h.tbg_fir4(P, P, 1, 4, 4, 4, 4, 12, -1, -1, 1.0, None, None, None, None, 0, 1.0, None),
         "tbg_fir4_down": lambda: h.tbg_fir4_down(P, P, 1, 4, 4, 2, 2, 8, 3, -1, -1, 1.0, None),
         "tbg_fir4_down_adjoint": lambda: h.tbg_fir4_down_adjoint(P, None, P, 1, 4, 4, 2, 2, 12, 2, -1, -1, 1.0, None),

@@ -319,3 +319,29 @@ def test_fir4_down_and_adjoint_kernels(sy, B, H, W, C):
     lhs = float((got.double() * g.double()).sum())
     rhs = float((x.double() * Kn.fir4_down_adjoint(g.to(DEV), (H, W), sy, (-1, -1), 1.0 / 64.0).cpu().double()).sum())
     assert abs(lhs - rhs) <= 2e-2 * (got.double() * g.double()).abs().sum() ** 0.5 + 1e-3 * abs(lhs)
+
+
+@pytest.mark.parametrize("B,H,W,C,has_g,has_noise", [(4, 16, 64, 128, True, True), (3, 8, 32, 256, False, True),
+                                                     (2, 64, 256, 128, True, True), (5, 4, 16, 512, True, False),
+                                                     (2, 5, 7, 64, False, True)])
+def test_bias_act_rgb_bwd_kernel_vs_emulated_semantics(B, H, W, C, has_g, has_noise):
+    """tbg_bias_act_rgb_bwd: the activation backward of a modulated layer with the ToRGB input gradient formed in the
+    kernel (g_out + g_rgb (x) ws), plus the ToRGB weight gradient — against the fp64 emulation (bf16 output, fp32 sums)."""
+    from textboxgan_b200 import kernels as Kn
+
+    gen = torch.Generator().manual_seed(B * 100 + C)
+    out = torch.randn(B, H, W, C, generator=gen).bfloat16()
+    g_out = torch.randn(B, H, W, C, generator=gen).bfloat16() if has_g else None
+    g_rgb = torch.randn(B, H, W, 3, generator=gen)
+    ws = torch.randn(B, C, 3, generator=gen) * 0.3
+    noise = torch.randn(B, H, W, generator=gen) if has_noise else None
+    d = torch.rand(B, C, generator=gen) + 0.5
+    got = Kn.bias_act_rgb_bwd(g_out.to(DEV) if has_g else None, out.to(DEV), g_rgb.to(DEV), ws.to(DEV),
+                              noise=noise.to(DEV) if has_noise else None, d=d.to(DEV), act=1, gain=math.sqrt(2.0))
+    want = emu.emu_bias_act_rgb_bwd(g_out, out, g_rgb, ws, noise=noise, d=d, act=1, gain=math.sqrt(2.0))
+    names = ("gy0", "S1", "Spre", "Snz", "gws")
+    for n, a, b in zip(names, got, want):
+        if n == "Snz" and not has_noise:
+            continue
+        tol = 4e-3 if n == "gy0" else 2e-4
+        assert rel_err(a.float().cpu(), b.float()) < tol, (n, rel_err(a.float().cpu(), b.float()))

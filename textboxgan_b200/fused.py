@@ -182,6 +182,65 @@ class ModConvAct(torch.autograd.Function):
         return gx, gs, gw_raw, None, gns.reshape(ns.shape), gbias, None, None
 
 
+class ModConvActRGB(torch.autograd.Function):
+    """ModConvAct (second convolution of a synthesis block) together with the ToRGB that reads its output and the skip sum
+    (fused.ToRGBSkip) — synthesis_block.py:143-152.  One Function so that the backward pass never materialises the
+    C-channel ToRGB input gradient: ``tbg_bias_act_rgb_bwd`` forms g_out + g_rgb (x) ws on the fly, applies the activation
+    gradient and also accumulates the ToRGB weight gradient in the same pass over ``out`` (previously torgb_bwd wrote
+    that gradient, autograd added it to the next block's, and bias_act_bwd re-read the sum).
+    Returns (out bf16 [B,H,W,O], y: the RGB skip sum [B,H,W,3] fp32, or the masked NCHW image on the last block)."""
+
+    @staticmethod
+    def forward(ctx, x, s, w_raw, noise, ns, bias, spec, gain: float, ws_rgb, bias_rgb, y_prev, words, nchw: bool):
+        geom = spec.geom
+        x = x.contiguous()
+        s = s.contiguous()
+        wmat, wadj, q = _prepared(w_raw, spec, True, True)
+        d = K.demod_coef(s, q)
+        xs = K.modulate(x, s)
+        K.PROFILE_TAG = (geom.tag, geom.algo_frac)
+        out = K.conv2d_igemm(xs, wmat, **geom.kernel_kwargs(), col_scale=d, noise=noise.contiguous(),
+                             noise_strength=ns.reshape(1), bias=bias, act=1, act_gain=gain)
+        ws_rgb = ws_rgb.contiguous()
+        if words is not None:
+            words = words.to(torch.int32).contiguous()
+        y_prev = y_prev.contiguous() if y_prev is not None else None
+        y = K.torgb_skip_fwd(out, ws_rgb, bias_rgb, y_prev, words, bool(nchw))
+        ctx.save_for_backward(x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias, ws_rgb, words)
+        ctx.spec, ctx.gain, ctx.nchw, ctx.has_prev = spec, gain, bool(nchw), y_prev is not None
+        ctx.set_materialize_grads(False)
+        return out, y
+
+    @staticmethod
+    def backward(ctx, g_out, g_y):
+        from . import upfirdn as U
+
+        x, xs, out, s, d, wadj, q, w_raw, noise, ns, bias, ws_rgb, words = ctx.saved_tensors
+        spec = ctx.spec
+        g = spec.geom
+        gws = gbias_rgb = g_prev = None
+        if g_y is not None:
+            gr = g_y.contiguous().float()
+            if ctx.nchw:
+                gr = K.image_grad_nhwc(gr, words)
+            elif words is not None:
+                gr = K.image_grad_nhwc(gr.permute(0, 3, 1, 2).contiguous(), words)
+            gy0, S1, Spre, Snz, gws = K.bias_act_rgb_bwd(g_out.contiguous() if g_out is not None else None, out, gr, ws_rgb,
+                                                         noise=noise.contiguous(), d=d, act=1, gain=ctx.gain)
+            gbias_rgb = gr.sum(dim=(0, 1, 2))
+            g_prev = U.upsample_2d_nhwc_adjoint(gr) if ctx.has_prev else None
+        else:
+            gy0, S1, Spre, Snz = K.bias_act_bwd(g_out.contiguous(), out, noise=noise.contiguous(), d=d, act=True,
+                                                gain=ctx.gain)
+        t, gbias, gns, gs = K.demod_bwd(S1, Spre, Snz, d, ns.reshape(1), _aligned_vec(bias), s, q)
+        K.PROFILE_TAG = (g.tag, g.algo_frac)
+        gxs = K.conv2d_igemm(gy0, wadj, **g.adjoint().kernel_kwargs())
+        gwmat = K.conv2d_wgrad(xs, gy0, **g.kernel_kwargs())
+        gx, gs = K.modulate_bwd(gxs, x, s, gs_init=gs)
+        gw_raw = K.wfold(gwmat, spec, w_raw=w_raw, s=s, t=t)
+        return (gx, gs, gw_raw, None, gns.reshape(ns.shape), gbias, None, None, gws, gbias_rgb, g_prev, None, None)
+
+
 class ModUpConvAct(torch.autograd.Function):
     """ModulatedConv2D(up=True) + Noise + BiasAct with upsample_conv_2d in the reference's own order
     (upfirdn_2d_v2.py:65-103): transposed stride-2 3x3 convolution on the tensor cores at its algorithmic

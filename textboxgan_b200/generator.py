@@ -188,6 +188,12 @@ class Generator(Model):
             x = L.modulated_conv2d(x, s0, P, pb + "/conv_0", up=True, noise=n0, noise_strength=P[pb + "/noise_0/w"],
                                    bias=P[pb + "/bias_0/b"], act=True, fused_epilogue=fused_epilogue,
                                    s_pre=sc[3 * i + 1])
+            if fused_rgb and L.FUSE_RGB_BACKWARD and not fused_epilogue:
+                x, y = L.modulated_conv2d_rgb(x, P, pb + "/conv_1", f"synthesis/{h}x{w}/ToRGB", noise=n1,
+                                              noise_strength=P[pb + "/noise_1/w"], bias=P[pb + "/bias_1/b"],
+                                              s_conv=sc[3 * i + 2], s_rgb=sc[3 * i + 3], y_prev=y,
+                                              mask_words=mask_words if i == last else None, nchw=i == last)
+                continue
             x = L.modulated_conv2d(x, s1, P, pb + "/conv_1", up=False, noise=n1, noise_strength=P[pb + "/noise_1/w"],
                                    bias=P[pb + "/bias_1/b"], act=True, fused_epilogue=fused_epilogue,
                                    s_pre=sc[3 * i + 2])

@@ -281,6 +281,27 @@ def bias_act_bwd(g_out: torch.Tensor, out: torch.Tensor, *, residual=None, noise
     return gy0, S1, Spre, Snz
 
 
+def bias_act_rgb_bwd(g_out: Optional[torch.Tensor], out: torch.Tensor, g_rgb: torch.Tensor, ws: torch.Tensor, *,
+                     noise: Optional[torch.Tensor], d: torch.Tensor, act: int = 1, gain: float = 1.0):
+    """bias_act_bwd with the ToRGB gradient formed in the kernel — see include/tbg.h (tbg_bias_act_rgb_bwd).
+    Returns (gy0 bf16, S1, Spre, Snz [B,C], gws [B,C,3])."""
+    _require(out, torch.bfloat16, "out")
+    _require(g_rgb, torch.float32, "g_rgb")
+    _require(ws, torch.float32, "ws")
+    _require(d, torch.float32, "d")
+    if g_out is not None:
+        _require(g_out, torch.bfloat16, "g_out")
+    B, HW, C_ = _bhwc(out)
+    gy0 = torch.empty_like(out)
+    sums = torch.zeros((6, B, C_), device=out.device, dtype=torch.float32)       # S1 | Spre | Snz | gws (3 planes)
+    gws = sums[3:].view(B, C_, 3)
+    st = _lib.load().tbg_bias_act_rgb_bwd(_ptr(g_out), _ptr(out), _ptr(noise), _ptr(d), _ptr(g_rgb), _ptr(ws), _ptr(gy0),
+                                          _ptr(sums[0]), _ptr(sums[1]), _ptr(sums[2]), _ptr(gws), B, HW, C_, int(act),
+                                          float(gain), _stream())
+    _lib.check(st, "tbg_bias_act_rgb_bwd")
+    return gy0, sums[0], sums[1], sums[2], gws
+
+
 def torgb_fwd(x: torch.Tensor, ws: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """x bf16 [B,H,W,C], ws fp32 [B,C,3], bias fp32 [3] -> y fp32 [B,H,W,3]."""
     _require(x, torch.bfloat16, "x")

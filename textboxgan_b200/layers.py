@@ -36,6 +36,7 @@ UNFOLD_UP = True
 # conv_downsample_2d: FIR pre-pass + k x k strided conv (forward, weight gradient) instead of the folded
 # (k+3) x (k+3) convolution; the input gradient stays folded
 UNFOLD_DOWN = True
+FUSE_RGB_BACKWARD = True   # conv_1 + ToRGB + skip sum of a synthesis block as one autograd node (fused.ModConvActRGB)
 SKIP_SPLIT = True          # residual skip branch: FIR at the strided pixels only + plain 1x1 GEMM (fused.SkipSplit)
 _DOUBLE_BACKWARD = False
 
@@ -134,6 +135,24 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
         return y
     return SO.bias_act(y, noise, noise_strength if noise is not None else None, bias, 1 if act else 0,
                        SQRT2 if act else 1.0)                               # noise.py:21, bias_act.py:25-34
+
+
+def modulated_conv2d_rgb(x: torch.Tensor, P: Params, prefix: str, rgb_prefix: str, *, noise: torch.Tensor,
+                         noise_strength: torch.Tensor, bias: torch.Tensor, s_conv: torch.Tensor, s_rgb: torch.Tensor,
+                         y_prev: Optional[torch.Tensor], mask_words: Optional[torch.Tensor], nchw: bool):
+    """Second convolution of a synthesis block + its ToRGB + the skip sum (synthesis_block.py:143-152) as one autograd
+    node (fused.ModConvActRGB).  Returns (x_out bf16 NHWC, y)."""
+    from .fused import ModConvActRGB
+
+    w_raw = P[prefix + "/w"]
+    kh, _, I, O = w_raw.shape
+    _, H, W_, _ = x.shape
+    spec = C.weight_spec("plain", H, W_, I, O, kh, True, "modconv")
+    w_rgb_raw = P[rgb_prefix + "/conv/w"]                                   # [1,1,C,3]
+    w_rgb = runtime_coef(w_rgb_raw.shape) * w_rgb_raw[0, 0]
+    ws = s_rgb[:, :, None] * w_rgb[None]                                    # [B,C,3]  (to_rgb.py:28-33: no demodulation)
+    return ModConvActRGB.apply(x, s_conv, w_raw, noise, noise_strength, bias, spec, SQRT2, ws, P[rgb_prefix + "/bias/b"],
+                               y_prev, mask_words, nchw)
 
 
 def all_style_scales(style: torch.Tensor, P: Params, prefixes, idxs):

@@ -80,6 +80,7 @@ _SIGNATURES = [
     ("tbg_modulate", c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     ("tbg_modulate_bwd", c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     ("tbg_bias_act_bwd", c_int, [c_void_p] * 9 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    ("tbg_bias_act_rgb_bwd", c_int, [c_void_p] * 11 + [c_int] * 4 + [c_float, c_void_p]),
     ("tbg_bias_act_fwd", c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_void_p]),
     ("tbg_rowdot", c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     ("tbg_torgb_fwd", c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
