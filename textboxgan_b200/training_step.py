@@ -80,6 +80,8 @@ class TrainingStep:
         self.use_cuda_graph = False
         self.batch_d_calls = True       # evaluate D(fake) and D(real) as one concatenated pass
         self.overlap_ocr = True         # OCR branch on a second CUDA stream (parallel sub-graph when captured)
+        self.overlap_reg = True         # path-length / R1 regulariser branches on their own streams (lazy-reg iterations)
+        self._reg_streams = {}
         self._side = None
         self._graphs = {}
         self._static = None
@@ -183,6 +185,11 @@ class TrainingStep:
             self._side = torch.cuda.Stream(device=dev)
         return self._side
 
+    def _reg_stream(self, dev, name: str):
+        if name not in self._reg_streams:
+            self._reg_streams[name] = torch.cuda.Stream(device=dev)
+        return self._reg_streams[name]
+
     def graph_launches(self, do_r1_reg: bool = False, do_pl_reg: bool = False) -> int:
         """Number of this repo's kernel launches inside the captured graph of a step variant."""
         e = self._graphs.get((bool(do_r1_reg), bool(do_pl_reg)))
@@ -223,6 +230,27 @@ class TrainingStep:
                 ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
                 ocr_loss = ocr_loss_weight * ocr_loss                                        # :191-192
 
+        # The two regulariser branches (path length :300-347 on its own generator pass, R1 :349-373 on D(real)) share only
+        # weights with the adversarial branch.  Their double-backward graphs are thousands of small launches at a reduced
+        # batch, so each is issued on its own stream: forward here, and — because autograd runs a node's backward on the
+        # stream of its forward — the second-order backward passes as well, next to the large kernels of the main branch.
+        reg_pre = {}
+        if main is not None and self.overlap_reg and (do_pl_reg or do_r1_reg):
+            # parameters are leaves created on the main stream and differentiated from several streams on purpose (all
+            # gradients are taken with torch.autograd.grad, which joins the streams before it returns)
+            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            if do_pl_reg:
+                st_pl = self._reg_stream(dev, "pl")
+                st_pl.wait_stream(main)
+                with torch.cuda.stream(st_pl):
+                    reg_pre["pl"] = self._path_length_reg(input_words, draws)
+            if do_r1_reg:
+                st_r1 = self._reg_stream(dev, "r1")
+                st_r1.wait_stream(main)
+                with torch.cuda.stream(st_r1):
+                    reg_pre["r1"] = self._r1_reg(real_images)
+
         # D(fake) and D(real) (training_step.py:260,288) as ONE concatenated pass when no R1 penalty is due:
         # every discriminator layer is per-sample except the minibatch statistic, taken per call.
         self._batched_d = bool(self.batch_d_calls and L.use_fused() and not do_r1_reg)
@@ -233,10 +261,17 @@ class TrainingStep:
             fake_scores, real_scores = scores[:nb], scores[nb:]
         else:
             fake_scores = None
+        if not self._batched_d and fake_scores is None and reg_pre:
+            fake_scores = self.discriminator(fake_images)          # issued before the joins below
+        for name, val in reg_pre.items():
+            main.wait_stream(self._reg_streams[name])
+            for t in (val if isinstance(val, tuple) else (val,)):
+                t.record_stream(main)
         fake_scores, reg_g_loss, g_loss, pl_penalty = self._get_generator_losses(fake_images, do_pl_reg,
-                                                                                 input_words, draws, fake_scores)
+                                                                                 input_words, draws, fake_scores,
+                                                                                 reg_pre.get("pl"))
         reg_d_loss, d_loss, r1_penalty = self._get_discriminator_losses(fake_scores, real_images, do_r1_reg,
-                                                                        real_scores)
+                                                                        real_scores, reg_pre.get("r1"))
         if self.aster_ocr is not None and side is None:
             ocr_loss = self._get_ocr_loss(fake_images, ocr_labels, ocr_images)
             ocr_loss = ocr_loss_weight * ocr_loss                                            # :191-192
@@ -287,10 +322,10 @@ class TrainingStep:
         return gen_losses, disc_losses, ocr_out
 
     # ------------------------------------------------------------------------------------------
-    def _get_discriminator_losses(self, fake_scores, real_images, do_r1_reg: bool, real_scores=None):
+    def _get_discriminator_losses(self, fake_scores, real_images, do_r1_reg: bool, real_scores=None, r1_pre=None):
         """training_step.py:237-266"""
         if do_r1_reg:
-            real_scores, r1_penalty = self._r1_reg(real_images)
+            real_scores, r1_penalty = r1_pre if r1_pre is not None else self._r1_reg(real_images)
         else:
             if real_scores is None:
                 real_scores = self.discriminator(real_images)
@@ -299,13 +334,17 @@ class TrainingStep:
         reg_d_loss = d_loss + r1_penalty
         return reg_d_loss, d_loss, r1_penalty
 
-    def _get_generator_losses(self, fake_images, do_pl_reg: bool, input_words, draws: dict, fake_scores=None):
+    def _get_generator_losses(self, fake_images, do_pl_reg: bool, input_words, draws: dict, fake_scores=None,
+                              pl_pre=None):
         """training_step.py:268-298"""
         if fake_scores is None:
             fake_scores = self.discriminator(fake_images)
         g_loss = generator_loss(fake_scores, self.batch_size)
-        pl_penalty = self._path_length_reg(input_words, draws) if do_pl_reg \
-            else torch.zeros((), device=fake_scores.device)
+        if pl_pre is not None:
+            pl_penalty = pl_pre
+        else:
+            pl_penalty = self._path_length_reg(input_words, draws) if do_pl_reg \
+                else torch.zeros((), device=fake_scores.device)
         reg_g_loss = g_loss + pl_penalty
         return fake_scores, reg_g_loss, g_loss, pl_penalty
 
