@@ -345,3 +345,58 @@ def test_bias_act_rgb_bwd_kernel_vs_emulated_semantics(B, H, W, C, has_g, has_no
             continue
         tol = 4e-3 if n == "gy0" else 2e-4
         assert rel_err(a.float().cpu(), b.float()) < tol, (n, rel_err(a.float().cpu(), b.float()))
+
+
+@pytest.mark.parametrize("kind,k,rh,H,W,I,O", [("plain", 3, True, 16, 32, 64, 128), ("plain", 1, True, 8, 16, 128, 64),
+                                               ("upT", 3, True, 8, 16, 128, 64), ("upT", 3, True, 16, 16, 64, 64),
+                                               ("downU", 3, True, 16, 32, 64, 128), ("downU", 3, False, 8, 32, 128, 128)])
+def test_lin_conv_triple_first_and_second_derivatives_vs_reference_convolution(kind, k, rh, H, W, I, O):
+    """second_order.lin_conv (F / A / G on the master weight, the regulariser passes' convolution): value, the
+    path-length-like first derivative J = d<y, n>/dx taken with create_graph, and d(sum J^2 + <y, m>)/d(x, w), against fp64
+    torch convolutions that restate the reference ops (plain SAME conv; upsample_conv_2d = transposed stride-2 conv + FIR,
+    upfirdn_2d_v2.py:65-103; conv_downsample_2d = FIR + strided conv, :106-113)."""
+    import torch.nn.functional as F_
+    from textboxgan_b200 import second_order as SO
+
+    gen = torch.Generator().manual_seed(H * 3 + W + I)
+    B = 3
+    x0 = _bf16_round(torch.randn(B, H, W, I, generator=gen))
+    w0 = torch.randn(k, k, I, O, generator=gen)
+    coef = 1.0 / math.sqrt(k * k * I)
+    kf = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    k2 = torch.outer(kf, kf) / 64.0
+
+    def ref_conv(x, w):                                   # x [B,H,W,I] fp64, w [k,k,I,O] fp64 -> NHWC
+        xn = x.permute(0, 3, 1, 2)
+        wk = (w * coef).permute(3, 2, 0, 1)               # OIHW
+        if kind == "plain":
+            y = F_.conv2d(xn, wk, padding=k // 2)
+        elif kind == "upT":
+            t = F_.conv_transpose2d(xn, (w * coef).flip(0, 1).permute(2, 3, 0, 1), stride=2)  # flipped kernel (:80)
+            kk = (k2 * 4.0)[None, None].expand(O, 1, 4, 4)
+            y = F_.conv2d(F_.pad(t, (1, 1, 1, 1)), kk, groups=O)                             # pad (1,1): 2H x 2W
+        else:
+            kk = k2[None, None].expand(I, 1, 4, 4)
+            xb = F_.conv2d(F_.pad(xn, (2, 2, 2, 2 if rh else 3)), kk, groups=I)
+            y = F_.conv2d(xb, wk, stride=(2 if rh else 1, 2))
+        return y.permute(0, 2, 3, 1)
+
+    def run(device, prim):
+        x = x0.to(device, torch.bfloat16 if prim else torch.float64).requires_grad_(True)
+        w = w0.to(device, torch.float32 if prim else torch.float64).requires_grad_(True)
+        y = SO.lin_conv(x, w, kind, k, rh, "t") if prim else ref_conv(x, w)
+        gn = torch.Generator().manual_seed(99)
+        n = torch.randn(y.shape, generator=gn).to(device, y.dtype)
+        m = torch.randn(y.shape, generator=gn).to(device, y.dtype)
+        (J,) = torch.autograd.grad((y * n).sum(), x, create_graph=True)
+        pen = (J.double() ** 2).sum() + (y.double() * m.double()).sum()
+        gx, gw = torch.autograd.grad(pen, [x, w])
+        return [t.detach().double().cpu() for t in (y, J, gx, gw)]
+
+    ref = run("cpu", False)
+    got = run(DEV, True)
+    rl2 = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    errs = [rl2(a, b) for a, b in zip(got, ref)]
+    print(kind, "rel-L2 of (y, J, d/dx, d/dw):", errs)
+    assert ref[0].shape == got[0].shape
+    assert errs[0] < 1e-2 and errs[1] < 1e-2 and errs[2] < 3e-2 and errs[3] < 3e-2, errs

@@ -199,3 +199,35 @@ def test_validation_step_infer_and_one_trainer_iteration_on_device(tmp_path):
     a = inf.generate(["ab", "hello"], z=zz)
     b = inf.generate(["ab", "hello"], z=zz, truncation_psi=0.5)
     assert a.shape == (2, cfg.char_height, cfg.image_width, 3) and a.dtype.name == "uint8" and (a != b).any()
+
+
+def test_cuda_graph_replay_of_all_three_step_variants_interleaved():
+    """The benchmark's execution mode: every step variant (plain / path length / path length + R1) runs once eagerly, is
+    captured, and is then replayed in the order of the lazy-regularisation schedule.  Later variants extend the grouped
+    weight-preparation plan (fused.StepWeights) after earlier graphs were captured: the earlier graphs must keep replaying
+    with their own (retired) plan and buffers.  Random draws are internal in this mode, so the check is on behaviour: no
+    CUDA error, finite losses in the range of the eager run, penalties only on their iterations, counters and weights move."""
+    B = 4
+    cfg = small_cfg(B)
+    GP, DP, g = perturbed_params(cfg)
+    G, D, aster, ts = _product(cfg, GP, DP, True)
+    ts.use_cuda_graph = True
+    real, words, labels = OT.synthetic_batch(cfg, B, g)
+    real, words, labels = real.to(DEV), words.to(DEV), labels.to(DEV)
+    zero = torch.zeros((), device=DEV)
+    w_before = G.flat.clone()
+    schedule = [(False, False)] * 3 + [(False, True)] * 2 + [(False, False)] + [(True, True)] * 2 + \
+               [(False, False), (False, True), (True, True), (False, False), (False, True), (False, False)]
+    outs = []
+    for do_r1, do_pl in schedule:
+        o = ts.dist_train_step(real, zero, words, labels, do_r1, do_pl, 1e-4)
+        outs.append((_flat(o), do_r1, do_pl))
+    torch.cuda.synchronize()
+    assert len(ts._graphs) == 3 and all(e["graph"] is not None for e in ts._graphs.values())
+    assert ts._step_weights.plan is not None
+    for vals, do_r1, do_pl in outs:
+        assert all(v == v and abs(v) < 1e4 for v in vals), vals
+        assert (vals[2] > 0) == do_pl and (vals[5] > 0) == do_r1, (vals, do_r1, do_pl)
+        assert 0.05 < vals[1] < 20 and 0.05 < vals[4] < 20, vals           # softplus adversarial losses stay O(1)
+    assert ts.g_optimizer.iterations.numpy() == len(schedule) and ts.d_optimizer.iterations.numpy() == len(schedule)
+    assert float((G.flat - w_before).abs().max()) > 0

@@ -76,6 +76,19 @@ class Discriminator(Model):
                 # (linear) skip branch, so the merge is a plain residual add in the epilogue
                 return ConvAct.apply(x, w_raw, P[bias], residual, spec, 1.0)
             return ConvAct.apply(x, w_raw, P[bias] if bias else None, None, spec, L.SQRT2)
+        if torch.is_grad_enabled() and L.SPEC_SECOND_ORDER and scale == 1.0 and (not down or (H % 2 == 0 and W_ % 2 == 0)):
+            # regulariser pass (R1, training_step.py:363-368): closed bilinear triple on the master weight
+            from . import second_order as SO
+
+            if down and k == 1:
+                y = SO.lin_conv(SO.fir4_down(x, 2 if reduce_height else 1), w_raw, "plain", 1, True, "dconv")
+            else:
+                y = SO.lin_conv(x, w_raw, "downU" if down else "plain", k, reduce_height, "dconv")
+            if bias is not None:
+                y = SO.bias_act(y, None, None, P[bias], 1, L.SQRT2)
+            if residual is not None:
+                y = (y + residual) * INV_SQRT2
+            return y
         w = (L.runtime_coef(w_raw.shape) * scale) * w_raw
         if down:
             geom = C.down_geom(H, W_, I, O, k, reduce_height, tag="dconv")
@@ -150,10 +163,15 @@ class Discriminator(Model):
             spec = C.weight_spec("plain", H, W_, Cc + 1, w_raw.shape[3], 3, True, "dconv")   # K padded 513 -> 576
             y = ConvAct.apply(xcat, w_raw, P[pl + "/bias_0/b"], None, spec, L.SQRT2).float()
         else:
-            w = L.runtime_coef(w_raw.shape) * w_raw
-            wpad = torch.cat([w, w.new_zeros(3, 3, cpad - Cc - 1, w.shape[3])], dim=2)
-            y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3, tag="dconv",
-                                                              algo_frac=(Cc + 1) / cpad)).float()
+            if torch.is_grad_enabled() and L.SPEC_SECOND_ORDER:
+                from . import second_order as SO
+
+                y = SO.lin_conv(xcat, w_raw, "plain", 3, True, "dconv").float()            # K padded 513 -> 576 by the spec
+            else:
+                w = L.runtime_coef(w_raw.shape) * w_raw
+                wpad = torch.cat([w, w.new_zeros(3, 3, cpad - Cc - 1, w.shape[3])], dim=2)
+                y = C.conv(xcat, C.plain_wmat(wpad), C.plain_geom(H, W_, cpad, w.shape[3], 3, tag="dconv",
+                                                                  algo_frac=(Cc + 1) / cpad)).float()
             y = L.lrelu(y + P[pl + "/bias_0/b"])
         # flatten in the reference's NCHW order (dense.py:26-27 on an NCHW tensor)
         y = y.permute(0, 3, 1, 2).reshape(B, -1)

@@ -47,6 +47,7 @@ class StepWeights:
     def __init__(self):
         self.plan = None
         self.keys: dict = {}
+        self.retired: list = []       # superseded plans: CUDA graphs captured earlier still replay their launch and buffers
 
     def begin_step(self) -> None:
         global _STEP_LOG
@@ -66,6 +67,12 @@ class StepWeights:
         covered = all(k in self.keys and self.keys[k][0] >= v[2] and self.keys[k][1] >= v[3] for k, v in log.items())
         if covered or (log[next(iter(log))][0].is_cuda and torch.cuda.is_current_stream_capturing()):
             return
+        if self.plan is not None:
+            self.retired.append(self.plan)
+            # keep what the old plan covered and this iteration did not ask for (another step variant's layers)
+            for k, ent in zip(self.keys, self.plan.entries):
+                if k not in log:
+                    log[k] = list(ent)
         self.keys = {k: (v[2], v[3]) for k, v in log.items()}
         self.plan = K.WPrepPlan([tuple(v) for v in log.values()])
 

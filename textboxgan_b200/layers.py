@@ -37,6 +37,7 @@ UNFOLD_UP = True
 # (k+3) x (k+3) convolution; the input gradient stays folded
 UNFOLD_DOWN = True
 FUSE_RGB_BACKWARD = True   # conv_1 + ToRGB + skip sum of a synthesis block as one autograd node (fused.ModConvActRGB)
+SPEC_SECOND_ORDER = True   # regulariser (double-backward) passes: convolutions as second_order.lin_conv on the master weight
 SKIP_SPLIT = True          # residual skip branch: FIR at the strided pixels only + plain 1x1 GEMM (fused.SkipSplit)
 _DOUBLE_BACKWARD = False
 
@@ -128,7 +129,10 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, P: Params, prefix: st
     from . import second_order as SO
 
     xs = SO.modulate(x.to(ACT_DTYPE), s)                                    # :96
-    y = C.conv(xs, wmat, geom)
+    if SPEC_SECOND_ORDER and kh == 3:
+        y = SO.lin_conv(xs, w_raw, "upT" if up else "plain", kh, True, "modconv")
+    else:
+        y = C.conv(xs, wmat, geom)
     if d is not None:
         y = SO.modulate(y, d)                                               # :121
     if noise is None and bias is None and not act:

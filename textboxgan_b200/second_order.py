@@ -13,7 +13,12 @@ path-length step in such passes, profiles/r02f_timeline_c2_pl.txt):
 * ``mask_mul(g, out)``         g * gain * act'(out)      (tbg_bias_act_bwd) linear in g with a piecewise-constant mask:
                                                                             d/dg = mask_mul(gg, out)
 * ``to_rgb(x, ws)`` / its pair of adjoints                (tbg_torgb_fwd / tbg_torgb_bwd)
-* convolutions and weight gradients: :func:`textboxgan_b200.conv.conv` / ``conv_wgrad`` (already closed).
+* convolutions and weight gradients: :func:`textboxgan_b200.conv.conv` / ``conv_wgrad`` (already closed), or —
+  ``layers.SPEC_SECOND_ORDER`` — the triple ``lin_conv`` F(x, w) / A(g, w) / G(x, g) below, which works on the MASTER weight
+  and reuses the launch recipes of the first-order path (``conv.weight_spec``): prepared matrices come from the step's
+  grouped weight preparation instead of torch re-layouts, the weight gradients of the resampling layers run unfolded
+  (9 taps on the filtered tensor instead of 36), and nothing is re-indexed with flip / pad / copy kernels.
+* ``fir4_down(x)`` / its adjoint (the skip branch of a discriminator block): linear, each the other's derivative.
 
 The only non-linear pieces of a modulated layer are the demodulation coefficient (parameter-sized, plain torch) and the
 leaky-ReLU mask (zero second derivative almost everywhere) — SURVEY.md Appendix F.
@@ -177,3 +182,165 @@ class _ToRGBAdjoint(torch.autograd.Function):
 
 def to_rgb(x: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
     return _ToRGB.apply(x, ws)
+
+
+# ----------------------------------------------------------------------------------------------
+# Convolution layers as a closed triple of bilinear maps on the master weight w [KH,KW,I,O] (fp32):
+#   F(x, w)   the layer's convolution (incl. the FIR of upsample_conv_2d / conv_downsample_2d, upfirdn_2d_v2.py:65-113)
+#   A(g, w)   its adjoint in x        (= dF/dx applied to g)
+#   G(x, g)   its adjoint in w        (= dF/dw applied to g, returned in the master layout, equalised-LR coefficient included)
+# d/dx F = A(., w), d/dw F = G(x, .);   d/dg A = F(., w), d/dw A = G(., g);   d/dx G = A(g, .), d/dg G = F(x, .)
+# so gradients of any order stay inside the set.  The launch recipes are those of the first-order Functions of fused.py:
+#   plain   : 3x3 / 1x1 SAME convolution
+#   downU   : F = FIR pre-pass + strided VALID convolution, A = folded 4-phase convolution straight to the input gradient,
+#             G on the filtered tensor (9 taps)
+#   upT     : F = FIR folded into a 4-phase 3x3 convolution, A = FIR adjoint + stride-2 VALID convolution, G = that
+#             convolution's weight gradient with the roles exchanged (9 taps)
+# ----------------------------------------------------------------------------------------------
+class LinConv:
+    def __init__(self, kind: str, H: int, W: int, I: int, O: int, k: int, reduce_height: bool = True, tag: str = ""):
+        from . import conv as C
+
+        assert kind in ("plain", "downU", "upT"), kind
+        self.kind = kind
+        self.spec = C.weight_spec(kind, H, W, I, O, k, reduce_height, tag)
+        self.fspec = C.weight_spec("up", H, W, I, O, k, True, tag) if kind == "upT" else None
+
+    @staticmethod
+    def _mats(w, spec, want_adj: bool, is_param: bool):
+        if is_param:                       # a model weight: prepared once per iteration (fused.StepWeights)
+            from .fused import _prepared
+
+            return _prepared(w, spec, want_adj, False)
+        return K.wprep(w.contiguous().float(), spec, want_adj=want_adj, want_q=False)    # a cotangent in weight layout
+
+    def F(self, x, w, is_param: bool):
+        x = _bf16(x)
+        if self.kind == "upT":
+            wf = self._mats(w, self.fspec, False, is_param)[0]
+            K.PROFILE_TAG = (self.spec.geom.tag, self.fspec.geom.algo_frac)
+            return K.conv2d_igemm(x, wf, **self.fspec.geom.kernel_kwargs())
+        spec = self.spec
+        wm = self._mats(w, spec, False, is_param)[0]
+        if spec.fir is not None:
+            x = K.fir4(x, spec.fir["out_hw"], spec.fir["off"], spec.fir["scale"])
+        K.PROFILE_TAG = (spec.geom.tag, spec.geom.algo_frac)
+        return K.conv2d_igemm(x, wm, **spec.fwd_kwargs)
+
+    def A(self, g, w, is_param: bool):
+        g = _bf16(g)
+        spec = self.spec
+        wa = self._mats(w, spec, True, is_param)[1]
+        if self.kind == "upT":
+            g = K.fir4(g, spec.t_hw, (-2, -2), 1.0 / 16.0)
+            K.PROFILE_TAG = (spec.geom.tag, 1.0)
+            return K.conv2d_igemm(g, wa, **spec.s2_kwargs)
+        K.PROFILE_TAG = (spec.geom.tag, spec.adj_frac)
+        return K.conv2d_igemm(g, wa, **spec.adj_kwargs)
+
+    def G(self, x, g):
+        x, g = _bf16(x), _bf16(g)
+        spec = self.spec
+        if self.kind == "upT":
+            gT = K.fir4(g, spec.t_hw, (-2, -2), 1.0 / 16.0)
+            K.PROFILE_TAG = (spec.geom.tag, 1.0)
+            return K.wfold_adj(K.conv2d_wgrad(gT, x, **spec.s2_kwargs), spec, flip=True)
+        if spec.fir is not None:
+            x = K.fir4(x, spec.fir["out_hw"], spec.fir["off"], spec.fir["scale"])
+        K.PROFILE_TAG = (spec.geom.tag, spec.geom.algo_frac)
+        return K.wfold(K.conv2d_wgrad(x, g, **spec.fwd_kwargs), spec)
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    from . import conv as C
+
+    return C._as_bf16(t)              # (the CPU emulation of the tests keeps its own activation dtype through this hook)
+
+
+class _LinF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, lc: LinConv, is_param: bool):
+        ctx.save_for_backward(x, w)
+        ctx.lc, ctx.is_param = lc, is_param
+        return lc.F(x, w, is_param)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = _LinA.apply(gy, w, ctx.lc, ctx.is_param) if ctx.needs_input_grad[0] else None
+        gw = _LinG.apply(x, gy, ctx.lc) if ctx.needs_input_grad[1] else None
+        return gx, gw, None, None
+
+
+class _LinA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, w, lc: LinConv, is_param: bool):
+        ctx.save_for_backward(g, w)
+        ctx.lc, ctx.is_param = lc, is_param
+        return lc.A(g, w, is_param)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, w = ctx.saved_tensors
+        gg = _LinF.apply(ggx, w, ctx.lc, ctx.is_param) if ctx.needs_input_grad[0] else None
+        gw = _LinG.apply(ggx, g, ctx.lc) if ctx.needs_input_grad[1] else None
+        return gg, gw, None, None
+
+
+class _LinG(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, lc: LinConv):
+        ctx.save_for_backward(x, g)
+        ctx.lc = lc
+        return lc.G(x, g)
+
+    @staticmethod
+    def backward(ctx, cw):
+        x, g = ctx.saved_tensors
+        gx = _LinA.apply(g, cw, ctx.lc, False) if ctx.needs_input_grad[0] else None
+        gg = _LinF.apply(x, cw, ctx.lc, False) if ctx.needs_input_grad[1] else None
+        return gx, gg, None
+
+
+_LIN_CACHE: dict = {}
+
+
+def lin_conv(x: torch.Tensor, w_raw: torch.Tensor, kind: str, k: int, reduce_height: bool = True, tag: str = "") -> torch.Tensor:
+    """The convolution of a layer (no bias / activation) on the master weight ``w_raw`` [k,k,I,O]; x bf16 [B,H,W,I]."""
+    _, H, W_, _ = x.shape
+    I, O = w_raw.shape[2], w_raw.shape[3]
+    key = (kind, H, W_, I, O, k, bool(reduce_height), tag)
+    lc = _LIN_CACHE.get(key)
+    if lc is None:
+        lc = _LIN_CACHE[key] = LinConv(kind, H, W_, I, O, k, reduce_height, tag)
+    return _LinF.apply(x, w_raw, lc, True)
+
+
+# ----------------------------------------------------------------------------------------------
+# FIR of the discriminator's skip branch at the pixels its strided 1x1 convolution reads (tbg_fir4_down) and its transpose
+# ----------------------------------------------------------------------------------------------
+class _Fir4Down(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sy: int):
+        x = _bf16(x)
+        ctx.sy, ctx.hw = sy, (x.shape[1], x.shape[2])
+        return K.fir4_down(x, (x.shape[1] // sy, x.shape[2] // 2), sy, (-1, -1), 1.0 / 64.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Fir4DownAdj.apply(g, ctx.sy, ctx.hw), None
+
+
+class _Fir4DownAdj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, sy: int, hw):
+        ctx.sy = sy
+        return K.fir4_down_adjoint(_bf16(g), hw, sy, (-1, -1), 1.0 / 64.0)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _Fir4Down.apply(gg, ctx.sy), None, None
+
+
+def fir4_down(x: torch.Tensor, sy: int) -> torch.Tensor:
+    return _Fir4Down.apply(x, sy)
