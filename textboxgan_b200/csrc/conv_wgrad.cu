@@ -351,14 +351,8 @@ extern "C" int tbg_conv2d_wgrad(const tbg_wgrad_args* a, void* stream_v) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int base_items = p.m_tiles * p.groups;
   const int items_override = g_tuning.wgrad_items_per_sm;     // tbg_set_tuning("wgrad_items_per_sm", n); 0 = heuristic
-  // Two work items per SM hide the accumulator drain behind the next item's MMAs, but only pay off
-  // when each item still owns >= 16 pixel blocks (measured on B200, profiles/r01_layer_perf.log).
-  int items_per_sm = items_override > 0 ? items_override : 2;
-  int splits = (items_per_sm * sms + base_items - 1) / base_items;
-  if (items_override <= 0 && k_tiles / (splits > 0 ? splits : 1) < 16) {
-    items_per_sm = 1;
-    splits = (sms + base_items - 1) / base_items;
-  }
+  // tbg_set_tuning("wgrad_items_per_sm", n) forces n rounds; 0 = cost model (host_util.h::pick_splits)
+  int splits = items_override > 0 ? (items_override * sms) / base_items : pick_splits(base_items, k_tiles, sms, 8.0);
   if (splits > k_tiles) splits = k_tiles;
   if (splits < 1) splits = 1;
   // every split must own at least one pixel tile

@@ -225,8 +225,7 @@ int wgrad_halo_launch(const tbg_wgrad_args* a, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int k_tiles = p.tiles_w * p.tiles_h * a->B;
   const int base_items = p.m_tiles * p.c_tiles * p.groups;
-  int splits = (2 * sms + base_items - 1) / base_items;          // ~2 items per SM: the drain of one overlaps nothing,
-  if (k_tiles / splits < 16) splits = (sms + base_items - 1) / base_items;   // so keep >= 16 K blocks per item
+  int splits = pick_splits(base_items, k_tiles, sms, 8.0);
   if (splits > k_tiles) splits = k_tiles;
   if (splits < 1) splits = 1;
   {

@@ -36,6 +36,31 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swizzle);
 
 // Process-wide tuning switches, set through tbg_set_tuning (never from the environment).
+// Split-K factor of the weight-gradient kernels: `base_items` independent (tile, tap-group) items are each cut into
+// `splits` ranges of K blocks and dealt round-robin to one persistent CTA per SM.  Cost model: every round costs the K
+// blocks of one item plus its accumulator drain (fp32 vector atomics of up to 512 TMEM columns, worth ~`drain_k` K blocks;
+// single-buffered TMEM, so it overlaps nothing): minimise  rounds(s) * (k_tiles / s + drain_k).  A plain
+// "2 items per SM, rounded up" left 2 * sms + 1 items = a whole third round on ONE SM while the others idled
+// (ncu: sm__cycles_active 70 % of elapsed, profiles/r02ab_ncu_conv_summary.txt).
+inline int pick_splits(int base_items, int k_tiles, int sms, double drain_k) {
+  int smax = (4 * sms + base_items - 1) / base_items;
+  if (smax > k_tiles) smax = k_tiles;
+  if (smax < 1) smax = 1;
+  int best = 1;
+  double best_t = 1e300;
+  for (int s = 1; s <= smax; ++s) {
+    const long long items = static_cast<long long>(base_items) * s;
+    const long long rounds = (items + sms - 1) / sms;
+    const double per = static_cast<double>((k_tiles + s - 1) / s);
+    const double t = static_cast<double>(rounds) * (per + drain_k);
+    if (t < best_t - 1e-9) {
+      best_t = t;
+      best = s;
+    }
+  }
+  return best;
+}
+
 struct Tuning {
   int conv_halo = 1;           // 3x3 stride-1 convolutions on the halo-reuse kernel when it applies
   int wgrad_staged = 0;        // conv_wgrad: staged vector atomics (measured slower on B200, profiles/r02b_layer_perf.log: off)
