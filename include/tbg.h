@@ -208,6 +208,9 @@ int tbg_fir4_down_adjoint(const void* g, const void* add, void* out, int B, int 
  *   "wgrad_halo" (1)          tbg_conv2d_wgrad runs 3x3 stride-1 pad-1 weight gradients on large grids on the halo-reuse
  *                             kernel of csrc/conv_wgrad_halo.cu;
  *   "halo_a_stages" (2..3), "halo_b_stages" (2..8), "halo_staged" (0|1): pipeline depth / store path of conv_halo.
+ *   "halo_cta2" (0)           conv3x3_halo on CTA pairs (thread-block clusters of 2, tcgen05.mma.cta_group::2, M = 256,
+ *                             each CTA stages half of every weight box): same results bit for bit; measured slower at
+ *                             N = 128 (profiles/r02ag_halo_cta2.txt), hence off.
  * tbg_get_tuning returns the current value or -1 for an unknown key. */
 int tbg_set_tuning(const char* key, int value);
 int tbg_get_tuning(const char* key);

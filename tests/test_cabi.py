@@ -115,7 +115,7 @@ def test_tuning_switches_round_trip_and_no_environment_reads():
     from textboxgan_b200 import lib
 
     assert lib.get_tuning("no_such_key") == -1
-    for key in ("conv_halo", "wgrad_halo", "halo_staged", "wgrad_staged", "lstm_cluster"):
+    for key in ("conv_halo", "wgrad_halo", "halo_staged", "wgrad_staged", "lstm_cluster", "halo_cta2"):
         old = lib.get_tuning(key)
         assert old in (0, 1)
         lib.set_tuning(key, 1 - old)

@@ -856,3 +856,35 @@ def test_wgrad_halo_kernel_vs_emulated_semantics_and_wgrad(B, H, W, I, O):
     for halo in (1, 0):
         assert rel_err(got[halo], want) < 2e-5, halo            # fp32 accumulation of exact bf16 products
     assert rel_err(got[1], got[0]) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,I,O,up", [(2, 16, 32, 64, 128, (0, 0)), (3, 32, 64, 128, 128, (0, 0)), (4, 16, 16, 128, 256, (0, 0)),
+                                          (2, 16, 32, 128, 128, (1, 1)), (2, 16, 32, 64, 64, (1, 1)), (64, 16, 64, 128, 128, (0, 0))])
+def test_halo_kernel_cta_pairs_bit_identical(B, H, W, I, O, up):
+    """conv3x3_halo_kernel<CTA2>: two CTAs of a cluster issue one tcgen05.mma.cta_group::2 over M = 256 rows, each staging
+    half of every weight box.  Same summation order per output element as the single-CTA kernel: bit-identical results,
+    with the full epilogue, on plain and 4-phase (up) geometries, few and many pair items."""
+    from textboxgan_b200 import kernels as K
+    from textboxgan_b200 import lib
+
+    gen = torch.Generator().manual_seed(B * 7 + H + O)
+    nph = (1 + up[0]) * (1 + up[1])
+    x = _bf16_round(torch.randn(B, H, W, I, generator=gen)).to(DEV).bfloat16()
+    w = _bf16_round(torch.randn(nph * O, 9 * I, generator=gen) / math.sqrt(9 * I)).to(DEV).bfloat16()
+    epi = dict(col_scale=(torch.rand(B, O, generator=gen) + 0.5).to(DEV),
+               noise=torch.randn(B, H * (1 + up[0]), W * (1 + up[1]), generator=gen).to(DEV),
+               noise_strength=torch.tensor([0.3], device=DEV), bias=(torch.randn(O, generator=gen) * 0.1).to(DEV),
+               act=1, act_gain=1.4)
+    kw = dict(Ho=H, Wo=W, taps=(3, 3), pad=(1, 1), stride=(1, 1), up=up)
+    saved = lib.get_tuning("halo_cta2")
+    got = {}
+    try:
+        for v in (0, 1):
+            lib.set_tuning("halo_cta2", v)
+            got[v] = (K.conv2d_igemm(x, w, **kw).float().cpu(), K.conv2d_igemm(x, w, **kw, **epi).float().cpu())
+    finally:
+        lib.set_tuning("halo_cta2", saved)
+    torch.cuda.synchronize()
+    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
+    want = emu_conv2d_igemm(x.float().cpu(), w.float().cpu(), **kw)
+    assert rel_err(got[1][0], want.float()) < 1e-2

@@ -55,12 +55,20 @@ static constexpr uint32_t kHStgWarp = 32 * kHStgRow;                    // 4608 
 static constexpr uint32_t kHVecWarp = 2 * 128 * 4;                      // scale + bias vectors per epilogue warp
 static constexpr int kHaloThreads = 128 + 32 * kHaloEpiWarps;
 
+// CTA2: two CTAs of a cluster (one TPC) work on two neighbouring pixel blocks with ONE tcgen05.mma.cta_group::2 per
+// (tap, sub-tile, K step): M = 256 rows, each CTA stages its own halo box and only HALF of every weight box (rows
+// rank*N/2 ..), which removes a quarter of the shared-memory operand reads per SM and halves the weight traffic.  Both
+// producers credit the LEADER's full barriers; the leader's commits arrive on the empty / accumulator-full barriers of
+// both CTAs; both epilogues release the leader's accumulator-empty barrier.
+template <bool CTA2>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int N = p.block_n;
-  const uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
+  const uint32_t b_bytes = static_cast<uint32_t>(CTA2 ? N / 2 : N) * 128u;     // weight box staged by THIS CTA
   const int kHaloAStages = p.a_stages, kHaloBStages = p.b_stages;
   uint8_t* smA = smem;                                         // a_stages x 54 KB (each 1024-aligned)
   uint8_t* smB = smem + kHaloAStages * kHaloBytes;             // b_stages x N*128 B
@@ -82,29 +90,44 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kHaloAStages; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], CTA2 ? 2 : 1);                     // pair: one arrive.expect_tx per producer
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < kHaloBStages; ++i) {
-      mbar_init(&b_full[i], 1);
+      mbar_init(&b_full[i], CTA2 ? 2 : 1);
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 32 * kHaloEpiWarps);
+      mbar_init(&tempty[i], CTA2 ? 2 * kHaloEpiWarps : 32 * kHaloEpiWarps);   // pair: one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_pair(tmem_ptr, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();                                // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int tiles_px = p.tiles_w * p.tiles_h * p.B;
-  const int total_items = tiles_px * p.tiles_n;      // item = n_tile-major: consecutive items of a CTA differ in pixels
+  // item = n_tile-major: consecutive items of a CTA differ in pixels.  Pair mode: a pair item is two neighbouring pixel
+  // blocks (2k, 2k+1) times an N tile; CTA `rank` owns block 2k + rank.
+  const int px_units = CTA2 ? tiles_px / 2 : tiles_px;
+  const int total_items = px_units * p.tiles_n;
+  const int item0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto px_of = [&](int item, int n_tile) -> int {
+    const int u = item - n_tile * px_units;
+    return CTA2 ? 2 * u + static_cast<int>(rank) : u;
+  };
   const bool has_up = (p.up_h | p.up_w) != 0;
   auto phase_of = [&](int n_tile) -> int { return has_up ? (n_tile * N) / p.cout : 0; };
 
@@ -113,20 +136,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int n_tile = item / tiles_px, px_item = item - n_tile * tiles_px;
+      for (int item = item0; item < total_items; item += item_step) {
+        const int n_tile = item / px_units, px_item = px_of(item, n_tile);
         const int tw = px_item % p.tiles_w, th = (px_item / p.tiles_w) % p.tiles_h, b = px_item / (p.tiles_w * p.tiles_h);
         const uint32_t mask = p.tap_mask[phase_of(n_tile) & 3];
         for (int ch = 0; ch < p.cin_chunks; ++ch) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_arrive_expect_tx(&a_full[as], kHaloBytes);
-          tma_load_4d(smA + as * kHaloBytes, &tmA, &a_full[as], ch * 64, tw * 16 - 1, th * 16 - 1, b);
+          if (CTA2) {
+            mbar_arrive_expect_tx_leader(&a_full[as], kHaloBytes);
+            tma_load_4d_pair(smA + as * kHaloBytes, &tmA, &a_full[as], ch * 64, tw * 16 - 1, th * 16 - 1, b);
+          } else {
+            mbar_arrive_expect_tx(&a_full[as], kHaloBytes);
+            tma_load_4d(smA + as * kHaloBytes, &tmA, &a_full[as], ch * 64, tw * 16 - 1, th * 16 - 1, b);
+          }
           if (++as == kHaloAStages) { as = 0; aph ^= 1u; }
           for (int tap = 0; tap < 9; ++tap) {
             if (!((mask >> tap) & 1u)) continue;
             mbar_wait(&b_empty[bs], bph ^ 1u);
-            mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-            tma_load_2d(smB + bs * b_bytes, &tmB, &b_full[bs], tap * p.cin + ch * 64, n_tile * N);
+            if (CTA2) {
+              mbar_arrive_expect_tx_leader(&b_full[bs], b_bytes);
+              tma_load_2d_pair(smB + bs * b_bytes, &tmB, &b_full[bs], tap * p.cin + ch * 64,
+                               n_tile * N + static_cast<int>(rank) * (N / 2));
+            } else {
+              mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+              tma_load_2d(smB + bs * b_bytes, &tmB, &b_full[bs], tap * p.cin + ch * 64, n_tile * N);
+            }
             if (++bs == kHaloBStages) { bs = 0; bph ^= 1u; }
           }
         }
@@ -134,12 +168,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(N), 0, 0);
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, static_cast<uint32_t>(N), 0, 0);
       int as = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        const int n_tile = item / tiles_px;
+      for (int item = item0; item < total_items; item += item_step, ++it) {
+        const int n_tile = item / px_units;
         const uint32_t mask = p.tap_mask[phase_of(n_tile) & 3];
         const int acc_stage = it & 1;
         mbar_wait(&tempty[acc_stage], ((it >> 1) & 1) ^ 1u);
@@ -163,17 +197,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint64_t da = umma_smem_desc_sw128(win + k * 32, 0, kHaloPitch * 128);
                 const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-                umma_bf16(d_tmem + static_cast<uint32_t>(sub * N), da, db, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                if (CTA2)
+                  umma_bf16_pair(d_tmem + static_cast<uint32_t>(sub * N), da, db, idesc, (accumulate | k) != 0 ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem + static_cast<uint32_t>(sub * N), da, db, idesc, (accumulate | k) != 0 ? 1u : 0u);
               }
             }
             accumulate = 1;
-            umma_commit(&b_empty[bs]);
+            if (CTA2) umma_commit_pair(&b_empty[bs]); else umma_commit(&b_empty[bs]);
             if (++bs == kHaloBStages) { bs = 0; bph ^= 1u; }
           }
-          umma_commit(&a_empty[as]);
+          if (CTA2) umma_commit_pair(&a_empty[as]); else umma_commit(&a_empty[as]);
           if (++as == kHaloAStages) { as = 0; aph ^= 1u; }
         }
-        umma_commit(&tfull[acc_stage]);
+        if (CTA2) umma_commit_pair(&tfull[acc_stage]); else umma_commit(&tfull[acc_stage]);
       }
     }
   } else if (warp >= 4) {
@@ -194,8 +231,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int rows_per_pass = 32 / lanes_per_row;
     const int sbl = lane % lanes_per_row;
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const int n_tile = item / tiles_px, px_item = item - n_tile * tiles_px;
+    for (int item = item0; item < total_items; item += item_step, ++it) {
+      const int n_tile = item / px_units, px_item = px_of(item, n_tile);
       const int tw = px_item % p.tiles_w, th = (px_item / p.tiles_w) % p.tiles_h, b = px_item / (p.tiles_w * p.tiles_h);
       const int acc_stage = it & 1;
       // per-column vectors of this item -> shared memory (broadcast reads below); overlaps the MMAs of the item.
@@ -283,14 +320,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc_stage]);
+      if (CTA2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty[acc_stage]);
+      } else {
+        mbar_arrive(&tempty[acc_stage]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();                                // nobody leaves while the peer may still signal / multicast
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CTA2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -325,6 +368,13 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
   p.tiles_n = a->n_total / block_n;
   p.col_scale = a->col_scale; p.bias = a->bias; p.noise = a->noise; p.noise_strength = a->noise_strength;
   p.act = a->act; p.act_gain = a->act_gain; p.out = a->out;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // CTA pairs (tcgen05 cta_group::2): 128-column tiles, an even number of pixel blocks, enough pair items for every TPC
+  const int tiles_px_all = p.tiles_w * p.tiles_h * a->B;
+  const bool cta2 = g_tuning.halo_cta2 && block_n == 128 && tiles_px_all % 2 == 0 && sms % 2 == 0 &&
+                    (tiles_px_all / 2) * p.tiles_n >= sms / 2;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
@@ -337,7 +387,7 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
     const uint64_t K = 9ull * a->Cin;
     const uint64_t dims[2] = {K, (uint64_t)a->n_total};
     const uint64_t strides[2] = {0, K * 2};
-    const uint32_t box[2] = {64, (uint32_t)block_n};
+    const uint32_t box[2] = {64, (uint32_t)(cta2 ? block_n / 2 : block_n)};       // pair: each CTA stages half the rows
     int rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -345,23 +395,40 @@ int conv_halo_launch(const tbg_conv_args* a, cudaStream_t stream) {
   p.a_stages = g_tuning.halo_a_stages;
   p.b_stages = g_tuning.halo_b_stages;
   const size_t epi_bytes = kHaloEpiWarps * (kHVecWarp + (p.staged ? kHStgWarp : 0u));
+  const size_t b_stage = (size_t)(cta2 ? block_n / 2 : block_n) * 128;
+  if (cta2) p.b_stages = 2 * p.b_stages > kHaloMaxB ? kHaloMaxB : 2 * p.b_stages;      // half-size boxes: same bytes in flight
   auto smem_need = [&]() {
-    return (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * block_n * 128 + 512 + epi_bytes + 1024;
+    return (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * b_stage + 512 + epi_bytes + 1024;
   };
   while (smem_need() > 227 * 1024 && p.b_stages > 2) --p.b_stages;
   while (smem_need() > 227 * 1024 && p.a_stages > 2) --p.a_stages;
   const size_t smem_bytes = smem_need();
   static bool attr_set = false;
   if (!attr_set) {
-    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   TBG_CHECK_ARG(smem_bytes <= 227 * 1024, "tbg_conv2d_igemm(halo): shared memory budget exceeded (%zu)", smem_bytes);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int total = p.tiles_w * p.tiles_h * a->B * p.tiles_n;
-  conv3x3_halo_kernel<<<total < sms ? total : sms, kHaloThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  if (cta2) {
+    // one cluster of two CTAs per TPC; every pair walks the pair items round-robin
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sms, 1, 1);
+    cfg.blockDim = dim3(kHaloThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TBG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true>, tmA, tmB, p));
+  } else {
+    const int total = tiles_px_all * p.tiles_n;
+    conv3x3_halo_kernel<false><<<total < sms ? total : sms, kHaloThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  }
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;

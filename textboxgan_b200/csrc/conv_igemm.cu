@@ -516,6 +516,7 @@ extern "C" int tbg_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "halo_b_stages")) g_tuning.halo_b_stages = value < 2 ? 2 : (value > 8 ? 8 : value);
   else if (!strcmp(key, "halo_staged")) g_tuning.halo_staged = value != 0;
   else if (!strcmp(key, "wgrad_halo")) g_tuning.wgrad_halo = value != 0;
+  else if (!strcmp(key, "halo_cta2")) g_tuning.halo_cta2 = value != 0;
   else return set_error(TBG_ERR_INVALID_ARG, "tbg_set_tuning: unknown key '%s'", key);
   return TBG_OK;
 }
@@ -530,5 +531,6 @@ extern "C" int tbg_get_tuning(const char* key) {
   if (!strcmp(key, "halo_b_stages")) return g_tuning.halo_b_stages;
   if (!strcmp(key, "halo_staged")) return g_tuning.halo_staged;
   if (!strcmp(key, "wgrad_halo")) return g_tuning.wgrad_halo;
+  if (!strcmp(key, "halo_cta2")) return g_tuning.halo_cta2;
   return -1;
 }

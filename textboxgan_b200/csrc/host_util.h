@@ -69,6 +69,7 @@ struct Tuning {
   int halo_b_stages = 4;       // conv3x3_halo: weight boxes in flight (N x 128 B each)
   int halo_staged = 1;         // conv3x3_halo epilogue: stores transposed through shared memory
   int wgrad_halo = 1;          // 3x3 stride-1 weight gradients on the halo-reuse kernel when it applies
+  int halo_cta2 = 0;           // conv3x3_halo: CTA pairs (tcgen05 cta_group::2) on 128-column tiles
   int lstm_cluster = 1;        // LSTM whole-sequence kernels on 4-CTA clusters with smem-resident W_hh
 };
 extern Tuning g_tuning;
