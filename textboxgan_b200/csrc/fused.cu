@@ -11,6 +11,9 @@
 //
 // Layout: NHWC bf16 activations, 8 channels (16 bytes) per thread, fp32 math.  Reductions over
 // pixels are done per CTA in registers and combined with fp32 atomics into [B, C] buffers.
+#include <map>
+#include <tuple>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -797,21 +800,51 @@ struct RedGeom {
   int threads, rows, pix_per_cta, chunks;
   size_t smem;
 };
-static RedGeom red_geom(int B, int hw, int c8, int per_elem_floats) {
+// Grid of the "stream over the pixels of a sample + reduce per (sample, channel)" kernels: (chunks, B) CTAs of rows x c8
+// threads.  The chunk count is chosen against the number of CTAs the GPU holds at once for THIS kernel (occupancy query,
+// cached): B * chunks just above one wave runs a second, nearly empty wave — with the former "~4 CTAs per SM" rule
+// bias_act_bwd<2> at batch 64 launched 640 CTAs on 444 slots = 72 % wave efficiency (profiles/r02ai_perf_pointwise.log).
+static RedGeom red_geom(int B, int hw, int c8, int per_elem_floats, const void* kernel) {
   RedGeom g;
   int rows = 256 / c8;
   if (rows < 1) rows = 1;
   if (rows > hw) rows = hw;
   g.rows = rows;
   g.threads = rows * c8;
-  // aim at ~4 CTAs per SM overall
-  int chunks = (4 * sms() + B - 1) / B;
-  int max_chunks = (hw + rows - 1) / rows;
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  g.pix_per_cta = (hw + chunks - 1) / chunks;
-  g.chunks = (hw + g.pix_per_cta - 1) / g.pix_per_cta;
   g.smem = static_cast<size_t>(rows) * c8 * 8 * per_elem_floats * sizeof(float);
+  static std::map<std::tuple<const void*, int, size_t>, int> occ;
+  const auto key = std::make_tuple(kernel, g.threads, g.smem);
+  auto it = occ.find(key);
+  if (it == occ.end()) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, g.threads, g.smem) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 2;
+    }
+    it = occ.emplace(key, n).first;
+  }
+  const long long slots = static_cast<long long>(it->second) * sms();
+  const int max_chunks = (hw + rows - 1) / rows;
+  int cmax = static_cast<int>((4 * slots + B - 1) / B);
+  if (cmax > max_chunks) cmax = max_chunks;
+  if (cmax < 1) cmax = 1;
+  // cost model: waves x (pixel-row iterations of one CTA + its fixed cost: launch, shared-memory reduction, atomics ~ 16
+  // iterations); more, smaller CTAs only pay while they fill the waves better
+  int best = 1;
+  double best_t = 1e300;
+  for (int c = 1; c <= cmax; ++c) {
+    const int ppc = (hw + c - 1) / c;
+    const int cc = (hw + ppc - 1) / ppc;                   // chunks actually launched
+    const long long total = static_cast<long long>(B) * cc;
+    const long long waves = (total + slots - 1) / slots;
+    const double t = static_cast<double>(waves) * (static_cast<double>((ppc + rows - 1) / rows) + 16.0);
+    if (t < best_t - 1e-9) {
+      best_t = t;
+      best = c;
+    }
+  }
+  g.pix_per_cta = (hw + best - 1) / best;
+  g.chunks = (hw + g.pix_per_cta - 1) / g.pix_per_cta;
   return g;
 }
 
@@ -844,7 +877,7 @@ extern "C" int tbg_modulate_bwd(const void* gxs, const void* x, const float* s, 
   TBG_CHECK_ARG(TBG_ALIGNED16(gxs) && TBG_ALIGNED16(x) && TBG_ALIGNED16(s) && TBG_ALIGNED16(gx),
                 "tbg_modulate_bwd: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, C / 8, 1);
+  const RedGeom g = red_geom(B, HW, C / 8, 1, reinterpret_cast<const void*>(&modulate_bwd_kernel));
   modulate_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
       reinterpret_cast<const uint4*>(gxs), reinterpret_cast<const uint4*>(x), s, reinterpret_cast<uint4*>(gx), gs, HW,
       C / 8, g.pix_per_cta);
@@ -858,7 +891,7 @@ extern "C" int tbg_rowdot(const void* a, const void* b, float* out, int B, int H
   TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_rowdot: bad shape B=%d HW=%d C=%d", B, HW, C);
   TBG_CHECK_ARG(TBG_ALIGNED16(a) && TBG_ALIGNED16(b), "tbg_rowdot: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, C / 8, 1);
+  const RedGeom g = red_geom(B, HW, C / 8, 1, reinterpret_cast<const void*>(&modulate_bwd_kernel));
   modulate_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), nullptr, nullptr, out, HW, C / 8, g.pix_per_cta);
   count_launch();
@@ -899,14 +932,17 @@ extern "C" int tbg_bias_act_bwd(const void* g_out, const void* out, const void* 
   TBG_CHECK_ARG(gain > 0.f, "tbg_bias_act_bwd: gain must be positive");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int mode = S1 == nullptr ? 0 : ((Spre != nullptr || noise != nullptr) ? 2 : 1);
-  const RedGeom g = red_geom(B, HW, C / 8, mode == 2 ? 3 : 1);
   static bool attr = false;
-  if (!attr) {
+  if (!attr) {                                       // before the occupancy query inside red_geom
     cudaFuncSetAttribute(bias_act_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(bias_act_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
+  const RedGeom g = red_geom(B, HW, C / 8, mode == 2 ? 3 : 1,
+                             mode == 2 ? reinterpret_cast<const void*>(&bias_act_bwd_kernel<2>)
+                                       : (mode == 1 ? reinterpret_cast<const void*>(&bias_act_bwd_kernel<1>)
+                                                    : reinterpret_cast<const void*>(&bias_act_bwd_kernel<0>)));
   const dim3 grid(g.chunks, B);
 #define TBG_BAB(M, SMEM)                                                                                                  \
   bias_act_bwd_kernel<M><<<grid, g.threads, SMEM, stream>>>(                                                              \
@@ -931,13 +967,15 @@ extern "C" int tbg_bias_act_rgb_bwd(const void* g_out, const void* out, const fl
   TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out) && TBG_ALIGNED16(d) && TBG_ALIGNED16(gy0),
                 "tbg_bias_act_rgb_bwd: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, C / 8, 6);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(bias_act_rgb_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(bias_act_rgb_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
+  const RedGeom g = red_geom(B, HW, C / 8, 6,
+                             g_out != nullptr ? reinterpret_cast<const void*>(&bias_act_rgb_bwd_kernel<true>)
+                                              : reinterpret_cast<const void*>(&bias_act_rgb_bwd_kernel<false>));
   TBG_CHECK_ARG(g.smem <= 96 * 1024, "tbg_bias_act_rgb_bwd: C=%d needs too much shared memory", C);
   const dim3 grid(g.chunks, B);
   if (g_out != nullptr)
@@ -975,12 +1013,12 @@ extern "C" int tbg_torgb_bwd(const void* x, const float* ws, const float* gy, vo
   TBG_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && B >= 1 && HW >= 1, "tbg_torgb_bwd: bad shape B=%d HW=%d C=%d", B, HW, C);
   TBG_CHECK_ARG(TBG_ALIGNED16(x) && TBG_ALIGNED16(gx), "tbg_torgb_bwd: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, C / 8, 3);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
+  const RedGeom g = red_geom(B, HW, C / 8, 3, reinterpret_cast<const void*>(&torgb_bwd_kernel));
   torgb_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(reinterpret_cast<const uint4*>(x), ws, gy,
                                                                       reinterpret_cast<uint4*>(gx), gws, HW, C / 8,
                                                                       g.pix_per_cta);
@@ -1087,12 +1125,12 @@ extern "C" int tbg_fromrgb_bwd(const float* img, const float* w, const void* g_o
                 "tbg_fromrgb_bwd: C=%d must be 8 * a power of two <= 256", C);
   TBG_CHECK_ARG(TBG_ALIGNED16(g_out) && TBG_ALIGNED16(out), "tbg_fromrgb_bwd: 16-byte alignment required");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  const RedGeom g = red_geom(B, HW, c8, 4);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(fromrgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
+  const RedGeom g = red_geom(B, HW, c8, 4, reinterpret_cast<const void*>(&fromrgb_bwd_kernel));
   fromrgb_bwd_kernel<<<dim3(g.chunks, B), g.threads, g.smem, stream>>>(
       img, w, reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(out), gimg, gw, gb, HW, c8, g.pix_per_cta,
       coef, gain, gw != nullptr);
