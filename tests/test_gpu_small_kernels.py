@@ -400,3 +400,40 @@ def test_lin_conv_triple_first_and_second_derivatives_vs_reference_convolution(k
     print(kind, "rel-L2 of (y, J, d/dx, d/dw):", errs)
     assert ref[0].shape == got[0].shape
     assert errs[0] < 1e-2 and errs[1] < 1e-2 and errs[2] < 3e-2 and errs[3] < 3e-2, errs
+
+
+def test_training_data_loader_device_transform_on_gpu(tmp_path):
+    """Row f2 on the device: TrainingDataLoader(device_transform=True) — host PNG decode, one packed host-to-device copy, one
+    tbg_batch_resize_normalize launch per batch — against the host cv2 transform of the same stream (same seed, same
+    order): labels identical, images within one uint8 level (cv2's fixed-point bilinear), zero pad exact."""
+    import os
+
+    import numpy as np
+    from common import small_cfg
+    from textboxgan_b200.data_loader import TrainingDataLoader
+
+    cv2 = pytest.importorskip("cv2")
+    cfg = small_cfg(2)
+    boxes = tmp_path / "text_boxes"
+    boxes.mkdir()
+    rng = np.random.RandomState(3)
+    words = ["Hi", "a,b", "World!", "x", "Text", "Boxes"]
+    lines = []
+    for i, w in enumerate(words):
+        cv2.imwrite(str(boxes / f"{i}.png"), rng.randint(0, 256, size=(17 + 3 * i, 25 + 9 * len(w), 3), dtype=np.uint8))
+        lines.append(f"{i}.png,{w}\n")
+    (boxes / "annotations_filtered.txt").write_text("".join(lines))
+    host = TrainingDataLoader(cfg, str(boxes), None, device=DEV, seed=5)
+    devl = TrainingDataLoader(cfg, str(boxes), None, device=DEV, seed=5, device_transform=True)
+    a = list(host.load_dataset(batch_size=3, repeat=False))
+    b = list(devl.load_dataset(batch_size=3, repeat=False))
+    assert len(a) == len(b) == 2
+    for (ra, _, ia, la), (rb, _, ib, lb) in zip(a, b):
+        assert torch.equal(ia, ib) and torch.equal(la, lb)
+        assert rb.is_cuda and rb.shape == ra.shape and rb.dtype == torch.float32
+        d = (ra - rb).abs()
+        assert float(d.max()) <= 1.0 / 127.5 + 1e-6
+        lens = (ia > 0).sum(1)
+        for i in range(ra.shape[0]):
+            wpx = int(cfg.char_width * int(lens[i]))
+            assert float(rb[i, :, :, wpx:].abs().max()) == 0.0
