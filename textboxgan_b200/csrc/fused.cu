@@ -461,11 +461,26 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
 // The kernel is symmetric, so the adjoint is the same call with off' = -3 - off and in/out swapped.
 // ---------------------------------------------------------------------------------------------
 static constexpr int kFirCols = 32, kFirStrip = 32;   // CTA: 32 output columns x 8 channel vectors, a strip of 32 rows
+static constexpr int kFirRing = 8, kFirAhead = 6;     // fir4_kernel: input rows staged in shared memory / copies in flight
 
-// 4 x 4 FIR [1,3,3,1] x [1,3,3,1] * scale on NHWC bf16 with the optional layer epilogue.  No shared memory: thread
-// (x, 8-channel vector) walks down a strip of output rows keeping the last four horizontally filtered rows in registers;
-// the four horizontal taps of a row are four fully coalesced 16-byte loads (neighbouring threads re-read the same
-// pixels: L1 hits), so HBM sees each input element once per 32-column tile (+3 halo columns, +3 halo rows per strip).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  // 16-byte global -> shared copy that bypasses registers; src-size 0 writes zeros (out-of-bounds taps)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 4 x 4 FIR [1,3,3,1] x [1,3,3,1] * scale on NHWC bf16 with the optional layer epilogue.
+// Thread (x, 8-channel vector) walks down a strip of output rows keeping the last four horizontally filtered rows in
+// registers.  The round-2 version loaded the four horizontal taps of a row straight from global memory: three of the
+// four are L1 hits, so a warp had only 512 UNIQUE bytes in flight per row and the kernel sat at 0.48 of HBM, bound by
+// memory latency (profiles/r02ai_perf_pointwise.log).  Now every input row of the CTA's tile (35 pixels x 64 channels) is
+// copied ONCE with cp.async into a shared-memory ring, six rows ahead of the row being filtered (zero-filled outside the
+// tensor), and the taps are conflict-free 16-byte shared-memory reads.
 // EPI = false: bare filter (the FIR adjoint of the up layers' backward pass, the blur in front of the strided
 // discriminator convolutions) with a smaller register footprint.
 template <bool EPI>
@@ -473,29 +488,51 @@ __global__ void __launch_bounds__(256)
 fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int IW, int OH, int OW, int c8, int offy,
             int offx, float scale, const float* __restrict__ d, const float* __restrict__ noise,
             const float* __restrict__ ns, const float* __restrict__ bias, int act, float gain, int cgroups) {
+  __shared__ uint4 ring[kFirRing][kFirCols + 3][8];
   const int x0 = blockIdx.x * kFirCols, y0 = blockIdx.y * kFirStrip;
   const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
   const int v = threadIdx.x & 7, xl = threadIdx.x >> 3;
   const int x = x0 + xl, cv = cg * 8 + v;
-  if (x >= OW || cv >= c8) return;
-  const uint4* src = in + static_cast<long long>(b) * IH * IW * c8 + cv;
-  const int ix0 = x + offx;
-  // horizontally filtered input row iy (zero outside the tensor)
-  auto hrow = [&](int iy, float (&h)[8]) {
+  const bool mine = x < OW && cv < c8;                     // this thread owns an output column (all threads copy / sync)
+  const uint4* src = in + static_cast<long long>(b) * IH * IW * c8;
+  const int rows_out = min(kFirStrip, OH - y0);
+  const int rows_in = rows_out + 3;
+  // input row r of the tile (tensor row y0 + offy + r) -> ring slot r % kFirRing; one commit group per row, always.
+  // Every thread copies pixel column xl (and threads 0..23 also one of the three halo columns 32..34); everything that
+  // does not depend on the row is hoisted: a copy costs one address add and one predicate per row.
+  const int ix_a = x0 + offx + xl, ix_b = ix_a + kFirCols;
+  const bool ok_a = cv < c8 && ix_a >= 0 && ix_a < IW;
+  const bool has_b = xl < 3;
+  const bool ok_b = has_b && cv < c8 && ix_b >= 0 && ix_b < IW;
+  const uint4* const pa = ok_a ? src + static_cast<long long>(ix_a) * c8 + cv : src;
+  const uint4* const pb = ok_b ? src + static_cast<long long>(ix_b) * c8 + cv : src;
+  const long long row_stride = static_cast<long long>(IW) * c8;
+  constexpr uint32_t kSlotBytes = (kFirCols + 3) * 8 * 16;
+  const uint32_t sa = smem_u32(&ring[0][xl][v]), sb = smem_u32(&ring[0][kFirCols + (xl % 3)][v]);
+  auto fetch = [&](int r) {
+    if (r < rows_in) {
+      const int iy = y0 + offy + r;
+      const bool row_ok = iy >= 0 && iy < IH;
+      const long long ro = row_ok ? static_cast<long long>(iy) * row_stride : 0;
+      const uint32_t so = static_cast<uint32_t>(r % kFirRing) * kSlotBytes;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + so), "l"(pa + ro), "r"(ok_a && row_ok ? 16 : 0)
+                   : "memory");
+      if (has_b)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + so), "l"(pb + ro),
+                     "r"(ok_b && row_ok ? 16 : 0)
+                     : "memory");
+    }
+    cp_async_commit();
+  };
+  // horizontally filtered input row r, from shared memory
+  auto hrow = [&](int r, float (&h)[8]) {
+    const uint4* row = &ring[r % kFirRing][xl][v];
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = 0.f;
-    if (iy < 0 || iy >= IH) return;
-    const uint4* row = src + static_cast<long long>(iy) * IW * c8;
-    uint4 t[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ix = ix0 + k;
-      t[k] = (ix >= 0 && ix < IW) ? __ldg(row + static_cast<long long>(ix) * c8) : make_uint4(0u, 0u, 0u, 0u);
-    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
-      unpack8(t[k], f);
+      unpack8(row[k * 8], f);
       const float wk = (k == 0 || k == 3) ? 1.f : 3.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) h[i] = fmaf(f[i], wk, h[i]);
@@ -507,46 +544,57 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
     nsv = (noise != nullptr) ? __ldg(ns) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      dv[i] = (d != nullptr) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) * scale : scale;
-      bv[i] = (bias != nullptr) ? __ldg(bias + cv * 8 + i) : 0.f;
+      dv[i] = (d != nullptr && cv < c8) ? __ldg(d + (static_cast<long long>(b) * c8 + cv) * 8 + i) * scale : scale;
+      bv[i] = (bias != nullptr && cv < c8) ? __ldg(bias + cv * 8 + i) : 0.f;
     }
   }
+#pragma unroll
+  for (int r = 0; r < kFirAhead; ++r) fetch(r);
   float win[4][8];
-  hrow(y0 + offy + 0, win[0]);
-  hrow(y0 + offy + 1, win[1]);
-  hrow(y0 + offy + 2, win[2]);
-  const int y_end = min(y0 + kFirStrip, OH);
-  for (int yb = y0; yb < y_end; yb += 4) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    cp_async_wait<kFirAhead - 1>();
+    __syncthreads();
+    hrow(r, win[r]);
+    fetch(r + kFirAhead);
+  }
+  for (int yb = 0; yb < rows_out; yb += 4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {          // q is a compile-time constant: the ring indices below stay in registers
-    const int y = yb + q;
-    if (y >= y_end) return;
-    hrow(y + offy + 3, win[(q + 3) & 3]);
-    float acc[8];
+      const int yy = yb + q;
+      if (yy >= rows_out) break;           // uniform over the CTA
+      cp_async_wait<kFirAhead - 1>();
+      __syncthreads();
+      hrow(yy + 3, win[(q + 3) & 3]);
+      fetch(yy + 3 + kFirAhead);
+      if (!mine) continue;
+      const int y = y0 + yy;
+      float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      acc[i] = win[q & 3][i] + win[(q + 3) & 3][i] + 3.f * (win[(q + 1) & 3][i] + win[(q + 2) & 3][i]);
-    if (EPI) {
+      for (int i = 0; i < 8; ++i)
+        acc[i] = win[q & 3][i] + win[(q + 3) & 3][i] + 3.f * (win[(q + 1) & 3][i] + win[(q + 2) & 3][i]);
+      if (EPI) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
-      if (noise != nullptr) {
-        const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
+        for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
+        if (noise != nullptr) {
+          const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += nz;
+          for (int i = 0; i < 8; ++i) acc[i] += nz;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float o = acc[i] + bv[i];
+          if (act == 1) o = o > 0.f ? o : 0.2f * o;
+          acc[i] = o * gain;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= scale;
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float o = acc[i] + bv[i];
-        if (act == 1) o = o > 0.f ? o : 0.2f * o;
-        acc[i] = o * gain;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] *= scale;
-    }
-    out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
+      out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
     }
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
