@@ -50,6 +50,8 @@ struct ConvKernelParams {
 static constexpr uint32_t kABytes = 128 * 128;  // 128 pixels x 64 bf16
 static constexpr int kMaxStages = 8;
 
+static constexpr int kEpiAffine = 1, kEpiRes = 2, kEpiMask = 4, kEpiF32 = 8, kEpiAll = 15;
+
 template <int EPI>
 __global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -179,14 +181,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Eight warps: warp e may read TMEM lanes 32*(e%4).. (its quadrant = 32 tile rows); the two warps of a quadrant take
     // alternate 32-column groups.  One warp per scheduler runs this code latency-bound (ncu: ~400 dependent instructions
     // per 32 x 32 block with every feature tested at run time, profiles/r02q_igemm_epilogue.txt), so the feature set is a
-    // template parameter: EPI 0 = bare bf16 store, 1 = column scale / noise / bias / activation, 2 = everything.
+    // template parameter (bit mask): kEpiAffine = column scale / noise / bias / activation, kEpiRes = residual,
+    // kEpiMask = ReLU-backward mask, kEpiF32 = fp32 output; 0 = bare bf16 store.  Instantiated: the combinations the
+    // training step uses (0, affine, affine + residual, mask, residual + mask) and the general one.
     const int e = warp - 4;
     const int quad = e & 3, grp = e >> 2;
     const int r = quad * 32 + lane;
     const int w_in = r % bw;
     const int h_in = (r / bw) % bh;
     const int n_in = r / (bw * bh);
-    const float nstr = (EPI >= 1 && p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
+    const float nstr = ((EPI & kEpiAffine) && p.noise != nullptr) ? __ldg(p.noise_strength) : 0.f;
     const bool has_up = (p.up_h | p.up_w) != 0;
     const int nj = p.block_n / 32;
     int it = 0;
@@ -236,9 +240,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           continue;
         }
-        const float nz = (p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
-        const float* cs = p.col_scale ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
-        const float* bs = p.bias ? p.bias + c0 : nullptr;
+        const float nz = ((EPI & kEpiAffine) && p.noise != nullptr) ? __ldg(p.noise + pix) * nstr : 0.f;
+        const float* cs = ((EPI & kEpiAffine) && p.col_scale) ? p.col_scale + static_cast<size_t>(b) * p.cout + c0 : nullptr;
+        const float* bs = ((EPI & kEpiAffine) && p.bias) ? p.bias + c0 : nullptr;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
@@ -250,8 +254,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
             f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
           }
+          if (EPI & kEpiAffine) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] += nz;
+            for (int i = 0; i < 8; ++i) f[i] += nz;
+          }
           if (bs) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g * 8));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g * 8 + 4));
@@ -259,7 +265,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
           float rres[8];
-          if (EPI == 2 && p.residual) {
+          if ((EPI & kEpiRes) && p.residual) {
             const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + off + g * 8));
             const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -273,20 +279,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
             }
           }
-          if (p.act == 1) {
+          if (EPI & kEpiAffine) {
+            if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
-          } else if (p.act == 2) {
+              for (int i = 0; i < 8; ++i) f[i] = (f[i] > 0.f ? f[i] : 0.2f * f[i]);
+            } else if (p.act == 2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] *= p.act_gain;
-          if (EPI == 2 && p.residual && !p.res_first) {
+          if ((EPI & kEpiRes) && p.residual && !p.res_first) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = (f[i] + rres[i]) * p.res_scale;
           }
-          if (EPI == 2 && p.relu_mask) {   // gradient of a ReLU whose output is relu_mask (fused ReLU backward)
+          if ((EPI & kEpiMask) && p.relu_mask) {   // gradient of a ReLU whose output is relu_mask (fused ReLU backward)
             const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + off + g * 8));
             const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
 #pragma unroll
@@ -296,7 +304,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (!(mf.y > 0.f)) f[2 * i + 1] = 0.f;
             }
           }
-          if (EPI == 2 && p.out_fp32) {
+          if ((EPI & kEpiF32) && p.out_fp32) {
             float* o = reinterpret_cast<float*>(p.out) + off + g * 8;
             *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
             *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -485,21 +493,33 @@ extern "C" int tbg_conv2d_igemm(const tbg_conv_args* a, void* stream_v) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define TBG_IGEMM_ATTR(E) \
+  TBG_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    TBG_IGEMM_ATTR(0);
+    TBG_IGEMM_ATTR(kEpiAffine);
+    TBG_IGEMM_ATTR(kEpiAffine | kEpiRes);
+    TBG_IGEMM_ATTR(kEpiMask);
+    TBG_IGEMM_ATTR(kEpiRes | kEpiMask);
+    TBG_IGEMM_ATTR(kEpiAll);
+#undef TBG_IGEMM_ATTR
     attr_set = true;
   }
   const int total_tiles = tiles_m * p.tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  const bool general = a->residual || a->relu_mask || a->out_fp32;
-  const bool bare = !general && !a->col_scale && !a->noise && !a->bias && a->act == 0 && a->act_gain == 1.f;
-  if (bare)
-    conv_igemm_kernel<0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-  else if (!general)
-    conv_igemm_kernel<1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-  else
-    conv_igemm_kernel<2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+  // an activation with gain 1 and no scale / noise / bias still needs the affine path only when act != 0
+  const bool affine = a->col_scale || a->noise || a->bias || a->act != 0 || a->act_gain != 1.f;
+  const int need = (affine ? kEpiAffine : 0) | (a->residual ? kEpiRes : 0) | (a->relu_mask ? kEpiMask : 0) |
+                   (a->out_fp32 ? kEpiF32 : 0);
+#define TBG_IGEMM_LAUNCH(E) conv_igemm_kernel<E><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p)
+  switch (need) {
+    case 0: TBG_IGEMM_LAUNCH(0); break;
+    case kEpiAffine: TBG_IGEMM_LAUNCH(kEpiAffine); break;
+    case kEpiAffine | kEpiRes: TBG_IGEMM_LAUNCH(kEpiAffine | kEpiRes); break;
+    case kEpiMask: TBG_IGEMM_LAUNCH(kEpiMask); break;
+    case kEpiRes | kEpiMask: TBG_IGEMM_LAUNCH(kEpiRes | kEpiMask); break;
+    default: TBG_IGEMM_LAUNCH(kEpiAll); break;
+  }
+#undef TBG_IGEMM_LAUNCH
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
