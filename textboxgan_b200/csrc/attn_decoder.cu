@@ -53,7 +53,7 @@ __device__ __forceinline__ void block_gemv(const float* __restrict__ x_s, int K,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const uint4* wp = reinterpret_cast<const uint4*>(W) + cv;
-#pragma unroll 8
+#pragma unroll 16
     for (int k = k0; k < k1; ++k) {
       const uint4 wv = __ldg(wp + static_cast<size_t>(k) * ncv);
       const float xk = x_s[k];
