@@ -561,8 +561,14 @@ def _roofline(recs, K, dev):
     achieved = iso_algo / max(iso_secs, 1e-12) / 1e12
     per_shape.sort(key=lambda r: -r["algorithmic_gflop"] * r["launches_per_step"])
     return {
-        "bound": "tensor", "kernel": "conv_igemm_kernel (modulated conv2d forward + input-gradient launches)",
+        "bound": "tensor",
+        "kernel": "tbg_conv2d_igemm entry on the modulated conv2d forward + input-gradient launches of one iteration "
+                  "(conv3x3_halo_kernel for the 3x3 stride-1 layers, conv_igemm_kernel for the strided ones)",
         "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+        # the single largest launch of that set (conv3x3_halo_kernel on the top-resolution layer), same timing method
+        "dominant_launch": ({"x": per_shape[0]["x"], "w": per_shape[0]["w"], "us": per_shape[0]["us"],
+                             "achieved": per_shape[0]["algorithmic_tflops"],
+                             "frac": per_shape[0]["algorithmic_tflops"] / burst} if per_shape else None),
         "peak_source": f"{which} bf16_tflops (burst: the launches are timed in isolation), MEASURED_PEAKS.json",
         "method": "every modconv launch configuration of one plain iteration re-issued 20x back-to-back over rotating "
                   "inputs > L2, CUDA events on the launching stream; FLOPs = algorithmic (SURVEY 8d); achieved = sum of "
