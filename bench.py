@@ -308,11 +308,19 @@ def run_ours(args) -> None:
         g_clone.set_as_moving_average_of(G)      # train.py:208 — part of every iteration
         return out
 
+    # end-to-end input path = the Trainer's (train.py): pinned host batches through the package's DevicePrefetcher — the
+    # copy of batch i+1 runs on its copy stream while iteration i computes; every iteration still copies its own inputs
+    from textboxgan_b200.prefetch import DevicePrefetcher
+
+    def host_batches():
+        while True:
+            yield real_h, words_h, labels_h
+
+    feed = DevicePrefetcher(host_batches(), dev)
+
     def step_e2e(i, plain=False):
         do_r1, do_pl = (False, False) if plain else _schedule(i, cfg)
-        r = real_h.to(dev, non_blocking=True)
-        w = words_h.to(dev, non_blocking=True)
-        l = labels_h.to(dev, non_blocking=True)
+        r, w, l = next(feed)
         out = ts.dist_train_step(r, zero, w, l, do_r1, do_pl, cfg.ocr_loss_weight)
         g_clone.set_as_moving_average_of(G)
         packed = torch.stack([*out[0], *out[1], out[2]]).float()

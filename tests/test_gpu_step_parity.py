@@ -231,3 +231,24 @@ def test_cuda_graph_replay_of_all_three_step_variants_interleaved():
         assert 0.05 < vals[1] < 20 and 0.05 < vals[4] < 20, vals           # softplus adversarial losses stay O(1)
     assert ts.g_optimizer.iterations.numpy() == len(schedule) and ts.d_optimizer.iterations.numpy() == len(schedule)
     assert float((G.flat - w_before).abs().max()) > 0
+
+
+def test_device_prefetcher_on_gpu_overlaps_and_delivers_every_batch():
+    """The copy of batch i+1 is issued on the prefetcher's own stream while the consumer works on batch i; every batch
+    arrives intact and in order even when the consumer's stream is busy and host buffers are reused by the producer."""
+    from textboxgan_b200.prefetch import DevicePrefetcher
+
+    host = [torch.randn(64, 3, 64, 256).pin_memory() for _ in range(3)]
+
+    def gen():
+        for i in range(12):
+            yield host[i % 3], torch.zeros(()), torch.full((4,), i, dtype=torch.int32)
+
+    busy = torch.randn(4096, 4096, device=DEV)
+    sums = []
+    for i, (real, z, idx) in enumerate(DevicePrefetcher(gen(), DEV)):
+        assert real.is_cuda and idx.is_cuda and int(idx[0]) == i
+        busy = busy @ busy * 1e-4                      # keep the consumer stream occupied
+        sums.append(float((real.double().sum() - host[i % 3].double().sum()).abs()))
+    torch.cuda.synchronize()
+    assert len(sums) == 12 and max(sums) < 1e-6

@@ -112,3 +112,17 @@ def test_bench_synthetic_inputs_follow_the_loader_contract():
     src = open(os.path.join(ROOT, "bench.py")).read()
     body = src[src.index("def run_ours"):src.index("def main")]
     assert "from oracle" not in body and "import oracle" not in body        # only the cpu_baseline leg calls it
+
+
+def test_device_prefetcher_preserves_order_and_ends():
+    """DevicePrefetcher (the Trainer's input stage): same batches in the same order, scalars passed through, StopIteration
+    at the end; on a CPU device it is a pass-through."""
+    import torch
+    from textboxgan_b200.prefetch import DevicePrefetcher
+
+    batches = [(torch.full((2, 3), float(i)), torch.zeros(()), torch.arange(4) + i, 0.5) for i in range(5)]
+    got = list(DevicePrefetcher(iter(batches), "cpu"))
+    assert len(got) == 5
+    for a, b in zip(got, batches):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and a[3] == 0.5
+    assert list(DevicePrefetcher(iter([]), "cpu")) == []

@@ -130,7 +130,12 @@ class Trainer:
         trackers = [LossTracker(TRAIN_LOSSES, every, log, num_replicas=replicas, printer=self._print)
                     for every, log in zip(freq["print_steps"], freq["log_losses"])]
         val_tracker = LossTracker(["validation_ocr_loss"], num_replicas=replicas, printer=self._print)
-        for batch in self.strategy.experimental_distribute_dataset(self.training_dataset):
+        from .prefetch import DevicePrefetcher
+
+        # this rank's shards, copied to the device one batch ahead of the iteration that consumes them
+        shards = DevicePrefetcher(self.strategy.experimental_distribute_dataset(self.training_dataset),
+                                  self.generator.device)
+        for batch in shards:
             losses = self._one_step(batch)
             step = self.g_optimizer.iterations.numpy()                     # counts generator updates (train.py:211)
             for tracker in trackers:
