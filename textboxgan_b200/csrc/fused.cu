@@ -33,14 +33,17 @@ static int sms() {
 struct bf16x8 {
   uint4 v;
 };
+// bf16 -> fp32 is a 16-bit shift: one instruction per element (shift for the low half, mask for the high half) instead
+// of the byte-permute + shift pair the bf162 intrinsic compiles to; these kernels are instruction-issue bound
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  f[0] = __uint_as_float(v.x << 16);
+  f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16);
+  f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16);
+  f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16);
+  f[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 v;
@@ -498,45 +501,53 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
   const int rows_out = min(kFirStrip, OH - y0);
   const int rows_in = rows_out + 3;
   // input row r of the tile (tensor row y0 + offy + r) -> ring slot r % kFirRing; one commit group per row, always.
-  // Every thread copies pixel column xl (and threads 0..23 also one of the three halo columns 32..34); everything that
-  // does not depend on the row is hoisted: a copy costs one address add and one predicate per row.
+  // Every thread copies pixel column xl (and threads 0..23 also one of the three halo columns 32..34).  The kernel is
+  // issue-bound (ncu: 0.89 instructions per scheduler cycle), so everything row-invariant is hoisted and the per-row
+  // state (source pointers, tensor row, ring slot) is carried incrementally: rows are fetched strictly in order.
   const int ix_a = x0 + offx + xl, ix_b = ix_a + kFirCols;
   const bool ok_a = cv < c8 && ix_a >= 0 && ix_a < IW;
   const bool has_b = xl < 3;
   const bool ok_b = has_b && cv < c8 && ix_b >= 0 && ix_b < IW;
-  const uint4* const pa = ok_a ? src + static_cast<long long>(ix_a) * c8 + cv : src;
-  const uint4* const pb = ok_b ? src + static_cast<long long>(ix_b) * c8 + cv : src;
   const long long row_stride = static_cast<long long>(IW) * c8;
+  int f_iy = y0 + offy;                                    // tensor row of the next fetch
+  int f_left = rows_in;                                    // rows still to fetch
+  const uint4* f_pa = (ok_a ? src + static_cast<long long>(ix_a) * c8 + cv : src) + static_cast<long long>(f_iy) * row_stride;
+  const uint4* f_pb = (ok_b ? src + static_cast<long long>(ix_b) * c8 + cv : src) + static_cast<long long>(f_iy) * row_stride;
   constexpr uint32_t kSlotBytes = (kFirCols + 3) * 8 * 16;
-  const uint32_t sa = smem_u32(&ring[0][xl][v]), sb = smem_u32(&ring[0][kFirCols + (xl % 3)][v]);
-  auto fetch = [&](int r) {
-    if (r < rows_in) {
-      const int iy = y0 + offy + r;
-      const bool row_ok = iy >= 0 && iy < IH;
-      const long long ro = row_ok ? static_cast<long long>(iy) * row_stride : 0;
-      const uint32_t so = static_cast<uint32_t>(r % kFirRing) * kSlotBytes;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + so), "l"(pa + ro), "r"(ok_a && row_ok ? 16 : 0)
+  const uint32_t sa0 = smem_u32(&ring[0][xl][v]), sb0 = smem_u32(&ring[0][kFirCols + (xl % 3)][v]);
+  uint32_t f_so = 0;                                       // byte offset of the ring slot of the next fetch
+  auto fetch = [&]() {
+    if (f_left > 0) {
+      const bool row_ok = f_iy >= 0 && f_iy < IH;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa0 + f_so), "l"(row_ok ? f_pa : src),
+                   "r"(ok_a && row_ok ? 16 : 0)
                    : "memory");
       if (has_b)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + so), "l"(pb + ro),
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb0 + f_so), "l"(row_ok ? f_pb : src),
                      "r"(ok_b && row_ok ? 16 : 0)
                      : "memory");
     }
     cp_async_commit();
+    --f_left;
+    ++f_iy;
+    f_pa += row_stride;
+    f_pb += row_stride;
+    f_so = (f_so == (kFirRing - 1) * kSlotBytes) ? 0u : f_so + kSlotBytes;
   };
-  // horizontally filtered input row r, from shared memory
-  auto hrow = [&](int r, float (&h)[8]) {
-    const uint4* row = &ring[r % kFirRing][xl][v];
+  // horizontally filtered input row, from the ring slot at byte offset h_so (rows are consumed strictly in order):
+  // (t0 + t3) + 3 (t1 + t2)
+  uint32_t h_so = 0;
+  const uint8_t* const ring_mine = reinterpret_cast<const uint8_t*>(&ring[0][xl][v]);
+  auto hrow = [&](float (&h)[8]) {
+    const uint4* row = reinterpret_cast<const uint4*>(ring_mine + h_so);
+    float f0[8], f1[8], f2[8], f3[8];
+    unpack8(row[0], f0);
+    unpack8(row[8], f1);
+    unpack8(row[16], f2);
+    unpack8(row[24], f3);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float f[8];
-      unpack8(row[k * 8], f);
-      const float wk = (k == 0 || k == 3) ? 1.f : 3.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) h[i] = fmaf(f[i], wk, h[i]);
-    }
+    for (int i = 0; i < 8; ++i) h[i] = fmaf(3.f, f1[i] + f2[i], f0[i] + f3[i]);
+    h_so = (h_so == (kFirRing - 1) * kSlotBytes) ? 0u : h_so + kSlotBytes;
   };
   float dv[8], bv[8];
   float nsv = 0.f;
@@ -549,15 +560,19 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
     }
   }
 #pragma unroll
-  for (int r = 0; r < kFirAhead; ++r) fetch(r);
+  for (int r = 0; r < kFirAhead; ++r) fetch();
   float win[4][8];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     cp_async_wait<kFirAhead - 1>();
     __syncthreads();
-    hrow(r, win[r]);
-    fetch(r + kFirAhead);
+    hrow(win[r]);
+    fetch();
   }
+  uint4* optr = out + ((static_cast<long long>(b) * OH + y0) * OW + x) * c8 + cv;     // output row y0 of this thread
+  const long long out_stride = static_cast<long long>(OW) * c8;
+  const float* nptr = (EPI && noise != nullptr) ? noise + (static_cast<long long>(b) * OH + y0) * OW + x : nullptr;
+  asm volatile("" : "+l"(optr));           // opaque to the optimiser: keep it in a register pair
   for (int yb = 0; yb < rows_out; yb += 4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {          // q is a compile-time constant: the ring indices below stay in registers
@@ -565,10 +580,13 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
       if (yy >= rows_out) break;           // uniform over the CTA
       cp_async_wait<kFirAhead - 1>();
       __syncthreads();
-      hrow(yy + 3, win[(q + 3) & 3]);
-      fetch(yy + 3 + kFirAhead);
+      hrow(win[(q + 3) & 3]);
+      fetch();
+      uint4* const o_row = optr;             // carried incrementally: the compiler otherwise re-derives the 64-bit
+      const float* const n_row = nptr;       // address from the block indices every row (~25 instructions)
+      optr += out_stride;
+      if (nptr != nullptr) nptr += OW;
       if (!mine) continue;
-      const int y = y0 + yy;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -576,8 +594,8 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
       if (EPI) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
-        if (noise != nullptr) {
-          const float nz = __ldg(noise + (static_cast<long long>(b) * OH + y) * OW + x) * nsv;
+        if (n_row != nullptr) {
+          const float nz = __ldg(n_row) * nsv;
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i] += nz;
         }
@@ -591,7 +609,7 @@ fir4_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int IH, int I
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= scale;
       }
-      out[((static_cast<long long>(b) * OH + y) * OW + x) * c8 + cv] = pack8(acc);
+      *o_row = pack8(acc);
     }
   }
   cp_async_wait<0>();
