@@ -57,6 +57,10 @@ for (H, W, C) in [(64, 256, 128), (32, 128, 128), (16, 64, 256), (64, 256, 64)]:
     report(f"torgb_bwd {B}x{H}x{W}x{C}", t, 2 * n * 2)
     t = bench(lambda i: K.torgb_skip_fwd(g[i], ws, None, None, None, False), n_rot)
     report(f"torgb_skip_fwd {B}x{H}x{W}x{C}", t, n * 2)
+    yprev = torch.randn(B, H // 2, W // 2, 3, device=dev)
+    wordsi = torch.randint(0, 2, (B, 12), device=dev, dtype=torch.int32)
+    t = bench(lambda i: K.torgb_skip_fwd(g[i], ws, None, yprev, wordsi, True), n_rot)
+    report(f"torgb_skip_fwd {B}x{H}x{W}x{C} + skip + mask, NCHW", t, n * 2)
     # FIR adjoint of an up layer's backward: [B,H,W,C] -> [B,H+2,W+2,C]
     t = bench(lambda i: K.fir4(g[i], (H + 2, W + 2), (-2, -2), 1.0 / 16.0), n_rot)
     report(f"fir4 adjoint {B}x{H}x{W}x{C} -> +2", t, 2 * n * 2)

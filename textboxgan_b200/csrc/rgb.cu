@@ -92,13 +92,11 @@ upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ k, T* 
 // upsample_2d per axis: out[2q] = (x[q-1] + 3 x[q]) / 4, out[2q+1] = (3 x[q] + x[q+1]) / 4 (zero outside).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  // bf16 -> fp32 is a 16-bit shift: one SHL / LOP per value instead of the PRMT pairs of __bfloat1622float2
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
 template <int LPP, int CV>   // lanes per pixel (<= 32), 8-channel vectors per lane (C = LPP * CV * 8)
@@ -163,17 +161,21 @@ torgb_skip_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws,
       o[0] = r0; o[1] = r1; o[2] = r2;
     }
   };
-  constexpr int U = (CV == 1) ? 4 : 2;                // pixels per group and iteration: U independent 16-byte loads in flight
+  // U pixels per group and iteration: U independent 16-byte loads in flight per lane.  The butterfly leaves every lane
+  // of the group with the three sums, so lane u finishes pixel u: ONE pass through the (long, divergent) epilogue per
+  // iteration with U of LPP lanes active instead of U passes with one lane each.
+  constexpr int U = (CV == 1) ? 8 : (CV == 2 ? 4 : 2);
+  static_assert(U <= LPP, "one finishing lane per pixel of the iteration");
   for (int pb = p0; pb < p1; pb += ngrp * U) {        // uniform trip count per CTA: the shuffles below need every lane
     uint4 xv[U][CV];
-    int pp[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      pp[u] = pb + u * ngrp + grp;
-      const size_t pix = static_cast<size_t>(b) * hw + (pp[u] < p1 ? pp[u] : p0);
+      const int p = pb + u * ngrp + grp;
+      const size_t pix = static_cast<size_t>(b) * hw + (p < p1 ? p : p0);
 #pragma unroll
       for (int v = 0; v < CV; ++v) xv[u][v] = __ldg(x + pix * c8 + v * LPP + sub);
     }
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -194,8 +196,10 @@ torgb_skip_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ ws,
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
         a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
-      if (sub == 0 && pp[u] < p1) finish(pp[u], a0, a1, a2);
+      if (sub == u) { m0 = a0; m1 = a1; m2 = a2; }
     }
+    const int pm = pb + sub * ngrp + grp;
+    if (sub < U && pm < p1) finish(pm, m0, m1, m2);
   }
 }
 
@@ -217,6 +221,23 @@ __global__ void image_grad_nhwc_kernel(const float* __restrict__ g, const int* _
     o[1] = keep ? gp[hw] : 0.f;
     o[2] = keep ? gp[2 * static_cast<size_t>(hw)] : 0.f;
   }
+}
+
+// Pixels per CTA of tbg_torgb_skip_fwd: the number of runs per sample (1 .. hw / 64) that minimises
+// waves x (iterations per CTA + a fixed per-CTA cost of ~6 iterations for the weight loads and the launch slot).
+static int torgb_run(int B, int hw, int slots, int pix_per_iter) {
+  int best_run = hw;
+  double best = 1e30;
+  const int max_runs = hw / 64 > 1 ? hw / 64 : 1;
+  for (int r = 1; r <= max_runs; ++r) {
+    const int run = (hw + r - 1) / r;
+    const long long ctas = static_cast<long long>((hw + run - 1) / run) * B;
+    const double waves = static_cast<double>((ctas + slots - 1) / slots);
+    const double cost = waves * ((run + pix_per_iter - 1) / pix_per_iter + 6.0);
+    if (cost < best) { best = cost; best_run = run; }
+    if (ctas > 8LL * slots) break;
+  }
+  return best_run;
 }
 
 }  // namespace tbg
@@ -278,14 +299,21 @@ extern "C" int tbg_torgb_skip_fwd(const void* x, const float* ws, const float* b
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // ~8 CTAs per SM over the whole batch, at least 64 pixels per CTA (weights are re-read per CTA)
-  int ctas_per_sample = (8 * sms + B - 1) / B;
-  int pix_per_cta = (hw + ctas_per_sample - 1) / ctas_per_sample;
-  if (pix_per_cta < 64) pix_per_cta = 64;
-  dim3 grid((hw + pix_per_cta - 1) / pix_per_cta, B);
   const uint4* xv = reinterpret_cast<const uint4*>(x);
-#define TBG_TORGB(LPP, CV) \
-  torgb_skip_fwd_kernel<LPP, CV><<<grid, 256, 0, stream>>>(xv, ws, bias, y_prev, words, out, H, W, mcn, nchw, pix_per_cta)
+  // Runs of pixels per sample sized from the kernel's real occupancy: whole waves of resident CTAs (a 5 % third wave
+  // cost a third of the launch), each CTA long enough (>= 64 pixels) to amortise its 24 weight loads per lane.
+#define TBG_TORGB(LPP, CV)                                                                                              \
+  do {                                                                                                                  \
+    static int occ = 0;                                                                                                 \
+    if (!occ) {                                                                                                         \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, torgb_skip_fwd_kernel<LPP, CV>, 256, 0);                      \
+      if (occ < 1) occ = 1;                                                                                             \
+    }                                                                                                                   \
+    const int pix_per_cta = torgb_run(B, hw, occ * sms, (256 / LPP) * ((CV) == 1 ? 8 : ((CV) == 2 ? 4 : 2)));            \
+    dim3 grid((hw + pix_per_cta - 1) / pix_per_cta, B);                                                                 \
+    torgb_skip_fwd_kernel<LPP, CV><<<grid, 256, 0, stream>>>(xv, ws, bias, y_prev, words, out, H, W, mcn, nchw,         \
+                                                             pix_per_cta);                                              \
+  } while (0)
   switch (C) {
     case 64: TBG_TORGB(8, 1); break;
     case 128: TBG_TORGB(16, 1); break;
