@@ -83,6 +83,7 @@ class TrainingStep:
         self.overlap_reg = True         # path-length / R1 regulariser branches on their own streams (lazy-reg iterations)
         self._reg_streams = {}
         self._side = None
+        self._capture = None            # stream of the eager warm-up of every step variant and of its capture
         self._graphs = {}
         self._static = None
         self._step_weights = None          # fused.StepWeights: grouped weight preparation plan
@@ -149,9 +150,18 @@ class TrainingStep:
         entry = self._graphs.get(key)
         if entry is None:
             # first use of this variant: run it eagerly once (lazy allocations, cuFuncSetAttribute,
-            # optimiser slots), then capture
-            out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0], key[1],
-                                           st["ocr_w"])
+            # optimiser slots), then capture.  The warm-up runs on the stream the capture will use: autograd pins every
+            # node -- including the parameters' gradient accumulators, which outlive the step for as long as a dead
+            # graph awaits garbage collection -- to the stream it was created on, and a node left on the legacy default
+            # stream makes the captured backward wait for it (cudaErrorStreamCaptureImplicit).
+            cs = self._capture_stream(dev)
+            cur = torch.cuda.current_stream(dev)
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0], key[1],
+                                               st["ocr_w"])
+            cur.wait_stream(cs)
+            out.record_stream(cur)
             self._graphs[key] = {"graph": None, "out": out, "warm": 1}
             res = out
         elif entry["graph"] is None:
@@ -159,10 +169,13 @@ class TrainingStep:
                 o.defer_iteration = True
             from . import lib as _lib
 
+            import gc
+
+            gc.collect()                       # dead autograd graphs of earlier eager steps (see the warm-up note above)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             n0 = _lib.load().tbg_launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._capture_stream(dev)):
                 out = self._eager_reduced_step(st["real"], st["ocr_images"], st["words"], st["labels"], key[0],
                                                key[1], st["ocr_w"])
             # launches of this repo's kernels recorded in the graph (replayed on every step)
@@ -179,6 +192,11 @@ class TrainingStep:
             res = entry["out"]
         r = res.unbind(0)
         return (r[0], r[1], r[2]), (r[3], r[4], r[5]), r[6]
+
+    def _capture_stream(self, dev):
+        if self._capture is None:
+            self._capture = torch.cuda.Stream(device=dev)
+        return self._capture
 
     def _side_stream(self, dev):
         if self._side is None:
