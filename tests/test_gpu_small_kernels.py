@@ -19,7 +19,8 @@ def _bf16_round(t):
 
 
 @pytest.mark.parametrize("M,K,N,act,bias", [(128, 512, 512, 1, True), (64, 8192, 512, 1, True), (5, 37, 3, 0, False),
-                                            (768, 32, 256, 2, True), (128, 512, 1, 0, True), (33, 70, 65, 1, True)])
+                                            (768, 32, 256, 2, True), (128, 512, 1, 0, True), (33, 70, 65, 1, True),
+                                            (128, 4096, 64, 1, True), (200, 300, 130, 2, True)])
 def test_dense_kernels_vs_emulated_semantics(M, K, N, act, bias):
     """tbg_dense_fwd / tbg_dense_bwd (Dense.call dense.py:23-29 + bias + activation), exact fp32: 1e-5."""
     from textboxgan_b200 import kernels as Kn

@@ -119,20 +119,33 @@ __global__ void dense_finish_kernel(float* __restrict__ C, long long ldc, int M,
 
 // gpre[m,n] = gy[m,n] * gain * act'(y[m,n]) (the slope is recovered from the sign of the output: gain > 0);
 // gb[n] = bias_coef * sum_m gpre[m,n].  One thread per column, rows streamed (coalesced across the warp).
-__global__ void dense_gpre_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gpre,
-                                  float* __restrict__ gb, int M, int N, int act, float gain, float bias_coef) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+__global__ void __launch_bounds__(256)
+dense_gpre_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gpre,
+                  float* __restrict__ gb, int M, int N, int act, float gain, float bias_coef) {
+  // 32 columns x 8 row groups per CTA: coalesced 128-byte rows, the column sums meet in shared memory
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), tyr = threadIdx.x >> 5;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) {
-    const size_t o = static_cast<size_t>(m) * N + n;
-    float g = gy[o] * gain;
-    if (act == 1) g *= (y[o] > 0.f ? 1.f : 0.2f);
-    else if (act == 2) g = (y[o] > 0.f ? g : 0.f);
-    gpre[o] = g;
-    s += g;
+  if (n < N) {
+#pragma unroll 4
+    for (int m = tyr; m < M; m += 8) {
+      const size_t o = static_cast<size_t>(m) * N + n;
+      float g = gy[o] * gain;
+      if (act == 1) g *= (y[o] > 0.f ? 1.f : 0.2f);
+      else if (act == 2) g = (y[o] > 0.f ? g : 0.f);
+      gpre[o] = g;
+      s += g;
+    }
   }
-  if (gb) gb[n] = s * bias_coef;
+  if (!gb) return;
+  red[tyr][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (tyr == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+    gb[n] = t * bias_coef;
+  }
 }
 
 // Pixel norm of the mapping network (mapping_block.py:15-18): y = x * rsqrt(mean_k x^2 + 1e-8); one warp per row.
@@ -290,7 +303,7 @@ extern "C" int tbg_dense_bwd(const float* x, const float* w, const float* y, con
   TBG_CHECK_ARG(M >= 1 && K >= 1 && N >= 1, "tbg_dense_bwd: bad shape M=%d K=%d N=%d", M, K, N);
   TBG_CHECK_ARG(act >= 0 && act <= 2, "tbg_dense_bwd: act must be 0, 1 or 2");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  dense_gpre_kernel<<<(N + 127) / 128, 128, 0, stream>>>(y, gy, gpre, gb, M, N, act, gain, bias_coef);
+  dense_gpre_kernel<<<(N + 31) / 32, 256, 0, stream>>>(y, gy, gpre, gb, M, N, act, gain, bias_coef);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   DenseEpilogue ep{nullptr, 0.f, 0, 1.f, 0};
