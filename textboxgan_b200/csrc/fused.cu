@@ -261,6 +261,17 @@ bias_act_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict__ o
   }
 }
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  // 16-byte global -> shared copy that bypasses registers; src-size 0 writes zeros (out-of-bounds taps)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // bias_act_bwd of a modulated layer whose output also feeds a ToRGB (synthesis_block.py:143-152): the gradient that
 // reaches `out` is g_out (from the next block, absent on the last one) + g_rgb (x) ws — a rank-3 term that is formed here
@@ -301,21 +312,49 @@ bias_act_rgb_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict
   const float neg_slope = act == 0 ? 1.f : (act == 2 ? 0.f : 0.2f);
   const float g_pos = gain, g_neg = gain * neg_slope;
   const float r_pos = 1.f / gain;
-  if (r < rows) {
-#pragma unroll 2
+  // The two 16-byte streams (g_out, out) go through a thread-private cp.async ring, kRgbStages - 1 pixels ahead: the
+  // 80 accumulator / weight registers leave room for two CTAs of 8 warps per SM only, and with the loads held in
+  // registers (one or two pixels per thread) that is ~32 KB in flight per SM, 0.53 of the HBM rate.  The ring lives in
+  // the shared memory of the final reduction (same size: 6 floats x 8 channels = 2 x 16 B x 6 stages per thread).
+  constexpr int kRgbStages = 6;
+  uint4* ring = reinterpret_cast<uint4*>(red);
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const long long pix0 = static_cast<long long>(b) * hw;
+  auto issue = [&](int p, int slot) {
+    const bool ok = p < p1;
+    const long long idx = (pix0 + (ok ? p : p0)) * c8 + cv;
+    if (HAS_G) cp_async_16(ring + (slot * 2 + 0) * nthr + tid, g_out + idx, ok);
+    cp_async_16(ring + (slot * 2 + 1) * nthr + tid, out + idx, ok);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < kRgbStages - 1; ++st) issue(p0 + r + st * rows, st);
+  {
+    int slot = 0, slot_new = kRgbStages - 1;
+    // per-pixel scalars (image gradient, noise) one pixel ahead in registers
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, nnz = 0.f;
+    if (p0 + r < p1) {
+      const long long pix = pix0 + p0 + r;
+      n0 = __ldg(g_rgb + pix * 3 + 0); n1 = __ldg(g_rgb + pix * 3 + 1); n2 = __ldg(g_rgb + pix * 3 + 2);
+      if (noise != nullptr) nnz = __ldg(noise + pix);
+    }
     for (int p = p0 + r; p < p1; p += rows) {
-      const long long pix = static_cast<long long>(b) * hw + p;
-      const long long idx = pix * c8 + cv;
-      const float r0 = __ldg(g_rgb + pix * 3 + 0), r1 = __ldg(g_rgb + pix * 3 + 1), r2 = __ldg(g_rgb + pix * 3 + 2);
+      issue(p + (kRgbStages - 1) * rows, slot_new);
+      const float r0 = n0, r1 = n1, r2 = n2, nz = nnz;
+      if (p + rows < p1) {
+        const long long pixn = pix0 + p + rows;
+        n0 = __ldg(g_rgb + pixn * 3 + 0); n1 = __ldg(g_rgb + pixn * 3 + 1); n2 = __ldg(g_rgb + pixn * 3 + 2);
+        if (noise != nullptr) nnz = __ldg(noise + pixn);
+      }
+      cp_async_wait<kRgbStages - 1>();
       float g[8], o[8];
       if (HAS_G) {
-        unpack8(__ldg(g_out + idx), g);
+        unpack8(ring[(slot * 2 + 0) * nthr + tid], g);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = 0.f;
       }
-      unpack8(__ldg(out + idx), o);
-      const float nz = (noise != nullptr) ? __ldg(noise + pix) : 0.f;
+      unpack8(ring[(slot * 2 + 1) * nthr + tid], o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         aw[i][0] = fmaf(o[i], r0, aw[i][0]);
@@ -329,9 +368,13 @@ bias_act_rgb_bwd_kernel(const uint4* __restrict__ g_out, const uint4* __restrict
         a3[i] = fmaf(gp, nz, a3[i]);
         g[i] = gp * dv[i];
       }
-      gy0[idx] = pack8(g);
+      gy0[(pix0 + p) * c8 + cv] = pack8(g);
+      slot = slot + 1 == kRgbStages ? 0 : slot + 1;
+      slot_new = slot_new + 1 == kRgbStages ? 0 : slot_new + 1;
     }
   }
+  cp_async_wait<0>();
+  __syncthreads();                          // the reduction buffer below aliases every thread's ring slots
   const int cw = c8 * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -465,17 +508,6 @@ __global__ void torgb_bwd_kernel(const uint4* __restrict__ x, const float* __res
 // ---------------------------------------------------------------------------------------------
 static constexpr int kFirCols = 32, kFirStrip = 32;   // CTA: 32 output columns x 8 channel vectors, a strip of 32 rows
 static constexpr int kFirRing = 8, kFirAhead = 6;     // fir4_kernel: input rows staged in shared memory / copies in flight
-
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
-  // 16-byte global -> shared copy that bypasses registers; src-size 0 writes zeros (out-of-bounds taps)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // 4 x 4 FIR [1,3,3,1] x [1,3,3,1] * scale on NHWC bf16 with the optional layer epilogue.
 // Thread (x, 8-channel vector) walks down a strip of output rows keeping the last four horizontally filtered rows in
