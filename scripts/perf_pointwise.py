@@ -66,3 +66,18 @@ for (H, W, C) in [(64, 256, 128), (32, 128, 128), (16, 64, 256), (64, 256, 64)]:
     report(f"fir4 adjoint {B}x{H}x{W}x{C} -> +2", t, 2 * n * 2)
     t = bench(lambda i: K.fir4(g[i], (H + 2, W + 2), (-2, -2), 1.0 / 64.0), n_rot)
     report(f"fir4 down pre-pass {B}x{H}x{W}x{C}", t, 2 * n * 2)
+
+# FromRGB backward of the discriminator (3 -> 64 channels at the full resolution; fake + real = 2 x batch)
+for Bf in (2 * B, B):
+    H, W, C = 64, 256, 64
+    n = Bf * H * W * C
+    n_rot = max(2, min(8, int(600e6 // (n * 2)) + 1))
+    g = [torch.randn(Bf, H, W, C, device=dev).bfloat16() for _ in range(n_rot)]
+    o = [torch.randn(Bf, H, W, C, device=dev).bfloat16() for _ in range(n_rot)]
+    img = torch.randn(Bf, 3, H, W, device=dev)
+    wf = torch.randn(3, C, device=dev)
+    t = bench(lambda i: K.fromrgb_bwd(img, wf, g[i], o[i], 0.5, 1.4), n_rot)
+    report(f"fromrgb_bwd {Bf}x{H}x{W}x{C} (image + weight gradients)", t, 2 * n * 2 + 2 * Bf * 3 * H * W * 4)
+    bf = torch.randn(C, device=dev)
+    t = bench(lambda i: K.fromrgb_fwd(img, wf, bf, 0.5, 1.4), n_rot)
+    report(f"fromrgb_fwd {Bf}x{H}x{W}x{C}", t, n * 2 + Bf * 3 * H * W * 4)

@@ -626,6 +626,22 @@ def test_fromrgb_kernels_vs_emulated_semantics(B, H, W, C):
     assert gw2 is None and gb2 is None and rel_err(gi2, ri) < 1e-4
 
 
+def test_fromrgb_fwd_channel_counts_outside_the_ladders():
+    """C / 8 that does not divide the block (24, 40 channels) takes the generic kernel: same semantics."""
+    import emu
+    from textboxgan_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(11)
+    for C in (24, 40, 8):
+        img = torch.rand(3, 3, 9, 13, generator=gen) * 2 - 1
+        w = torch.randn(3, C, generator=gen)
+        bias = torch.randn(C, generator=gen) * 0.1
+        out = K.fromrgb_fwd(img.to(DEV), w.to(DEV), bias.to(DEV), 0.5, 1.4)
+        with emu.emulated_kernels(act_dtype=torch.float32):
+            ref = emu.emu_fromrgb_fwd(img, w, bias, 0.5, 1.4)
+        assert rel_err(out.float(), ref) < 1e-2
+
+
 @pytest.mark.parametrize("B,H,W,mcn,cw", [(5, 16, 64, 8, 8), (4, 32, 128, 8, 16), (3, 64, 256, 12, "64/3")])
 def test_crop_resize_kernels_vs_emulated_semantics(B, H, W, mcn, cw):
     """tbg_crop_resize_fwd / bwd (convert_inputs) against the crop + tf.image.resize semantics (fp32, 1e-5), incl.
