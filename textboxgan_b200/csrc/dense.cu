@@ -374,7 +374,7 @@ extern "C" int tbg_word_encoder_bwd(const int* words, const float* mask, float k
   GemmOperand A{emb, 1, E}, Bm{gpre, 1, D};
   int rc = launch_gemm(A, Bm, g_fc_w, D, E, D, M, 1.f, ep, stream);
   if (rc) return rc;
-  dense_gpre_kernel<<<(D + 127) / 128, 128, 0, stream>>>(nullptr, gpre, gpre, g_fc_b, M, D, 0, 1.f, 1.f);
+  dense_gpre_kernel<<<(D + 31) / 32, 256, 0, stream>>>(nullptr, gpre, gpre, g_fc_b, M, D, 0, 1.f, 1.f);
   count_launch();
   TBG_CHECK_CUDA(cudaGetLastError());
   return TBG_OK;
