@@ -295,6 +295,8 @@ def run_ours(args) -> None:
     ts = TrainingStep(G, D, aster, mk(go), mk(go), mk(do), cfg.g_opt["reg_interval"], cfg.d_opt["reg_interval"],
                       torch.zeros((), device=dev), cfg)
     ts.use_cuda_graph = not args.eager      # whole iteration replayed from a CUDA graph (one per schedule variant)
+    if getattr(args, "late_comm", False):
+        ts.overlap_comm = False
 
     real_h, words_h, labels_h = synthetic_inputs(cfg, B, 4444 + rank)          # reference shuffle_seed, config.py:114
     real_h, words_h, labels_h = real_h.pin_memory(), words_h.pin_memory(), labels_h.pin_memory()
@@ -618,6 +620,8 @@ def main():
     ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--plain-only", action="store_true", help="time non-regularised iterations only")
     ap.add_argument("--no-roofline", action="store_true", help="short line: skip the roofline / cpu_baseline passes")
+    ap.add_argument("--late-comm", action="store_true",
+                    help="experiment: all gradient all-reduces after the last backward pass (TrainingStep.overlap_comm = False)")
     ap.add_argument("--no-scaling-base", action="store_true", help="skip the configs[3]-per-GPU-batch child measurement")
     args = ap.parse_args()
     if args.impl == "reference":

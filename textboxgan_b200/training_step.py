@@ -81,6 +81,7 @@ class TrainingStep:
         self.batch_d_calls = True       # evaluate D(fake) and D(real) as one concatenated pass
         self.overlap_ocr = True         # OCR branch on a second CUDA stream (parallel sub-graph when captured)
         self.overlap_reg = True         # path-length / R1 regulariser branches on their own streams (lazy-reg iterations)
+        self.overlap_comm = True        # start each group's gradient all-reduce as soon as its backward pass is done
         self._reg_streams = {}
         self._side = None
         self._capture = None            # stream of the eager warm-up of every step variant and of its capture
@@ -303,7 +304,7 @@ class TrainingStep:
         # order of the tape.gradient calls is free).
         updates = not draws.get("skip_updates")
         d_grads = torch.autograd.grad(reg_d_loss, d_vars, retain_graph=True, allow_unused=True)
-        if updates:
+        if updates and self.overlap_comm:
             self.d_optimizer.begin_apply(D, self._d_names, list(d_grads))
         g_fake_ocr = None
         if side is not None:
@@ -315,7 +316,7 @@ class TrainingStep:
                 _fused.backward_batch_limit("dconv", fake_images.shape[0] if self._batched_d else 1 << 30):
             # only generator variables are wanted from this pass
             g_grads = torch.autograd.grad(reg_g_loss, g_vars, retain_graph=True, allow_unused=True)
-        if updates:
+        if updates and self.overlap_comm:
             self.g_optimizer.begin_apply(G, self._g_names, list(g_grads))
         if g_fake_ocr is not None:
             main.wait_stream(side)
@@ -327,11 +328,24 @@ class TrainingStep:
 
         if updates:
             # reference order of the three updates (:194-213): generator group, OCR group (synthesis is updated twice), D
-            self.g_optimizer.finish_apply()
-            if o_grads is not None:
-                self.ocr_optimizer.begin_apply(G, self._ocr_names, list(o_grads))
-                self.ocr_optimizer.finish_apply()
-            self.d_optimizer.finish_apply()
+            if not self.overlap_comm:
+                # all three cross-replica sums after the last backward pass, back to back on the communication stream:
+                # they then overlap only the (many-CTA, bandwidth-bound) Adam kernels, never the persistent one-CTA-per-SM
+                # tensor-core kernels, which wait for a whole wave when NCCL holds a few SMs
+                self.g_optimizer.begin_apply(G, self._g_names, list(g_grads))
+                if o_grads is not None:
+                    self.ocr_optimizer.begin_apply(G, self._ocr_names, list(o_grads))
+                self.d_optimizer.begin_apply(D, self._d_names, list(d_grads))
+                self.g_optimizer.finish_apply()
+                if o_grads is not None:
+                    self.ocr_optimizer.finish_apply()
+                self.d_optimizer.finish_apply()
+            else:
+                self.g_optimizer.finish_apply()
+                if o_grads is not None:
+                    self.ocr_optimizer.begin_apply(G, self._ocr_names, list(o_grads))
+                    self.ocr_optimizer.finish_apply()
+                self.d_optimizer.finish_apply()
 
         self._step_weights.end_step()
         gen_losses = (reg_g_loss.detach(), g_loss.detach(), pl_penalty.detach())
