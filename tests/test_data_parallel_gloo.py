@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(rank, world, port, ret, shard=None):
+def _run(rank, world, port, ret, shard=None, late_comm=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -49,6 +49,7 @@ def _run(rank, world, port, ret, shard=None):
         go, do = update_optimizer_params(cfg.g_opt), update_optimizer_params(cfg.d_opt)
         mk = lambda o: Adam(o["learning_rate"], beta_1=o["beta1"], beta_2=o["beta2"], epsilon=o["epsilon"])
         ts = TrainingStep(G, D, None, mk(go), mk(go), mk(do), 8, 16, torch.zeros(()), cfg)
+        ts.overlap_comm = not late_comm
         out = ts.dist_train_step(real[sl], torch.zeros(()), words[sl], labels[sl], False, False, 1e-4, draws=d)
     if rank == 0:
         ret["losses"] = [float(v) for v in (*out[0], *out[1], out[2])]
@@ -89,6 +90,18 @@ def test_two_ranks_sum_gradients_of_their_shards():
     # identical replicas stay identical: rank 0's weights after the update are what a single process
     # applying the summed gradient would hold (checked through the Adam step bound)
     assert (r2["G"] - s0["G"]).abs().max().item() < 5e-3
+
+
+def test_all_reduces_after_the_last_backward_pass_give_the_same_update():
+    """TrainingStep.overlap_comm = False (the three cross-replica sums issued after the last backward pass instead of
+    after each group's own pass) changes only the issue order: same summed gradients, same weights."""
+    mgr = mp.Manager()
+    a, b = mgr.dict(), mgr.dict()
+    mp.spawn(_run, args=(2, _free_port(), a), nprocs=2, join=True)
+    mp.spawn(_run, args=(2, _free_port(), b, None, True), nprocs=2, join=True)
+    for key in ("gG", "gD", "G", "D"):
+        assert torch.equal(a[key], b[key]), key
+    assert a["losses"] == b["losses"]
 
 
 def _init_run(rank, world, port, ret):
